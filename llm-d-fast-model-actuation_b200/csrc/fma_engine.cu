@@ -1,0 +1,1619 @@
+// fma_engine.cu — host side of the B200 sleep/wake weight-movement engine (C-ABI in
+// include/fma_engine.h).  No kernels live here; see fma_kernels.cu.
+//
+// What it replaces in the reference's hot path:
+//   a1 CuMemAllocator.sleep      vllm:device_allocator/cumem.py:177-225   -> fma_sleep
+//   a2 CuMemAllocator.wake_up    vllm:device_allocator/cumem.py:227-249   -> fma_wake
+//   a3 pointer_to_data registry  cumem.py:47-55,131,140-175               -> Engine::segs
+//   a5 my_malloc/my_free/create_and_map/unmap_and_release (cumem_allocator.abi3.so, T3)
+//   a6 blocking cudaMemcpy       cuda_wrapper.py:168-173                  -> multi-stream async copy engines / K1,K2
+//
+// Design (B200-first, not a port):
+//   * one Engine per GPU / process (rank); segments are CUDA-VMM ranges whose VA reservation
+//     outlives unmap so every tensor keeps its device address across sleep -> wake;
+//   * a sleeping model is a PACKED IMAGE: its offloaded segments concatenated page by page
+//     (2 MiB VMM pages) in allocation order, held in one pre-pinned NUMA-local host store,
+//     or a parking buffer in a peer GPU's HBM (NVLink tier);
+//   * wake overlaps three things the reference serialises: cuMemCreate/Map/SetAccess of the
+//     next segments (mapper thread), H2D DMA on several copy-engine streams, and (staged /
+//     kernel modes) the K2 page scatter;
+//   * the driver API is resolved at run time (cudaGetDriverEntryPoint) so the library loads
+//     on a box without libcuda — and then refuses to do anything (FMA_ENODRIVER).
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cctype>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include <sys/mman.h>
+#include <sys/syscall.h>
+#include <unistd.h>
+
+#include "../../include/fma_engine.h"
+#include "fma_kernels.h"
+
+namespace {
+
+// ------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------
+thread_local char tl_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(tl_err, sizeof(tl_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+double now_s() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+#define RT(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t _e = (call);                                                                          \
+        if (_e != cudaSuccess)                                                                            \
+            return fail(FMA_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+// ------------------------------------------------------------------------------------
+// driver API, resolved lazily through the (static) runtime: no link-time libcuda dependency
+// ------------------------------------------------------------------------------------
+struct Driver {
+    bool ok = false;
+    CUresult (*GetErrorString)(CUresult, const char**) = nullptr;
+    CUresult (*MemAddressReserve)(CUdeviceptr*, size_t, size_t, CUdeviceptr, unsigned long long) = nullptr;
+    CUresult (*MemAddressFree)(CUdeviceptr, size_t) = nullptr;
+    CUresult (*MemCreate)(CUmemGenericAllocationHandle*, size_t, const CUmemAllocationProp*, unsigned long long) = nullptr;
+    CUresult (*MemRelease)(CUmemGenericAllocationHandle) = nullptr;
+    CUresult (*MemMap)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long) = nullptr;
+    CUresult (*MemUnmap)(CUdeviceptr, size_t) = nullptr;
+    CUresult (*MemSetAccess)(CUdeviceptr, size_t, const CUmemAccessDesc*, size_t) = nullptr;
+    CUresult (*MemGetAllocationGranularity)(size_t*, const CUmemAllocationProp*, CUmemAllocationGranularity_flags) = nullptr;
+};
+Driver g_drv;
+std::once_flag g_drv_once;
+char g_drv_err[256] = "";
+
+template <typename F>
+bool resolve(const char* name, F& fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !p) {
+        snprintf(g_drv_err, sizeof(g_drv_err), "cannot resolve driver symbol %s: %s", name,
+                 e != cudaSuccess ? cudaGetErrorString(e) : "not found");
+        cudaGetLastError();
+        return false;
+    }
+    fn = reinterpret_cast<F>(p);
+    return true;
+}
+
+void load_driver() {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        snprintf(g_drv_err, sizeof(g_drv_err), "no usable CUDA driver/device: %s",
+                 e != cudaSuccess ? cudaGetErrorString(e) : "0 devices");
+        cudaGetLastError();
+        return;
+    }
+    bool ok = resolve("cuGetErrorString", g_drv.GetErrorString) && resolve("cuMemAddressReserve", g_drv.MemAddressReserve) &&
+              resolve("cuMemAddressFree", g_drv.MemAddressFree) && resolve("cuMemCreate", g_drv.MemCreate) &&
+              resolve("cuMemRelease", g_drv.MemRelease) && resolve("cuMemMap", g_drv.MemMap) &&
+              resolve("cuMemUnmap", g_drv.MemUnmap) && resolve("cuMemSetAccess", g_drv.MemSetAccess) &&
+              resolve("cuMemGetAllocationGranularity", g_drv.MemGetAllocationGranularity);
+    g_drv.ok = ok;
+}
+
+bool driver_ready() {
+    std::call_once(g_drv_once, load_driver);
+    return g_drv.ok;
+}
+
+const char* cu_err(CUresult r) {
+    const char* s = nullptr;
+    if (g_drv.GetErrorString && g_drv.GetErrorString(r, &s) == CUDA_SUCCESS && s) return s;
+    return "unknown CUresult";
+}
+
+#define DRV(call)                                                                                         \
+    do {                                                                                                  \
+        CUresult _r = (call);                                                                             \
+        if (_r != CUDA_SUCCESS)                                                                           \
+            return fail(_r == CUDA_ERROR_OUT_OF_MEMORY ? FMA_ENOMEM : FMA_ECUDA, "%s failed: %s (%s:%d)", #call, \
+                        cu_err(_r), __FILE__, __LINE__);                                                  \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool changed = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) {
+            cudaSetDevice(dev);
+            changed = true;
+        }
+    }
+    ~DeviceGuard() {
+        if (changed && prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+size_t round_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
+// ------------------------------------------------------------------------------------
+// data structures
+// ------------------------------------------------------------------------------------
+constexpr uint64_t kNoOffset = UINT64_MAX;
+
+struct Segment {
+    CUdeviceptr va = 0;
+    size_t bytes = 0;       // page-aligned
+    size_t requested = 0;
+    int tag = 0;
+    uint64_t seq = 0;
+    CUmemGenericAllocationHandle handle = 0;
+    bool mapped = false;
+    bool has_backup = false;
+    int backup_tier = FMA_TIER_HOST;
+    uint64_t packed_off = kNoOffset;
+    uint64_t digest = 0;
+    bool digest_valid = false;
+};
+
+struct HostStore {
+    void* base = nullptr;       // host pointer
+    void* dev_alias = nullptr;  // device-visible alias of base (mapped pinned)
+    size_t cap = 0;
+    bool registered = false;    // mmap + cudaHostRegister (else cudaHostAlloc)
+    int numa_node = -1;
+    double pin_seconds = 0;
+};
+
+struct ParkStore {  // peer-HBM or local-HBM parking buffer (VMM, P2P mapped)
+    CUdeviceptr va = 0;
+    size_t cap = 0;
+    CUmemGenericAllocationHandle handle = 0;
+    int device = -1;
+};
+
+constexpr int kMaxStreams = 8;
+constexpr int kMaxRing = 8;
+
+}  // namespace
+
+struct fma_engine {
+    int device = 0;
+    size_t gran = FMA_PAGE_BYTES;
+    fma_config_t cfg{};
+    std::mutex mu;  // guards segs / tags (my_malloc can arrive from any torch thread)
+    std::vector<Segment> segs;  // allocation order == reference dict order (cumem.py:198,237)
+    std::map<CUdeviceptr, size_t> by_va;
+    uint64_t next_seq = 0;
+    std::vector<std::string> tags;
+    int current_tag = 0;
+
+    HostStore host;
+    ParkStore park;
+    uint64_t image_bytes = 0;  // W of the current packed image
+    int image_tier = FMA_TIER_HOST;
+
+    cudaStream_t cs[kMaxStreams] = {};  // copy-engine streams
+    int n_cs = 0;
+    cudaStream_t ks = nullptr;          // kernel stream
+    cudaEvent_t ev_start = nullptr, ev_end = nullptr;
+    cudaEvent_t ev_cs[kMaxStreams] = {};
+    std::vector<cudaEvent_t> ev_pool;   // timing pairs for kernels
+    // HBM staging ring (STAGED mode)
+    void* ring[kMaxRing] = {};
+    cudaEvent_t ev_ring_full[kMaxRing] = {};
+    cudaEvent_t ev_ring_free[kMaxRing] = {};
+    int n_ring = 0;
+    size_t ring_slot_bytes = 0;
+    // device page tables (uploaded per operation)
+    uint64_t* d_tab = nullptr;
+    size_t d_tab_cap = 0;  // entries
+    uint64_t* h_tab = nullptr;  // pinned mirror
+    fma_k_page_desc* d_desc = nullptr;
+    fma_k_page_desc* h_desc = nullptr;
+    uint64_t* d_dig = nullptr;
+    uint64_t* h_dig = nullptr;
+    size_t desc_cap = 0;
+
+    fma_k_tma_cfg tma = fma_k_default_tma_cfg();
+    fma_stats_t st{};
+};
+
+namespace {
+
+fma_engine_t* g_current = nullptr;
+std::mutex g_current_mu;
+
+int tag_bit_set(uint64_t mask, int tag) { return (int)((mask >> tag) & 1ull); }
+
+// ------------------------------------------------------------------------------------
+// VMM primitives (replace cumem_allocator's create_and_map / unmap_and_release)
+// ------------------------------------------------------------------------------------
+CUmemAllocationProp device_prop(int device) {
+    CUmemAllocationProp prop;
+    memset(&prop, 0, sizeof(prop));
+    prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+    prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    prop.location.id = device;
+    return prop;
+}
+
+int vmm_create_and_map(int device, CUdeviceptr va, size_t bytes, CUmemGenericAllocationHandle* out) {
+    CUmemAllocationProp prop = device_prop(device);
+    CUmemGenericAllocationHandle h = 0;
+    DRV(g_drv.MemCreate(&h, bytes, &prop, 0));
+    CUresult r = g_drv.MemMap(va, bytes, 0, h, 0);
+    if (r != CUDA_SUCCESS) {
+        g_drv.MemRelease(h);
+        return fail(FMA_ECUDA, "cuMemMap failed: %s", cu_err(r));
+    }
+    CUmemAccessDesc acc;
+    memset(&acc, 0, sizeof(acc));
+    acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    acc.location.id = device;
+    acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+    r = g_drv.MemSetAccess(va, bytes, &acc, 1);
+    if (r != CUDA_SUCCESS) {
+        g_drv.MemUnmap(va, bytes);
+        g_drv.MemRelease(h);
+        return fail(FMA_ECUDA, "cuMemSetAccess failed: %s", cu_err(r));
+    }
+    *out = h;
+    return FMA_OK;
+}
+
+int vmm_unmap_and_release(CUdeviceptr va, size_t bytes, CUmemGenericAllocationHandle h) {
+    DRV(g_drv.MemUnmap(va, bytes));
+    DRV(g_drv.MemRelease(h));
+    return FMA_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// engine resources
+// ------------------------------------------------------------------------------------
+int ensure_streams(fma_engine_t* e) {
+    if (e->ks) return FMA_OK;
+    int n = e->cfg.copy_streams > 0 ? e->cfg.copy_streams : 4;
+    n = std::min(n, kMaxStreams);
+    for (int i = 0; i < kMaxStreams; ++i) {  // all created up front; n_cs selects how many are used
+        RT(cudaStreamCreateWithFlags(&e->cs[i], cudaStreamNonBlocking));
+        RT(cudaEventCreateWithFlags(&e->ev_cs[i], cudaEventDisableTiming));
+    }
+    e->n_cs = n;
+    RT(cudaStreamCreateWithFlags(&e->ks, cudaStreamNonBlocking));
+    RT(cudaEventCreate(&e->ev_start));
+    RT(cudaEventCreate(&e->ev_end));
+    return FMA_OK;
+}
+
+int ensure_tables(fma_engine_t* e, size_t n_pages) {
+    if (n_pages <= e->d_tab_cap) return FMA_OK;
+    size_t cap = std::max<size_t>(round_up(n_pages, 4096), 16384);
+    if (e->d_tab) cudaFree(e->d_tab);
+    if (e->h_tab) cudaFreeHost(e->h_tab);
+    e->d_tab = nullptr;
+    e->h_tab = nullptr;
+    e->d_tab_cap = 0;
+    RT(cudaMalloc(&e->d_tab, 2 * cap * sizeof(uint64_t)));       // [src table | dst table]
+    RT(cudaHostAlloc(&e->h_tab, 2 * cap * sizeof(uint64_t), cudaHostAllocDefault));
+    e->d_tab_cap = cap;
+    return FMA_OK;
+}
+
+int ensure_desc(fma_engine_t* e, size_t n_pages) {
+    if (n_pages <= e->desc_cap) return FMA_OK;
+    size_t cap = std::max<size_t>(round_up(n_pages, 4096), 16384);
+    if (e->d_desc) cudaFree(e->d_desc);
+    if (e->h_desc) cudaFreeHost(e->h_desc);
+    if (e->d_dig) cudaFree(e->d_dig);
+    if (e->h_dig) cudaFreeHost(e->h_dig);
+    e->d_desc = nullptr; e->h_desc = nullptr; e->d_dig = nullptr; e->h_dig = nullptr;
+    e->desc_cap = 0;
+    RT(cudaMalloc(&e->d_desc, cap * sizeof(fma_k_page_desc)));
+    RT(cudaHostAlloc(&e->h_desc, cap * sizeof(fma_k_page_desc), cudaHostAllocDefault));
+    RT(cudaMalloc(&e->d_dig, cap * sizeof(uint64_t)));
+    RT(cudaHostAlloc(&e->h_dig, cap * sizeof(uint64_t), cudaHostAllocDefault));
+    e->desc_cap = cap;
+    return FMA_OK;
+}
+
+int ensure_ring(fma_engine_t* e) {
+    size_t slot = e->cfg.chunk_bytes ? (size_t)e->cfg.chunk_bytes : ((size_t)32 << 20);
+    slot = round_up(slot, FMA_PAGE_BYTES);
+    int n = e->cfg.ring_slots > 0 ? std::min(e->cfg.ring_slots, kMaxRing) : 4;
+    if (e->n_ring == n && e->ring_slot_bytes == slot) return FMA_OK;
+    for (int i = 0; i < e->n_ring; ++i) {
+        cudaFree(e->ring[i]);
+        e->ring[i] = nullptr;
+    }
+    e->n_ring = 0;
+    for (int i = 0; i < n; ++i) {
+        RT(cudaMalloc(&e->ring[i], slot));
+        if (!e->ev_ring_full[i]) RT(cudaEventCreateWithFlags(&e->ev_ring_full[i], cudaEventDisableTiming));
+        if (!e->ev_ring_free[i]) RT(cudaEventCreateWithFlags(&e->ev_ring_free[i], cudaEventDisableTiming));
+        e->n_ring = i + 1;
+    }
+    e->ring_slot_bytes = slot;
+    return FMA_OK;
+}
+
+int ensure_event_pool(fma_engine_t* e, size_t n) {
+    while (e->ev_pool.size() < n) {
+        cudaEvent_t ev;
+        RT(cudaEventCreate(&ev));
+        e->ev_pool.push_back(ev);
+    }
+    return FMA_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// host store: one NUMA-local, pre-pinned arena (replaces per-segment torch.empty(pin_memory=True),
+// cumem.py:204-209).  mmap + mbind + parallel first-touch + cudaHostRegister, fallback cudaHostAlloc.
+// ------------------------------------------------------------------------------------
+int gpu_numa_node(int device) {
+    char bus[64] = "";
+    if (cudaDeviceGetPCIBusId(bus, sizeof(bus), device) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    for (char* p = bus; *p; ++p) *p = (char)tolower(*p);
+    char path[160];
+    snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
+    FILE* f = fopen(path, "r");
+    if (!f) return -1;
+    int node = -1;
+    if (fscanf(f, "%d", &node) != 1) node = -1;
+    fclose(f);
+    return node;
+}
+
+void host_store_free(HostStore& h) {
+    if (!h.base) return;
+    if (h.registered) {
+        cudaHostUnregister(h.base);
+        munmap(h.base, h.cap);
+    } else {
+        cudaFreeHost(h.base);
+    }
+    cudaGetLastError();
+    h = HostStore{};
+}
+
+int host_store_reserve(fma_engine_t* e, size_t bytes) {
+    bytes = round_up(std::max<size_t>(bytes, FMA_PAGE_BYTES), FMA_PAGE_BYTES);
+    if (e->host.base && e->host.cap >= bytes) return FMA_OK;
+    host_store_free(e->host);
+    const double t0 = now_s();
+    HostStore h;
+    h.cap = bytes;
+    const int want_bind = e->cfg.numa_bind != 0;  // -1 (default) and 1 both bind
+    const int node = want_bind ? gpu_numa_node(e->device) : -1;
+    const bool use_register = env_int("FMA_HOST_REGISTER", 1) != 0;
+    if (use_register) {
+        void* p = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+        if (p != MAP_FAILED) {
+            madvise(p, bytes, MADV_HUGEPAGE);
+            if (node >= 0 && node < 64) {
+                unsigned long mask = 1ul << node;
+                // MPOL_PREFERRED = 1: fall back to the other node rather than fail under pressure
+                if (syscall(SYS_mbind, p, bytes, 1, &mask, sizeof(mask) * 8, 0) == 0) h.numa_node = node;
+            }
+            // parallel first touch so the pages exist before the (serial) pin
+            int nt = std::max(1, std::min(env_int("FMA_TOUCH_THREADS", 8), 32));
+            std::vector<std::thread> th;
+            const size_t per = round_up((bytes + nt - 1) / nt, FMA_PAGE_BYTES);
+            for (int t = 0; t < nt; ++t) {
+                size_t lo = (size_t)t * per, hi = std::min(bytes, lo + per);
+                if (lo >= hi) break;
+                th.emplace_back([p, lo, hi] { memset((char*)p + lo, 0, hi - lo); });
+            }
+            for (auto& t : th) t.join();
+            cudaError_t r = cudaHostRegister(p, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped);
+            if (r == cudaSuccess) {
+                h.base = p;
+                h.registered = true;
+            } else {
+                cudaGetLastError();
+                munmap(p, bytes);
+            }
+        }
+    }
+    if (!h.base) {
+        void* p = nullptr;
+        cudaError_t r = cudaHostAlloc(&p, bytes, cudaHostAllocPortable | cudaHostAllocMapped);
+        if (r != cudaSuccess) {
+            cudaGetLastError();
+            return fail(FMA_ENOMEM, "cannot pin %zu bytes of host store: %s", bytes, cudaGetErrorString(r));
+        }
+        h.base = p;
+        h.registered = false;
+        h.numa_node = -1;
+    }
+    void* alias = nullptr;
+    if (cudaHostGetDevicePointer(&alias, h.base, 0) == cudaSuccess) h.dev_alias = alias;
+    else cudaGetLastError();
+    h.pin_seconds = now_s() - t0;
+    e->host = h;
+    e->st.host_store_bytes = h.cap;
+    e->st.host_store_pin_seconds = h.pin_seconds;
+    e->st.host_store_numa_node = h.numa_node;
+    return FMA_OK;
+}
+
+int park_release(fma_engine_t* e) {
+    if (!e->park.va) return FMA_OK;
+    cudaDeviceSynchronize();
+    g_drv.MemUnmap(e->park.va, e->park.cap);
+    g_drv.MemRelease(e->park.handle);
+    g_drv.MemAddressFree(e->park.va, e->park.cap);
+    e->park = ParkStore{};
+    return FMA_OK;
+}
+
+int park_reserve(fma_engine_t* e, int park_device, size_t bytes) {
+    bytes = round_up(std::max<size_t>(bytes, FMA_PAGE_BYTES), e->gran);
+    if (e->park.va && e->park.device == park_device && e->park.cap >= bytes) return FMA_OK;
+    park_release(e);
+    int ndev = 0;
+    RT(cudaGetDeviceCount(&ndev));
+    if (park_device < 0 || park_device >= ndev) return fail(FMA_EINVAL, "parking device %d not visible (have %d)", park_device, ndev);
+    if (park_device != e->device) {
+        int can = 0;
+        RT(cudaDeviceCanAccessPeer(&can, e->device, park_device));
+        if (!can) return fail(FMA_ECUDA, "device %d cannot access peer %d (no NVLink/P2P path)", e->device, park_device);
+        // make sure the peer's primary context exists (cuMemCreate needs the device initialised)
+        DeviceGuard g(park_device);
+        RT(cudaFree(nullptr));
+    }
+    ParkStore p;
+    p.device = park_device;
+    p.cap = bytes;
+    CUmemAllocationProp prop = device_prop(park_device);
+    DRV(g_drv.MemCreate(&p.handle, bytes, &prop, 0));
+    CUresult r = g_drv.MemAddressReserve(&p.va, bytes, FMA_PAGE_BYTES, 0, 0);
+    if (r != CUDA_SUCCESS) {
+        g_drv.MemRelease(p.handle);
+        return fail(FMA_ECUDA, "cuMemAddressReserve(park) failed: %s", cu_err(r));
+    }
+    r = g_drv.MemMap(p.va, bytes, 0, p.handle, 0);
+    if (r != CUDA_SUCCESS) {
+        g_drv.MemAddressFree(p.va, bytes);
+        g_drv.MemRelease(p.handle);
+        return fail(FMA_ECUDA, "cuMemMap(park) failed: %s", cu_err(r));
+    }
+    CUmemAccessDesc acc[2];
+    memset(acc, 0, sizeof(acc));
+    acc[0].location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    acc[0].location.id = e->device;
+    acc[0].flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+    acc[1] = acc[0];
+    acc[1].location.id = park_device;
+    r = g_drv.MemSetAccess(p.va, bytes, acc, park_device != e->device ? 2 : 1);
+    if (r != CUDA_SUCCESS) {
+        g_drv.MemUnmap(p.va, bytes);
+        g_drv.MemAddressFree(p.va, bytes);
+        g_drv.MemRelease(p.handle);
+        return fail(FMA_ECUDA, "cuMemSetAccess(park, P2P) failed: %s", cu_err(r));
+    }
+    e->park = p;
+    return FMA_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// allocation
+// ------------------------------------------------------------------------------------
+int engine_alloc(fma_engine_t* e, size_t bytes, int tag, void** out) {
+    if (bytes == 0) bytes = 1;
+    const size_t sz = round_up(bytes, e->gran);
+    CUdeviceptr va = 0;
+    DRV(g_drv.MemAddressReserve(&va, sz, e->gran, 0, 0));
+    CUmemGenericAllocationHandle h = 0;
+    int rc = vmm_create_and_map(e->device, va, sz, &h);
+    if (rc != FMA_OK) {
+        g_drv.MemAddressFree(va, sz);
+        return rc;
+    }
+    Segment s;
+    s.va = va;
+    s.bytes = sz;
+    s.requested = bytes;
+    s.tag = tag;
+    s.handle = h;
+    s.mapped = true;
+    {
+        std::lock_guard<std::mutex> lk(e->mu);
+        s.seq = e->next_seq++;
+        e->by_va[va] = e->segs.size();
+        e->segs.push_back(s);
+    }
+    *out = reinterpret_cast<void*>(va);
+    return FMA_OK;
+}
+
+int engine_free(fma_engine_t* e, void* ptr) {
+    Segment s;
+    {
+        std::lock_guard<std::mutex> lk(e->mu);
+        auto it = e->by_va.find(reinterpret_cast<CUdeviceptr>(ptr));
+        if (it == e->by_va.end()) return fail(FMA_ENOTFOUND, "pointer %p is not an engine segment", ptr);
+        const size_t idx = it->second;
+        s = e->segs[idx];
+        e->segs.erase(e->segs.begin() + idx);
+        e->by_va.clear();
+        for (size_t i = 0; i < e->segs.size(); ++i) e->by_va[e->segs[i].va] = i;
+    }
+    if (s.mapped) {
+        // Drain work that may still touch the range before it is unmapped — the reference does
+        // torch.cuda.synchronize() in its free callback for the same reason (cumem.py:156-169).
+        cudaDeviceSynchronize();
+        int rc = vmm_unmap_and_release(s.va, s.bytes, s.handle);
+        if (rc != FMA_OK) return rc;
+    }
+    DRV(g_drv.MemAddressFree(s.va, s.bytes));
+    return FMA_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// packed image planning
+// ------------------------------------------------------------------------------------
+struct Extent {          // one segment's slice of the packed image
+    size_t seg_index;
+    CUdeviceptr va;
+    size_t bytes;
+    uint64_t packed_off;
+};
+
+// Fill h_tab[0..n) with the device address of every page of the packed image, in order.
+size_t build_page_table(const std::vector<Extent>& ex, uint64_t* tab) {
+    size_t n = 0;
+    for (const Extent& x : ex)
+        for (size_t o = 0; o < x.bytes; o += FMA_PAGE_BYTES) tab[n++] = (uint64_t)x.va + o;
+    return n;
+}
+
+struct CopyTimer {  // device-time bracket over all engine streams
+    fma_engine_t* e;
+    int begin() {
+        RT(cudaEventRecord(e->ev_start, e->ks));
+        for (int i = 0; i < e->n_cs; ++i) RT(cudaStreamWaitEvent(e->cs[i], e->ev_start, 0));
+        return FMA_OK;
+    }
+    int end(double* seconds) {
+        for (int i = 0; i < e->n_cs; ++i) {
+            RT(cudaEventRecord(e->ev_cs[i], e->cs[i]));
+            RT(cudaStreamWaitEvent(e->ks, e->ev_cs[i], 0));
+        }
+        RT(cudaEventRecord(e->ev_end, e->ks));
+        RT(cudaEventSynchronize(e->ev_end));
+        float ms = 0;
+        RT(cudaEventElapsedTime(&ms, e->ev_start, e->ev_end));
+        *seconds = ms * 1e-3;
+        return FMA_OK;
+    }
+};
+
+struct KernelTimes {  // event pairs around each K1/K2 launch on the kernel stream
+    fma_engine_t* e;
+    size_t used = 0;
+    uint64_t bytes = 0;
+    int launch(const uint64_t* src_tab, uint64_t src_base, const uint64_t* dst_tab, uint64_t dst_base, uint32_t n_pages) {
+        int rc = ensure_event_pool(e, used + 2);
+        if (rc != FMA_OK) return rc;
+        RT(cudaEventRecord(e->ev_pool[used], e->ks));
+        RT(fma_k_launch_page_copy(src_tab, src_base, dst_tab, dst_base, n_pages, e->cfg.kernel, &e->tma, e->ks));
+        RT(cudaEventRecord(e->ev_pool[used + 1], e->ks));
+        used += 2;
+        bytes += 2ull * n_pages * FMA_PAGE_BYTES;
+        return FMA_OK;
+    }
+    int collect() {  // call after the streams are synchronised
+        double s = 0;
+        for (size_t i = 0; i + 1 < used; i += 2) {
+            float ms = 0;
+            RT(cudaEventElapsedTime(&ms, e->ev_pool[i], e->ev_pool[i + 1]));
+            s += ms * 1e-3;
+        }
+        e->st.kernel_seconds = s;
+        e->st.kernel_bytes = bytes;
+        e->st.kernel_launches = (uint32_t)(used / 2);
+        e->st.total_kernel_launches += used / 2;
+        return FMA_OK;
+    }
+};
+
+int resolve_mode(const fma_engine_t* e, int tier) {
+    int m = e->cfg.mode;
+    if (m == FMA_MODE_AUTO) m = (tier == FMA_TIER_HOST) ? FMA_MODE_DIRECT : FMA_MODE_KERNEL;
+    if (tier != FMA_TIER_HOST && m == FMA_MODE_STAGED) m = FMA_MODE_KERNEL;  // staging only helps across PCIe
+    return m;
+}
+
+uint64_t store_dev_base(const fma_engine_t* e, int tier) {
+    return tier == FMA_TIER_HOST ? (uint64_t)(uintptr_t)e->host.dev_alias : (uint64_t)e->park.va;
+}
+void* store_copy_base(const fma_engine_t* e, int tier) {
+    return tier == FMA_TIER_HOST ? e->host.base : reinterpret_cast<void*>(e->park.va);
+}
+
+// ------------------------------------------------------------------------------------
+// digest of a set of segments in ONE launch (K3)
+// ------------------------------------------------------------------------------------
+int digest_segments(fma_engine_t* e, const std::vector<size_t>& idx, std::vector<uint64_t>* out) {
+    size_t n_pages = 0;
+    for (size_t i : idx) n_pages += e->segs[i].bytes / FMA_PAGE_BYTES;
+    out->assign(idx.size(), 0);
+    if (!n_pages) return FMA_OK;
+    int rc = ensure_streams(e);
+    if (rc != FMA_OK) return rc;
+    rc = ensure_desc(e, n_pages);
+    if (rc != FMA_OK) return rc;
+    size_t p = 0;
+    for (size_t i : idx) {
+        const Segment& s = e->segs[i];
+        for (size_t o = 0; o < s.bytes; o += FMA_PAGE_BYTES, ++p) {
+            e->h_desc[p].addr = (uint64_t)s.va + o;
+            e->h_desc[p].first_word = o / 8;
+        }
+    }
+    RT(cudaMemcpyAsync(e->d_desc, e->h_desc, n_pages * sizeof(fma_k_page_desc), cudaMemcpyHostToDevice, e->ks));
+    RT(cudaMemsetAsync(e->d_dig, 0, n_pages * sizeof(uint64_t), e->ks));
+    RT(fma_k_launch_page_digest(e->d_desc, (uint32_t)n_pages, e->d_dig, e->ks));
+    RT(cudaMemcpyAsync(e->h_dig, e->d_dig, n_pages * sizeof(uint64_t), cudaMemcpyDeviceToHost, e->ks));
+    RT(cudaStreamSynchronize(e->ks));
+    e->st.total_kernel_launches += 1;
+    p = 0;
+    for (size_t k = 0; k < idx.size(); ++k) {
+        uint64_t acc = 0;
+        const size_t np = e->segs[idx[k]].bytes / FMA_PAGE_BYTES;
+        for (size_t j = 0; j < np; ++j) acc += e->h_dig[p++];
+        (*out)[k] = acc;
+    }
+    return FMA_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// SLEEP
+// ------------------------------------------------------------------------------------
+int do_sleep(fma_engine_t* e, uint64_t offload_mask, int tier, uint32_t flags) {
+    const double t_entry = now_s();
+    DeviceGuard guard(e->device);
+    int rc = ensure_streams(e);
+    if (rc != FMA_OK) return rc;
+
+    // Executor.sleep is a no-op while sleeping (abstract.py:323-325)
+    bool any_unmapped = false, any_mapped = false;
+    for (const Segment& s : e->segs) (s.mapped ? any_mapped : any_unmapped) = true;
+    if (any_unmapped || !any_mapped) return FMA_OK;
+
+    // plan: offloaded segments in allocation order -> packed image
+    std::vector<Extent> ex;
+    uint64_t W = 0, discarded = 0;
+    for (size_t i = 0; i < e->segs.size(); ++i) {
+        Segment& s = e->segs[i];
+        s.has_backup = false;
+        s.packed_off = kNoOffset;
+        s.digest_valid = false;
+        if (tag_bit_set(offload_mask, s.tag)) {
+            ex.push_back(Extent{i, s.va, s.bytes, W});
+            W += s.bytes;
+        } else {
+            discarded += s.bytes;
+        }
+    }
+    const int mode = resolve_mode(e, tier);
+    if (W) {
+        if (tier == FMA_TIER_HOST) {
+            rc = host_store_reserve(e, W);
+            if (rc != FMA_OK) return rc;
+            if (mode == FMA_MODE_KERNEL && !e->host.dev_alias) return fail(FMA_ECUDA, "host store has no device alias for zero-copy mode");
+        } else if (tier == FMA_TIER_PEER) {
+            if (!e->park.va || e->park.cap < W || e->park.device == e->device)
+                return fail(FMA_ESTATE, "peer tier needs fma_peer_reserve(peer_device, >= %llu bytes) first", (unsigned long long)W);
+        } else if (tier == FMA_TIER_LOCAL) {
+            rc = park_reserve(e, e->device, W);
+            if (rc != FMA_OK) return rc;
+        } else {
+            return fail(FMA_EINVAL, "unknown tier %d", tier);
+        }
+    }
+
+    if ((flags & FMA_FLAG_VERIFY) && W) {
+        std::vector<size_t> idx;
+        for (const Extent& x : ex) idx.push_back(x.seg_index);
+        std::vector<uint64_t> dg;
+        rc = digest_segments(e, idx, &dg);
+        if (rc != FMA_OK) return rc;
+        for (size_t k = 0; k < idx.size(); ++k) {
+            e->segs[idx[k]].digest = dg[k];
+            e->segs[idx[k]].digest_valid = true;
+        }
+    }
+
+    // The caller's own streams may still be writing weights: drain the device once, as the
+    // reference's blocking cudaMemcpy on the legacy stream implicitly does.
+    RT(cudaDeviceSynchronize());
+
+    CopyTimer timer{e};
+    KernelTimes kt{e};
+    uint32_t copy_ops = 0;
+    double copy_s = 0;
+    if (W) {
+        const size_t chunk = e->cfg.chunk_bytes ? round_up((size_t)e->cfg.chunk_bytes, FMA_PAGE_BYTES) : ((size_t)32 << 20);
+        char* store = static_cast<char*>(store_copy_base(e, tier));
+        rc = timer.begin();
+        if (rc != FMA_OK) return rc;
+        if (mode == FMA_MODE_DIRECT) {
+            // copy engines straight from each segment into the packed image, chunked round-robin over streams
+            int k = 0;
+            for (const Extent& x : ex)
+                for (size_t o = 0; o < x.bytes; o += chunk, ++k) {
+                    const size_t n = std::min(chunk, x.bytes - o);
+                    RT(cudaMemcpyAsync(store + x.packed_off + o, reinterpret_cast<void*>(x.va + o), n, cudaMemcpyDefault,
+                                       e->cs[k % e->n_cs]));
+                    ++copy_ops;
+                }
+        } else {
+            const size_t n_pages = W / FMA_PAGE_BYTES;
+            rc = ensure_tables(e, n_pages);
+            if (rc != FMA_OK) return rc;
+            build_page_table(ex, e->h_tab);
+            RT(cudaMemcpyAsync(e->d_tab, e->h_tab, n_pages * sizeof(uint64_t), cudaMemcpyHostToDevice, e->ks));
+            if (mode == FMA_MODE_KERNEL) {
+                // K1 writes the store itself: mapped pinned host memory (PCIe posted writes) or peer/local HBM
+                rc = kt.launch(e->d_tab, 0, nullptr, store_dev_base(e, tier), (uint32_t)n_pages);
+                if (rc != FMA_OK) return rc;
+            } else {  // STAGED: K1 gather -> HBM ring slot -> copy engine D2H
+                rc = ensure_ring(e);
+                if (rc != FMA_OK) return rc;
+                const size_t slot_pages = e->ring_slot_bytes / FMA_PAGE_BYTES;
+                size_t c = 0;
+                for (size_t p0 = 0; p0 < n_pages; p0 += slot_pages, ++c) {
+                    const int slot = (int)(c % e->n_ring);
+                    const size_t np = std::min(slot_pages, n_pages - p0);
+                    cudaStream_t cstream = e->cs[c % e->n_cs];
+                    if (c >= (size_t)e->n_ring) RT(cudaStreamWaitEvent(e->ks, e->ev_ring_free[slot], 0));
+                    rc = kt.launch(e->d_tab + p0, 0, nullptr, (uint64_t)(uintptr_t)e->ring[slot], (uint32_t)np);
+                    if (rc != FMA_OK) return rc;
+                    RT(cudaEventRecord(e->ev_ring_full[slot], e->ks));
+                    RT(cudaStreamWaitEvent(cstream, e->ev_ring_full[slot], 0));
+                    RT(cudaMemcpyAsync(store + p0 * FMA_PAGE_BYTES, e->ring[slot], np * FMA_PAGE_BYTES, cudaMemcpyDefault, cstream));
+                    RT(cudaEventRecord(e->ev_ring_free[slot], cstream));
+                    ++copy_ops;
+                }
+            }
+        }
+        rc = timer.end(&copy_s);
+        if (rc != FMA_OK) return rc;
+        rc = kt.collect();
+        if (rc != FMA_OK) return rc;
+    }
+
+    // unmap + release EVERYTHING (cumem.py:213), VAs stay reserved
+    const double t_un0 = now_s();
+    for (const Extent& x : ex) {
+        Segment& s = e->segs[x.seg_index];
+        s.has_backup = true;
+        s.backup_tier = tier;
+        s.packed_off = x.packed_off;
+    }
+    for (Segment& s : e->segs) {
+        if (!s.mapped) continue;
+        rc = vmm_unmap_and_release(s.va, s.bytes, s.handle);
+        if (rc != FMA_OK) return rc;
+        s.mapped = false;
+        s.handle = 0;
+    }
+    const double t_un1 = now_s();
+    e->image_bytes = W;
+    e->image_tier = tier;
+
+    e->st.sleep_seconds = now_s() - t_entry;
+    e->st.sleep_copy_seconds = copy_s;
+    e->st.sleep_unmap_seconds = t_un1 - t_un0;
+    e->st.sleep_bytes_offloaded = W;
+    e->st.sleep_bytes_discarded = discarded;
+    e->st.copy_ops = copy_ops;
+    e->st.total_copy_ops += copy_ops;
+    e->st.tier = tier;
+    e->st.mode = mode;
+    if (!W) {
+        e->st.kernel_seconds = 0;
+        e->st.kernel_bytes = 0;
+        e->st.kernel_launches = 0;
+    }
+    return FMA_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// WAKE
+// ------------------------------------------------------------------------------------
+struct MapProgress {
+    std::mutex mu;
+    std::condition_variable cv;
+    size_t done = 0;      // number of work items fully mapped (prefix)
+    int error = FMA_OK;
+    char msg[512] = "";
+};
+
+int do_wake(fma_engine_t* e, uint64_t tag_mask, uint32_t flags) {
+    const double t_entry = now_s();
+    DeviceGuard guard(e->device);
+    int rc = ensure_streams(e);
+    if (rc != FMA_OK) return rc;
+
+    // work list in allocation order: segments with a backup first keep their relative order (they
+    // gate the copy pipeline); remap-only segments (e.g. kv_cache) are mapped after them.
+    std::vector<size_t> with_backup, remap_only;
+    for (size_t i = 0; i < e->segs.size(); ++i) {
+        const Segment& s = e->segs[i];
+        if (s.mapped) continue;                                  // idempotent: already awake
+        if (tag_mask && !tag_bit_set(tag_mask, s.tag)) continue;  // tags is None or data.tag in tags (cumem.py:238)
+        (s.has_backup ? with_backup : remap_only).push_back(i);
+    }
+    if (with_backup.empty() && remap_only.empty()) return FMA_OK;
+
+    std::vector<size_t> order = with_backup;
+    order.insert(order.end(), remap_only.begin(), remap_only.end());
+    const int tier = e->image_tier;
+    const int mode = resolve_mode(e, tier);
+
+    // ---- mapper thread(s): cuMemCreate + cuMemMap + cuMemSetAccess in `order` -------------------
+    MapProgress prog;
+    std::vector<char> item_done(order.size(), 0);
+    std::atomic<size_t> next_item{0};
+    std::atomic<uint64_t> map_ns{0};
+    const int n_map = std::max(1, std::min(e->cfg.map_threads > 0 ? e->cfg.map_threads : 1, 8));
+    auto mapper = [&]() {
+        cudaSetDevice(e->device);
+        for (;;) {
+            const size_t k = next_item.fetch_add(1);
+            if (k >= order.size()) break;
+            {
+                std::lock_guard<std::mutex> lk(prog.mu);
+                if (prog.error != FMA_OK) break;
+            }
+            Segment& s = e->segs[order[k]];
+            const double t0 = now_s();
+            CUmemGenericAllocationHandle h = 0;
+            int r = vmm_create_and_map(e->device, s.va, s.bytes, &h);
+            map_ns.fetch_add((uint64_t)((now_s() - t0) * 1e9));
+            std::lock_guard<std::mutex> lk(prog.mu);
+            if (r != FMA_OK) {
+                prog.error = r;
+                snprintf(prog.msg, sizeof(prog.msg), "%s", tl_err);
+            } else {
+                s.handle = h;
+                s.mapped = true;
+                item_done[k] = 1;
+                while (prog.done < order.size() && item_done[prog.done]) ++prog.done;
+            }
+            prog.cv.notify_all();
+        }
+    };
+    std::vector<std::thread> mappers;
+    for (int t = 0; t < n_map; ++t) mappers.emplace_back(mapper);
+    auto join_mappers = [&]() {
+        for (auto& t : mappers)
+            if (t.joinable()) t.join();
+    };
+    auto wait_mapped = [&](size_t upto) -> int {  // wait until items [0, upto) are mapped
+        std::unique_lock<std::mutex> lk(prog.mu);
+        prog.cv.wait(lk, [&] { return prog.done >= upto || prog.error != FMA_OK; });
+        return prog.error;
+    };
+    auto mapped_now = [&]() -> size_t {
+        std::lock_guard<std::mutex> lk(prog.mu);
+        return prog.done;
+    };
+#define WAKE_CHECK(x)                     \
+    do {                                  \
+        int _rc = (x);                    \
+        if (_rc != FMA_OK) {              \
+            {                             \
+                std::lock_guard<std::mutex> lk(prog.mu); \
+                if (prog.error == FMA_OK) prog.error = _rc; \
+            }                             \
+            join_mappers();               \
+            cudaDeviceSynchronize();      \
+            return _rc;                   \
+        }                                 \
+    } while (0)
+#define WAKE_RT(call)                                                                              \
+    do {                                                                                           \
+        cudaError_t _e = (call);                                                                   \
+        if (_e != cudaSuccess) WAKE_CHECK(fail(FMA_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__)); \
+    } while (0)
+
+    // ---- copy pipeline --------------------------------------------------------------------------
+    uint64_t W = 0;
+    for (size_t i : with_backup) W += e->segs[i].bytes;
+    CopyTimer timer{e};
+    KernelTimes kt{e};
+    uint32_t copy_ops = 0;
+    double copy_s = 0, first_copy_delay = 0;
+    if (W) {
+        const size_t chunk = e->cfg.chunk_bytes ? round_up((size_t)e->cfg.chunk_bytes, FMA_PAGE_BYTES) : ((size_t)32 << 20);
+        const char* store = static_cast<const char*>(store_copy_base(e, tier));
+        if (!store) WAKE_CHECK(fail(FMA_ESTATE, "backup store of tier %d is gone", tier));
+        if (tier == FMA_TIER_HOST && mode == FMA_MODE_KERNEL && !e->host.dev_alias)
+            WAKE_CHECK(fail(FMA_ECUDA, "host store has no device alias for zero-copy mode"));
+        WAKE_CHECK(timer.begin());
+        if (mode == FMA_MODE_DIRECT) {
+            int k = 0;
+            for (size_t w = 0; w < with_backup.size(); ++w) {
+                int mrc = wait_mapped(w + 1);
+                if (mrc != FMA_OK) WAKE_CHECK(fail(mrc, "%s", prog.msg));
+                const Segment& s = e->segs[with_backup[w]];
+                for (size_t o = 0; o < s.bytes; o += chunk, ++k) {
+                    const size_t n = std::min(chunk, s.bytes - o);
+                    WAKE_RT(cudaMemcpyAsync(reinterpret_cast<void*>(s.va + o), store + s.packed_off + o, n, cudaMemcpyDefault,
+                                            e->cs[k % e->n_cs]));
+                    if (!copy_ops) first_copy_delay = now_s() - t_entry;
+                    ++copy_ops;
+                }
+            }
+        } else {
+            // page table of the DESTINATIONS, ordered by packed offset (== with_backup order by construction
+            // only if every backed-up segment is woken; build explicitly from packed offsets to stay general)
+            struct Dst { uint64_t packed_off; size_t w; };
+            std::vector<Dst> d;
+            for (size_t w = 0; w < with_backup.size(); ++w) d.push_back(Dst{e->segs[with_backup[w]].packed_off, w});
+            std::sort(d.begin(), d.end(), [](const Dst& a, const Dst& b) { return a.packed_off < b.packed_off; });
+            // runs of pages: (image page index, destination address), plus the latest work item each page needs
+            size_t n_pages = W / FMA_PAGE_BYTES;
+            WAKE_CHECK(ensure_tables(e, n_pages));
+            uint64_t* dst_tab = e->h_tab;                 // destination page addresses
+            uint64_t* src_tab = e->h_tab + e->d_tab_cap;  // source page addresses inside the store (may be sparse)
+            std::vector<size_t> need_item(n_pages);
+            const uint64_t sbase = store_dev_base(e, tier);
+            size_t p = 0;
+            for (const Dst& x : d) {
+                const Segment& s = e->segs[with_backup[x.w]];
+                for (size_t o = 0; o < s.bytes; o += FMA_PAGE_BYTES, ++p) {
+                    dst_tab[p] = (uint64_t)s.va + o;
+                    src_tab[p] = sbase + s.packed_off + o;
+                    need_item[p] = x.w + 1;
+                }
+            }
+            WAKE_RT(cudaMemcpyAsync(e->d_tab, dst_tab, n_pages * sizeof(uint64_t), cudaMemcpyHostToDevice, e->ks));
+            WAKE_RT(cudaMemcpyAsync(e->d_tab + e->d_tab_cap, src_tab, n_pages * sizeof(uint64_t), cudaMemcpyHostToDevice, e->ks));
+            const uint64_t* d_dst = e->d_tab;
+            const uint64_t* d_src = e->d_tab + e->d_tab_cap;
+            if (mode == FMA_MODE_KERNEL) {
+                // K2 reads the store itself (zero-copy PCIe reads, or NVLink/HBM loads); launch batches as the
+                // mapper makes progress so the scatter overlaps cuMemCreate/Map of later segments
+                const size_t batch_pages = std::max<size_t>(chunk / FMA_PAGE_BYTES, 1) * 8;
+                size_t p0 = 0;
+                while (p0 < n_pages) {
+                    size_t np = std::min(batch_pages, n_pages - p0);
+                    size_t need = 0;
+                    for (size_t q = p0; q < p0 + np; ++q) need = std::max(need, need_item[q]);
+                    int mrc = wait_mapped(need);
+                    if (mrc != FMA_OK) WAKE_CHECK(fail(mrc, "%s", prog.msg));
+                    // opportunistically extend the batch over everything already mapped
+                    const size_t have = mapped_now();
+                    while (p0 + np < n_pages && need_item[p0 + np] <= have) ++np;
+                    WAKE_CHECK(kt.launch(d_src + p0, 0, d_dst + p0, 0, (uint32_t)np));
+                    if (!copy_ops) first_copy_delay = now_s() - t_entry;
+                    ++copy_ops;
+                    p0 += np;
+                }
+            } else {  // STAGED: copy engine H2D store -> ring slot (starts at t=0), K2 scatter once the targets are mapped
+                WAKE_CHECK(ensure_ring(e));
+                const size_t slot_pages = e->ring_slot_bytes / FMA_PAGE_BYTES;
+                // the store image may be only partially woken; H2D works on runs that are contiguous in the store
+                size_t c = 0;
+                size_t p0 = 0;
+                while (p0 < n_pages) {
+                    size_t np = 1;
+                    while (np < slot_pages && p0 + np < n_pages && src_tab[p0 + np] == src_tab[p0 + np - 1] + FMA_PAGE_BYTES) ++np;
+                    const int slot = (int)(c % e->n_ring);
+                    cudaStream_t cstream = e->cs[c % e->n_cs];
+                    if (c >= (size_t)e->n_ring) WAKE_RT(cudaStreamWaitEvent(cstream, e->ev_ring_free[slot], 0));
+                    WAKE_RT(cudaMemcpyAsync(e->ring[slot], store + (src_tab[p0] - sbase), np * FMA_PAGE_BYTES, cudaMemcpyDefault, cstream));
+                    if (!copy_ops) first_copy_delay = now_s() - t_entry;
+                    ++copy_ops;
+                    WAKE_RT(cudaEventRecord(e->ev_ring_full[slot], cstream));
+                    size_t need = 0;
+                    for (size_t q = p0; q < p0 + np; ++q) need = std::max(need, need_item[q]);
+                    int mrc = wait_mapped(need);
+                    if (mrc != FMA_OK) WAKE_CHECK(fail(mrc, "%s", prog.msg));
+                    WAKE_RT(cudaStreamWaitEvent(e->ks, e->ev_ring_full[slot], 0));
+                    WAKE_CHECK(kt.launch(nullptr, (uint64_t)(uintptr_t)e->ring[slot], d_dst + p0, 0, (uint32_t)np));
+                    WAKE_RT(cudaEventRecord(e->ev_ring_free[slot], e->ks));
+                    p0 += np;
+                    ++c;
+                }
+            }
+        }
+    }
+    // every requested segment must be mapped before wake returns (cumem.py:237-240)
+    {
+        int mrc = wait_mapped(order.size());
+        if (mrc != FMA_OK) WAKE_CHECK(fail(mrc, "%s", prog.msg));
+    }
+    join_mappers();
+    if (W) {
+        rc = timer.end(&copy_s);
+        if (rc != FMA_OK) return rc;
+        rc = kt.collect();
+        if (rc != FMA_OK) return rc;
+    }
+#undef WAKE_CHECK
+#undef WAKE_RT
+
+    uint64_t remapped_only = 0;
+    for (size_t i : remap_only) remapped_only += e->segs[i].bytes;
+
+    int verify_rc = FMA_OK;
+    if ((flags & FMA_FLAG_VERIFY) && W) {
+        std::vector<size_t> idx;
+        for (size_t i : with_backup)
+            if (e->segs[i].digest_valid) idx.push_back(i);
+        std::vector<uint64_t> dg;
+        rc = digest_segments(e, idx, &dg);
+        if (rc != FMA_OK) return rc;
+        for (size_t k = 0; k < idx.size(); ++k)
+            if (dg[k] != e->segs[idx[k]].digest)
+                verify_rc = fail(FMA_EINTEGRITY, "segment %zu (va 0x%llx): digest %016llx after wake != %016llx before sleep", idx[k],
+                                 (unsigned long long)e->segs[idx[k]].va, (unsigned long long)dg[k],
+                                 (unsigned long long)e->segs[idx[k]].digest);
+    }
+    if (!(flags & FMA_FLAG_KEEP_BACKUP))
+        for (size_t i : with_backup) {  // data.cpu_backup_tensor = None (cumem.py:249)
+            e->segs[i].has_backup = false;
+            e->segs[i].packed_off = kNoOffset;
+        }
+
+    e->st.wake_seconds = now_s() - t_entry;
+    e->st.wake_copy_seconds = copy_s;
+    e->st.wake_map_seconds = map_ns.load() * 1e-9;
+    e->st.wake_first_copy_delay = first_copy_delay;
+    e->st.wake_bytes_restored = W;
+    e->st.wake_bytes_remapped_only = remapped_only;
+    e->st.copy_ops = copy_ops;
+    e->st.total_copy_ops += copy_ops;
+    e->st.tier = tier;
+    e->st.mode = mode;
+    if (!W) {
+        e->st.kernel_seconds = 0;
+        e->st.kernel_bytes = 0;
+        e->st.kernel_launches = 0;
+    }
+    return verify_rc;
+}
+
+int check_engine(fma_engine_t* e) {
+    if (!e) return fail(FMA_EINVAL, "engine handle is NULL");
+    return FMA_OK;
+}
+
+}  // namespace
+
+// ======================================================================================
+// C ABI
+// ======================================================================================
+extern "C" {
+
+int fma_abi_version(void) { return FMA_ABI_VERSION; }
+const char* fma_last_error(void) { return tl_err; }
+
+int fma_driver_available(void) {
+    if (driver_ready()) return FMA_OK;
+    return fail(FMA_ENODRIVER, "%s", g_drv_err[0] ? g_drv_err : "CUDA driver not available");
+}
+
+int fma_engine_create(int device, const fma_config_t* cfg, fma_engine_t** out) {
+    if (!out) return fail(FMA_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (cfg && cfg->abi_version != FMA_ABI_VERSION)
+        return fail(FMA_EINVAL, "config abi_version %u != library %d", cfg->abi_version, FMA_ABI_VERSION);
+    if (!driver_ready()) return fail(FMA_ENODRIVER, "%s", g_drv_err[0] ? g_drv_err : "CUDA driver not available");
+    int ndev = 0;
+    RT(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(FMA_EINVAL, "device %d out of range (have %d)", device, ndev);
+    DeviceGuard guard(device);
+    RT(cudaFree(nullptr));  // make the primary context current on this thread
+    fma_engine_t* e = new fma_engine();
+    e->device = device;
+    if (cfg) e->cfg = *cfg;
+    e->cfg.abi_version = FMA_ABI_VERSION;
+    if (e->cfg.numa_bind == 0 && !cfg) e->cfg.numa_bind = -1;
+    // experiment knobs (documented in DESIGN.md); the config struct wins when set
+    if (!e->cfg.mode) e->cfg.mode = env_int("FMA_MODE", 0);
+    if (!e->cfg.kernel) e->cfg.kernel = env_int("FMA_KERNEL", 0);
+    if (!e->cfg.copy_streams) e->cfg.copy_streams = env_int("FMA_COPY_STREAMS", 0);
+    if (!e->cfg.chunk_bytes) e->cfg.chunk_bytes = (uint64_t)env_int("FMA_CHUNK_MIB", 0) << 20;
+    if (!e->cfg.ring_slots) e->cfg.ring_slots = env_int("FMA_RING_SLOTS", 0);
+    if (!e->cfg.map_threads) e->cfg.map_threads = env_int("FMA_MAP_THREADS", 0);
+    e->tma.tile_bytes = (uint32_t)env_int("FMA_TMA_TILE_KIB", (int)(e->tma.tile_bytes >> 10)) << 10;
+    e->tma.stages = (uint32_t)env_int("FMA_TMA_STAGES", (int)e->tma.stages);
+    e->tma.pipes = (uint32_t)env_int("FMA_TMA_PIPES", (int)e->tma.pipes);
+    e->tma.ctas_per_sm = (uint32_t)env_int("FMA_TMA_CTAS_PER_SM", (int)e->tma.ctas_per_sm);
+    CUmemAllocationProp prop = device_prop(device);
+    size_t gran = 0;
+    CUresult r = g_drv.MemGetAllocationGranularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_MINIMUM);
+    if (r != CUDA_SUCCESS || gran == 0) {
+        delete e;
+        return fail(FMA_ECUDA, "cuMemGetAllocationGranularity failed: %s", cu_err(r));
+    }
+    if (gran % FMA_PAGE_BYTES != 0 && FMA_PAGE_BYTES % gran != 0) {
+        delete e;
+        return fail(FMA_ECUDA, "VMM granularity %zu incompatible with the 2 MiB engine page", gran);
+    }
+    e->gran = std::max(gran, FMA_PAGE_BYTES);
+    e->tags.push_back("default");  // tag 0 == CuMemAllocator.default_tag (cumem.py:116)
+    int rc = ensure_streams(e);
+    if (rc != FMA_OK) {
+        delete e;
+        return rc;
+    }
+    *out = e;
+    return FMA_OK;
+}
+
+int fma_engine_destroy(fma_engine_t* e) {
+    if (!e) return FMA_OK;
+    {
+        std::lock_guard<std::mutex> lk(g_current_mu);
+        if (g_current == e) g_current = nullptr;
+    }
+    DeviceGuard guard(e->device);
+    cudaDeviceSynchronize();
+    for (Segment& s : e->segs) {
+        if (s.mapped) {
+            g_drv.MemUnmap(s.va, s.bytes);
+            g_drv.MemRelease(s.handle);
+        }
+        g_drv.MemAddressFree(s.va, s.bytes);
+    }
+    e->segs.clear();
+    host_store_free(e->host);
+    park_release(e);
+    for (int i = 0; i < e->n_ring; ++i) cudaFree(e->ring[i]);
+    for (int i = 0; i < kMaxRing; ++i) {
+        if (e->ev_ring_full[i]) cudaEventDestroy(e->ev_ring_full[i]);
+        if (e->ev_ring_free[i]) cudaEventDestroy(e->ev_ring_free[i]);
+    }
+    if (e->d_tab) cudaFree(e->d_tab);
+    if (e->h_tab) cudaFreeHost(e->h_tab);
+    if (e->d_desc) cudaFree(e->d_desc);
+    if (e->h_desc) cudaFreeHost(e->h_desc);
+    if (e->d_dig) cudaFree(e->d_dig);
+    if (e->h_dig) cudaFreeHost(e->h_dig);
+    for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
+    for (int i = 0; i < kMaxStreams; ++i) {
+        if (e->cs[i]) cudaStreamDestroy(e->cs[i]);
+        if (e->ev_cs[i]) cudaEventDestroy(e->ev_cs[i]);
+    }
+    if (e->ks) cudaStreamDestroy(e->ks);
+    if (e->ev_start) cudaEventDestroy(e->ev_start);
+    if (e->ev_end) cudaEventDestroy(e->ev_end);
+    cudaGetLastError();
+    delete e;
+    return FMA_OK;
+}
+
+int fma_set_current(fma_engine_t* e) {
+    std::lock_guard<std::mutex> lk(g_current_mu);
+    g_current = e;
+    return FMA_OK;
+}
+fma_engine_t* fma_get_current(void) {
+    std::lock_guard<std::mutex> lk(g_current_mu);
+    return g_current;
+}
+
+int fma_tag_intern(fma_engine_t* e, const char* name) {
+    if (check_engine(e) != FMA_OK) return FMA_EINVAL;
+    if (!name) return fail(FMA_EINVAL, "tag name is NULL");
+    std::lock_guard<std::mutex> lk(e->mu);
+    for (size_t i = 0; i < e->tags.size(); ++i)
+        if (e->tags[i] == name) return (int)i;
+    if (e->tags.size() >= FMA_MAX_TAGS) return fail(FMA_ENOMEM, "more than %d tags", FMA_MAX_TAGS);
+    e->tags.push_back(name);
+    return (int)e->tags.size() - 1;
+}
+
+int fma_tag_name(fma_engine_t* e, int tag, char* buf, size_t buflen) {
+    if (check_engine(e) != FMA_OK) return FMA_EINVAL;
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (tag < 0 || (size_t)tag >= e->tags.size() || !buf || !buflen) return fail(FMA_ENOTFOUND, "unknown tag %d", tag);
+    snprintf(buf, buflen, "%s", e->tags[tag].c_str());
+    return FMA_OK;
+}
+
+int fma_set_current_tag(fma_engine_t* e, int tag) {
+    if (check_engine(e) != FMA_OK) return FMA_EINVAL;
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (tag < 0 || (size_t)tag >= e->tags.size()) return fail(FMA_ENOTFOUND, "unknown tag %d", tag);
+    e->current_tag = tag;
+    return FMA_OK;
+}
+
+void* my_malloc(ssize_t size, int device, void* /*stream*/) {
+    fma_engine_t* e = fma_get_current();
+    if (!e) {
+        // same convenience as the reference module, whose globals exist as soon as it is loaded
+        if (fma_engine_create(device, nullptr, &e) != FMA_OK) return nullptr;
+        fma_set_current(e);
+    }
+    if (e->device != device) {
+        fail(FMA_EINVAL, "my_malloc for device %d but the current engine owns device %d", device, e->device);
+        return nullptr;
+    }
+    if (size < 0) return nullptr;
+    DeviceGuard guard(e->device);
+    int tag;
+    {
+        std::lock_guard<std::mutex> lk(e->mu);
+        tag = e->current_tag;
+    }
+    void* p = nullptr;
+    if (engine_alloc(e, (size_t)size, tag, &p) != FMA_OK) return nullptr;
+    return p;
+}
+
+void my_free(void* ptr, ssize_t /*size*/, int /*device*/, void* /*stream*/) {
+    fma_engine_t* e = fma_get_current();
+    if (!e || !ptr) return;
+    DeviceGuard guard(e->device);
+    engine_free(e, ptr);
+}
+
+int fma_alloc(fma_engine_t* e, size_t bytes, int tag, void** out_ptr) {
+    if (check_engine(e) != FMA_OK) return FMA_EINVAL;
+    if (!out_ptr) return fail(FMA_EINVAL, "out_ptr is NULL");
+    {
+        std::lock_guard<std::mutex> lk(e->mu);
+        if (tag < 0 || (size_t)tag >= e->tags.size()) return fail(FMA_ENOTFOUND, "unknown tag %d", tag);
+    }
+    DeviceGuard guard(e->device);
+    return engine_alloc(e, bytes, tag, out_ptr);
+}
+
+int fma_free(fma_engine_t* e, void* ptr) {
+    if (check_engine(e) != FMA_OK) return FMA_EINVAL;
+    DeviceGuard guard(e->device);
+    return engine_free(e, ptr);
+}
+
+int fma_segment_count(fma_engine_t* e) {
+    if (check_engine(e) != FMA_OK) return FMA_EINVAL;
+    std::lock_guard<std::mutex> lk(e->mu);
+    return (int)e->segs.size();
+}
+
+int fma_segment_info(fma_engine_t* e, int index, fma_segment_info_t* out) {
+    if (check_engine(e) != FMA_OK) return FMA_EINVAL;
+    if (!out) return fail(FMA_EINVAL, "out is NULL");
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (index < 0 || (size_t)index >= e->segs.size()) return fail(FMA_ENOTFOUND, "segment index %d out of range", index);
+    const Segment& s = e->segs[index];
+    out->va = (uint64_t)s.va;
+    out->bytes = s.bytes;
+    out->requested_bytes = s.requested;
+    out->packed_offset = s.packed_off;
+    out->seq = s.seq;
+    out->tag = s.tag;
+    out->mapped = s.mapped ? 1 : 0;
+    out->has_backup = s.has_backup ? 1 : 0;
+    out->tier = s.backup_tier;
+    return FMA_OK;
+}
+
+int fma_segment_find(fma_engine_t* e, const void* ptr) {
+    if (check_engine(e) != FMA_OK) return FMA_EINVAL;
+    std::lock_guard<std::mutex> lk(e->mu);
+    auto it = e->by_va.find(reinterpret_cast<CUdeviceptr>(ptr));
+    if (it == e->by_va.end()) return fail(FMA_ENOTFOUND, "pointer %p is not an engine segment", ptr);
+    return (int)it->second;
+}
+
+uint64_t fma_current_usage(fma_engine_t* e) {
+    if (!e) return 0;
+    std::lock_guard<std::mutex> lk(e->mu);
+    uint64_t sum = 0;
+    for (const Segment& s : e->segs) sum += s.bytes;
+    return sum;
+}
+
+int fma_sleep(fma_engine_t* e, uint64_t offload_tag_mask, int tier, uint32_t flags) {
+    if (check_engine(e) != FMA_OK) return FMA_EINVAL;
+    return do_sleep(e, offload_tag_mask, tier, flags);
+}
+
+int fma_wake(fma_engine_t* e, uint64_t tag_mask, uint32_t flags) {
+    if (check_engine(e) != FMA_OK) return FMA_EINVAL;
+    return do_wake(e, tag_mask, flags);
+}
+
+int fma_is_sleeping(fma_engine_t* e) {
+    if (check_engine(e) != FMA_OK) return FMA_EINVAL;
+    std::lock_guard<std::mutex> lk(e->mu);
+    for (const Segment& s : e->segs)
+        if (!s.mapped) return 1;
+    return 0;
+}
+
+int fma_swap(fma_engine_t* out_e, uint64_t offload_tag_mask, int tier, fma_engine_t* in_e, uint64_t wake_tag_mask,
+             uint32_t flags) {
+    if (check_engine(out_e) != FMA_OK || check_engine(in_e) != FMA_OK) return FMA_EINVAL;
+    if (out_e == in_e) return fail(FMA_EINVAL, "swap needs two different engines");
+    int rc_sleep = FMA_OK;
+    char sleep_msg[512] = "";
+    std::thread t([&] {
+        rc_sleep = do_sleep(out_e, offload_tag_mask, tier, flags);
+        if (rc_sleep != FMA_OK) snprintf(sleep_msg, sizeof(sleep_msg), "%s", tl_err);
+    });
+    int rc_wake = do_wake(in_e, wake_tag_mask, flags);
+    t.join();
+    if (rc_wake != FMA_OK) return rc_wake;
+    if (rc_sleep != FMA_OK) return fail(rc_sleep, "%s", sleep_msg);
+    return FMA_OK;
+}
+
+int fma_host_reserve(fma_engine_t* e, size_t bytes) {
+    if (check_engine(e) != FMA_OK) return FMA_EINVAL;
+    for (const Segment& s : e->segs)
+        if (s.has_backup && s.backup_tier == FMA_TIER_HOST && e->host.cap < bytes)
+            return fail(FMA_ESTATE, "cannot regrow the host store while it holds a sleeping image");
+    DeviceGuard guard(e->device);
+    return host_store_reserve(e, bytes);
+}
+
+int fma_host_release(fma_engine_t* e) {
+    if (check_engine(e) != FMA_OK) return FMA_EINVAL;
+    for (const Segment& s : e->segs)
+        if (s.has_backup && s.backup_tier == FMA_TIER_HOST) return fail(FMA_ESTATE, "host store holds a sleeping image");
+    DeviceGuard guard(e->device);
+    cudaDeviceSynchronize();
+    host_store_free(e->host);
+    e->st.host_store_bytes = 0;
+    return FMA_OK;
+}
+
+int fma_host_store_view(fma_engine_t* e, const void** base, uint64_t* bytes) {
+    if (check_engine(e) != FMA_OK) return FMA_EINVAL;
+    if (!base || !bytes) return fail(FMA_EINVAL, "NULL out pointer");
+    if (!e->host.base || e->image_tier != FMA_TIER_HOST) return fail(FMA_ESTATE, "no host image");
+    *base = e->host.base;
+    *bytes = e->image_bytes;
+    return FMA_OK;
+}
+
+int fma_peer_reserve(fma_engine_t* e, int peer_device, size_t bytes) {
+    if (check_engine(e) != FMA_OK) return FMA_EINVAL;
+    for (const Segment& s : e->segs)
+        if (s.has_backup && s.backup_tier != FMA_TIER_HOST) return fail(FMA_ESTATE, "parking buffer holds a sleeping image");
+    DeviceGuard guard(e->device);
+    return park_reserve(e, peer_device, bytes);
+}
+
+int fma_peer_release(fma_engine_t* e) {
+    if (check_engine(e) != FMA_OK) return FMA_EINVAL;
+    for (const Segment& s : e->segs)
+        if (s.has_backup && s.backup_tier != FMA_TIER_HOST) return fail(FMA_ESTATE, "parking buffer holds a sleeping image");
+    DeviceGuard guard(e->device);
+    return park_release(e);
+}
+
+int fma_digest_segment(fma_engine_t* e, int index, uint64_t* out) {
+    if (check_engine(e) != FMA_OK) return FMA_EINVAL;
+    if (!out) return fail(FMA_EINVAL, "out is NULL");
+    if (index < 0 || (size_t)index >= e->segs.size()) return fail(FMA_ENOTFOUND, "segment index %d out of range", index);
+    if (!e->segs[index].mapped) return fail(FMA_ESTATE, "segment %d is not mapped", index);
+    DeviceGuard guard(e->device);
+    std::vector<uint64_t> dg;
+    int rc = digest_segments(e, {(size_t)index}, &dg);
+    if (rc == FMA_OK) *out = dg[0];
+    return rc;
+}
+
+int fma_digest_all(fma_engine_t* e, uint64_t tag_mask, uint64_t* out, int n) {
+    if (check_engine(e) != FMA_OK) return FMA_EINVAL;
+    if (!out || n < (int)e->segs.size()) return fail(FMA_EINVAL, "out too small: %d < %zu", n, e->segs.size());
+    DeviceGuard guard(e->device);
+    std::vector<size_t> idx;
+    for (size_t i = 0; i < e->segs.size(); ++i) {
+        out[i] = 0;
+        const Segment& s = e->segs[i];
+        if (s.mapped && (!tag_mask || tag_bit_set(tag_mask, s.tag))) idx.push_back(i);
+    }
+    std::vector<uint64_t> dg;
+    int rc = digest_segments(e, idx, &dg);
+    if (rc != FMA_OK) return rc;
+    for (size_t k = 0; k < idx.size(); ++k) out[idx[k]] = dg[k];
+    return FMA_OK;
+}
+
+int fma_fill_segment(fma_engine_t* e, int index, uint64_t seed, uint64_t first_word) {
+    if (check_engine(e) != FMA_OK) return FMA_EINVAL;
+    if (index < 0 || (size_t)index >= e->segs.size()) return fail(FMA_ENOTFOUND, "segment index %d out of range", index);
+    const Segment& s = e->segs[index];
+    if (!s.mapped) return fail(FMA_ESTATE, "segment %d is not mapped", index);
+    DeviceGuard guard(e->device);
+    const size_t n_pages = s.bytes / FMA_PAGE_BYTES;
+    int rc = ensure_desc(e, n_pages);
+    if (rc != FMA_OK) return rc;
+    for (size_t p = 0; p < n_pages; ++p) {
+        e->h_desc[p].addr = (uint64_t)s.va + p * FMA_PAGE_BYTES;
+        e->h_desc[p].first_word = first_word + p * (FMA_PAGE_BYTES / 8);
+    }
+    RT(cudaMemcpyAsync(e->d_desc, e->h_desc, n_pages * sizeof(fma_k_page_desc), cudaMemcpyHostToDevice, e->ks));
+    RT(fma_k_launch_fill(e->d_desc, (uint32_t)n_pages, seed, e->ks));
+    RT(cudaStreamSynchronize(e->ks));
+    e->st.total_kernel_launches += 1;
+    return FMA_OK;
+}
+
+int fma_segment_write(fma_engine_t* e, int index, uint64_t offset, const void* host_src, uint64_t bytes) {
+    if (check_engine(e) != FMA_OK) return FMA_EINVAL;
+    if (index < 0 || (size_t)index >= e->segs.size()) return fail(FMA_ENOTFOUND, "segment index %d out of range", index);
+    const Segment& s = e->segs[index];
+    if (!s.mapped) return fail(FMA_ESTATE, "segment %d is not mapped", index);
+    if (offset + bytes > s.bytes) return fail(FMA_EINVAL, "write past the end of segment %d", index);
+    DeviceGuard guard(e->device);
+    RT(cudaMemcpyAsync(reinterpret_cast<void*>(s.va + offset), host_src, bytes, cudaMemcpyHostToDevice, e->ks));
+    RT(cudaStreamSynchronize(e->ks));
+    return FMA_OK;
+}
+
+int fma_segment_read(fma_engine_t* e, int index, uint64_t offset, void* host_dst, uint64_t bytes) {
+    if (check_engine(e) != FMA_OK) return FMA_EINVAL;
+    if (index < 0 || (size_t)index >= e->segs.size()) return fail(FMA_ENOTFOUND, "segment index %d out of range", index);
+    const Segment& s = e->segs[index];
+    if (!s.mapped) return fail(FMA_ESTATE, "segment %d is not mapped", index);
+    if (offset + bytes > s.bytes) return fail(FMA_EINVAL, "read past the end of segment %d", index);
+    DeviceGuard guard(e->device);
+    RT(cudaMemcpyAsync(host_dst, reinterpret_cast<const void*>(s.va + offset), bytes, cudaMemcpyDeviceToHost, e->ks));
+    RT(cudaStreamSynchronize(e->ks));
+    return FMA_OK;
+}
+
+int fma_op_page_copy(fma_engine_t* e, const uint64_t* src_pages, uint64_t src_base, const uint64_t* dst_pages,
+                     uint64_t dst_base, uint32_t n_pages, int kernel_variant, float* out_ms) {
+    if (check_engine(e) != FMA_OK) return FMA_EINVAL;
+    if (!n_pages) return FMA_OK;
+    DeviceGuard guard(e->device);
+    int rc = ensure_tables(e, n_pages);
+    if (rc != FMA_OK) return rc;
+    const uint64_t* d_src = nullptr;
+    const uint64_t* d_dst = nullptr;
+    if (src_pages) {
+        memcpy(e->h_tab, src_pages, n_pages * sizeof(uint64_t));
+        RT(cudaMemcpyAsync(e->d_tab, e->h_tab, n_pages * sizeof(uint64_t), cudaMemcpyHostToDevice, e->ks));
+        d_src = e->d_tab;
+    }
+    if (dst_pages) {
+        memcpy(e->h_tab + e->d_tab_cap, dst_pages, n_pages * sizeof(uint64_t));
+        RT(cudaMemcpyAsync(e->d_tab + e->d_tab_cap, e->h_tab + e->d_tab_cap, n_pages * sizeof(uint64_t), cudaMemcpyHostToDevice, e->ks));
+        d_dst = e->d_tab + e->d_tab_cap;
+    }
+    RT(cudaEventRecord(e->ev_start, e->ks));
+    RT(fma_k_launch_page_copy(d_src, src_base, d_dst, dst_base, n_pages, kernel_variant, &e->tma, e->ks));
+    RT(cudaEventRecord(e->ev_end, e->ks));
+    RT(cudaEventSynchronize(e->ev_end));
+    e->st.total_kernel_launches += 1;
+    if (out_ms) RT(cudaEventElapsedTime(out_ms, e->ev_start, e->ev_end));
+    return FMA_OK;
+}
+
+int fma_op_page_digest(fma_engine_t* e, const uint64_t* pages, uint64_t base, const uint64_t* first_word, uint32_t n_pages,
+                       uint64_t* out_page_digests, float* out_ms) {
+    if (check_engine(e) != FMA_OK) return FMA_EINVAL;
+    if (!n_pages) return FMA_OK;
+    if (!out_page_digests) return fail(FMA_EINVAL, "out is NULL");
+    DeviceGuard guard(e->device);
+    int rc = ensure_desc(e, n_pages);
+    if (rc != FMA_OK) return rc;
+    for (uint32_t p = 0; p < n_pages; ++p) {
+        e->h_desc[p].addr = pages ? pages[p] : base + (uint64_t)p * FMA_PAGE_BYTES;
+        e->h_desc[p].first_word = first_word ? first_word[p] : (uint64_t)p * (FMA_PAGE_BYTES / 8);
+    }
+    RT(cudaMemcpyAsync(e->d_desc, e->h_desc, n_pages * sizeof(fma_k_page_desc), cudaMemcpyHostToDevice, e->ks));
+    RT(cudaMemsetAsync(e->d_dig, 0, n_pages * sizeof(uint64_t), e->ks));
+    RT(cudaEventRecord(e->ev_start, e->ks));
+    RT(fma_k_launch_page_digest(e->d_desc, n_pages, e->d_dig, e->ks));
+    RT(cudaEventRecord(e->ev_end, e->ks));
+    RT(cudaMemcpyAsync(e->h_dig, e->d_dig, n_pages * sizeof(uint64_t), cudaMemcpyDeviceToHost, e->ks));
+    RT(cudaStreamSynchronize(e->ks));
+    e->st.total_kernel_launches += 1;
+    memcpy(out_page_digests, e->h_dig, n_pages * sizeof(uint64_t));
+    if (out_ms) RT(cudaEventElapsedTime(out_ms, e->ev_start, e->ev_end));
+    return FMA_OK;
+}
+
+int fma_scratch_alloc(fma_engine_t* e, size_t bytes, uint64_t* out_dev_ptr) {
+    if (check_engine(e) != FMA_OK) return FMA_EINVAL;
+    if (!out_dev_ptr) return fail(FMA_EINVAL, "out is NULL");
+    DeviceGuard guard(e->device);
+    void* p = nullptr;
+    cudaError_t r = cudaMalloc(&p, bytes);
+    if (r != cudaSuccess) {
+        cudaGetLastError();
+        return fail(FMA_ENOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(r));
+    }
+    *out_dev_ptr = (uint64_t)(uintptr_t)p;
+    return FMA_OK;
+}
+
+int fma_scratch_free(fma_engine_t* e, uint64_t dev_ptr) {
+    if (check_engine(e) != FMA_OK) return FMA_EINVAL;
+    DeviceGuard guard(e->device);
+    RT(cudaFree(reinterpret_cast<void*>((uintptr_t)dev_ptr)));
+    return FMA_OK;
+}
+
+int fma_set_option(fma_engine_t* e, const char* key, int64_t value) {
+    if (check_engine(e) != FMA_OK) return FMA_EINVAL;
+    if (!key) return fail(FMA_EINVAL, "key is NULL");
+    const std::string k(key);
+    if (k == "mode") {
+        if (value < FMA_MODE_AUTO || value > FMA_MODE_KERNEL) return fail(FMA_EINVAL, "bad mode %lld", (long long)value);
+        e->cfg.mode = (int32_t)value;
+    } else if (k == "kernel") {
+        if (value != FMA_KERNEL_TMA && value != FMA_KERNEL_LDG) return fail(FMA_EINVAL, "bad kernel %lld", (long long)value);
+        e->cfg.kernel = (int32_t)value;
+    } else if (k == "copy_streams") {
+        if (value < 1 || value > kMaxStreams) return fail(FMA_EINVAL, "copy_streams must be 1..%d", kMaxStreams);
+        e->cfg.copy_streams = (int32_t)value;
+        e->n_cs = (int)value;
+    } else if (k == "chunk_bytes") {
+        if (value < (int64_t)FMA_PAGE_BYTES) return fail(FMA_EINVAL, "chunk_bytes must be >= 2 MiB");
+        e->cfg.chunk_bytes = (uint64_t)value;
+    } else if (k == "ring_slots") {
+        if (value < 2 || value > kMaxRing) return fail(FMA_EINVAL, "ring_slots must be 2..%d", kMaxRing);
+        e->cfg.ring_slots = (int32_t)value;
+    } else if (k == "map_threads") {
+        if (value < 1 || value > 8) return fail(FMA_EINVAL, "map_threads must be 1..8");
+        e->cfg.map_threads = (int32_t)value;
+    } else if (k == "tma_tile_bytes") {
+        if (value < 1024 || (FMA_PAGE_BYTES % (size_t)value) != 0 || value % 16) return fail(FMA_EINVAL, "bad tma tile %lld", (long long)value);
+        e->tma.tile_bytes = (uint32_t)value;
+    } else if (k == "tma_stages") {
+        e->tma.stages = (uint32_t)value;
+    } else if (k == "tma_pipes") {
+        e->tma.pipes = (uint32_t)value;
+    } else if (k == "tma_ctas_per_sm") {
+        e->tma.ctas_per_sm = (uint32_t)value;
+    } else {
+        return fail(FMA_ENOTFOUND, "unknown option %s", key);
+    }
+    return FMA_OK;
+}
+
+int fma_stats(fma_engine_t* e, fma_stats_t* out) {
+    if (check_engine(e) != FMA_OK) return FMA_EINVAL;
+    if (!out) return fail(FMA_EINVAL, "out is NULL");
+    *out = e->st;
+    return FMA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,195 @@
+"""Drop-in for ``vllm.device_allocator.cumem.CuMemAllocator`` (surface B2).
+
+Same class name, singleton accessor, method names, argument meaning and error behaviour as the
+reference's allocator shim, so vLLM's ``Worker.sleep`` / ``Worker.wake_up`` / ``load_model``
+(vllm:v1/worker/gpu_worker.py:157-209,335-342) run unchanged on top of the B200 engine:
+
+    reference (vllm:device_allocator/cumem.py)            this module
+    ------------------------------------------            -----------------------------------
+    CuMemAllocator.get_instance()          :118-128       CuMemAllocator.get_instance()
+    .use_memory_pool(tag)                  :251-308       .use_memory_pool(tag)
+    .sleep(offload_tags)                   :177-225       .sleep(offload_tags)   -> fma_sleep
+    .wake_up(tags)                         :227-249       .wake_up(tags)         -> fma_wake
+    .get_current_usage()                   :310-318       .get_current_usage()   -> fma_current_usage
+    .pointer_to_data                       :131           .pointer_to_data (read-only view of the C table)
+    my_malloc / my_free in cumem_allocator.abi3.so        my_malloc / my_free in libfma_b200.so
+
+Differences that are the point of the rewrite: the registry lives in C (no Python callbacks from
+inside the allocator), the host backup is ONE pre-pinned NUMA-local arena instead of a
+``torch.empty(pin_memory=True)`` per segment inside the sleep loop, and copies are asynchronous
+over several copy-engine streams overlapped with cuMemCreate/cuMemMap.
+
+``install_into_vllm()`` swaps the class into an imported vLLM so the unmodified reference launcher
+(inference_server/launcher/launcher.py:799-837) serves /sleep and /wake_up through this engine.
+"""
+from __future__ import annotations
+
+import dataclasses
+import gc
+import logging
+import os
+import threading
+from contextlib import contextmanager
+from typing import Any
+
+from . import _lib as L
+from .engine import Engine, EngineConfig
+
+logger = logging.getLogger("fma_b200.cumem")
+
+# py_device, py_alignedSize, py_d_mem, py_p_memHandle  (cumem.py:47-48); the 4th slot carries the
+# engine's segment sequence number instead of a heap pointer to a CUmemGenericAllocationHandle.
+HandleType = tuple[int, int, int, int]
+
+
+@dataclasses.dataclass
+class AllocationData:
+    handle: HandleType
+    tag: str
+    cpu_backup_tensor: Any = None  # always None: the backup lives in the engine's packed host store
+    mapped: bool = True
+    has_backup: bool = False
+
+
+def _tier_from_env() -> int:
+    return {"host": L.FMA_TIER_HOST, "peer": L.FMA_TIER_PEER, "local": L.FMA_TIER_LOCAL}[
+        os.environ.get("FMA_TIER", "host").lower()]
+
+
+class CuMemAllocator:
+    """Singleton per process, exactly like the reference (the C side keeps the current engine in a
+    process global because torch's pluggable-allocator signature has no user pointer)."""
+
+    instance: "CuMemAllocator | None" = None
+    default_tag: str = "default"
+
+    @staticmethod
+    def get_instance() -> "CuMemAllocator":
+        if CuMemAllocator.instance is None:
+            CuMemAllocator.instance = CuMemAllocator()
+        return CuMemAllocator.instance
+
+    def __init__(self, device: int | None = None, config: EngineConfig | None = None):
+        import torch
+
+        if not torch.cuda.is_available():
+            raise L.FmaError(L.FMA_ENODRIVER, "CuMemAllocator needs a CUDA device; there is no CPU fallback")
+        self.device = torch.cuda.current_device() if device is None else device
+        self.engine = Engine(self.device, config)
+        self.engine.make_current()
+        self.current_tag: str = CuMemAllocator.default_tag
+        self.allocator_and_pools: dict[str, Any] = {}
+        self._reserve_thread: threading.Thread | None = None
+
+    # ---- registry view -----------------------------------------------------------------
+    @property
+    def pointer_to_data(self) -> dict[int, AllocationData]:
+        out: dict[int, AllocationData] = {}
+        for s in self.engine.segments():
+            out[s.va] = AllocationData((self.device, s.bytes, s.va, s.seq), s.tag, None, s.mapped, s.has_backup)
+        return out
+
+    def get_current_usage(self) -> int:
+        return self.engine.current_usage()
+
+    # ---- hot path ----------------------------------------------------------------------
+    def sleep(self, offload_tags: tuple[str, ...] | str | None = None) -> None:
+        if offload_tags is None:
+            offload_tags = (CuMemAllocator.default_tag,)
+        elif isinstance(offload_tags, str):
+            offload_tags = (offload_tags,)
+        assert isinstance(offload_tags, tuple)
+        self._join_reserve()
+        import torch
+
+        self.engine.sleep(offload_tags, tier=_tier_from_env())
+        st = self.engine.stats()
+        total = st["sleep_bytes_offloaded"] + st["sleep_bytes_discarded"]
+        # same INFO line the reference emits (cumem.py:215-222; parsed by llm-d-benchmark), plus GB/s
+        logger.info(
+            "CuMemAllocator: sleep freed %.2f GiB memory in total, of which %.2f GiB is backed up in CPU and the "
+            "rest %.2f GiB is discarded directly.", total / 1024**3, st["sleep_bytes_offloaded"] / 1024**3,
+            st["sleep_bytes_discarded"] / 1024**3)
+        if st["sleep_copy_seconds"] > 0:
+            logger.info("fma_b200: sleep %.3f s, D2H %.1f GB/s", st["sleep_seconds"],
+                        st["sleep_bytes_offloaded"] / st["sleep_copy_seconds"] / 1e9)
+        gc.collect()
+        torch.cuda.empty_cache()
+
+    def wake_up(self, tags: list[str] | None = None) -> None:
+        self.engine.wake(tags)
+        st = self.engine.stats()
+        if st["wake_copy_seconds"] > 0:
+            logger.info("fma_b200: wake %.3f s, H2D %.1f GB/s", st["wake_seconds"],
+                        st["wake_bytes_restored"] / st["wake_copy_seconds"] / 1e9)
+
+    # ---- pool --------------------------------------------------------------------------
+    @contextmanager
+    def use_memory_pool(self, tag: str | None = None):
+        import torch
+
+        if tag is None:
+            tag = CuMemAllocator.default_tag
+        assert isinstance(tag, str)
+        conf = os.environ.get("PYTORCH_CUDA_ALLOC_CONF", "")
+        expandable_was_enabled = "expandable_segments:True" in conf  # incompatible with the pool (cumem.py:266-274)
+        if expandable_was_enabled:
+            torch.cuda.memory._set_allocator_settings("expandable_segments:False")
+        old_tag = self.current_tag
+        self.current_tag = tag
+        self.engine.make_current()
+        self.engine.set_current_tag(tag)
+        try:
+            new_alloc = torch.cuda.memory.CUDAPluggableAllocator(L.lib_path(), "my_malloc", "my_free")
+            mem_pool = torch.cuda.memory.MemPool(new_alloc._allocator)
+            data = (mem_pool, new_alloc)
+            with torch.cuda.memory.use_mem_pool(mem_pool):
+                self.allocator_and_pools[tag] = data  # keep alive (pytorch#146431, cumem.py:285-289)
+                yield
+                # release segments that ended up empty (e.g. load-time temporaries), cumem.py:299-303
+                for allocation in mem_pool.snapshot():
+                    if allocation["allocated_size"] == 0:
+                        try:
+                            self.engine.free(allocation["address"])
+                        except L.FmaError:
+                            pass
+        finally:
+            self.current_tag = old_tag
+            self.engine.set_current_tag(old_tag)
+            if expandable_was_enabled:
+                torch.cuda.memory._set_allocator_settings("expandable_segments:True")
+        if tag == "weights" and os.environ.get("FMA_PREPIN", "1") != "0":
+            self._start_reserve()
+
+    # ---- pre-pinning off the critical path -----------------------------------------------
+    def _start_reserve(self) -> None:
+        """Pin the host store for the weights as soon as they are loaded, in the background, so the
+        first /sleep does not pay for it (the reference pins inside its sleep loop, cumem.py:204-209)."""
+        nbytes = sum(s.bytes for s in self.engine.segments() if s.tag == "weights")
+        if not nbytes:
+            return
+
+        def run():
+            try:
+                self.engine.host_reserve(nbytes)
+            except L.FmaError as e:  # sleep will retry and report
+                logger.warning("background host_reserve failed: %s", e)
+
+        self._reserve_thread = threading.Thread(target=run, name="fma-prepin", daemon=True)
+        self._reserve_thread.start()
+
+    def _join_reserve(self) -> None:
+        if self._reserve_thread is not None:
+            self._reserve_thread.join()
+            self._reserve_thread = None
+
+
+def install_into_vllm() -> None:
+    """Replace vLLM's allocator class with this one (call before the engine core starts workers)."""
+    import vllm.device_allocator.cumem as ref
+
+    ref.CuMemAllocator = CuMemAllocator  # type: ignore[misc]
+    ref.cumem_available = True
+
+
+__all__ = ["CuMemAllocator", "AllocationData", "HandleType", "install_into_vllm"]

@@ -1,0 +1,238 @@
+"""Object wrapper over the C-ABI engine handle (thin; all work happens in libfma_b200.so)."""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+from typing import Iterable, Sequence
+
+from . import _lib as L
+from ._lib import FmaError, check
+
+
+@dataclasses.dataclass
+class EngineConfig:
+    mode: int = L.FMA_MODE_AUTO
+    kernel: int = L.FMA_KERNEL_TMA
+    copy_streams: int = 0
+    chunk_bytes: int = 0
+    ring_slots: int = 0
+    map_threads: int = 0
+    numa_bind: int = -1
+
+    def to_c(self) -> L.fma_config_t:
+        c = L.fma_config_t()
+        c.abi_version = L.FMA_ABI_VERSION
+        c.mode, c.kernel, c.copy_streams = self.mode, self.kernel, self.copy_streams
+        c.chunk_bytes, c.ring_slots, c.map_threads, c.numa_bind = (
+            self.chunk_bytes, self.ring_slots, self.map_threads, self.numa_bind)
+        return c
+
+
+@dataclasses.dataclass
+class SegmentInfo:
+    index: int
+    va: int
+    bytes: int
+    requested_bytes: int
+    packed_offset: int | None
+    seq: int
+    tag: str
+    mapped: bool
+    has_backup: bool
+    tier: int
+
+
+class Engine:
+    """One engine per GPU (rank).  Mirrors the role of the per-process ``CuMemAllocator`` singleton
+    (vllm:device_allocator/cumem.py:92-138) but holds no Python-side registry: the segment table
+    lives in C so sleep/wake never need the GIL."""
+
+    def __init__(self, device: int = 0, config: EngineConfig | None = None):
+        self._lib = L.load_library()
+        self._h = C.c_void_p()
+        cfg = (config or EngineConfig()).to_c()
+        check(self._lib.fma_engine_create(device, C.byref(cfg), C.byref(self._h)))
+        self.device = device
+        self._tag_ids: dict[str, int] = {"default": 0}
+
+    # -- lifecycle ------------------------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.fma_engine_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    @property
+    def handle(self) -> C.c_void_p:
+        return self._h
+
+    def make_current(self) -> None:
+        check(self._lib.fma_set_current(self._h))
+
+    # -- tags -----------------------------------------------------------------------------
+    def tag_id(self, name: str) -> int:
+        if name not in self._tag_ids:
+            self._tag_ids[name] = check(self._lib.fma_tag_intern(self._h, name.encode()))
+        return self._tag_ids[name]
+
+    def tag_mask(self, names: Iterable[str] | None) -> int:
+        if names is None:
+            return 0
+        m = 0
+        for n in names:
+            m |= 1 << self.tag_id(n)
+        return m
+
+    def set_current_tag(self, name: str) -> None:
+        check(self._lib.fma_set_current_tag(self._h, self.tag_id(name)))
+
+    def _tag_name(self, tag: int) -> str:
+        for k, v in self._tag_ids.items():
+            if v == tag:
+                return k
+        buf = C.create_string_buffer(128)
+        check(self._lib.fma_tag_name(self._h, tag, buf, len(buf)))
+        name = buf.value.decode()
+        self._tag_ids[name] = tag
+        return name
+
+    # -- allocation -----------------------------------------------------------------------
+    def alloc(self, nbytes: int, tag: str = "default") -> int:
+        p = C.c_void_p()
+        check(self._lib.fma_alloc(self._h, nbytes, self.tag_id(tag), C.byref(p)))
+        return int(p.value)
+
+    def free(self, ptr: int) -> None:
+        check(self._lib.fma_free(self._h, C.c_void_p(ptr)))
+
+    def segment_count(self) -> int:
+        return check(self._lib.fma_segment_count(self._h))
+
+    def segment(self, index: int) -> SegmentInfo:
+        s = L.fma_segment_info_t()
+        check(self._lib.fma_segment_info(self._h, index, C.byref(s)))
+        return SegmentInfo(index, s.va, s.bytes, s.requested_bytes,
+                           None if s.packed_offset == L.NO_OFFSET else s.packed_offset, s.seq, self._tag_name(s.tag),
+                           bool(s.mapped), bool(s.has_backup), s.tier)
+
+    def segments(self) -> list[SegmentInfo]:
+        return [self.segment(i) for i in range(self.segment_count())]
+
+    def find(self, ptr: int) -> int:
+        return check(self._lib.fma_segment_find(self._h, C.c_void_p(ptr)))
+
+    def current_usage(self) -> int:
+        return int(self._lib.fma_current_usage(self._h))
+
+    # -- hot path -------------------------------------------------------------------------
+    def sleep(self, offload_tags: Sequence[str] = ("default",), tier: int = L.FMA_TIER_HOST, flags: int = 0) -> None:
+        check(self._lib.fma_sleep(self._h, self.tag_mask(offload_tags), tier, flags))
+
+    def wake(self, tags: Sequence[str] | None = None, flags: int = 0) -> None:
+        check(self._lib.fma_wake(self._h, self.tag_mask(tags), flags))
+
+    def is_sleeping(self) -> bool:
+        return bool(check(self._lib.fma_is_sleeping(self._h)))
+
+    def swap_out_for(self, incoming: "Engine", offload_tags: Sequence[str] = ("default",),
+                     tier: int = L.FMA_TIER_HOST, wake_tags: Sequence[str] | None = None, flags: int = 0) -> None:
+        """Sleep *this* engine's model while waking ``incoming``'s, both PCIe directions at once."""
+        check(self._lib.fma_swap(self._h, self.tag_mask(offload_tags), tier, incoming._h,
+                                 incoming.tag_mask(wake_tags), flags))
+
+    # -- stores ---------------------------------------------------------------------------
+    def host_reserve(self, nbytes: int) -> None:
+        check(self._lib.fma_host_reserve(self._h, nbytes))
+
+    def host_release(self) -> None:
+        check(self._lib.fma_host_release(self._h))
+
+    def host_store_view(self) -> tuple[int, int]:
+        base, n = C.c_void_p(), C.c_uint64()
+        check(self._lib.fma_host_store_view(self._h, C.byref(base), C.byref(n)))
+        return int(base.value), int(n.value)
+
+    def peer_reserve(self, peer_device: int, nbytes: int) -> None:
+        check(self._lib.fma_peer_reserve(self._h, peer_device, nbytes))
+
+    def peer_release(self) -> None:
+        check(self._lib.fma_peer_release(self._h))
+
+    # -- integrity / synthetic data -------------------------------------------------------
+    def digest(self, index: int) -> int:
+        out = C.c_uint64()
+        check(self._lib.fma_digest_segment(self._h, index, C.byref(out)))
+        return int(out.value)
+
+    def digest_all(self, tags: Sequence[str] | None = None) -> list[int]:
+        n = self.segment_count()
+        out = (C.c_uint64 * max(n, 1))()
+        check(self._lib.fma_digest_all(self._h, self.tag_mask(tags), out, n))
+        return [int(out[i]) for i in range(n)]
+
+    def fill(self, index: int, seed: int, first_word: int = 0) -> None:
+        check(self._lib.fma_fill_segment(self._h, index, seed, first_word))
+
+    def write(self, index: int, data: bytes | bytearray | memoryview, offset: int = 0) -> None:
+        buf = (C.c_char * len(data)).from_buffer_copy(bytes(data))
+        check(self._lib.fma_segment_write(self._h, index, offset, buf, len(data)))
+
+    def read(self, index: int, nbytes: int, offset: int = 0) -> bytes:
+        buf = C.create_string_buffer(nbytes)
+        check(self._lib.fma_segment_read(self._h, index, offset, buf, nbytes))
+        return buf.raw
+
+    def write_ptr(self, index: int, host_ptr: int, nbytes: int, offset: int = 0) -> None:
+        check(self._lib.fma_segment_write(self._h, index, offset, C.c_void_p(host_ptr), nbytes))
+
+    def read_ptr(self, index: int, host_ptr: int, nbytes: int, offset: int = 0) -> None:
+        check(self._lib.fma_segment_read(self._h, index, offset, C.c_void_p(host_ptr), nbytes))
+
+    # -- raw kernels ----------------------------------------------------------------------
+    def op_page_copy(self, n_pages: int, src_pages: Sequence[int] | None = None, src_base: int = 0,
+                     dst_pages: Sequence[int] | None = None, dst_base: int = 0, variant: int = L.FMA_KERNEL_TMA) -> float:
+        sp = (C.c_uint64 * n_pages)(*src_pages) if src_pages is not None else None
+        dp = (C.c_uint64 * n_pages)(*dst_pages) if dst_pages is not None else None
+        ms = C.c_float()
+        check(self._lib.fma_op_page_copy(self._h, sp, src_base, dp, dst_base, n_pages, variant, C.byref(ms)))
+        return float(ms.value)
+
+    def op_page_digest(self, n_pages: int, pages: Sequence[int] | None = None, base: int = 0,
+                       first_word: Sequence[int] | None = None) -> tuple[list[int], float]:
+        pp = (C.c_uint64 * n_pages)(*pages) if pages is not None else None
+        fw = (C.c_uint64 * n_pages)(*first_word) if first_word is not None else None
+        out = (C.c_uint64 * n_pages)()
+        ms = C.c_float()
+        check(self._lib.fma_op_page_digest(self._h, pp, base, fw, n_pages, out, C.byref(ms)))
+        return [int(x) for x in out], float(ms.value)
+
+    def scratch_alloc(self, nbytes: int) -> int:
+        out = C.c_uint64()
+        check(self._lib.fma_scratch_alloc(self._h, nbytes, C.byref(out)))
+        return int(out.value)
+
+    def scratch_free(self, ptr: int) -> None:
+        check(self._lib.fma_scratch_free(self._h, ptr))
+
+    def set_option(self, key: str, value: int) -> None:
+        check(self._lib.fma_set_option(self._h, key.encode(), int(value)))
+
+    # -- stats ----------------------------------------------------------------------------
+    def stats(self) -> dict:
+        st = L.fma_stats_t()
+        check(self._lib.fma_stats(self._h, C.byref(st)))
+        return st.as_dict()
+
+
+__all__ = ["Engine", "EngineConfig", "SegmentInfo", "FmaError"]
