@@ -243,6 +243,9 @@ struct fma_engine {
 
     fma_k_tma_cfg tma = fma_k_default_tma_cfg();
     fma_stats_t st{};
+    // K1/K2 event pairs of the last operation whose elapsed times have not been read yet
+    size_t pending_events = 0;
+    uint64_t pending_kernel_bytes = 0;
 };
 
 namespace {
@@ -343,18 +346,39 @@ int ensure_desc(fma_engine_t* e, size_t n_pages) {
     return FMA_OK;
 }
 
-int ensure_ring(fma_engine_t* e) {
-    size_t slot = e->cfg.chunk_bytes ? (size_t)e->cfg.chunk_bytes : ((size_t)32 << 20);
-    slot = round_up(slot, FMA_PAGE_BYTES);
-    int n = e->cfg.ring_slots > 0 ? std::min(e->cfg.ring_slots, kMaxRing) : 4;
-    if (e->n_ring == n && e->ring_slot_bytes == slot) return FMA_OK;
+// DMA chunk for DIRECT (round-robin over copy streams) and ring-slot size for STAGED.  Defaults come from the
+// sweep in profiles/: H2D saturates from 32 MiB chunks; K2/K1 launches need >= 256 MiB to amortise launch + ramp.
+size_t direct_chunk(const fma_engine_t* e) {
+    return e->cfg.chunk_bytes ? round_up((size_t)e->cfg.chunk_bytes, FMA_PAGE_BYTES) : ((size_t)32 << 20);
+}
+size_t staged_slot(const fma_engine_t* e) {
+    return e->cfg.chunk_bytes ? round_up((size_t)e->cfg.chunk_bytes, FMA_PAGE_BYTES) : ((size_t)256 << 20);
+}
+
+void release_ring(fma_engine_t* e) {
     for (int i = 0; i < e->n_ring; ++i) {
         cudaFree(e->ring[i]);
         e->ring[i] = nullptr;
     }
     e->n_ring = 0;
+    e->ring_slot_bytes = 0;
+    cudaGetLastError();
+}
+
+// The HBM staging ring is transient: allocated when a STAGED sleep/wake starts and freed when it ends, so a
+// sleeping (or serving) model does not keep it resident.  `image_bytes` caps the slot size for small models.
+int ensure_ring(fma_engine_t* e, size_t image_bytes) {
+    size_t slot = std::min(staged_slot(e), round_up(std::max<size_t>(image_bytes, 1), FMA_PAGE_BYTES));
+    int n = e->cfg.ring_slots > 0 ? std::min(e->cfg.ring_slots, kMaxRing) : 2;
+    if (e->n_ring == n && e->ring_slot_bytes == slot) return FMA_OK;
+    release_ring(e);
     for (int i = 0; i < n; ++i) {
-        RT(cudaMalloc(&e->ring[i], slot));
+        cudaError_t r = cudaMalloc(&e->ring[i], slot);
+        if (r != cudaSuccess) {
+            cudaGetLastError();
+            release_ring(e);
+            return fail(FMA_ENOMEM, "cannot allocate %d x %zu byte HBM staging ring: %s", n, slot, cudaGetErrorString(r));
+        }
         if (!e->ev_ring_full[i]) RT(cudaEventCreateWithFlags(&e->ev_ring_full[i], cudaEventDisableTiming));
         if (!e->ev_ring_free[i]) RT(cudaEventCreateWithFlags(&e->ev_ring_free[i], cudaEventDisableTiming));
         e->n_ring = i + 1;
@@ -632,24 +656,35 @@ struct KernelTimes {  // event pairs around each K1/K2 launch on the kernel stre
         bytes += 2ull * n_pages * FMA_PAGE_BYTES;
         return FMA_OK;
     }
-    int collect() {  // call after the streams are synchronised
-        double s = 0;
-        for (size_t i = 0; i + 1 < used; i += 2) {
-            float ms = 0;
-            RT(cudaEventElapsedTime(&ms, e->ev_pool[i], e->ev_pool[i + 1]));
-            s += ms * 1e-3;
-        }
-        e->st.kernel_seconds = s;
-        e->st.kernel_bytes = bytes;
+    // Called after the streams are synchronised.  Reading ~100s of event pairs costs ~1 ms, so it is
+    // deferred to fma_stats() / the next operation instead of sitting inside the wake latency.
+    int collect() {
+        e->pending_events = used;
+        e->pending_kernel_bytes = bytes;
         e->st.kernel_launches = (uint32_t)(used / 2);
         e->st.total_kernel_launches += used / 2;
         return FMA_OK;
     }
 };
 
+int flush_kernel_times(fma_engine_t* e) {
+    if (!e->pending_events) return FMA_OK;
+    double s = 0;
+    for (size_t i = 0; i + 1 < e->pending_events; i += 2) {
+        float ms = 0;
+        RT(cudaEventElapsedTime(&ms, e->ev_pool[i], e->ev_pool[i + 1]));
+        s += ms * 1e-3;
+    }
+    e->st.kernel_seconds = s;
+    e->st.kernel_bytes = e->pending_kernel_bytes;
+    e->pending_events = 0;
+    e->pending_kernel_bytes = 0;
+    return FMA_OK;
+}
+
 int resolve_mode(const fma_engine_t* e, int tier) {
     int m = e->cfg.mode;
-    if (m == FMA_MODE_AUTO) m = (tier == FMA_TIER_HOST) ? FMA_MODE_DIRECT : FMA_MODE_KERNEL;
+    if (m == FMA_MODE_AUTO) m = (tier == FMA_TIER_HOST) ? FMA_MODE_STAGED : FMA_MODE_KERNEL;
     if (tier != FMA_TIER_HOST && m == FMA_MODE_STAGED) m = FMA_MODE_KERNEL;  // staging only helps across PCIe
     return m;
 }
@@ -701,9 +736,11 @@ int digest_segments(fma_engine_t* e, const std::vector<size_t>& idx, std::vector
 // SLEEP
 // ------------------------------------------------------------------------------------
 int do_sleep(fma_engine_t* e, uint64_t offload_mask, int tier, uint32_t flags) {
-    const double t_entry = now_s();
     DeviceGuard guard(e->device);
-    int rc = ensure_streams(e);
+    int rc = flush_kernel_times(e);
+    if (rc != FMA_OK) return rc;
+    const double t_entry = now_s();
+    rc = ensure_streams(e);
     if (rc != FMA_OK) return rc;
 
     // Executor.sleep is a no-op while sleeping (abstract.py:323-325)
@@ -764,7 +801,7 @@ int do_sleep(fma_engine_t* e, uint64_t offload_mask, int tier, uint32_t flags) {
     uint32_t copy_ops = 0;
     double copy_s = 0;
     if (W) {
-        const size_t chunk = e->cfg.chunk_bytes ? round_up((size_t)e->cfg.chunk_bytes, FMA_PAGE_BYTES) : ((size_t)32 << 20);
+        const size_t chunk = direct_chunk(e);
         char* store = static_cast<char*>(store_copy_base(e, tier));
         rc = timer.begin();
         if (rc != FMA_OK) return rc;
@@ -789,7 +826,7 @@ int do_sleep(fma_engine_t* e, uint64_t offload_mask, int tier, uint32_t flags) {
                 rc = kt.launch(e->d_tab, 0, nullptr, store_dev_base(e, tier), (uint32_t)n_pages);
                 if (rc != FMA_OK) return rc;
             } else {  // STAGED: K1 gather -> HBM ring slot -> copy engine D2H
-                rc = ensure_ring(e);
+                rc = ensure_ring(e, W);
                 if (rc != FMA_OK) return rc;
                 const size_t slot_pages = e->ring_slot_bytes / FMA_PAGE_BYTES;
                 size_t c = 0;
@@ -812,6 +849,7 @@ int do_sleep(fma_engine_t* e, uint64_t offload_mask, int tier, uint32_t flags) {
         if (rc != FMA_OK) return rc;
         rc = kt.collect();
         if (rc != FMA_OK) return rc;
+        release_ring(e);
     }
 
     // unmap + release EVERYTHING (cumem.py:213), VAs stay reserved
@@ -822,10 +860,19 @@ int do_sleep(fma_engine_t* e, uint64_t offload_mask, int tier, uint32_t flags) {
         s.backup_tier = tier;
         s.packed_off = x.packed_off;
     }
+    const bool dbg = env_int("FMA_DEBUG_VMM", 0) != 0;
     for (Segment& s : e->segs) {
         if (!s.mapped) continue;
-        rc = vmm_unmap_and_release(s.va, s.bytes, s.handle);
-        if (rc != FMA_OK) return rc;
+        const double a = now_s();
+        CUresult r1 = g_drv.MemUnmap(s.va, s.bytes);
+        const double b = now_s();
+        CUresult r2 = g_drv.MemRelease(s.handle);
+        const double c = now_s();
+        if (r1 != CUDA_SUCCESS) return fail(FMA_ECUDA, "cuMemUnmap failed: %s", cu_err(r1));
+        if (r2 != CUDA_SUCCESS) return fail(FMA_ECUDA, "cuMemRelease failed: %s", cu_err(r2));
+        if (dbg && (c - a) > 5e-3)
+            fprintf(stderr, "[fma] slow unmap seg seq=%llu bytes=%zu tag=%d unmap=%.1f ms release=%.1f ms\n",
+                    (unsigned long long)s.seq, s.bytes, s.tag, (b - a) * 1e3, (c - b) * 1e3);
         s.mapped = false;
         s.handle = 0;
     }
@@ -843,6 +890,7 @@ int do_sleep(fma_engine_t* e, uint64_t offload_mask, int tier, uint32_t flags) {
     e->st.tier = tier;
     e->st.mode = mode;
     if (!W) {
+        e->pending_events = 0;
         e->st.kernel_seconds = 0;
         e->st.kernel_bytes = 0;
         e->st.kernel_launches = 0;
@@ -862,9 +910,11 @@ struct MapProgress {
 };
 
 int do_wake(fma_engine_t* e, uint64_t tag_mask, uint32_t flags) {
-    const double t_entry = now_s();
     DeviceGuard guard(e->device);
-    int rc = ensure_streams(e);
+    int rc = flush_kernel_times(e);
+    if (rc != FMA_OK) return rc;
+    const double t_entry = now_s();
+    rc = ensure_streams(e);
     if (rc != FMA_OK) return rc;
 
     // work list in allocation order: segments with a backup first keep their relative order (they
@@ -958,7 +1008,7 @@ int do_wake(fma_engine_t* e, uint64_t tag_mask, uint32_t flags) {
     uint32_t copy_ops = 0;
     double copy_s = 0, first_copy_delay = 0;
     if (W) {
-        const size_t chunk = e->cfg.chunk_bytes ? round_up((size_t)e->cfg.chunk_bytes, FMA_PAGE_BYTES) : ((size_t)32 << 20);
+        const size_t chunk = direct_chunk(e);
         const char* store = static_cast<const char*>(store_copy_base(e, tier));
         if (!store) WAKE_CHECK(fail(FMA_ESTATE, "backup store of tier %d is gone", tier));
         if (tier == FMA_TIER_HOST && mode == FMA_MODE_KERNEL && !e->host.dev_alias)
@@ -1008,7 +1058,7 @@ int do_wake(fma_engine_t* e, uint64_t tag_mask, uint32_t flags) {
             if (mode == FMA_MODE_KERNEL) {
                 // K2 reads the store itself (zero-copy PCIe reads, or NVLink/HBM loads); launch batches as the
                 // mapper makes progress so the scatter overlaps cuMemCreate/Map of later segments
-                const size_t batch_pages = std::max<size_t>(chunk / FMA_PAGE_BYTES, 1) * 8;
+                const size_t batch_pages = std::max<size_t>(staged_slot(e) / FMA_PAGE_BYTES, 1);
                 size_t p0 = 0;
                 while (p0 < n_pages) {
                     size_t np = std::min(batch_pages, n_pages - p0);
@@ -1025,7 +1075,7 @@ int do_wake(fma_engine_t* e, uint64_t tag_mask, uint32_t flags) {
                     p0 += np;
                 }
             } else {  // STAGED: copy engine H2D store -> ring slot (starts at t=0), K2 scatter once the targets are mapped
-                WAKE_CHECK(ensure_ring(e));
+                WAKE_CHECK(ensure_ring(e, W));
                 const size_t slot_pages = e->ring_slot_bytes / FMA_PAGE_BYTES;
                 // the store image may be only partially woken; H2D works on runs that are contiguous in the store
                 size_t c = 0;
@@ -1064,6 +1114,7 @@ int do_wake(fma_engine_t* e, uint64_t tag_mask, uint32_t flags) {
         if (rc != FMA_OK) return rc;
         rc = kt.collect();
         if (rc != FMA_OK) return rc;
+        release_ring(e);
     }
 #undef WAKE_CHECK
 #undef WAKE_RT
@@ -1102,6 +1153,7 @@ int do_wake(fma_engine_t* e, uint64_t tag_mask, uint32_t flags) {
     e->st.tier = tier;
     e->st.mode = mode;
     if (!W) {
+        e->pending_events = 0;
         e->st.kernel_seconds = 0;
         e->st.kernel_bytes = 0;
         e->st.kernel_launches = 0;
@@ -1196,7 +1248,7 @@ int fma_engine_destroy(fma_engine_t* e) {
     e->segs.clear();
     host_store_free(e->host);
     park_release(e);
-    for (int i = 0; i < e->n_ring; ++i) cudaFree(e->ring[i]);
+    release_ring(e);
     for (int i = 0; i < kMaxRing; ++i) {
         if (e->ev_ring_full[i]) cudaEventDestroy(e->ev_ring_full[i]);
         if (e->ev_ring_free[i]) cudaEventDestroy(e->ev_ring_free[i]);
@@ -1612,6 +1664,11 @@ int fma_set_option(fma_engine_t* e, const char* key, int64_t value) {
 int fma_stats(fma_engine_t* e, fma_stats_t* out) {
     if (check_engine(e) != FMA_OK) return FMA_EINVAL;
     if (!out) return fail(FMA_EINVAL, "out is NULL");
+    {
+        DeviceGuard guard(e->device);
+        int rc = flush_kernel_times(e);
+        if (rc != FMA_OK) return rc;
+    }
     *out = e->st;
     return FMA_OK;
 }

@@ -37,25 +37,35 @@ def _round_up(x: int, a: int) -> int:
 
 
 def simulate_segments(tensors: list[tuple[str, int]], tag: str) -> list[SegmentSpec]:
-    """Bump-allocate tensors (no frees during load) through the caching-allocator size classes and
-    return the segments it would request from the pluggable allocator, in request order."""
+    """Run tensors (no frees during load) through the caching allocator's placement rules and return the
+    segments it requests from the pluggable allocator, in request order.  Modelled (and pinned against a live
+    vLLM + torch run by tests/golden/vllm_cumem_roundtrip.json): 512 B size rounding; two pools (<= 1 MiB small,
+    else large); best-fit reuse of the free remainder of earlier segments of the same pool — a 12 MiB tensor does
+    land in the tail of a 20 MiB segment; a remainder is only split off when it is worth keeping
+    (> 1 MiB in the large pool, >= 512 B in the small pool)."""
     segs: list[SegmentSpec] = []
-    small_free = 0   # bytes left in the open small-pool segment
-    medium_free = 0  # bytes left in the open 20 MiB segment
+    free = {"small": [], "large": []}  # free block sizes per pool
+
+    def place(pool: str, size: int, seg_bytes: int, note: str) -> None:
+        blocks = free[pool]
+        fit = min((b for b in blocks if b >= size), default=None)   # lower_bound: smallest block that fits
+        if fit is None:
+            segs.append(SegmentSpec(seg_bytes, tag, note))
+            fit = seg_bytes
+        else:
+            blocks.remove(fit)
+        rem = fit - size
+        if (pool == "small" and rem >= K_MIN_BLOCK) or (pool == "large" and rem > K_SMALL_SIZE):
+            blocks.append(rem)
+
     for name, nbytes in tensors:
         size = _round_up(max(nbytes, 1), K_MIN_BLOCK)
         if size <= K_SMALL_SIZE:
-            if small_free < size:
-                segs.append(SegmentSpec(K_SMALL_BUFFER, tag, "small-pool"))
-                small_free = K_SMALL_BUFFER
-            small_free -= size
+            place("small", size, K_SMALL_BUFFER, "small-pool")
         elif size < K_MIN_LARGE_ALLOC:
-            if medium_free < size:
-                segs.append(SegmentSpec(K_LARGE_BUFFER, tag, "20MiB-pool"))
-                medium_free = K_LARGE_BUFFER
-            medium_free -= size
+            place("large", size, K_LARGE_BUFFER, "20MiB-pool")
         else:
-            segs.append(SegmentSpec(_round_up(size, K_ROUND_LARGE), tag, name))
+            place("large", size, _round_up(size, K_ROUND_LARGE), name)
     return segs
 
 

@@ -1,0 +1,306 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path through the C-ABI vs the CPU oracle on the
+same seeded inputs — bit-exact, since everything on this path is byte movement and integer arithmetic."""
+import ctypes as C
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+PAGE = 2 << 20
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "vllm_cumem_roundtrip.json")
+
+
+def _L():
+    from fma_b200 import _lib as L
+
+    return L
+
+
+def _tiny_table():
+    from fma_b200 import workloads as W
+
+    return W.allocation_table("tiny-llama-test", kv_cache_bytes=32 << 20, kv_tensors=2)
+
+
+def _load(engine, oracle, table, seed=1234):
+    """Allocate the table; fill weights on the device (K0) and on the CPU (oracle)."""
+    ptrs = [engine.alloc(s.bytes, s.tag) for s in table]
+    ref, first = {}, 0
+    for i, s in enumerate(table):
+        if s.tag == "weights":
+            engine.fill(i, seed, first)
+            ref[i] = oracle.fill(s.bytes, seed, first)
+            first += s.bytes // 8
+    return ptrs, ref
+
+
+def _host_image(engine):
+    base, n = engine.host_store_view()
+    return np.ctypeslib.as_array((C.c_uint8 * n).from_address(base)) if n else np.empty(0, np.uint8)
+
+
+# ---- K0 / K3 ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("first_word", [0, 1, (1 << 40) + 12345])
+def test_fill_kernel_matches_oracle(engine, oracle, first_word):
+    engine.alloc(3 * PAGE, "default")
+    engine.fill(0, 0xDEADBEEF, first_word)
+    assert engine.read(0, 3 * PAGE) == oracle.fill(3 * PAGE, 0xDEADBEEF, first_word).tobytes()
+
+
+def test_digest_kernel_matches_oracle(engine, oracle):
+    rng = np.random.default_rng(7)
+    sizes = [PAGE, 5 * PAGE, 2 * PAGE]
+    data = [rng.integers(0, 256, s, dtype=np.uint8) for s in sizes]
+    for i, d in enumerate(data):
+        engine.alloc(sizes[i], "default")
+        engine.write(i, d.tobytes())
+    assert engine.digest_all() == [oracle.digest(d) for d in data]
+    assert engine.digest(1) == oracle.digest(data[1])
+    # per-page digests are additive (checksum of checksums) and position sensitive
+    seg = engine.segment(1)
+    per_page, _ = engine.op_page_digest(5, base=seg.va)
+    assert sum(per_page) % (1 << 64) == oracle.digest(data[1])
+    swapped, _ = engine.op_page_digest(5, pages=[seg.va + ((p + 1) % 5) * PAGE for p in range(5)])
+    assert sum(swapped) % (1 << 64) != oracle.digest(data[1])
+
+
+# ---- K1 / K2 raw ------------------------------------------------------------------------------------
+@pytest.mark.parametrize("variant", ["tma", "ldg"])
+@pytest.mark.parametrize("tma_cfg", [(32, 3, 2, 1), (8, 2, 1, 1), (64, 3, 1, 1), (8, 3, 4, 2)])
+def test_page_gather_scatter_match_oracle(engine, oracle, variant, tma_cfg):
+    L = _L()
+    if variant == "ldg" and tma_cfg != (32, 3, 2, 1):
+        pytest.skip("tma config irrelevant for ldg")
+    tile, stages, pipes, cps = tma_cfg
+    engine.set_option("tma_tile_bytes", tile << 10); engine.set_option("tma_stages", stages)
+    engine.set_option("tma_pipes", pipes); engine.set_option("tma_ctas_per_sm", cps)
+    v = L.FMA_KERNEL_TMA if variant == "tma" else L.FMA_KERNEL_LDG
+    n = 37
+    rng = np.random.default_rng(3)
+    engine.alloc(n * PAGE, "default")
+    src = oracle.fill(n * PAGE, 99, 0)
+    engine.write(0, src.tobytes())
+    base = engine.segment(0).va
+    perm = rng.permutation(n).tolist()
+    dst = engine.scratch_alloc(n * PAGE)
+    # K1: gather scattered pages -> contiguous
+    engine.op_page_copy(n, src_pages=[base + p * PAGE for p in perm], dst_base=dst, variant=v)
+    want = oracle.gather([src[p * PAGE:(p + 1) * PAGE] for p in perm])
+    engine.alloc(n * PAGE, "default")
+    out_va = engine.segment(1).va
+    engine.op_page_copy(n, src_base=dst, dst_base=out_va, variant=v)          # contiguous -> contiguous
+    assert engine.read(1, n * PAGE) == want.tobytes()
+    # K2: scatter the packed image back to the permuted pages of segment 1 -> original order
+    engine.op_page_copy(n, src_base=dst, dst_pages=[out_va + p * PAGE for p in perm], variant=v)
+    assert engine.read(1, n * PAGE) == src.tobytes()
+    engine.scratch_free(dst)
+
+
+# ---- sleep / wake ------------------------------------------------------------------------------------
+MODES = ["direct", "staged", "kernel"]
+
+
+@pytest.mark.parametrize("tier", ["host", "local"])
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("kernel", ["tma", "ldg"])
+def test_sleep_wake_roundtrip_matches_oracle(engine, oracle, tier, mode, kernel):
+    L = _L()
+    if mode == "direct" and kernel == "ldg":
+        pytest.skip("no kernel in direct mode")
+    table = _tiny_table()
+    ptrs, ref = _load(engine, oracle, table)
+    model = oracle.CuMemModel()
+    for i, s in enumerate(table):
+        model.malloc(s.bytes, s.tag, ref.get(i))
+    engine.set_option("mode", {"direct": L.FMA_MODE_DIRECT, "staged": L.FMA_MODE_STAGED, "kernel": L.FMA_MODE_KERNEL}[mode])
+    engine.set_option("kernel", L.FMA_KERNEL_TMA if kernel == "tma" else L.FMA_KERNEL_LDG)
+    engine.set_option("chunk_bytes", 6 << 20)   # ragged: chunks straddle segment boundaries
+    t = L.FMA_TIER_HOST if tier == "host" else L.FMA_TIER_LOCAL
+    engine.sleep(["weights"], tier=t, flags=L.FMA_FLAG_VERIFY)
+    total, backed = model.sleep(("weights",))
+    st = engine.stats()
+    assert engine.is_sleeping() and model.is_sleeping()
+    assert st["sleep_bytes_offloaded"] == backed and st["sleep_bytes_offloaded"] + st["sleep_bytes_discarded"] == total
+    assert all(not s.mapped for s in engine.segments())
+    if tier == "host":
+        image = oracle.packed_image([ref[i] for i in sorted(ref)])
+        assert np.array_equal(_host_image(engine), image)          # packed image == oracle's K1
+    engine.wake(None, flags=L.FMA_FLAG_VERIFY)
+    restored = model.wake_up(None)
+    assert engine.stats()["wake_bytes_restored"] == restored
+    assert not engine.is_sleeping()
+    segs = engine.segments()
+    assert [s.va for s in segs] == ptrs                            # same device addresses
+    assert all(s.mapped and not s.has_backup for s in segs)
+    for i in ref:
+        assert engine.read(i, table[i].bytes) == model.dev[i].tobytes()
+    for i, s in enumerate(table):                                   # kv_cache is mapped again and usable
+        if s.tag == "kv_cache":
+            engine.write(i, b"\x11" * 4096)
+            assert engine.read(i, 4096) == b"\x11" * 4096
+
+
+def test_state_machine_idempotence_and_tag_selective_wake(engine, oracle):
+    L = _L()
+    table = _tiny_table()
+    ptrs, ref = _load(engine, oracle, table)
+    assert not engine.is_sleeping()
+    engine.wake(None)                                               # waking when awake is harmless (abstract.py:336-338)
+    engine.sleep(["weights"])
+    before = engine.stats()["total_copy_ops"]
+    engine.sleep(["weights"])                                       # sleeping twice is a no-op (abstract.py:323-325)
+    assert engine.stats()["total_copy_ops"] == before
+    engine.wake(["weights"])                                        # tags=["weights"] only
+    segs = engine.segments()
+    assert all(s.mapped == (s.tag == "weights") for s in segs) and engine.is_sleeping()
+    for i in ref:
+        assert engine.read(i, table[i].bytes) == ref[i].tobytes()
+    engine.sleep(["weights"])                                       # still "sleeping": no-op, weights stay mapped
+    assert all(s.mapped == (s.tag == "weights") for s in engine.segments())
+    engine.wake(["kv_cache"])
+    assert not engine.is_sleeping() and all(s.mapped for s in engine.segments())
+    engine.wake(None); engine.wake(None)                            # retry-safe (/wake_up is retried by the controller)
+    assert [s.va for s in engine.segments()] == ptrs
+
+
+def test_level2_sleep_discards_everything(engine, oracle):
+    table = _tiny_table()
+    _load(engine, oracle, table)
+    engine.sleep([])                                                # Worker.sleep(level=2): offload_tags = tuple()
+    st = engine.stats()
+    assert st["sleep_bytes_offloaded"] == 0 and st["sleep_bytes_discarded"] == sum(s.bytes for s in table)
+    engine.wake(None)
+    assert engine.stats()["wake_bytes_restored"] == 0 and not engine.is_sleeping()
+
+
+def test_edge_cases_empty_single_page_and_many_small_segments(engine, oracle):
+    L = _L()
+    engine.sleep(["default"]); engine.wake(None)                    # empty table
+    assert not engine.is_sleeping() and engine.current_usage() == 0
+    p = engine.alloc(1, "default")                                  # 1 byte -> one whole page
+    assert engine.segment(0).bytes == PAGE and engine.segment(0).requested_bytes == 1
+    engine.alloc(PAGE + 1, "default")
+    assert engine.segment(1).bytes == 2 * PAGE
+    for _ in range(150):
+        engine.alloc(PAGE, "default")
+    n = engine.segment_count()
+    ref = []
+    for i in range(n):
+        engine.fill(i, 5, i * 1000)
+        ref.append(oracle.fill(engine.segment(i).bytes, 5, i * 1000))
+    for mode in (L.FMA_MODE_STAGED, L.FMA_MODE_DIRECT, L.FMA_MODE_KERNEL):
+        engine.set_option("mode", mode)
+        engine.sleep(["default"], flags=L.FMA_FLAG_VERIFY)
+        assert np.array_equal(_host_image(engine), oracle.packed_image(ref))
+        engine.wake(None, flags=L.FMA_FLAG_VERIFY)
+        assert engine.digest_all() == [oracle.digest(r) for r in ref]
+    engine.free(p)
+    assert engine.segment_count() == n - 1
+    engine.sleep(["default"]); engine.wake(None)                    # table with a hole still round-trips
+    assert engine.digest_all() == [oracle.digest(r) for r in ref[1:]]
+
+
+def test_free_while_sleeping_and_realloc(engine, oracle):
+    a = engine.alloc(4 * PAGE, "default"); b = engine.alloc(2 * PAGE, "default")
+    engine.fill(1, 9, 0)
+    engine.sleep(["default"])
+    engine.free(a)                                                  # dropping a sleeping segment releases its VA
+    engine.wake(None)
+    assert engine.segment_count() == 1 and engine.segment(0).va == b
+    assert engine.read(0, 2 * PAGE) == oracle.fill(2 * PAGE, 9, 0).tobytes()
+
+
+def test_hot_swap_overlaps_and_preserves_both_models(built, oracle):
+    """BASELINE config 4 in miniature: A sleeps while B wakes (two engines on one GPU)."""
+    import fma_b200
+
+    L = _L()
+    with fma_b200.Engine(0) as A, fma_b200.Engine(0) as B:
+        ra, rb = [], []
+        for i in range(6):
+            A.alloc(8 * PAGE, "weights"); A.fill(i, 1, i * 77); ra.append(oracle.fill(8 * PAGE, 1, i * 77))
+            B.alloc(6 * PAGE, "weights"); B.fill(i, 2, i * 55); rb.append(oracle.fill(6 * PAGE, 2, i * 55))
+        B.sleep(["weights"])
+        A.swap_out_for(B, offload_tags=["weights"])                 # D2H(A) || H2D(B)
+        assert A.is_sleeping() and not B.is_sleeping()
+        assert B.digest_all() == [oracle.digest(r) for r in rb]
+        B.swap_out_for(A, offload_tags=["weights"])
+        assert B.is_sleeping() and not A.is_sleeping()
+        assert A.digest_all() == [oracle.digest(r) for r in ra]
+
+
+# ---- torch pluggable allocator + the CuMemAllocator mirror (B2) -----------------------------------------
+def test_cumem_shim_with_torch_pool(built, oracle):
+    import torch
+
+    from fma_b200 import cumem
+
+    cumem.CuMemAllocator.instance = None
+    os.environ["FMA_PREPIN"] = "0"
+    alloc = cumem.CuMemAllocator.get_instance()
+    assert cumem.CuMemAllocator.get_instance() is alloc             # singleton
+    with alloc.use_memory_pool(tag="weights"):
+        ws = [torch.empty(n, dtype=torch.uint8, device="cuda") for n in (24 << 20, 3 << 20, 8 << 10, 12 << 20)]
+    with alloc.use_memory_pool(tag="kv_cache"):
+        kv = torch.full((16 << 20,), 7, dtype=torch.uint8, device="cuda")
+    host = [torch.from_numpy(oracle.fill(w.numel(), 42, i * 10**6).copy()) for i, w in enumerate(ws)]
+    for w, h in zip(ws, host):
+        w.copy_(h)
+    torch.cuda.synchronize()
+    ptrs = [w.data_ptr() for w in ws]
+    usage = alloc.get_current_usage()
+    assert usage > 0 and usage % PAGE == 0
+    tags = {d.tag for d in alloc.pointer_to_data.values()}
+    assert tags == {"weights", "kv_cache"}
+    free_before = torch.cuda.mem_get_info()[0]
+    alloc.sleep(offload_tags=("weights",))
+    assert torch.cuda.mem_get_info()[0] - free_before >= usage - (64 << 20)   # physical memory really released
+    alloc.wake_up()
+    torch.cuda.synchronize()
+    assert [w.data_ptr() for w in ws] == ptrs
+    for w, h in zip(ws, host):
+        assert torch.equal(w.cpu(), h)
+    kv.fill_(3); torch.cuda.synchronize()
+    assert int(kv[123]) == 3                                        # remapped kv_cache is usable
+    alloc.wake_up(tags=["weights"])                                  # harmless when awake
+    del ws, kv
+    cumem.CuMemAllocator.instance = None
+
+
+# ---- the reference's own round trip (golden fixture produced by vLLM's CuMemAllocator on a B200) -------
+def test_shim_roundtrip_equals_reference_golden(built, oracle):
+    """Same torch allocation sequence, same bytes, through THIS allocator: every tensor must hash to what the
+    reference's sleep -> wake produced, at an unchanged data_ptr, with the same segment sizes."""
+    import torch
+
+    from fma_b200 import cumem
+    from fma_b200 import workloads as W
+
+    g = json.load(open(GOLDEN))
+    cumem.CuMemAllocator.instance = None
+    os.environ["FMA_PREPIN"] = "0"
+    alloc = cumem.CuMemAllocator.get_instance()
+    with alloc.use_memory_pool(tag="weights"):
+        ws = [torch.empty(b, dtype=torch.uint8, device="cuda") for _, b in W.model_tensors(g["model"])]
+    with alloc.use_memory_pool(tag="kv_cache"):
+        kv = [torch.full((b,), 0x5A, dtype=torch.uint8, device="cuda") for _, b in g["kv_specs"]]
+    for w, meta in zip(ws, g["weights"]):
+        w.copy_(torch.from_numpy(oracle.fill(w.numel(), g["seed"], meta["first_word"]).copy()))
+    torch.cuda.synchronize()
+    ptrs = [t.data_ptr() for t in ws + kv]
+    segs = sorted((d.handle[1], d.tag) for d in alloc.pointer_to_data.values())
+    assert segs == sorted((s["bytes"], s["tag"]) for s in g["reference_segments"])
+    for mode in ("staged", "direct", "kernel"):
+        alloc.engine.set_option("mode", {"direct": 1, "staged": 2, "kernel": 3}[mode])
+        alloc.sleep(offload_tags=("weights",))
+        alloc.wake_up()
+        torch.cuda.synchronize()
+        assert [t.data_ptr() for t in ws + kv] == ptrs
+        got = [hashlib.sha256(w.cpu().numpy().tobytes()).hexdigest() for w in ws]
+        assert got == [m["sha256"] for m in g["weights"]], mode
+    del ws, kv
+    cumem.CuMemAllocator.instance = None

@@ -44,4 +44,6 @@ def test_kv_cache_is_tagged_and_never_counted_as_weights():
 
 def test_segment_size_classes():
     segs = W.simulate_segments([("a", 8 << 10)] * 65 + [("m", 3 * MiB)] * 7 + [("big", 10 * MiB + 1)], "weights")
-    assert [s.bytes // MiB for s in segs] == [2, 20, 20, 12]
+    assert [s.bytes // MiB for s in segs] == [2, 20, 20]           # "big" best-fits into the 17 MiB tail of the 2nd 20 MiB segment
+    segs = W.simulate_segments([("m", 3 * MiB)] * 6 + [("big", 18 * MiB + 1)], "weights")
+    assert [s.bytes // MiB for s in segs] == [20, 20]              # >= 10 MiB with no fitting tail: own segment rounded to 2 MiB
