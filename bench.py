@@ -118,40 +118,21 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------
 def run_ours(args) -> None:
     import torch
-    import torch.distributed as dist
 
     import fma_b200
     from fma_b200 import _lib as L
     from fma_b200 import workloads as W
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    from fma_b200 import ranks
+
+    rank, world, local_rank = ranks.rank_env()
     if world != args.gpus:
         if world == 1 and args.gpus > 1:
             raise SystemExit(f"--gpus {args.gpus} needs torchrun (python -m torch.distributed.run --nproc-per-node {args.gpus} ...)")
         args.gpus = world
     torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-
-    def max_over_ranks(x: float) -> float:
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def sum_over_ranks(x: float) -> float:
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+    group = ranks.RankGroup(backend="nccl" if world > 1 else None)   # plumbing only: barrier + max/sum of timings
+    barrier, max_over_ranks, sum_over_ranks = group.barrier, group.max, group.sum
 
     tier = {"host": L.FMA_TIER_HOST, "peer": L.FMA_TIER_PEER, "local": L.FMA_TIER_LOCAL}[args.tier]
     mode = {"auto": L.FMA_MODE_AUTO, "direct": L.FMA_MODE_DIRECT, "staged": L.FMA_MODE_STAGED, "kernel": L.FMA_MODE_KERNEL}[args.mode]
@@ -167,13 +148,13 @@ def run_ours(args) -> None:
     first = 0
     for i, s in enumerate(table):
         if s.tag == "weights":
-            eng.fill(i, 1234 + rank, first)   # K0, device side
+            eng.fill(i, ranks.shard_seed(rank), first)   # K0, device side
             first += s.bytes // 8
     before = eng.digest_all(["weights"])    # K3
     if tier == L.FMA_TIER_HOST:
         eng.host_reserve(Wb)                # pre-pin off the critical path (the engine's load-time hook does this)
     elif tier == L.FMA_TIER_PEER:
-        eng.peer_reserve((local_rank + max(1, world // 2)) % world, Wb)
+        eng.peer_reserve(ranks.parking_device(local_rank, world), Wb)
     pin_s = eng.stats()["host_store_pin_seconds"]
 
     def cycle():
@@ -218,7 +199,7 @@ def run_ours(args) -> None:
     sleep_dev_m, sleep_wall_m = max_over_ranks(sleep_dev), max_over_ranks(sleep_wall)
     W_total = sum_over_ranks(float(Wb))
     launches_total = int(sum_over_ranks(float(launches)))
-    all_exact = sum_over_ranks(0.0 if bit_exact else 1.0) == 0.0
+    all_exact = group.all_true(bit_exact)
     map_s = max_over_ranks(mean([r[1]["wake_map_seconds"] for r in rows]))
     unmap_s = max_over_ranks(mean([r[0]["sleep_unmap_seconds"] for r in rows]))
     st = eng.stats()
@@ -275,14 +256,15 @@ def run_ours(args) -> None:
             out["cpu_baseline"] = reference_sample(args, workload)
         print(json.dumps(out), flush=True)
     eng.close()
-    if world > 1:
-        dist.destroy_process_group()
+    group.close()
 
 
 def measure_peer(eng, L, Wb, local_rank, world, barrier, max_over_ranks, before, steps=3):
     """Same shard parked in a peer GPU's HBM over NVLink (FMA_TIER_PEER): K1 gather -> peer, K2 scatter <- peer."""
     try:
-        peer_dev = (local_rank + max(1, world // 2)) % world
+        from fma_b200 import ranks
+
+        peer_dev = ranks.parking_device(local_rank, world)
         eng.peer_reserve(peer_dev, Wb)
         rows = []
         for i in range(steps + 1):

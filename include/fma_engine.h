@@ -85,7 +85,7 @@ typedef struct fma_config {
     int32_t  mode;              /* FMA_MODE_*            (0 = auto)                        */
     int32_t  kernel;            /* FMA_KERNEL_*                                            */
     int32_t  copy_streams;      /* copy-engine streams per direction (0 = default 4)       */
-    uint64_t chunk_bytes;       /* DMA chunk (DIRECT, 0 = 32 MiB) / ring-slot size (STAGED, 0 = 256 MiB) */
+    uint64_t chunk_bytes;       /* DMA chunk (DIRECT, 0 = 32 MiB) / ring-slot size (STAGED, 0 = 512 MiB) */
     int32_t  ring_slots;        /* HBM staging ring slots for STAGED (0 = default 2); the ring is
                                    transient: allocated per sleep/wake call, freed before return */
     int32_t  map_threads;       /* host threads doing cuMemCreate/Map on wake (0 = 1)      */

@@ -225,6 +225,7 @@ struct fma_engine {
     cudaEvent_t ev_start = nullptr, ev_end = nullptr;
     cudaEvent_t ev_cs[kMaxStreams] = {};
     std::vector<cudaEvent_t> ev_pool;   // timing pairs for kernels
+    std::vector<cudaEvent_t> ev_stage;  // "these segments are dead" markers for the sleep-side unmapper
     // HBM staging ring (STAGED mode)
     void* ring[kMaxRing] = {};
     cudaEvent_t ev_ring_full[kMaxRing] = {};
@@ -347,12 +348,13 @@ int ensure_desc(fma_engine_t* e, size_t n_pages) {
 }
 
 // DMA chunk for DIRECT (round-robin over copy streams) and ring-slot size for STAGED.  Defaults come from the
-// sweep in profiles/: H2D saturates from 32 MiB chunks; K2/K1 launches need >= 256 MiB to amortise launch + ramp.
+// sweeps in profiles/: H2D saturates from 32 MiB chunks; a K1/K2 launch issued while a copy engine is busy pays a
+// fixed ~25 us (H2D) / ~40 us (D2H) of launch latency, so slots of 512 MiB keep that under 15% of the launch.
 size_t direct_chunk(const fma_engine_t* e) {
     return e->cfg.chunk_bytes ? round_up((size_t)e->cfg.chunk_bytes, FMA_PAGE_BYTES) : ((size_t)32 << 20);
 }
 size_t staged_slot(const fma_engine_t* e) {
-    return e->cfg.chunk_bytes ? round_up((size_t)e->cfg.chunk_bytes, FMA_PAGE_BYTES) : ((size_t)256 << 20);
+    return e->cfg.chunk_bytes ? round_up((size_t)e->cfg.chunk_bytes, FMA_PAGE_BYTES) : ((size_t)512 << 20);
 }
 
 void release_ring(fma_engine_t* e) {
@@ -763,7 +765,8 @@ int do_sleep(fma_engine_t* e, uint64_t offload_mask, int tier, uint32_t flags) {
             discarded += s.bytes;
         }
     }
-    const int mode = resolve_mode(e, tier);
+    int mode = resolve_mode(e, tier);
+    if (W && mode == FMA_MODE_STAGED && ensure_ring(e, W) != FMA_OK) mode = FMA_MODE_DIRECT;  // HBM too full for a ring
     if (W) {
         if (tier == FMA_TIER_HOST) {
             rc = host_store_reserve(e, W);
@@ -796,6 +799,107 @@ int do_sleep(fma_engine_t* e, uint64_t offload_mask, int tier, uint32_t flags) {
     // reference's blocking cudaMemcpy on the legacy stream implicitly does.
     RT(cudaDeviceSynchronize());
 
+    // ---- unmapper thread: cuMemUnmap + cuMemRelease run UNDER the copy pipeline instead of after it --------
+    // (cumem.py:213 unmaps each segment right after its blocking copy; here a segment is released as soon as the
+    // stage that read it last has completed on the device.)  Discarded tags are released immediately.
+    struct Stage {
+        cudaEvent_t ev;
+        std::vector<size_t> segs;
+    };
+    struct Unmapper {
+        fma_engine_t* e;
+        std::mutex mu;
+        std::condition_variable cv;
+        std::vector<Stage> stages;
+        bool closed = false;
+        int error = FMA_OK;
+        char msg[512] = "";
+        double seconds = 0;
+        std::vector<size_t> first;  // segments with nothing to wait for
+        std::thread th;
+        void unmap_one(size_t i, bool dbg) {
+            Segment& s = e->segs[i];
+            if (!s.mapped) return;
+            const double a = now_s();
+            CUresult r1 = g_drv.MemUnmap(s.va, s.bytes);
+            const double b = now_s();
+            CUresult r2 = r1 == CUDA_SUCCESS ? g_drv.MemRelease(s.handle) : r1;
+            const double c = now_s();
+            seconds += c - a;
+            if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) {
+                std::lock_guard<std::mutex> lk(mu);
+                if (error == FMA_OK) {
+                    error = FMA_ECUDA;
+                    snprintf(msg, sizeof(msg), "cuMemUnmap/cuMemRelease failed: %s", cu_err(r1 != CUDA_SUCCESS ? r1 : r2));
+                }
+                return;
+            }
+            if (dbg && (c - a) > 5e-3)
+                fprintf(stderr, "[fma] slow unmap seg seq=%llu bytes=%zu tag=%d unmap=%.1f ms release=%.1f ms\n",
+                        (unsigned long long)s.seq, s.bytes, s.tag, (b - a) * 1e3, (c - b) * 1e3);
+            s.mapped = false;
+            s.handle = 0;
+        }
+        void run() {
+            cudaSetDevice(e->device);
+            const bool dbg = env_int("FMA_DEBUG_VMM", 0) != 0;
+            for (size_t i : first) unmap_one(i, dbg);
+            size_t k = 0;
+            for (;;) {
+                Stage st;
+                {
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv.wait(lk, [&] { return stages.size() > k || closed; });
+                    if (k >= stages.size()) break;
+                    st = stages[k];
+                }
+                cudaError_t r = cudaEventSynchronize(st.ev);
+                if (r != cudaSuccess) {
+                    std::lock_guard<std::mutex> lk(mu);
+                    if (error == FMA_OK) {
+                        error = FMA_ECUDA;
+                        snprintf(msg, sizeof(msg), "cudaEventSynchronize(stage) failed: %s", cudaGetErrorString(r));
+                    }
+                    break;  // never unmap memory whose copy may not have finished
+                }
+                for (size_t i : st.segs) unmap_one(i, dbg);
+                ++k;
+            }
+        }
+        void publish(Stage&& st) {
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                stages.push_back(std::move(st));
+            }
+            cv.notify_all();
+        }
+        void finish() {
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                closed = true;
+            }
+            cv.notify_all();
+            if (th.joinable()) th.join();
+        }
+        ~Unmapper() { finish(); }
+    } un;
+    un.e = e;
+    for (size_t i = 0; i < e->segs.size(); ++i)
+        if (!tag_bit_set(offload_mask, e->segs[i].tag)) un.first.push_back(i);
+    size_t stage_events_used = 0;
+    auto stage_event = [&](cudaStream_t stream, cudaEvent_t* out) -> int {
+        if (stage_events_used == e->ev_stage.size()) {
+            cudaEvent_t ev;
+            RT(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            e->ev_stage.push_back(ev);
+        }
+        *out = e->ev_stage[stage_events_used++];
+        RT(cudaEventRecord(*out, stream));
+        return FMA_OK;
+    };
+    const bool overlap_unmap = env_int("FMA_OVERLAP_UNMAP", 1) != 0;
+    if (overlap_unmap) un.th = std::thread([&un] { un.run(); });
+
     CopyTimer timer{e};
     KernelTimes kt{e};
     uint32_t copy_ops = 0;
@@ -806,25 +910,52 @@ int do_sleep(fma_engine_t* e, uint64_t offload_mask, int tier, uint32_t flags) {
         rc = timer.begin();
         if (rc != FMA_OK) return rc;
         if (mode == FMA_MODE_DIRECT) {
-            // copy engines straight from each segment into the packed image, chunked round-robin over streams
-            int k = 0;
-            for (const Extent& x : ex)
-                for (size_t o = 0; o < x.bytes; o += chunk, ++k) {
+            // copy engines straight from each segment into the packed image; one segment stays on one stream so
+            // that a single event marks it dead, segments alternate over the streams
+            size_t j = 0;
+            for (const Extent& x : ex) {
+                cudaStream_t cstream = e->cs[j++ % e->n_cs];
+                for (size_t o = 0; o < x.bytes; o += chunk) {
                     const size_t n = std::min(chunk, x.bytes - o);
-                    RT(cudaMemcpyAsync(store + x.packed_off + o, reinterpret_cast<void*>(x.va + o), n, cudaMemcpyDefault,
-                                       e->cs[k % e->n_cs]));
+                    RT(cudaMemcpyAsync(store + x.packed_off + o, reinterpret_cast<void*>(x.va + o), n, cudaMemcpyDefault, cstream));
                     ++copy_ops;
                 }
+                Stage st;
+                rc = stage_event(cstream, &st.ev);
+                if (rc != FMA_OK) return rc;
+                st.segs.push_back(x.seg_index);
+                un.publish(std::move(st));
+            }
         } else {
             const size_t n_pages = W / FMA_PAGE_BYTES;
             rc = ensure_tables(e, n_pages);
             if (rc != FMA_OK) return rc;
             build_page_table(ex, e->h_tab);
             RT(cudaMemcpyAsync(e->d_tab, e->h_tab, n_pages * sizeof(uint64_t), cudaMemcpyHostToDevice, e->ks));
+            size_t next_ex = 0;  // first extent not yet handed to the unmapper
+            auto publish_gathered = [&](size_t pages_done) -> int {
+                Stage st;
+                while (next_ex < ex.size() && ex[next_ex].packed_off + ex[next_ex].bytes <= pages_done * FMA_PAGE_BYTES)
+                    st.segs.push_back(ex[next_ex++].seg_index);
+                if (st.segs.empty()) return FMA_OK;
+                int r = stage_event(e->ks, &st.ev);
+                if (r != FMA_OK) return r;
+                un.publish(std::move(st));
+                return FMA_OK;
+            };
             if (mode == FMA_MODE_KERNEL) {
-                // K1 writes the store itself: mapped pinned host memory (PCIe posted writes) or peer/local HBM
-                rc = kt.launch(e->d_tab, 0, nullptr, store_dev_base(e, tier), (uint32_t)n_pages);
-                if (rc != FMA_OK) return rc;
+                // K1 writes the store itself: mapped pinned host memory (PCIe posted writes) or peer/local HBM;
+                // launched in slot-sized batches so finished segments can be released while later ones still move
+                const size_t batch = std::max<size_t>(staged_slot(e) / FMA_PAGE_BYTES, 1);
+                const uint64_t dbase = store_dev_base(e, tier);
+                for (size_t p0 = 0; p0 < n_pages; p0 += batch) {
+                    const size_t np = std::min(batch, n_pages - p0);
+                    rc = kt.launch(e->d_tab + p0, 0, nullptr, dbase + p0 * FMA_PAGE_BYTES, (uint32_t)np);
+                    if (rc != FMA_OK) return rc;
+                    ++copy_ops;
+                    rc = publish_gathered(p0 + np);
+                    if (rc != FMA_OK) return rc;
+                }
             } else {  // STAGED: K1 gather -> HBM ring slot -> copy engine D2H
                 rc = ensure_ring(e, W);
                 if (rc != FMA_OK) return rc;
@@ -842,17 +973,26 @@ int do_sleep(fma_engine_t* e, uint64_t offload_mask, int tier, uint32_t flags) {
                     RT(cudaMemcpyAsync(store + p0 * FMA_PAGE_BYTES, e->ring[slot], np * FMA_PAGE_BYTES, cudaMemcpyDefault, cstream));
                     RT(cudaEventRecord(e->ev_ring_free[slot], cstream));
                     ++copy_ops;
+                    rc = publish_gathered(p0 + np);  // once gathered into the ring the source segments are dead
+                    if (rc != FMA_OK) return rc;
                 }
             }
         }
+        {
+            std::lock_guard<std::mutex> lk(un.mu);
+            un.closed = true;
+        }
+        un.cv.notify_all();
         rc = timer.end(&copy_s);
         if (rc != FMA_OK) return rc;
         rc = kt.collect();
         if (rc != FMA_OK) return rc;
         release_ring(e);
     }
+    un.finish();
+    if (un.error != FMA_OK) return fail(un.error, "%s", un.msg);
 
-    // unmap + release EVERYTHING (cumem.py:213), VAs stay reserved
+    // whatever is still mapped (FMA_OVERLAP_UNMAP=0, or nothing offloaded): unmap + release now (cumem.py:213)
     const double t_un0 = now_s();
     for (const Extent& x : ex) {
         Segment& s = e->segs[x.seg_index];
@@ -860,29 +1000,20 @@ int do_sleep(fma_engine_t* e, uint64_t offload_mask, int tier, uint32_t flags) {
         s.backup_tier = tier;
         s.packed_off = x.packed_off;
     }
-    const bool dbg = env_int("FMA_DEBUG_VMM", 0) != 0;
-    for (Segment& s : e->segs) {
-        if (!s.mapped) continue;
-        const double a = now_s();
-        CUresult r1 = g_drv.MemUnmap(s.va, s.bytes);
-        const double b = now_s();
-        CUresult r2 = g_drv.MemRelease(s.handle);
-        const double c = now_s();
-        if (r1 != CUDA_SUCCESS) return fail(FMA_ECUDA, "cuMemUnmap failed: %s", cu_err(r1));
-        if (r2 != CUDA_SUCCESS) return fail(FMA_ECUDA, "cuMemRelease failed: %s", cu_err(r2));
-        if (dbg && (c - a) > 5e-3)
-            fprintf(stderr, "[fma] slow unmap seg seq=%llu bytes=%zu tag=%d unmap=%.1f ms release=%.1f ms\n",
-                    (unsigned long long)s.seq, s.bytes, s.tag, (b - a) * 1e3, (c - b) * 1e3);
-        s.mapped = false;
-        s.handle = 0;
+    {
+        const bool dbg = env_int("FMA_DEBUG_VMM", 0) != 0;
+        for (size_t i = 0; i < e->segs.size(); ++i) un.unmap_one(i, dbg);
+        if (un.error != FMA_OK) return fail(un.error, "%s", un.msg);
     }
     const double t_un1 = now_s();
+    (void)t_un0;
+    (void)t_un1;
     e->image_bytes = W;
     e->image_tier = tier;
 
     e->st.sleep_seconds = now_s() - t_entry;
     e->st.sleep_copy_seconds = copy_s;
-    e->st.sleep_unmap_seconds = t_un1 - t_un0;
+    e->st.sleep_unmap_seconds = un.seconds;
     e->st.sleep_bytes_offloaded = W;
     e->st.sleep_bytes_discarded = discarded;
     e->st.copy_ops = copy_ops;
@@ -931,7 +1062,13 @@ int do_wake(fma_engine_t* e, uint64_t tag_mask, uint32_t flags) {
     std::vector<size_t> order = with_backup;
     order.insert(order.end(), remap_only.begin(), remap_only.end());
     const int tier = e->image_tier;
-    const int mode = resolve_mode(e, tier);
+    int mode = resolve_mode(e, tier);
+    {
+        uint64_t w_bytes = 0;
+        for (size_t i : with_backup) w_bytes += e->segs[i].bytes;
+        // the ring must exist BEFORE the mapper starts taking HBM; if it does not fit, copy engines go direct
+        if (w_bytes && mode == FMA_MODE_STAGED && ensure_ring(e, w_bytes) != FMA_OK) mode = FMA_MODE_DIRECT;
+    }
 
     // ---- mapper thread(s): cuMemCreate + cuMemMap + cuMemSetAccess in `order` -------------------
     MapProgress prog;
@@ -1260,6 +1397,7 @@ int fma_engine_destroy(fma_engine_t* e) {
     if (e->d_dig) cudaFree(e->d_dig);
     if (e->h_dig) cudaFreeHost(e->h_dig);
     for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : e->ev_stage) cudaEventDestroy(ev);
     for (int i = 0; i < kMaxStreams; ++i) {
         if (e->cs[i]) cudaStreamDestroy(e->cs[i]);
         if (e->ev_cs[i]) cudaEventDestroy(e->ev_cs[i]);

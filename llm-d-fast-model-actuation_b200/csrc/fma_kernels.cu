@@ -278,10 +278,13 @@ int sm_count() {
 // launch wrappers (internal C++ interface used by fma_engine.cu)
 // ------------------------------------------------------------------------------------
 fma_k_tma_cfg fma_k_default_tma_cfg() {
+    // Picked from the launch-size sweep on B200 (profiles/k_size_sweep_r1.md): 2 pipes x 3 stages x 16 KiB =
+    // 96 KiB in flight per SM is the best or within 1% of the best from 256 MiB to 4 GiB per launch
+    // (6.22 -> 6.62 TB/s read+write); deeper rings or 2 CTAs/SM lose 3-6% (more DRAM page conflicts).
     fma_k_tma_cfg c;
-    c.tile_bytes = 32u << 10;
+    c.tile_bytes = 16u << 10;
     c.stages = 3;
-    c.pipes = 2;          // 2 pipes x 3 stages x 32 KiB = 192 KiB dynamic smem, 1 CTA per SM
+    c.pipes = 2;
     c.ctas_per_sm = 1;
     return c;
 }

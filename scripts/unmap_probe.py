@@ -3,7 +3,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 os.environ["FMA_DEBUG_VMM"] = "1"
 import fma_b200
 from fma_b200 import workloads as W, _lib as L
-for kv in (0,):
+for kv in (32,):
     eng = fma_b200.Engine(0)
     table = W.allocation_table("llama-3-8b", kv_cache_bytes=kv << 30)
     ptrs = [eng.alloc(s.bytes, s.tag) for s in table]
