@@ -31,6 +31,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <iterator>
 #include <map>
 #include <mutex>
 #include <string>
@@ -173,13 +174,37 @@ struct Segment {
     size_t requested = 0;
     int tag = 0;
     uint64_t seq = 0;
-    CUmemGenericAllocationHandle handle = 0;
+    int arena = -1;         // VA arena the segment lives in
+    CUdeviceptr unit_va = 0;  // key of the mapping unit that backs it (0 while unmapped)
     bool mapped = false;
     bool has_backup = false;
     int backup_tier = FMA_TIER_HOST;
     uint64_t packed_off = kNoOffset;
     uint64_t digest = 0;
     bool digest_valid = false;
+};
+
+// One VA arena per tag: segments of a tag are bump-allocated next to each other, so that after a sleep the
+// whole tag can be re-created with ONE cuMemCreate + cuMemMap + cuMemSetAccess (a "run") instead of three driver
+// calls per segment.  Measured on B200: 15 GiB as 131 pieces = 8 ms map + 17 ms unmap alone, 16 + 22 ms with a
+// second process making VMM calls, and 325 ms inside a 2-rank wake; as one run = 1.4 ms + 5 ms, contention-proof
+// (profiles/vmm_span_probe_r1.json).
+struct Arena {
+    CUdeviceptr base = 0;
+    size_t cap = 0;
+    size_t top = 0;                     // bump pointer
+    int tag = 0;
+    std::map<size_t, size_t> holes;     // freed ranges below top: offset -> length
+};
+
+// A live physical mapping: [va, va+bytes).  At load time a unit is one segment; after a wake it is a whole run.
+// The physical handle is released right after cuMemMap (the memory lives until cuMemUnmap), so a unit is just a range.
+struct Unit {
+    CUdeviceptr va = 0;
+    size_t bytes = 0;
+    size_t live_bytes = 0;              // bytes of segments still allocated inside it
+    int arena = -1;
+    std::vector<std::pair<CUdeviceptr, size_t>> zombies;  // freed segments whose VA returns when the unit is unmapped
 };
 
 struct HostStore {
@@ -210,6 +235,8 @@ struct fma_engine {
     std::mutex mu;  // guards segs / tags (my_malloc can arrive from any torch thread)
     std::vector<Segment> segs;  // allocation order == reference dict order (cumem.py:198,237)
     std::map<CUdeviceptr, size_t> by_va;
+    std::vector<Arena> arenas;
+    std::map<CUdeviceptr, Unit> units;  // live mappings, keyed (and therefore ordered) by VA
     uint64_t next_seq = 0;
     std::vector<std::string> tags;
     int current_tag = 0;
@@ -268,7 +295,9 @@ CUmemAllocationProp device_prop(int device) {
     return prop;
 }
 
-int vmm_create_and_map(int device, CUdeviceptr va, size_t bytes, CUmemGenericAllocationHandle* out) {
+// create + map + set access, then drop the handle: the physical memory stays alive until cuMemUnmap
+// (verified on B200, scripts/vmm_span_probe.py), which makes teardown a single driver call per range.
+int vmm_create_and_map(int device, CUdeviceptr va, size_t bytes) {
     CUmemAllocationProp prop = device_prop(device);
     CUmemGenericAllocationHandle h = 0;
     DRV(g_drv.MemCreate(&h, bytes, &prop, 0));
@@ -288,13 +317,79 @@ int vmm_create_and_map(int device, CUdeviceptr va, size_t bytes, CUmemGenericAll
         g_drv.MemRelease(h);
         return fail(FMA_ECUDA, "cuMemSetAccess failed: %s", cu_err(r));
     }
-    *out = h;
+    DRV(g_drv.MemRelease(h));
     return FMA_OK;
 }
 
-int vmm_unmap_and_release(CUdeviceptr va, size_t bytes, CUmemGenericAllocationHandle h) {
-    DRV(g_drv.MemUnmap(va, bytes));
-    DRV(g_drv.MemRelease(h));
+// ---- arenas ----------------------------------------------------------------------------------------
+void arena_give_back(Arena& a, size_t off, size_t len) {
+    auto it = a.holes.emplace(off, len).first;
+    if (it != a.holes.begin()) {  // merge with the hole before
+        auto prev = std::prev(it);
+        if (prev->first + prev->second == it->first) {
+            prev->second += it->second;
+            a.holes.erase(it);
+            it = prev;
+        }
+    }
+    auto next = std::next(it);
+    if (next != a.holes.end() && it->first + it->second == next->first) {  // merge with the hole after
+        it->second += next->second;
+        a.holes.erase(next);
+    }
+    if (it->first + it->second == a.top) {  // a hole that touches the bump pointer lowers it
+        a.top = it->first;
+        a.holes.erase(it);
+    }
+}
+
+int arena_take(fma_engine_t* e, int tag, size_t bytes, int* out_arena, CUdeviceptr* out_va) {
+    for (size_t i = 0; i < e->arenas.size(); ++i) {
+        Arena& a = e->arenas[i];
+        if (a.tag != tag) continue;
+        for (auto it = a.holes.begin(); it != a.holes.end(); ++it) {  // first fit
+            if (it->second < bytes) continue;
+            const size_t off = it->first, len = it->second;
+            a.holes.erase(it);
+            if (len > bytes) a.holes.emplace(off + bytes, len - bytes);
+            *out_arena = (int)i;
+            *out_va = a.base + off;
+            return FMA_OK;
+        }
+        if (a.top + bytes <= a.cap) {
+            *out_arena = (int)i;
+            *out_va = a.base + a.top;
+            a.top += bytes;
+            return FMA_OK;
+        }
+    }
+    Arena a;
+    a.tag = tag;
+    size_t want = std::max<size_t>((size_t)std::max(env_int("FMA_ARENA_GIB", 256), 1) << 30, round_up(bytes, e->gran));
+    CUresult r = CUDA_ERROR_OUT_OF_MEMORY;
+    while (true) {  // VA is plentiful, but shrink gracefully if a huge reservation is refused
+        r = g_drv.MemAddressReserve(&a.base, want, e->gran, 0, 0);
+        if (r == CUDA_SUCCESS || want <= round_up(bytes, e->gran)) break;
+        want = std::max(want / 2, round_up(bytes, e->gran));
+    }
+    if (r != CUDA_SUCCESS) return fail(FMA_ENOMEM, "cuMemAddressReserve(%zu) failed: %s", want, cu_err(r));
+    a.cap = want;
+    a.top = bytes;
+    e->arenas.push_back(a);
+    *out_arena = (int)e->arenas.size() - 1;
+    *out_va = a.base;
+    return FMA_OK;
+}
+
+// Unmap one unit (or, for `span_bytes` > unit.bytes, a VA-contiguous group of units in one driver call) and return
+// the VA of its zombies to their arena.  Caller has made sure nothing on the device still touches the range.
+int unmap_units(fma_engine_t* e, CUdeviceptr va, size_t span_bytes) {
+    DRV(g_drv.MemUnmap(va, span_bytes));
+    auto it = e->units.find(va);
+    while (it != e->units.end() && it->first < va + span_bytes) {
+        for (auto& z : it->second.zombies) arena_give_back(e->arenas[it->second.arena], z.first - e->arenas[it->second.arena].base, z.second);
+        it = e->units.erase(it);
+    }
     return FMA_OK;
 }
 
@@ -367,8 +462,11 @@ void release_ring(fma_engine_t* e) {
     cudaGetLastError();
 }
 
-// The HBM staging ring is transient: allocated when a STAGED sleep/wake starts and freed when it ends, so a
-// sleeping (or serving) model does not keep it resident.  `image_bytes` caps the slot size for small models.
+// The HBM staging ring lives from the start of a wake to the end of the next sleep: a serving model keeps it
+// (1 GiB of 180 GB) so that /sleep needs no allocation, a SLEEPING model does not hold it.  It is freed at the END
+// of sleep, synchronously: on these shared hosts a cudaFree of 2 x 512 MiB takes anywhere from 0.8 ms to 300 ms
+// (driver stalls), which must never sit inside the wake latency — and freeing it from a background thread was
+// measured to block the next wake's first driver call instead.  `image_bytes` caps the slot size for small models.
 int ensure_ring(fma_engine_t* e, size_t image_bytes) {
     size_t slot = std::min(staged_slot(e), round_up(std::max<size_t>(image_bytes, 1), FMA_PAGE_BYTES));
     int n = e->cfg.ring_slots > 0 ? std::min(e->cfg.ring_slots, kMaxRing) : 2;
@@ -557,51 +655,64 @@ int park_reserve(fma_engine_t* e, int park_device, size_t bytes) {
 int engine_alloc(fma_engine_t* e, size_t bytes, int tag, void** out) {
     if (bytes == 0) bytes = 1;
     const size_t sz = round_up(bytes, e->gran);
+    std::lock_guard<std::mutex> lk(e->mu);
+    int arena = -1;
     CUdeviceptr va = 0;
-    DRV(g_drv.MemAddressReserve(&va, sz, e->gran, 0, 0));
-    CUmemGenericAllocationHandle h = 0;
-    int rc = vmm_create_and_map(e->device, va, sz, &h);
+    int rc = arena_take(e, tag, sz, &arena, &va);
+    if (rc != FMA_OK) return rc;
+    rc = vmm_create_and_map(e->device, va, sz);
     if (rc != FMA_OK) {
-        g_drv.MemAddressFree(va, sz);
+        arena_give_back(e->arenas[arena], va - e->arenas[arena].base, sz);
         return rc;
     }
+    Unit u;
+    u.va = va;
+    u.bytes = sz;
+    u.live_bytes = sz;
+    u.arena = arena;
+    e->units[va] = u;
     Segment s;
     s.va = va;
     s.bytes = sz;
     s.requested = bytes;
     s.tag = tag;
-    s.handle = h;
+    s.arena = arena;
+    s.unit_va = va;
     s.mapped = true;
-    {
-        std::lock_guard<std::mutex> lk(e->mu);
-        s.seq = e->next_seq++;
-        e->by_va[va] = e->segs.size();
-        e->segs.push_back(s);
-    }
+    s.seq = e->next_seq++;
+    e->by_va[va] = e->segs.size();
+    e->segs.push_back(s);
     *out = reinterpret_cast<void*>(va);
     return FMA_OK;
 }
 
 int engine_free(fma_engine_t* e, void* ptr) {
-    Segment s;
-    {
-        std::lock_guard<std::mutex> lk(e->mu);
-        auto it = e->by_va.find(reinterpret_cast<CUdeviceptr>(ptr));
-        if (it == e->by_va.end()) return fail(FMA_ENOTFOUND, "pointer %p is not an engine segment", ptr);
-        const size_t idx = it->second;
-        s = e->segs[idx];
-        e->segs.erase(e->segs.begin() + idx);
-        e->by_va.clear();
-        for (size_t i = 0; i < e->segs.size(); ++i) e->by_va[e->segs[i].va] = i;
+    std::lock_guard<std::mutex> lk(e->mu);
+    auto it = e->by_va.find(reinterpret_cast<CUdeviceptr>(ptr));
+    if (it == e->by_va.end()) return fail(FMA_ENOTFOUND, "pointer %p is not an engine segment", ptr);
+    const size_t idx = it->second;
+    const Segment s = e->segs[idx];
+    e->segs.erase(e->segs.begin() + idx);
+    e->by_va.clear();
+    for (size_t i = 0; i < e->segs.size(); ++i) e->by_va[e->segs[i].va] = i;
+    Arena& a = e->arenas[s.arena];
+    if (!s.mapped) {  // asleep: nothing is mapped there, the VA is free again at once
+        arena_give_back(a, s.va - a.base, s.bytes);
+        return FMA_OK;
     }
-    if (s.mapped) {
+    auto uit = e->units.find(s.unit_va);
+    if (uit == e->units.end()) return fail(FMA_ESTATE, "segment %p has no mapping unit", ptr);
+    Unit& u = uit->second;
+    u.live_bytes -= s.bytes;
+    u.zombies.emplace_back(s.va, s.bytes);
+    if (u.live_bytes == 0) {
         // Drain work that may still touch the range before it is unmapped — the reference does
         // torch.cuda.synchronize() in its free callback for the same reason (cumem.py:156-169).
         cudaDeviceSynchronize();
-        int rc = vmm_unmap_and_release(s.va, s.bytes, s.handle);
-        if (rc != FMA_OK) return rc;
+        return unmap_units(e, u.va, u.bytes);
     }
-    DRV(g_drv.MemAddressFree(s.va, s.bytes));
+    // The segment sits inside a run that was mapped as one unit (cuMemUnmap cannot split a mapping): it is gone
+    // from the table now; its physical pages go with the unit at the next sleep / when the run empties.
     return FMA_OK;
 }
 
@@ -750,10 +861,17 @@ int do_sleep(fma_engine_t* e, uint64_t offload_mask, int tier, uint32_t flags) {
     for (const Segment& s : e->segs) (s.mapped ? any_mapped : any_unmapped) = true;
     if (any_unmapped || !any_mapped) return FMA_OK;
 
-    // plan: offloaded segments in allocation order -> packed image
+    // plan: offloaded segments -> packed image, in (arena, VA) order.  Arenas are bump-allocated per tag, so this is
+    // allocation order (the reference's dict order, cumem.py:198) unless a freed hole was reused.
+    std::vector<size_t> by_addr(e->segs.size());
+    for (size_t i = 0; i < by_addr.size(); ++i) by_addr[i] = i;
+    std::sort(by_addr.begin(), by_addr.end(), [&](size_t a, size_t b) {
+        const Segment &x = e->segs[a], &y = e->segs[b];
+        return x.arena != y.arena ? x.arena < y.arena : x.va < y.va;
+    });
     std::vector<Extent> ex;
     uint64_t W = 0, discarded = 0;
-    for (size_t i = 0; i < e->segs.size(); ++i) {
+    for (size_t i : by_addr) {
         Segment& s = e->segs[i];
         s.has_backup = false;
         s.packed_off = kNoOffset;
@@ -799,12 +917,17 @@ int do_sleep(fma_engine_t* e, uint64_t offload_mask, int tier, uint32_t flags) {
     // reference's blocking cudaMemcpy on the legacy stream implicitly does.
     RT(cudaDeviceSynchronize());
 
-    // ---- unmapper thread: cuMemUnmap + cuMemRelease run UNDER the copy pipeline instead of after it --------
-    // (cumem.py:213 unmaps each segment right after its blocking copy; here a segment is released as soon as the
-    // stage that read it last has completed on the device.)  Discarded tags are released immediately.
+    // ---- unmapper thread: cuMemUnmap runs UNDER the copy pipeline instead of after it -----------------------
+    // (cumem.py:213 unmaps each segment right after its blocking copy.)  The thread only issues driver calls on
+    // ranges planned here; the table is updated by this thread after it has been joined.  Adjacent units are
+    // unmapped with ONE spanning cuMemUnmap (allowed across whole mappings, scripts/vmm_span_probe.py).
+    struct Range {
+        CUdeviceptr va;
+        size_t bytes;
+    };
     struct Stage {
         cudaEvent_t ev;
-        std::vector<size_t> segs;
+        std::vector<Range> ranges;
     };
     struct Unmapper {
         fma_engine_t* e;
@@ -815,35 +938,30 @@ int do_sleep(fma_engine_t* e, uint64_t offload_mask, int tier, uint32_t flags) {
         int error = FMA_OK;
         char msg[512] = "";
         double seconds = 0;
-        std::vector<size_t> first;  // segments with nothing to wait for
+        std::vector<Range> first;  // ranges with nothing to wait for (discarded tags)
+        std::vector<Range> done;   // ranges actually unmapped
         std::thread th;
-        void unmap_one(size_t i, bool dbg) {
-            Segment& s = e->segs[i];
-            if (!s.mapped) return;
+        void unmap_range(const Range& r, bool dbg) {
             const double a = now_s();
-            CUresult r1 = g_drv.MemUnmap(s.va, s.bytes);
+            CUresult r1 = g_drv.MemUnmap(r.va, r.bytes);
             const double b = now_s();
-            CUresult r2 = r1 == CUDA_SUCCESS ? g_drv.MemRelease(s.handle) : r1;
-            const double c = now_s();
-            seconds += c - a;
-            if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) {
+            seconds += b - a;
+            if (r1 != CUDA_SUCCESS) {
                 std::lock_guard<std::mutex> lk(mu);
                 if (error == FMA_OK) {
                     error = FMA_ECUDA;
-                    snprintf(msg, sizeof(msg), "cuMemUnmap/cuMemRelease failed: %s", cu_err(r1 != CUDA_SUCCESS ? r1 : r2));
+                    snprintf(msg, sizeof(msg), "cuMemUnmap(%zu bytes) failed: %s", r.bytes, cu_err(r1));
                 }
                 return;
             }
-            if (dbg && (c - a) > 5e-3)
-                fprintf(stderr, "[fma] slow unmap seg seq=%llu bytes=%zu tag=%d unmap=%.1f ms release=%.1f ms\n",
-                        (unsigned long long)s.seq, s.bytes, s.tag, (b - a) * 1e3, (c - b) * 1e3);
-            s.mapped = false;
-            s.handle = 0;
+            if (dbg && (b - a) > 5e-3)
+                fprintf(stderr, "[fma] slow unmap va=0x%llx bytes=%zu unmap=%.1f ms\n", (unsigned long long)r.va, r.bytes, (b - a) * 1e3);
+            done.push_back(r);
         }
         void run() {
             cudaSetDevice(e->device);
             const bool dbg = env_int("FMA_DEBUG_VMM", 0) != 0;
-            for (size_t i : first) unmap_one(i, dbg);
+            for (const Range& r : first) unmap_range(r, dbg);
             size_t k = 0;
             for (;;) {
                 Stage st;
@@ -862,7 +980,7 @@ int do_sleep(fma_engine_t* e, uint64_t offload_mask, int tier, uint32_t flags) {
                     }
                     break;  // never unmap memory whose copy may not have finished
                 }
-                for (size_t i : st.segs) unmap_one(i, dbg);
+                for (const Range& rg : st.ranges) unmap_range(rg, dbg);
                 ++k;
             }
         }
@@ -884,8 +1002,37 @@ int do_sleep(fma_engine_t* e, uint64_t offload_mask, int tier, uint32_t flags) {
         ~Unmapper() { finish(); }
     } un;
     un.e = e;
-    for (size_t i = 0; i < e->segs.size(); ++i)
-        if (!tag_bit_set(offload_mask, e->segs[i].tag)) un.first.push_back(i);
+
+    // Units in VA order, split into "discarded" (release now) and "offloaded" (release once the image has their
+    // bytes).  image_end = packed offset just past the unit's last live segment.
+    struct PlannedUnit {
+        CUdeviceptr va;
+        size_t bytes;
+        uint64_t image_end;
+    };
+    std::vector<PlannedUnit> off_units;  // same order as the image
+    auto add_range = [](std::vector<Range>& v, CUdeviceptr va, size_t bytes) {
+        if (!v.empty() && v.back().va + v.back().bytes == va) v.back().bytes += bytes;  // VA-adjacent: one driver call
+        else v.push_back(Range{va, bytes});
+    };
+    {
+        std::map<CUdeviceptr, uint64_t> unit_end;  // unit -> image_end (offloaded units only)
+        for (const Extent& x : ex) {
+            const CUdeviceptr key = e->segs[x.seg_index].unit_va;
+            uint64_t& end = unit_end[key];
+            end = std::max<uint64_t>(end, x.packed_off + x.bytes);
+        }
+        // arenas in index order, units by VA inside: identical to the image order
+        std::vector<const Unit*> ordered;
+        for (auto& kv : e->units) ordered.push_back(&kv.second);
+        std::sort(ordered.begin(), ordered.end(), [](const Unit* a, const Unit* b) { return a->arena != b->arena ? a->arena < b->arena : a->va < b->va; });
+        for (const Unit* u : ordered) {
+            auto it = unit_end.find(u->va);
+            if (it == unit_end.end()) add_range(un.first, u->va, u->bytes);
+            else off_units.push_back(PlannedUnit{u->va, u->bytes, it->second});
+        }
+    }
+    size_t next_unit = 0;  // first offloaded unit not yet handed to the unmapper
     size_t stage_events_used = 0;
     auto stage_event = [&](cudaStream_t stream, cudaEvent_t* out) -> int {
         if (stage_events_used == e->ev_stage.size()) {
@@ -895,6 +1042,19 @@ int do_sleep(fma_engine_t* e, uint64_t offload_mask, int tier, uint32_t flags) {
         }
         *out = e->ev_stage[stage_events_used++];
         RT(cudaEventRecord(*out, stream));
+        return FMA_OK;
+    };
+    // everything whose bytes are inside image[0, image_done) and has been read by work enqueued on `stream` so far
+    auto publish_consumed = [&](uint64_t image_done, cudaStream_t stream) -> int {
+        Stage st;
+        while (next_unit < off_units.size() && off_units[next_unit].image_end <= image_done) {
+            add_range(st.ranges, off_units[next_unit].va, off_units[next_unit].bytes);
+            ++next_unit;
+        }
+        if (st.ranges.empty()) return FMA_OK;
+        int r = stage_event(stream, &st.ev);
+        if (r != FMA_OK) return r;
+        un.publish(std::move(st));
         return FMA_OK;
     };
     const bool overlap_unmap = env_int("FMA_OVERLAP_UNMAP", 1) != 0;
@@ -910,21 +1070,28 @@ int do_sleep(fma_engine_t* e, uint64_t offload_mask, int tier, uint32_t flags) {
         rc = timer.begin();
         if (rc != FMA_OK) return rc;
         if (mode == FMA_MODE_DIRECT) {
-            // copy engines straight from each segment into the packed image; one segment stays on one stream so
-            // that a single event marks it dead, segments alternate over the streams
-            size_t j = 0;
+            // copy engines straight from the segments into the packed image, chunks round-robin over the streams;
+            // every `slot` bytes of image the streams are joined so that one event marks the units behind it dead
+            const size_t slot = staged_slot(e);
+            uint64_t next_join = slot;
+            int k = 0;
             for (const Extent& x : ex) {
-                cudaStream_t cstream = e->cs[j++ % e->n_cs];
-                for (size_t o = 0; o < x.bytes; o += chunk) {
+                for (size_t o = 0; o < x.bytes; o += chunk, ++k) {
                     const size_t n = std::min(chunk, x.bytes - o);
-                    RT(cudaMemcpyAsync(store + x.packed_off + o, reinterpret_cast<void*>(x.va + o), n, cudaMemcpyDefault, cstream));
+                    RT(cudaMemcpyAsync(store + x.packed_off + o, reinterpret_cast<void*>(x.va + o), n, cudaMemcpyDefault,
+                                       e->cs[k % e->n_cs]));
                     ++copy_ops;
                 }
-                Stage st;
-                rc = stage_event(cstream, &st.ev);
-                if (rc != FMA_OK) return rc;
-                st.segs.push_back(x.seg_index);
-                un.publish(std::move(st));
+                const uint64_t image_done = x.packed_off + x.bytes;
+                if (image_done >= next_join || &x == &ex.back()) {
+                    for (int i = 1; i < e->n_cs; ++i) {  // stream 0 waits for the others
+                        RT(cudaEventRecord(e->ev_cs[i], e->cs[i]));
+                        RT(cudaStreamWaitEvent(e->cs[0], e->ev_cs[i], 0));
+                    }
+                    rc = publish_consumed(image_done, e->cs[0]);
+                    if (rc != FMA_OK) return rc;
+                    next_join = image_done + slot;
+                }
             }
         } else {
             const size_t n_pages = W / FMA_PAGE_BYTES;
@@ -932,17 +1099,7 @@ int do_sleep(fma_engine_t* e, uint64_t offload_mask, int tier, uint32_t flags) {
             if (rc != FMA_OK) return rc;
             build_page_table(ex, e->h_tab);
             RT(cudaMemcpyAsync(e->d_tab, e->h_tab, n_pages * sizeof(uint64_t), cudaMemcpyHostToDevice, e->ks));
-            size_t next_ex = 0;  // first extent not yet handed to the unmapper
-            auto publish_gathered = [&](size_t pages_done) -> int {
-                Stage st;
-                while (next_ex < ex.size() && ex[next_ex].packed_off + ex[next_ex].bytes <= pages_done * FMA_PAGE_BYTES)
-                    st.segs.push_back(ex[next_ex++].seg_index);
-                if (st.segs.empty()) return FMA_OK;
-                int r = stage_event(e->ks, &st.ev);
-                if (r != FMA_OK) return r;
-                un.publish(std::move(st));
-                return FMA_OK;
-            };
+            auto publish_gathered = [&](size_t pages_done) -> int { return publish_consumed((uint64_t)pages_done * FMA_PAGE_BYTES, e->ks); };
             if (mode == FMA_MODE_KERNEL) {
                 // K1 writes the store itself: mapped pinned host memory (PCIe posted writes) or peer/local HBM;
                 // launched in slot-sized batches so finished segments can be released while later ones still move
@@ -987,13 +1144,13 @@ int do_sleep(fma_engine_t* e, uint64_t offload_mask, int tier, uint32_t flags) {
         if (rc != FMA_OK) return rc;
         rc = kt.collect();
         if (rc != FMA_OK) return rc;
-        release_ring(e);
+        if (env_int("FMA_RING_PERSIST", 0) == 0) release_ring(e);  // while the unmapper finishes its last ranges
     }
     un.finish();
     if (un.error != FMA_OK) return fail(un.error, "%s", un.msg);
 
-    // whatever is still mapped (FMA_OVERLAP_UNMAP=0, or nothing offloaded): unmap + release now (cumem.py:213)
-    const double t_un0 = now_s();
+    // apply what the unmapper did to the table, then unmap whatever is left (FMA_OVERLAP_UNMAP=0, nothing
+    // offloaded, ...) — every unit goes (cumem.py:213), VAs stay reserved
     for (const Extent& x : ex) {
         Segment& s = e->segs[x.seg_index];
         s.has_backup = true;
@@ -1001,13 +1158,28 @@ int do_sleep(fma_engine_t* e, uint64_t offload_mask, int tier, uint32_t flags) {
         s.packed_off = x.packed_off;
     }
     {
-        const bool dbg = env_int("FMA_DEBUG_VMM", 0) != 0;
-        for (size_t i = 0; i < e->segs.size(); ++i) un.unmap_one(i, dbg);
-        if (un.error != FMA_OK) return fail(un.error, "%s", un.msg);
+        std::lock_guard<std::mutex> lk(e->mu);
+        for (const auto& r : un.done) {
+            auto it = e->units.lower_bound(r.va);
+            while (it != e->units.end() && it->first < r.va + r.bytes) {
+                Arena& a = e->arenas[it->second.arena];
+                for (auto& z : it->second.zombies) arena_give_back(a, z.first - a.base, z.second);
+                it = e->units.erase(it);
+            }
+        }
+        std::vector<Range> rest;
+        for (auto& kv : e->units) add_range(rest, kv.second.va, kv.second.bytes);
+        const double a0 = now_s();
+        for (const Range& r : rest) {
+            rc = unmap_units(e, r.va, r.bytes);
+            if (rc != FMA_OK) return rc;
+        }
+        un.seconds += now_s() - a0;
+        for (Segment& s : e->segs) {
+            s.mapped = false;
+            s.unit_va = 0;
+        }
     }
-    const double t_un1 = now_s();
-    (void)t_un0;
-    (void)t_un1;
     e->image_bytes = W;
     e->image_tier = tier;
 
@@ -1048,19 +1220,61 @@ int do_wake(fma_engine_t* e, uint64_t tag_mask, uint32_t flags) {
     rc = ensure_streams(e);
     if (rc != FMA_OK) return rc;
 
-    // work list in allocation order: segments with a backup first keep their relative order (they
-    // gate the copy pipeline); remap-only segments (e.g. kv_cache) are mapped after them.
-    std::vector<size_t> with_backup, remap_only;
-    for (size_t i = 0; i < e->segs.size(); ++i) {
-        const Segment& s = e->segs[i];
-        if (s.mapped) continue;                                  // idempotent: already awake
-        if (tag_mask && !tag_bit_set(tag_mask, s.tag)) continue;  // tags is None or data.tag in tags (cumem.py:238)
-        (s.has_backup ? with_backup : remap_only).push_back(i);
+    // Work list: RUNS — maximal VA-contiguous groups of sleeping segments of one arena — so a whole tag is
+    // re-created with one cuMemCreate + cuMemMap + cuMemSetAccess.  Runs that have a backup come first, in image
+    // order (they gate the copy pipeline); remap-only runs (e.g. kv_cache) are mapped after them.
+    struct Run {
+        CUdeviceptr va = 0;
+        size_t bytes = 0;
+        int arena = -1;
+        bool has_backup = false;
+        uint64_t first_off = 0;       // packed offset of its first segment (ordering key)
+        std::vector<size_t> segs;     // indices into e->segs, ascending VA
+    };
+    std::vector<Run> runs;
+    {
+        std::vector<size_t> cand;
+        for (size_t i = 0; i < e->segs.size(); ++i) {
+            const Segment& s = e->segs[i];
+            if (s.mapped) continue;                                  // idempotent: already awake
+            if (tag_mask && !tag_bit_set(tag_mask, s.tag)) continue;  // tags is None or data.tag in tags (cumem.py:238)
+            cand.push_back(i);
+        }
+        if (cand.empty()) return FMA_OK;
+        std::sort(cand.begin(), cand.end(), [&](size_t a, size_t b) {
+            const Segment &x = e->segs[a], &y = e->segs[b];
+            return x.arena != y.arena ? x.arena < y.arena : x.va < y.va;
+        });
+        const bool merge = env_int("FMA_MERGE_RUNS", 1) != 0;
+        for (size_t i : cand) {
+            const Segment& s = e->segs[i];
+            if (merge && !runs.empty() && runs.back().arena == s.arena && runs.back().va + runs.back().bytes == s.va &&
+                runs.back().has_backup == s.has_backup) {
+                runs.back().bytes += s.bytes;
+                runs.back().segs.push_back(i);
+            } else {
+                Run r;
+                r.va = s.va; r.bytes = s.bytes; r.arena = s.arena; r.has_backup = s.has_backup;
+                r.first_off = s.has_backup ? s.packed_off : kNoOffset;
+                r.segs.push_back(i);
+                runs.push_back(std::move(r));
+            }
+        }
+        std::stable_sort(runs.begin(), runs.end(), [](const Run& a, const Run& b) {
+            if (a.has_backup != b.has_backup) return a.has_backup;
+            return a.first_off < b.first_off;
+        });
     }
-    if (with_backup.empty() && remap_only.empty()) return FMA_OK;
-
-    std::vector<size_t> order = with_backup;
-    order.insert(order.end(), remap_only.begin(), remap_only.end());
+    std::vector<size_t> with_backup, remap_only;  // segment indices, image order
+    std::vector<size_t> seg_run(e->segs.size(), 0);  // segment -> index of its run in `runs`
+    size_t n_backup_runs = 0;
+    for (size_t r = 0; r < runs.size(); ++r) {
+        if (runs[r].has_backup) ++n_backup_runs;
+        for (size_t i : runs[r].segs) {
+            seg_run[i] = r;
+            (runs[r].has_backup ? with_backup : remap_only).push_back(i);
+        }
+    }
     const int tier = e->image_tier;
     int mode = resolve_mode(e, tier);
     {
@@ -1069,10 +1283,12 @@ int do_wake(fma_engine_t* e, uint64_t tag_mask, uint32_t flags) {
         // the ring must exist BEFORE the mapper starts taking HBM; if it does not fit, copy engines go direct
         if (w_bytes && mode == FMA_MODE_STAGED && ensure_ring(e, w_bytes) != FMA_OK) mode = FMA_MODE_DIRECT;
     }
+    const bool dbg_t = env_int("FMA_DEBUG_TIMING", 0) != 0;
+    const double t_ring = now_s();
 
-    // ---- mapper thread(s): cuMemCreate + cuMemMap + cuMemSetAccess in `order` -------------------
+    // ---- mapper thread(s): one create + map + set-access per run, in `runs` order ----------------------
     MapProgress prog;
-    std::vector<char> item_done(order.size(), 0);
+    std::vector<char> item_done(runs.size(), 0);
     std::atomic<size_t> next_item{0};
     std::atomic<uint64_t> map_ns{0};
     const int n_map = std::max(1, std::min(e->cfg.map_threads > 0 ? e->cfg.map_threads : 1, 8));
@@ -1080,25 +1296,31 @@ int do_wake(fma_engine_t* e, uint64_t tag_mask, uint32_t flags) {
         cudaSetDevice(e->device);
         for (;;) {
             const size_t k = next_item.fetch_add(1);
-            if (k >= order.size()) break;
+            if (k >= runs.size()) break;
             {
                 std::lock_guard<std::mutex> lk(prog.mu);
                 if (prog.error != FMA_OK) break;
             }
-            Segment& s = e->segs[order[k]];
+            const Run& run = runs[k];
             const double t0 = now_s();
-            CUmemGenericAllocationHandle h = 0;
-            int r = vmm_create_and_map(e->device, s.va, s.bytes, &h);
+            int r = vmm_create_and_map(e->device, run.va, run.bytes);
             map_ns.fetch_add((uint64_t)((now_s() - t0) * 1e9));
             std::lock_guard<std::mutex> lk(prog.mu);
             if (r != FMA_OK) {
                 prog.error = r;
                 snprintf(prog.msg, sizeof(prog.msg), "%s", tl_err);
             } else {
-                s.handle = h;
-                s.mapped = true;
+                Unit u;
+                u.va = run.va; u.bytes = run.bytes; u.arena = run.arena;
+                for (size_t i : run.segs) {
+                    u.live_bytes += e->segs[i].bytes;
+                    e->segs[i].mapped = true;
+                    e->segs[i].unit_va = run.va;
+                }
+                // holes inside a run cannot exist (runs are VA-contiguous live segments), so bytes == live_bytes
+                e->units[run.va] = u;
                 item_done[k] = 1;
-                while (prog.done < order.size() && item_done[prog.done]) ++prog.done;
+                while (prog.done < runs.size() && item_done[prog.done]) ++prog.done;
             }
             prog.cv.notify_all();
         }
@@ -1154,7 +1376,7 @@ int do_wake(fma_engine_t* e, uint64_t tag_mask, uint32_t flags) {
         if (mode == FMA_MODE_DIRECT) {
             int k = 0;
             for (size_t w = 0; w < with_backup.size(); ++w) {
-                int mrc = wait_mapped(w + 1);
+                int mrc = wait_mapped(seg_run[with_backup[w]] + 1);
                 if (mrc != FMA_OK) WAKE_CHECK(fail(mrc, "%s", prog.msg));
                 const Segment& s = e->segs[with_backup[w]];
                 for (size_t o = 0; o < s.bytes; o += chunk, ++k) {
@@ -1185,7 +1407,7 @@ int do_wake(fma_engine_t* e, uint64_t tag_mask, uint32_t flags) {
                 for (size_t o = 0; o < s.bytes; o += FMA_PAGE_BYTES, ++p) {
                     dst_tab[p] = (uint64_t)s.va + o;
                     src_tab[p] = sbase + s.packed_off + o;
-                    need_item[p] = x.w + 1;
+                    need_item[p] = seg_run[with_backup[x.w]] + 1;
                 }
             }
             WAKE_RT(cudaMemcpyAsync(e->d_tab, dst_tab, n_pages * sizeof(uint64_t), cudaMemcpyHostToDevice, e->ks));
@@ -1242,17 +1464,22 @@ int do_wake(fma_engine_t* e, uint64_t tag_mask, uint32_t flags) {
     }
     // every requested segment must be mapped before wake returns (cumem.py:237-240)
     {
-        int mrc = wait_mapped(order.size());
+        int mrc = wait_mapped(runs.size());
         if (mrc != FMA_OK) WAKE_CHECK(fail(mrc, "%s", prog.msg));
     }
     join_mappers();
+    const double t_joined = now_s();
+    double t_copy_end = t_joined;
     if (W) {
         rc = timer.end(&copy_s);
         if (rc != FMA_OK) return rc;
         rc = kt.collect();
         if (rc != FMA_OK) return rc;
-        release_ring(e);
+        t_copy_end = now_s();
     }
+    if (dbg_t)
+        fprintf(stderr, "[fma] wake phases: plan+ring %.1f ms | enqueue+map-wait %.1f ms | drain %.1f ms | ring free %.1f ms | runs %zu\n",
+                (t_ring - t_entry) * 1e3, (t_joined - t_ring) * 1e3, (t_copy_end - t_joined) * 1e3, (now_s() - t_copy_end) * 1e3, runs.size());
 #undef WAKE_CHECK
 #undef WAKE_RT
 
@@ -1375,13 +1602,10 @@ int fma_engine_destroy(fma_engine_t* e) {
     }
     DeviceGuard guard(e->device);
     cudaDeviceSynchronize();
-    for (Segment& s : e->segs) {
-        if (s.mapped) {
-            g_drv.MemUnmap(s.va, s.bytes);
-            g_drv.MemRelease(s.handle);
-        }
-        g_drv.MemAddressFree(s.va, s.bytes);
-    }
+    for (auto& kv : e->units) g_drv.MemUnmap(kv.second.va, kv.second.bytes);
+    e->units.clear();
+    for (Arena& a : e->arenas) g_drv.MemAddressFree(a.base, a.cap);
+    e->arenas.clear();
     e->segs.clear();
     host_store_free(e->host);
     park_release(e);
