@@ -204,6 +204,17 @@ def run_ours(args) -> None:
     unmap_s = max_over_ranks(mean([r[0]["sleep_unmap_seconds"] for r in rows]))
     st = eng.stats()
 
+    # Raw copy-engine ceiling of THIS box/slot (plain pinned cudaMemcpyAsync, nothing of ours): boxes of the pool differ
+    # by several GB/s, so the fraction of the ceiling says more about the engine than the fraction of the nominal 64.
+    ceiling = None
+    if tier == L.FMA_TIER_HOST:
+        try:
+            barrier()
+            ceiling = max_over_ranks(-pcie_ceiling_gbs(torch))   # min over ranks, via max of the negation
+            ceiling = -ceiling
+        except Exception:
+            ceiling = None
+
     peer = None
     if args.peer_extra and world > 1 and tier == L.FMA_TIER_HOST:
         peer = measure_peer(eng, L, Wb, local_rank, world, barrier, max_over_ranks, before, steps=3)
@@ -247,7 +258,9 @@ def run_ours(args) -> None:
             "pcie" if tier == L.FMA_TIER_HOST else "nvlink": {
                 "bound": "pcie_gen5_x16" if tier == L.FMA_TIER_HOST else "nvlink5",
                 "achieved_per_gpu": round(e2e_gbs / world, 3), "device_timed_per_gpu": round(W_total / wake_dev_m / 1e9 / world, 3),
-                "peak": link_peak, "unit": "GB/s", "frac": round(e2e_gbs / world / link_peak, 4)},
+                "peak": link_peak, "unit": "GB/s", "frac": round(e2e_gbs / world / link_peak, 4),
+                "copy_engine_ceiling_per_gpu": round(ceiling, 3) if ceiling else None,
+                "frac_of_ceiling": round(e2e_gbs / world / ceiling, 4) if ceiling else None},
             "clocks": clocks,
         }
         if peer:
@@ -257,6 +270,19 @@ def run_ours(args) -> None:
         print(json.dumps(out), flush=True)
     eng.close()
     group.close()
+
+
+def pcie_ceiling_gbs(torch, nbytes: int = 2 << 30, reps: int = 3) -> float:
+    """Best-of-N plain H2D of one large pinned buffer on this rank's GPU (all ranks run it at the same time)."""
+    h = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    d = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    best = 0.0
+    for _ in range(reps + 1):
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(); d.copy_(h, non_blocking=True); e1.record(); torch.cuda.synchronize()
+        best = max(best, nbytes / e0.elapsed_time(e1) / 1e6)
+    del h, d
+    return best
 
 
 def measure_peer(eng, L, Wb, local_rank, world, barrier, max_over_ranks, before, steps=3):

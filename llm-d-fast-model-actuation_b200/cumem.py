@@ -35,7 +35,7 @@ from typing import Any
 from . import _lib as L
 from .engine import Engine, EngineConfig
 
-logger = logging.getLogger("fma_b200.cumem")
+logger = logging.getLogger("vllm.fma_b200.cumem")  # child of vLLM's configured logger, so INFO lines reach the instance log
 
 # py_device, py_alignedSize, py_d_mem, py_p_memHandle  (cumem.py:47-48); the 4th slot carries the
 # engine's segment sequence number instead of a heap pointer to a CUmemGenericAllocationHandle.

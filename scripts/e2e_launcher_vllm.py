@@ -1,0 +1,91 @@
+"""End-to-end drop-in check on a GPU box: the UNMODIFIED reference launcher
+(baseline/_ref/launcher/launcher.py, staged by __graft_entry__.build()) forks a real vLLM server with a dummy-weight
+Llama model; the same HTTP calls the dual-pods controller makes (`POST /sleep`, `GET /is_sleeping`, `POST /wake_up`,
+pkg/controller/dual-pods/inference-server.go:1329-1339,1595-1607,1118-1137) are timed by wall clock, once with vLLM's
+own allocator and once with FMA_B200=1 in the instance's env_vars (-> plugin/ -> fma_b200.cumem).  A generation
+request before sleep and after wake must return identical tokens (greedy), i.e. the weights came back bit-identical."""
+import json, os, subprocess, sys, time, urllib.request, urllib.error
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+MODEL = sys.argv[1] if len(sys.argv) > 1 else "llama-3-8b"
+CFGS = {
+    "llama-3-8b": dict(hidden_size=4096, intermediate_size=14336, num_hidden_layers=32, num_attention_heads=32, num_key_value_heads=8, vocab_size=128256),
+    "llama-1b": dict(hidden_size=2048, intermediate_size=8192, num_hidden_layers=16, num_attention_heads=32, num_key_value_heads=8, vocab_size=128256),
+}
+mdir = f"/tmp/fma_models/{MODEL}"; os.makedirs(mdir, exist_ok=True)
+cfg = dict(architectures=["LlamaForCausalLM"], model_type="llama", hidden_act="silu", max_position_embeddings=8192, rms_norm_eps=1e-5,
+           rope_theta=500000.0, tie_word_embeddings=False, torch_dtype="bfloat16", bos_token_id=128000, eos_token_id=128001, **CFGS[MODEL])
+json.dump(cfg, open(f"{mdir}/config.json", "w"))
+OUT = os.path.join(ROOT, "gpurun_out", "e2e"); os.makedirs(OUT, exist_ok=True)
+LPORT, VPORT = 8001, 8005
+
+def http(method, url, body=None, timeout=600):
+    data = json.dumps(body).encode() if body is not None else (b"" if method in ("POST", "PUT") else None)
+    req = urllib.request.Request(url, data=data, method=method, headers={"Content-Type": "application/json"})
+    t0 = time.perf_counter()
+    try:
+        with urllib.request.urlopen(req, timeout=timeout) as r:
+            return r.status, r.read().decode(), time.perf_counter() - t0
+    except urllib.error.HTTPError as e:
+        return e.code, e.read().decode(), time.perf_counter() - t0
+
+env = dict(os.environ)
+env["PYTHONPATH"] = os.pathsep.join([os.path.join(ROOT, "plugin"), ROOT, os.path.join(ROOT, "scripts", "k8s_stub"), env.get("PYTHONPATH", "")])
+launcher = subprocess.Popen([sys.executable, os.path.join(ROOT, "baseline", "_ref", "launcher", "launcher.py"), "--port", str(LPORT), "--host", "127.0.0.1"],
+                            env=env, cwd=os.path.join(ROOT, "baseline", "_ref", "launcher"), stdout=open(f"{OUT}/launcher.log", "w"), stderr=subprocess.STDOUT)
+results = {}
+try:
+    for _ in range(240):
+        try:
+            if http("GET", f"http://127.0.0.1:{LPORT}/health", timeout=2)[0] == 200: break
+        except Exception:
+            time.sleep(1)
+    else:
+        raise SystemExit("launcher did not come up")
+    options = (f"--model {mdir} --load-format dummy --skip-tokenizer-init --enable-sleep-mode --port {VPORT} --host 127.0.0.1 "
+               f"--enforce-eager --max-model-len 2048 --gpu-memory-utilization 0.30 --no-enable-prefix-caching")
+    for arm, extra_env in (("reference", {}), ("fma_b200", {"FMA_B200": "1"})):
+        iid = f"e2e-{arm}"
+        body = {"options": options, "env_vars": {"VLLM_SERVER_DEV_MODE": "1", **extra_env}, "annotations": {"isc-name": "e2e", "inference-port": str(VPORT)}}
+        st, txt, _ = http("PUT", f"http://127.0.0.1:{LPORT}/v2/vllm/instances/{iid}", body)
+        assert st == 201, (st, txt)
+        t0 = time.time(); up = False
+        while time.time() - t0 < 600:
+            try:
+                if http("GET", f"http://127.0.0.1:{VPORT}/health", timeout=2)[0] == 200: up = True; break
+            except Exception:
+                pass
+            time.sleep(2)
+        log = http("GET", f"http://127.0.0.1:{LPORT}/v2/vllm/instances/{iid}/log")[1]
+        if not up:
+            open(f"{OUT}/{arm}_vllm.log", "w").write(log); results[arm] = {"error": "vLLM did not become healthy", "log_tail": log[-1500:]}
+            http("DELETE", f"http://127.0.0.1:{LPORT}/v2/vllm/instances/{iid}"); continue
+        load_s = time.time() - t0
+        def gen():
+            st, txt, _ = http("POST", f"http://127.0.0.1:{VPORT}/v1/completions", {"model": mdir, "prompt": [1, 2, 3, 4, 5, 6, 7, 8], "max_tokens": 16, "temperature": 0.0, "return_token_ids": True})
+            try:
+                c = json.loads(txt)["choices"][0]; return c.get("token_ids") or c.get("text")
+            except Exception:
+                return f"ERR {st} {txt[:200]}"
+        before = gen()
+        rows = []
+        for rep in range(4):
+            s_st, _, s_t = http("POST", f"http://127.0.0.1:{VPORT}/sleep")
+            sl = json.loads(http("GET", f"http://127.0.0.1:{VPORT}/is_sleeping")[1])
+            w_st, _, w_t = http("POST", f"http://127.0.0.1:{VPORT}/wake_up")
+            aw = json.loads(http("GET", f"http://127.0.0.1:{VPORT}/is_sleeping")[1])
+            rows.append(dict(sleep_status=s_st, sleep_s=s_t, is_sleeping_after_sleep=sl["is_sleeping"], wake_status=w_st, wake_s=w_t, is_sleeping_after_wake=aw["is_sleeping"]))
+        after = gen()
+        log = http("GET", f"http://127.0.0.1:{LPORT}/v2/vllm/instances/{iid}/log")[1]
+        open(f"{OUT}/{arm}_vllm.log", "w").write(log)
+        lines = [l for l in log.splitlines() if "It took" in l or "sleep freed" in l or "fma_b200" in l]
+        results[arm] = dict(load_s=load_s, rows=rows, tokens_before=before, tokens_after=after, same_tokens=before == after,
+                            uses_fma=any("fma_b200" in l for l in lines), vllm_log_lines=lines[-12:])
+        print(arm, json.dumps(results[arm])[:1800], flush=True)
+        st, _, _ = http("DELETE", f"http://127.0.0.1:{LPORT}/v2/vllm/instances/{iid}")
+        time.sleep(8)
+finally:
+    json.dump(results, open(f"{OUT}/e2e_launcher_vllm.json", "w"), indent=1)
+    launcher.terminate()
+    try: launcher.wait(timeout=20)
+    except Exception: launcher.kill()
