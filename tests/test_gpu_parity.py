@@ -214,6 +214,47 @@ def test_free_while_sleeping_and_realloc(engine, oracle):
     assert engine.read(0, 2 * PAGE) == oracle.fill(2 * PAGE, 9, 0).tobytes()
 
 
+def test_arena_layout_merged_runs_zombies_and_hole_reuse(engine, oracle):
+    """Per-tag VA arenas: segments of a tag are VA-contiguous; after a wake they share ONE mapping unit, so freeing
+    one of them is deferred (zombie) until the unit goes; freed VA is reused first-fit."""
+    L = _L()
+    a = engine.alloc(4 * PAGE, "weights"); b = engine.alloc(2 * PAGE, "weights"); c = engine.alloc(6 * PAGE, "weights")
+    k = engine.alloc(3 * PAGE, "kv_cache")
+    assert b == a + 4 * PAGE and c == b + 2 * PAGE                  # bump allocation inside the weights arena
+    assert not (a <= k < c + 6 * PAGE)                              # another tag lives in another arena
+    ref = {}
+    for i, n in enumerate((4, 2, 6)):
+        engine.fill(i, 77, i * 10**6); ref[i] = oracle.fill(n * PAGE, 77, i * 10**6)
+    free0 = engine.stats()
+    engine.sleep(["weights"]); engine.wake(None)                    # weights come back as ONE run / unit
+    assert [s.va for s in engine.segments()] == [a, b, c, k]
+    engine.free(b)                                                  # inside a merged unit: table entry goes, others intact
+    assert [s.va for s in engine.segments()] == [a, c, k]
+    assert engine.read(0, 4 * PAGE) == ref[0].tobytes() and engine.read(1, 6 * PAGE) == ref[2].tobytes()
+    for mode in (L.FMA_MODE_STAGED, L.FMA_MODE_DIRECT, L.FMA_MODE_KERNEL):
+        engine.set_option("mode", mode)
+        engine.sleep(["weights"], flags=L.FMA_FLAG_VERIFY)          # image = a ++ c (the hole is not part of it)
+        assert np.array_equal(_host_image(engine), oracle.packed_image([ref[0], ref[2]]))
+        engine.wake(None, flags=L.FMA_FLAG_VERIFY)                  # two runs now (a | hole | c)
+        assert engine.read(0, 4 * PAGE) == ref[0].tobytes() and engine.read(1, 6 * PAGE) == ref[2].tobytes()
+    d = engine.alloc(2 * PAGE, "weights")                           # first fit: exactly b's old VA
+    assert d == b
+    engine.fill(3, 78, 5); ref_d = oracle.fill(2 * PAGE, 78, 5)
+    e2 = engine.alloc(PAGE, "weights")
+    assert e2 == c + 6 * PAGE                                       # no hole left: bump
+    engine.sleep(["weights"]); engine.wake(None)
+    segs = engine.segments()
+    assert [s.va for s in segs] == [a, c, k, d, e2]
+    assert engine.read(3, 2 * PAGE) == ref_d.tobytes() and engine.read(0, 4 * PAGE) == ref[0].tobytes()
+    # image order is VA order inside the arena: a, d (in b's slot), c, e2
+    engine.sleep(["weights"])
+    offs = {s.va: s.packed_offset for s in engine.segments() if s.tag == "weights"}
+    assert offs[a] == 0 and offs[d] == 4 * PAGE and offs[c] == 6 * PAGE and offs[e2] == 12 * PAGE
+    engine.wake(None)
+    engine.free(a); engine.free(c); engine.free(d); engine.free(e2); engine.free(k)
+    assert engine.segment_count() == 0 and engine.current_usage() == 0
+
+
 def test_hot_swap_overlaps_and_preserves_both_models(built, oracle):
     """BASELINE config 4 in miniature: A sleeps while B wakes (two engines on one GPU)."""
     import fma_b200
