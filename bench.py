@@ -204,8 +204,8 @@ def run_ours(args) -> None:
     unmap_s = max_over_ranks(mean([r[0]["sleep_unmap_seconds"] for r in rows]))
     st = eng.stats()
 
-    # Raw copy-engine ceiling of THIS box/slot (plain pinned cudaMemcpyAsync, nothing of ours): boxes of the pool differ
-    # by several GB/s, so the fraction of the ceiling says more about the engine than the fraction of the nominal 64.
+    # Plain pinned cudaMemcpyAsync on THIS box/slot (nothing of ours): boxes of the pool differ by several GB/s, so at
+    # N=1 the fraction of this ceiling says more about the engine than the fraction of the nominal 64 GB/s.
     ceiling = None
     if tier == L.FMA_TIER_HOST:
         try:
@@ -259,8 +259,10 @@ def run_ours(args) -> None:
                 "bound": "pcie_gen5_x16" if tier == L.FMA_TIER_HOST else "nvlink5",
                 "achieved_per_gpu": round(e2e_gbs / world, 3), "device_timed_per_gpu": round(W_total / wake_dev_m / 1e9 / world, 3),
                 "peak": link_peak, "unit": "GB/s", "frac": round(e2e_gbs / world / link_peak, 4),
-                "copy_engine_ceiling_per_gpu": round(ceiling, 3) if ceiling else None,
-                "frac_of_ceiling": round(e2e_gbs / world / ceiling, 4) if ceiling else None},
+                "naive_pinned_h2d_per_gpu": round(ceiling, 3) if ceiling else None,
+                "vs_naive_pinned_h2d": round(e2e_gbs / world / ceiling, 4) if ceiling else None,
+                "naive_note": "min over ranks of a plain 2 GiB cudaMemcpyAsync from a torch pin_memory buffer, all ranks at once "
+                              "(no NUMA placement): at N=1 this is the box's copy-engine ceiling"},
             "clocks": clocks,
         }
         if peer:

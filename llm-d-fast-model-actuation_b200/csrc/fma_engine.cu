@@ -453,36 +453,37 @@ size_t staged_slot(const fma_engine_t* e) {
 }
 
 void release_ring(fma_engine_t* e) {
-    for (int i = 0; i < e->n_ring; ++i) {
-        cudaFree(e->ring[i]);
-        e->ring[i] = nullptr;
-    }
+    if (e->n_ring && e->ring[0]) cudaFree(e->ring[0]);  // one allocation backs every slot
+    for (int i = 0; i < kMaxRing; ++i) e->ring[i] = nullptr;
     e->n_ring = 0;
     e->ring_slot_bytes = 0;
     cudaGetLastError();
 }
 
 // The HBM staging ring lives from the start of a wake to the end of the next sleep: a serving model keeps it
-// (1 GiB of 180 GB) so that /sleep needs no allocation, a SLEEPING model does not hold it.  It is freed at the END
-// of sleep, synchronously: on these shared hosts a cudaFree of 2 x 512 MiB takes anywhere from 0.8 ms to 300 ms
-// (driver stalls), which must never sit inside the wake latency — and freeing it from a background thread was
-// measured to block the next wake's first driver call instead.  `image_bytes` caps the slot size for small models.
+// (1 GiB of 180 GB) so that /sleep needs no allocation, a SLEEPING model does not hold it (FMA_RING_PERSIST=1 keeps
+// it, trading 1 GiB of a sleeper's HBM for one driver call less at wake).  It is freed at the END of sleep,
+// synchronously: on these shared hosts a cudaFree of 1 GiB takes anywhere from 0.8 ms to 300 ms (driver stalls), which
+// must never sit inside the wake latency — and freeing it from a background thread was measured to block the next
+// wake's first driver call instead.  ONE cudaMalloc backs all slots: every driver call at the start of a wake is
+// on the critical path and is serialised with the other ranks' calls.  `image_bytes` caps the slot size.
 int ensure_ring(fma_engine_t* e, size_t image_bytes) {
     size_t slot = std::min(staged_slot(e), round_up(std::max<size_t>(image_bytes, 1), FMA_PAGE_BYTES));
     int n = e->cfg.ring_slots > 0 ? std::min(e->cfg.ring_slots, kMaxRing) : 2;
     if (e->n_ring == n && e->ring_slot_bytes == slot) return FMA_OK;
     release_ring(e);
+    void* base = nullptr;
+    cudaError_t r = cudaMalloc(&base, slot * n);
+    if (r != cudaSuccess) {
+        cudaGetLastError();
+        return fail(FMA_ENOMEM, "cannot allocate %d x %zu byte HBM staging ring: %s", n, slot, cudaGetErrorString(r));
+    }
     for (int i = 0; i < n; ++i) {
-        cudaError_t r = cudaMalloc(&e->ring[i], slot);
-        if (r != cudaSuccess) {
-            cudaGetLastError();
-            release_ring(e);
-            return fail(FMA_ENOMEM, "cannot allocate %d x %zu byte HBM staging ring: %s", n, slot, cudaGetErrorString(r));
-        }
+        e->ring[i] = static_cast<char*>(base) + (size_t)i * slot;
         if (!e->ev_ring_full[i]) RT(cudaEventCreateWithFlags(&e->ev_ring_full[i], cudaEventDisableTiming));
         if (!e->ev_ring_free[i]) RT(cudaEventCreateWithFlags(&e->ev_ring_free[i], cudaEventDisableTiming));
-        e->n_ring = i + 1;
     }
+    e->n_ring = n;
     e->ring_slot_bytes = slot;
     return FMA_OK;
 }
