@@ -102,7 +102,15 @@ class CuMemAllocator:
         self._join_reserve()
         import torch
 
-        self.engine.sleep(offload_tags, tier=_tier_from_env())
+        tier = _tier_from_env()
+        if tier == L.FMA_TIER_PEER:
+            # parking GPU for the NVLink tier: FMA_PEER_DEVICE (index among the devices this process sees)
+            peer = int(os.environ.get("FMA_PEER_DEVICE", "-1"))
+            if peer < 0:
+                raise L.FmaError(L.FMA_EINVAL, "FMA_TIER=peer needs FMA_PEER_DEVICE=<visible device index of the parking GPU>")
+            nbytes = sum(s.bytes for s in self.engine.segments() if s.tag in offload_tags)
+            self.engine.peer_reserve(peer, nbytes)
+        self.engine.sleep(offload_tags, tier=tier)
         st = self.engine.stats()
         total = st["sleep_bytes_offloaded"] + st["sleep_bytes_discarded"]
         # same INFO line the reference emits (cumem.py:215-222; parsed by llm-d-benchmark), plus GB/s
@@ -158,7 +166,7 @@ class CuMemAllocator:
             self.engine.set_current_tag(old_tag)
             if expandable_was_enabled:
                 torch.cuda.memory._set_allocator_settings("expandable_segments:True")
-        if tag == "weights" and os.environ.get("FMA_PREPIN", "1") != "0":
+        if tag == "weights" and os.environ.get("FMA_PREPIN", "1") != "0" and _tier_from_env() == L.FMA_TIER_HOST:
             self._start_reserve()
 
     # ---- pre-pinning off the critical path -----------------------------------------------

@@ -8,6 +8,7 @@ import json, os, subprocess, sys, time, urllib.request, urllib.error
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 MODEL = sys.argv[1] if len(sys.argv) > 1 else "llama-3-8b"
+TP = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 CFGS = {
     "llama-3-8b": dict(hidden_size=4096, intermediate_size=14336, num_hidden_layers=32, num_attention_heads=32, num_key_value_heads=8, vocab_size=128256),
     "llama-1b": dict(hidden_size=2048, intermediate_size=8192, num_hidden_layers=16, num_attention_heads=32, num_key_value_heads=8, vocab_size=128256),
@@ -43,7 +44,8 @@ try:
     else:
         raise SystemExit("launcher did not come up")
     options = (f"--model {mdir} --load-format dummy --skip-tokenizer-init --enable-sleep-mode --port {VPORT} --host 127.0.0.1 "
-               f"--enforce-eager --max-model-len 2048 --gpu-memory-utilization 0.30 --no-enable-prefix-caching")
+               f"--enforce-eager --max-model-len 2048 --gpu-memory-utilization 0.30 --no-enable-prefix-caching"
+               + (f" --tensor-parallel-size {TP}" if TP > 1 else ""))
     for arm, extra_env in (("reference", {}), ("fma_b200", {"FMA_B200": "1"})):
         iid = f"e2e-{arm}"
         body = {"options": options, "env_vars": {"VLLM_SERVER_DEV_MODE": "1", **extra_env}, "annotations": {"isc-name": "e2e", "inference-port": str(VPORT)}}
@@ -85,7 +87,7 @@ try:
         st, _, _ = http("DELETE", f"http://127.0.0.1:{LPORT}/v2/vllm/instances/{iid}")
         time.sleep(8)
 finally:
-    json.dump(results, open(f"{OUT}/e2e_launcher_vllm.json", "w"), indent=1)
+    json.dump(results, open(f"{OUT}/e2e_launcher_vllm_{MODEL}_tp{TP}.json", "w"), indent=1)
     launcher.terminate()
     try: launcher.wait(timeout=20)
     except Exception: launcher.kill()
