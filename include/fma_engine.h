@@ -136,7 +136,12 @@ typedef struct fma_stats {
     /* lifetime counters */
     uint64_t total_kernel_launches;
     uint64_t total_copy_ops;
-    uint64_t reserved[4];
+    /* memory accounting NOW (for sleeper budgets: the controller today assumes 4096 MiB per sleeper,
+     * cmd/dual-pods-controller/main.go:72-74, and scrapes nvidia-smi, inference-server.go:1609-1636) */
+    uint64_t hbm_mapped_bytes;      /* physical HBM behind live mapping units of this engine            */
+    uint64_t hbm_aux_bytes;         /* staging ring + page tables + digest scratch on this GPU           */
+    uint64_t parked_bytes;          /* parking buffer held in a peer's (or this GPU's) HBM               */
+    uint64_t reserved[1];
 } fma_stats_t;
 
 /* ---- library ---------------------------------------------------------------------- */

@@ -57,7 +57,9 @@ class fma_stats_t(C.Structure):
         ("copy_ops", C.c_uint32),
         ("host_store_bytes", C.c_uint64), ("host_store_pin_seconds", C.c_double),
         ("host_store_numa_node", C.c_int32), ("tier", C.c_int32), ("mode", C.c_int32), ("reserved_i32", C.c_int32),
-        ("total_kernel_launches", C.c_uint64), ("total_copy_ops", C.c_uint64), ("reserved", C.c_uint64 * 4),
+        ("total_kernel_launches", C.c_uint64), ("total_copy_ops", C.c_uint64),
+        ("hbm_mapped_bytes", C.c_uint64), ("hbm_aux_bytes", C.c_uint64), ("parked_bytes", C.c_uint64),
+        ("reserved", C.c_uint64 * 1),
     ]
 
     def as_dict(self) -> dict:

@@ -2033,6 +2033,15 @@ int fma_stats(fma_engine_t* e, fma_stats_t* out) {
         if (rc != FMA_OK) return rc;
     }
     *out = e->st;
+    {
+        std::lock_guard<std::mutex> lk(e->mu);
+        uint64_t mapped = 0;
+        for (const auto& kv : e->units) mapped += kv.second.bytes;
+        out->hbm_mapped_bytes = mapped;
+    }
+    out->hbm_aux_bytes = (uint64_t)e->n_ring * e->ring_slot_bytes + 2 * e->d_tab_cap * sizeof(uint64_t) +
+                         e->desc_cap * (sizeof(fma_k_page_desc) + sizeof(uint64_t));
+    out->parked_bytes = e->park.cap;
     return FMA_OK;
 }
 

@@ -167,6 +167,20 @@ def test_state_machine_idempotence_and_tag_selective_wake(engine, oracle):
     assert [s.va for s in engine.segments()] == ptrs
 
 
+def test_memory_accounting_for_sleeper_budgets(engine, oracle):
+    """What a sleeping instance still holds on the GPU: nothing mapped, no ring, only tables."""
+    table = _tiny_table()
+    _load(engine, oracle, table)
+    awake = engine.stats()
+    assert awake["hbm_mapped_bytes"] == sum(s.bytes for s in table)
+    engine.sleep(["weights"])
+    asleep = engine.stats()
+    assert asleep["hbm_mapped_bytes"] == 0 and asleep["hbm_aux_bytes"] < (8 << 20) and asleep["parked_bytes"] == 0
+    assert asleep["host_store_bytes"] >= asleep["sleep_bytes_offloaded"]
+    engine.wake(None)
+    assert engine.stats()["hbm_mapped_bytes"] == awake["hbm_mapped_bytes"]
+
+
 def test_level2_sleep_discards_everything(engine, oracle):
     table = _tiny_table()
     _load(engine, oracle, table)
