@@ -259,6 +259,8 @@ struct fma_engine {
     cudaEvent_t ev_ring_free[kMaxRing] = {};
     int n_ring = 0;
     size_t ring_slot_bytes = 0;
+    bool ring_attached = false;         // ring lives in the tail of a mapping unit (no cudaMalloc / cudaFree of its own)
+    CUdeviceptr ring_unit_va = 0;       // that unit's key
     // device page tables (uploaded per operation)
     uint64_t* d_tab = nullptr;
     size_t d_tab_cap = 0;  // entries
@@ -385,6 +387,13 @@ int arena_take(fma_engine_t* e, int tag, size_t bytes, int* out_arena, CUdevicep
 // the VA of its zombies to their arena.  Caller has made sure nothing on the device still touches the range.
 int unmap_units(fma_engine_t* e, CUdeviceptr va, size_t span_bytes) {
     DRV(g_drv.MemUnmap(va, span_bytes));
+    if (e->ring_attached && e->ring_unit_va >= va && e->ring_unit_va < va + span_bytes) {  // the ring went with its unit
+        for (int i = 0; i < kMaxRing; ++i) e->ring[i] = nullptr;
+        e->n_ring = 0;
+        e->ring_slot_bytes = 0;
+        e->ring_attached = false;
+        e->ring_unit_va = 0;
+    }
     auto it = e->units.find(va);
     while (it != e->units.end() && it->first < va + span_bytes) {
         for (auto& z : it->second.zombies) arena_give_back(e->arenas[it->second.arena], z.first - e->arenas[it->second.arena].base, z.second);
@@ -453,7 +462,9 @@ size_t staged_slot(const fma_engine_t* e) {
 }
 
 void release_ring(fma_engine_t* e) {
-    if (e->n_ring && e->ring[0]) cudaFree(e->ring[0]);  // one allocation backs every slot
+    if (e->n_ring && e->ring[0] && !e->ring_attached) cudaFree(e->ring[0]);  // one allocation backs every slot
+    e->ring_attached = false;           // an attached ring goes away with its unit's cuMemUnmap
+    e->ring_unit_va = 0;
     for (int i = 0; i < kMaxRing; ++i) e->ring[i] = nullptr;
     e->n_ring = 0;
     e->ring_slot_bytes = 0;
@@ -467,10 +478,24 @@ void release_ring(fma_engine_t* e) {
 // must never sit inside the wake latency — and freeing it from a background thread was measured to block the next
 // wake's first driver call instead.  ONE cudaMalloc backs all slots: every driver call at the start of a wake is
 // on the critical path and is serialised with the other ranks' calls.  `image_bytes` caps the slot size.
+size_t ring_slot_for(const fma_engine_t* e, size_t image_bytes) {
+    return std::min(staged_slot(e), round_up(std::max<size_t>(image_bytes, 1), FMA_PAGE_BYTES));
+}
+int ring_slots_for(const fma_engine_t* e) { return e->cfg.ring_slots > 0 ? std::min(e->cfg.ring_slots, kMaxRing) : 2; }
+
+int ensure_ring_events(fma_engine_t* e, int n) {
+    for (int i = 0; i < n; ++i) {
+        if (!e->ev_ring_full[i]) RT(cudaEventCreateWithFlags(&e->ev_ring_full[i], cudaEventDisableTiming));
+        if (!e->ev_ring_free[i]) RT(cudaEventCreateWithFlags(&e->ev_ring_free[i], cudaEventDisableTiming));
+    }
+    return FMA_OK;
+}
+
 int ensure_ring(fma_engine_t* e, size_t image_bytes) {
-    size_t slot = std::min(staged_slot(e), round_up(std::max<size_t>(image_bytes, 1), FMA_PAGE_BYTES));
-    int n = e->cfg.ring_slots > 0 ? std::min(e->cfg.ring_slots, kMaxRing) : 2;
+    size_t slot = ring_slot_for(e, image_bytes);
+    int n = ring_slots_for(e);
     if (e->n_ring == n && e->ring_slot_bytes == slot) return FMA_OK;
+    if (e->ring_attached && e->n_ring >= 2 && e->ring_slot_bytes >= FMA_PAGE_BYTES) return FMA_OK;  // keep what the unit carries
     release_ring(e);
     void* base = nullptr;
     cudaError_t r = cudaMalloc(&base, slot * n);
@@ -1029,6 +1054,7 @@ int do_sleep(fma_engine_t* e, uint64_t offload_mask, int tier, uint32_t flags) {
         std::sort(ordered.begin(), ordered.end(), [](const Unit* a, const Unit* b) { return a->arena != b->arena ? a->arena < b->arena : a->va < b->va; });
         for (const Unit* u : ordered) {
             auto it = unit_end.find(u->va);
+            if (e->ring_attached && u->va == e->ring_unit_va && mode == FMA_MODE_STAGED) continue;  // holds the ring: unmapped after the last D2H
             if (it == unit_end.end()) add_range(un.first, u->va, u->bytes);
             else off_units.push_back(PlannedUnit{u->va, u->bytes, it->second});
         }
@@ -1145,7 +1171,7 @@ int do_sleep(fma_engine_t* e, uint64_t offload_mask, int tier, uint32_t flags) {
         if (rc != FMA_OK) return rc;
         rc = kt.collect();
         if (rc != FMA_OK) return rc;
-        if (env_int("FMA_RING_PERSIST", 0) == 0) release_ring(e);  // while the unmapper finishes its last ranges
+        if (env_int("FMA_RING_PERSIST", 0) == 0 || e->ring_attached) release_ring(e);  // while the unmapper finishes its last ranges
     }
     un.finish();
     if (un.error != FMA_OK) return fail(un.error, "%s", un.msg);
@@ -1278,11 +1304,34 @@ int do_wake(fma_engine_t* e, uint64_t tag_mask, uint32_t flags) {
     }
     const int tier = e->image_tier;
     int mode = resolve_mode(e, tier);
+    // Staging ring.  Steady state: the ring rides in the TAIL of the first backed-up run's mapping (the run is created
+    // `ring_total` bytes longer), so it costs no driver call of its own at wake and none at the next sleep (it goes with
+    // the unit's cuMemUnmap).  That needs the run to end at its arena's bump pointer; otherwise (or FMA_RING_ATTACH=0)
+    // one cudaMalloc provides it.  Either way the ring must exist BEFORE the other runs start taking HBM.
+    size_t ring_attach_bytes = 0;
     {
         uint64_t w_bytes = 0;
         for (size_t i : with_backup) w_bytes += e->segs[i].bytes;
-        // the ring must exist BEFORE the mapper starts taking HBM; if it does not fit, copy engines go direct
-        if (w_bytes && mode == FMA_MODE_STAGED && ensure_ring(e, w_bytes) != FMA_OK) mode = FMA_MODE_DIRECT;
+        if (w_bytes && mode == FMA_MODE_STAGED && !e->n_ring) {
+            const Run& r0 = runs[0];
+            Arena& a = e->arenas[r0.arena];
+            const size_t slot = ring_slot_for(e, w_bytes);
+            const size_t total = slot * ring_slots_for(e);
+            const bool at_top = r0.has_backup && (r0.va + r0.bytes == a.base + a.top) && a.top + total <= a.cap;
+            if (at_top && env_int("FMA_RING_ATTACH", 1) != 0 && ensure_ring_events(e, ring_slots_for(e)) == FMA_OK) {
+                ring_attach_bytes = total;
+                a.top += total;  // later allocations of this tag land after the ring; the range returns at unmap
+                e->n_ring = ring_slots_for(e);
+                e->ring_slot_bytes = slot;
+                e->ring_attached = true;
+                e->ring_unit_va = r0.va;
+                for (int i = 0; i < e->n_ring; ++i) e->ring[i] = reinterpret_cast<void*>(r0.va + r0.bytes + (size_t)i * slot);
+            } else if (ensure_ring(e, w_bytes) != FMA_OK) {
+                mode = FMA_MODE_DIRECT;  // HBM too full for a ring: copy engines go straight into the runs
+            }
+        } else if (w_bytes && mode == FMA_MODE_STAGED && ensure_ring(e, w_bytes) != FMA_OK) {
+            mode = FMA_MODE_DIRECT;
+        }
     }
     const bool dbg_t = env_int("FMA_DEBUG_TIMING", 0) != 0;
     const double t_ring = now_s();
@@ -1303,16 +1352,22 @@ int do_wake(fma_engine_t* e, uint64_t tag_mask, uint32_t flags) {
                 if (prog.error != FMA_OK) break;
             }
             const Run& run = runs[k];
+            const size_t extra = (k == 0) ? ring_attach_bytes : 0;  // run 0 carries the staging ring in its tail
             const double t0 = now_s();
-            int r = vmm_create_and_map(e->device, run.va, run.bytes);
+            int r = vmm_create_and_map(e->device, run.va, run.bytes + extra);
             map_ns.fetch_add((uint64_t)((now_s() - t0) * 1e9));
             std::lock_guard<std::mutex> lk(prog.mu);
             if (r != FMA_OK) {
                 prog.error = r;
                 snprintf(prog.msg, sizeof(prog.msg), "%s", tl_err);
+                if (extra) {  // the ring never came to exist
+                    arena_give_back(e->arenas[run.arena], run.va + run.bytes - e->arenas[run.arena].base, extra);
+                    release_ring(e);
+                }
             } else {
                 Unit u;
-                u.va = run.va; u.bytes = run.bytes; u.arena = run.arena;
+                u.va = run.va; u.bytes = run.bytes + extra; u.arena = run.arena;
+                if (extra) u.zombies.emplace_back(run.va + run.bytes, extra);  // ring VA returns to the arena with the unit
                 for (size_t i : run.segs) {
                     u.live_bytes += e->segs[i].bytes;
                     e->segs[i].mapped = true;
@@ -1435,7 +1490,12 @@ int do_wake(fma_engine_t* e, uint64_t tag_mask, uint32_t flags) {
                     p0 += np;
                 }
             } else {  // STAGED: copy engine H2D store -> ring slot (starts at t=0), K2 scatter once the targets are mapped
-                WAKE_CHECK(ensure_ring(e, W));
+                if (ring_attach_bytes) {  // the ring is part of run 0's mapping: ~1.4 ms before the first H2D can land
+                    int mrc0 = wait_mapped(1);
+                    if (mrc0 != FMA_OK) WAKE_CHECK(fail(mrc0, "%s", prog.msg));
+                } else {
+                    WAKE_CHECK(ensure_ring(e, W));
+                }
                 const size_t slot_pages = e->ring_slot_bytes / FMA_PAGE_BYTES;
                 // the store image may be only partially woken; H2D works on runs that are contiguous in the store
                 size_t c = 0;
@@ -2039,7 +2099,7 @@ int fma_stats(fma_engine_t* e, fma_stats_t* out) {
         for (const auto& kv : e->units) mapped += kv.second.bytes;
         out->hbm_mapped_bytes = mapped;
     }
-    out->hbm_aux_bytes = (uint64_t)e->n_ring * e->ring_slot_bytes + 2 * e->d_tab_cap * sizeof(uint64_t) +
+    out->hbm_aux_bytes = (e->ring_attached ? 0 : (uint64_t)e->n_ring * e->ring_slot_bytes) + 2 * e->d_tab_cap * sizeof(uint64_t) +
                          e->desc_cap * (sizeof(fma_k_page_desc) + sizeof(uint64_t));
     out->parked_bytes = e->park.cap;
     return FMA_OK;
