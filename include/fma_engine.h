@@ -248,10 +248,37 @@ FMA_API int  fma_op_page_digest(fma_engine_t* e, const uint64_t* pages, uint64_t
 FMA_API int  fma_scratch_alloc(fma_engine_t* e, size_t bytes, uint64_t* out_dev_ptr);
 FMA_API int  fma_scratch_free(fma_engine_t* e, uint64_t dev_ptr);
 
+/* ---- cold load: file -> HBM through the same pinned-ring + copy-engine mover ------------- */
+/* "load_model" in the reference is create-instance -> vLLM's own checkpoint loader
+ * (inference_server/launcher/launcher.py:656-669,799-837; vllm:v1/worker/gpu_worker.py:335-342), which copies tensor
+ * by tensor from pageable (mmap'ed safetensors) memory.  fma_load_file streams byte ranges of one file into device
+ * addresses inside engine segments: reader threads pread() into a small pinned bounce ring, copy engines move each
+ * chunk as soon as it is read.  Spans are (file offset, bytes, destination device address); a safetensors header
+ * maps to spans directly (llm-d-fast-model-actuation_b200/loader.py). */
+typedef struct fma_load_span {
+    uint64_t file_offset;
+    uint64_t bytes;
+    uint64_t dst;               /* device address; must lie inside a mapped segment of this engine */
+} fma_load_span_t;
+
+typedef struct fma_load_stats {
+    double   seconds;           /* wall, entry -> all bytes resident in HBM                          */
+    double   read_seconds;      /* summed over reader threads: time inside pread()                   */
+    uint64_t bytes;
+    uint32_t chunks;
+    uint32_t threads;
+    uint64_t reserved[4];
+} fma_load_stats_t;
+
+#define FMA_LOAD_O_DIRECT (1u << 0)  /* bypass the page cache (4 KiB-aligned reads into the bounce ring)  */
+
+FMA_API int  fma_load_file(fma_engine_t* e, const char* path, const fma_load_span_t* spans, uint32_t n_spans,
+                           uint32_t flags, fma_load_stats_t* out_stats);
+
 /* ---- tuning ----------------------------------------------------------------------- */
 /* Change one knob of a live engine (between operations).  Keys: "mode", "kernel",
  * "copy_streams", "chunk_bytes", "ring_slots", "map_threads", "tma_tile_bytes",
- * "tma_stages", "tma_pipes", "tma_ctas_per_sm". */
+ * "tma_stages", "tma_pipes", "tma_ctas_per_sm", "load_threads", "load_chunk_bytes", "load_slots". */
 FMA_API int  fma_set_option(fma_engine_t* e, const char* key, int64_t value);
 
 /* ---- stats ------------------------------------------------------------------------ */

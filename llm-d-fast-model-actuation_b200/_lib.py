@@ -66,6 +66,18 @@ class fma_stats_t(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_ if not n.startswith("reserved")}
 
 
+class fma_load_span_t(C.Structure):
+    _fields_ = [("file_offset", C.c_uint64), ("bytes", C.c_uint64), ("dst", C.c_uint64)]
+
+
+class fma_load_stats_t(C.Structure):
+    _fields_ = [("seconds", C.c_double), ("read_seconds", C.c_double), ("bytes", C.c_uint64), ("chunks", C.c_uint32),
+                ("threads", C.c_uint32), ("reserved", C.c_uint64 * 4)]
+
+
+FMA_LOAD_O_DIRECT = 1
+
+
 def lib_path() -> str:
     """Path of the in-tree shared library (built by ``__graft_entry__.build()`` / csrc/Makefile)."""
     return os.environ.get("FMA_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libfma_b200.so")
@@ -111,6 +123,8 @@ _PROTOTYPES = {
                                      C.POINTER(C.c_uint64), C.POINTER(C.c_float)]),
     "fma_scratch_alloc": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64)]),
     "fma_scratch_free": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "fma_load_file": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(fma_load_span_t), C.c_uint32, C.c_uint32,
+                                C.POINTER(fma_load_stats_t)]),
     "fma_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
     "fma_stats": (C.c_int, [C.c_void_p, C.POINTER(fma_stats_t)]),
 }

@@ -225,6 +225,16 @@ class Engine:
     def scratch_free(self, ptr: int) -> None:
         check(self._lib.fma_scratch_free(self._h, ptr))
 
+    # -- cold load -------------------------------------------------------------------------
+    def load_file(self, path: str, spans: Sequence[tuple[int, int, int]], o_direct: bool = False) -> dict:
+        """Stream (file_offset, nbytes, device_address) spans of one file into mapped segments."""
+        arr = (L.fma_load_span_t * max(len(spans), 1))()
+        for i, (off, n, dst) in enumerate(spans):
+            arr[i].file_offset, arr[i].bytes, arr[i].dst = off, n, dst
+        st = L.fma_load_stats_t()
+        check(self._lib.fma_load_file(self._h, path.encode(), arr, len(spans), L.FMA_LOAD_O_DIRECT if o_direct else 0, C.byref(st)))
+        return {"seconds": st.seconds, "read_seconds": st.read_seconds, "bytes": st.bytes, "chunks": st.chunks, "threads": st.threads}
+
     def set_option(self, key: str, value: int) -> None:
         check(self._lib.fma_set_option(self._h, key.encode(), int(value)))
 

@@ -362,3 +362,50 @@ def test_shim_roundtrip_equals_reference_golden(built, oracle):
         assert got == [m["sha256"] for m in g["weights"]], mode
     del ws, kv
     cumem.CuMemAllocator.instance = None
+
+
+# ---- cold load: safetensors file -> HBM ---------------------------------------------------
+@pytest.mark.parametrize("o_direct", [False, True])
+def test_load_file_matches_file_bytes(engine, oracle, tmp_path, o_direct):
+    from fma_b200 import loader
+    from fma_b200 import workloads as W
+
+    tensors = W.model_tensors("tiny-llama-test")
+    raws, first = {}, 0
+    for name, nbytes in tensors:
+        raws[name] = oracle.fill(nbytes, 4321, first); first += nbytes // 8
+    path = str(tmp_path / "tiny.safetensors")
+    loader.write_safetensors(path, [(n, "U8", (b,), raws[n].tobytes()) for n, b in tensors])
+    # destinations: one segment per tensor, every second one at an odd (16 B aligned) offset inside its segment
+    dst, where = {}, {}
+    for k, (name, nbytes) in enumerate(tensors):
+        off = 4112 if k % 2 else 0
+        va = engine.alloc(nbytes + off, "weights")
+        dst[name] = va + off; where[name] = (engine.segment_count() - 1, off)
+    engine.set_option("load_chunk_bytes", 3 << 20)      # ragged chunks
+    engine.set_option("load_threads", 5); engine.set_option("load_slots", 4)
+    st = loader.load_safetensors(engine, path, dst, o_direct=o_direct)
+    assert st["bytes"] == sum(b for _, b in tensors) and st["chunks"] >= len(tensors)
+    for name, nbytes in tensors:
+        idx, off = where[name]
+        assert engine.read(idx, nbytes, off) == raws[name].tobytes(), name
+    # the loaded model then sleeps and wakes like any other
+    before = engine.digest_all(["weights"])
+    engine.sleep(["weights"]); engine.wake(None)
+    assert engine.digest_all(["weights"]) == before
+
+
+def test_load_file_rejects_bad_spans(engine, tmp_path):
+    from fma_b200 import FmaError
+
+    p = str(tmp_path / "f.bin"); open(p, "wb").write(b"\x01" * 8192)
+    va = engine.alloc(PAGE, "weights")
+    with pytest.raises(FmaError):
+        engine.load_file(p, [(0, 8192, va + PAGE - 100)])       # runs off the end of the segment
+    with pytest.raises(FmaError):
+        engine.load_file(p, [(4096, 8192, va)])                 # reads past the end of the file
+    with pytest.raises(FmaError):
+        engine.load_file(str(tmp_path / "missing.bin"), [(0, 1, va)])
+    assert engine.load_file(p, [])["bytes"] == 0
+    st = engine.load_file(p, [(0, 8192, va)])
+    assert st["bytes"] == 8192 and engine.read(0, 8192) == b"\x01" * 8192
