@@ -409,3 +409,39 @@ def test_load_file_rejects_bad_spans(engine, tmp_path):
     assert engine.load_file(p, [])["bytes"] == 0
     st = engine.load_file(p, [(0, 8192, va)])
     assert st["bytes"] == 8192 and engine.read(0, 8192) == b"\x01" * 8192
+
+
+# ---- peer-HBM parking tier over NVLink (needs >= 2 GPUs; skipped on a 1-GPU box) ------------------------------
+def _n_gpus():
+    import torch
+
+    return torch.cuda.device_count()
+
+
+@pytest.mark.parametrize("kernel", ["tma", "ldg"])
+def test_peer_tier_roundtrip(engine, oracle, kernel):
+    if _n_gpus() < 2:
+        pytest.skip("peer tier needs a second GPU")
+    L = _L()
+    table = _tiny_table()
+    ptrs, ref = _load(engine, oracle, table)
+    Wb = sum(table[i].bytes for i in ref)
+    from fma_b200 import FmaError
+
+    with pytest.raises(FmaError):
+        engine.sleep(["weights"], tier=L.FMA_TIER_PEER)            # no parking buffer reserved yet
+    assert not engine.is_sleeping()
+    engine.peer_reserve(1, Wb)
+    engine.set_option("kernel", L.FMA_KERNEL_TMA if kernel == "tma" else L.FMA_KERNEL_LDG)
+    for mode in (L.FMA_MODE_KERNEL, L.FMA_MODE_DIRECT):
+        engine.set_option("mode", mode)
+        engine.sleep(["weights"], tier=L.FMA_TIER_PEER, flags=L.FMA_FLAG_VERIFY)
+        st = engine.stats()
+        assert engine.is_sleeping() and st["parked_bytes"] >= Wb and st["hbm_mapped_bytes"] == 0
+        engine.wake(None, flags=L.FMA_FLAG_VERIFY)
+        assert [s.va for s in engine.segments()] == ptrs
+        for i in ref:
+            assert engine.read(i, table[i].bytes) == ref[i].tobytes()
+    with pytest.raises(FmaError):
+        engine.peer_reserve(99, Wb)                                   # not a visible device
+    engine.peer_release()
