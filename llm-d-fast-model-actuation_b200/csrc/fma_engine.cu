@@ -1303,6 +1303,46 @@ int do_wake(fma_engine_t* e, uint64_t tag_mask, uint32_t flags) {
             return a.first_off < b.first_off;
         });
     }
+    const int tier = e->image_tier;
+    int mode = resolve_mode(e, tier);
+
+    // Staging ring.  Steady state: the ring is its OWN small run (2 x 512 MiB) placed right after the first backed-up
+    // run at the arena's bump pointer and mapped FIRST — a 1 GiB cuMemCreate/Map/SetAccess costs ~0.2 ms, the H2D
+    // stream starts as soon as it exists, and the big weights run (whose mapping takes 1.4 ms alone but tens of ms
+    // when 8 ranks wake at once) keeps the ring's ~19 ms of slack.  At the next sleep the ring goes with a cuMemUnmap
+    // like every other unit: no cudaMalloc / cudaFree anywhere (a cudaFree of 1 GiB stalls 0.8-300 ms on these hosts).
+    // Needs the run to end at its arena's bump pointer; otherwise (or FMA_RING_ATTACH=0) one cudaMalloc provides it.
+    // Either way the ring must exist BEFORE the other runs start taking HBM.
+    bool ring_run = false;
+    {
+        uint64_t w_bytes = 0;
+        for (const Run& r : runs)
+            if (r.has_backup) w_bytes += r.bytes;
+        if (w_bytes && mode == FMA_MODE_STAGED && !e->n_ring) {
+            const Run& r0 = runs[0];
+            Arena& a = e->arenas[r0.arena];
+            const size_t slot = ring_slot_for(e, w_bytes);
+            const size_t total = slot * ring_slots_for(e);
+            const bool at_top = r0.has_backup && (r0.va + r0.bytes == a.base + a.top) && a.top + total <= a.cap;
+            if (at_top && env_int("FMA_RING_ATTACH", 1) != 0 && ensure_ring_events(e, ring_slots_for(e)) == FMA_OK) {
+                Run rr;
+                rr.va = r0.va + r0.bytes; rr.bytes = total; rr.arena = r0.arena; rr.has_backup = true; rr.first_off = 0;
+                a.top += total;  // later allocations of this tag land after the ring; the range returns at unmap
+                e->n_ring = ring_slots_for(e);
+                e->ring_slot_bytes = slot;
+                e->ring_attached = true;
+                e->ring_unit_va = rr.va;
+                for (int i = 0; i < e->n_ring; ++i) e->ring[i] = reinterpret_cast<void*>(rr.va + (size_t)i * slot);
+                runs.insert(runs.begin(), std::move(rr));
+                ring_run = true;
+            } else if (ensure_ring(e, w_bytes) != FMA_OK) {
+                mode = FMA_MODE_DIRECT;  // HBM too full for a ring: copy engines go straight into the runs
+            }
+        } else if (w_bytes && mode == FMA_MODE_STAGED && ensure_ring(e, w_bytes) != FMA_OK) {
+            mode = FMA_MODE_DIRECT;
+        }
+    }
+
     std::vector<size_t> with_backup, remap_only;  // segment indices, image order
     std::vector<size_t> seg_run(e->segs.size(), 0);  // segment -> index of its run in `runs`
     size_t n_backup_runs = 0;
@@ -1313,39 +1353,17 @@ int do_wake(fma_engine_t* e, uint64_t tag_mask, uint32_t flags) {
             (runs[r].has_backup ? with_backup : remap_only).push_back(i);
         }
     }
-    const int tier = e->image_tier;
-    int mode = resolve_mode(e, tier);
-    // Staging ring.  Steady state: the ring rides in the TAIL of the first backed-up run's mapping (the run is created
-    // `ring_total` bytes longer), so it costs no driver call of its own at wake and none at the next sleep (it goes with
-    // the unit's cuMemUnmap).  That needs the run to end at its arena's bump pointer; otherwise (or FMA_RING_ATTACH=0)
-    // one cudaMalloc provides it.  Either way the ring must exist BEFORE the other runs start taking HBM.
-    size_t ring_attach_bytes = 0;
+    const bool dbg_t = env_int("FMA_DEBUG_TIMING", 0) != 0;
+    const double t_ring = now_s();
+    double remap_delay_s;
     {
         uint64_t w_bytes = 0;
         for (size_t i : with_backup) w_bytes += e->segs[i].bytes;
-        if (w_bytes && mode == FMA_MODE_STAGED && !e->n_ring) {
-            const Run& r0 = runs[0];
-            Arena& a = e->arenas[r0.arena];
-            const size_t slot = ring_slot_for(e, w_bytes);
-            const size_t total = slot * ring_slots_for(e);
-            const bool at_top = r0.has_backup && (r0.va + r0.bytes == a.base + a.top) && a.top + total <= a.cap;
-            if (at_top && env_int("FMA_RING_ATTACH", 1) != 0 && ensure_ring_events(e, ring_slots_for(e)) == FMA_OK) {
-                ring_attach_bytes = total;
-                a.top += total;  // later allocations of this tag land after the ring; the range returns at unmap
-                e->n_ring = ring_slots_for(e);
-                e->ring_slot_bytes = slot;
-                e->ring_attached = true;
-                e->ring_unit_va = r0.va;
-                for (int i = 0; i < e->n_ring; ++i) e->ring[i] = reinterpret_cast<void*>(r0.va + r0.bytes + (size_t)i * slot);
-            } else if (ensure_ring(e, w_bytes) != FMA_OK) {
-                mode = FMA_MODE_DIRECT;  // HBM too full for a ring: copy engines go straight into the runs
-            }
-        } else if (w_bytes && mode == FMA_MODE_STAGED && ensure_ring(e, w_bytes) != FMA_OK) {
-            mode = FMA_MODE_DIRECT;
-        }
+        // a fifth of the expected host-tier copy time (55 GB/s), half of the NVLink one (600 GB/s): far below the slack
+        const double expected = (double)w_bytes / (tier == FMA_TIER_HOST ? 55e9 : 600e9);
+        const int forced = env_int("FMA_REMAP_DELAY_MS", -1);
+        remap_delay_s = forced >= 0 ? forced * 1e-3 : expected * (tier == FMA_TIER_HOST ? 0.2 : 0.5);
     }
-    const bool dbg_t = env_int("FMA_DEBUG_TIMING", 0) != 0;
-    const double t_ring = now_s();
 
     // ---- mapper thread(s): one create + map + set-access per run, in `runs` order ----------------------
     MapProgress prog;
@@ -1363,22 +1381,29 @@ int do_wake(fma_engine_t* e, uint64_t tag_mask, uint32_t flags) {
                 if (prog.error != FMA_OK) break;
             }
             const Run& run = runs[k];
-            const size_t extra = (k == 0) ? ring_attach_bytes : 0;  // run 0 carries the staging ring in its tail
+            if (!run.has_backup && n_backup_runs && remap_delay_s > 0) {
+                // Remap-only runs (kv_cache) have the whole copy time as slack, the weights run only the ring's worth
+                // (~19 ms).  Driver VMM calls of ALL processes on the host serialise, so a rank that maps its kv early
+                // delays another rank's weights mapping: give every rank's weights a head start.
+                const double wait = t_entry + remap_delay_s - now_s();
+                if (wait > 0) std::this_thread::sleep_for(std::chrono::duration<double>(wait));
+            }
+            const bool is_ring = ring_run && k == 0;
             const double t0 = now_s();
-            int r = vmm_create_and_map(e->device, run.va, run.bytes + extra);
+            int r = vmm_create_and_map(e->device, run.va, run.bytes);
             map_ns.fetch_add((uint64_t)((now_s() - t0) * 1e9));
             std::lock_guard<std::mutex> lk(prog.mu);
             if (r != FMA_OK) {
                 prog.error = r;
                 snprintf(prog.msg, sizeof(prog.msg), "%s", tl_err);
-                if (extra) {  // the ring never came to exist
-                    arena_give_back(e->arenas[run.arena], run.va + run.bytes - e->arenas[run.arena].base, extra);
+                if (is_ring) {  // the ring never came to exist
+                    arena_give_back(e->arenas[run.arena], run.va - e->arenas[run.arena].base, run.bytes);
                     release_ring(e);
                 }
             } else {
                 Unit u;
-                u.va = run.va; u.bytes = run.bytes + extra; u.arena = run.arena;
-                if (extra) u.zombies.emplace_back(run.va + run.bytes, extra);  // ring VA returns to the arena with the unit
+                u.va = run.va; u.bytes = run.bytes; u.arena = run.arena;
+                if (is_ring) u.zombies.emplace_back(run.va, run.bytes);  // ring VA returns to the arena when the unit is unmapped
                 for (size_t i : run.segs) {
                     u.live_bytes += e->segs[i].bytes;
                     e->segs[i].mapped = true;
@@ -1501,7 +1526,7 @@ int do_wake(fma_engine_t* e, uint64_t tag_mask, uint32_t flags) {
                     p0 += np;
                 }
             } else {  // STAGED: copy engine H2D store -> ring slot (starts at t=0), K2 scatter once the targets are mapped
-                if (ring_attach_bytes) {  // the ring is part of run 0's mapping: ~1.4 ms before the first H2D can land
+                if (ring_run) {  // the ring is run 0 (1 GiB, ~0.2 ms to map): wait for it before the first H2D
                     int mrc0 = wait_mapped(1);
                     if (mrc0 != FMA_OK) WAKE_CHECK(fail(mrc0, "%s", prog.msg));
                 } else {
