@@ -1039,6 +1039,38 @@ int do_sleep(fma_engine_t* e, uint64_t offload_mask, int tier, uint32_t flags) {
         ~Unmapper() { finish(); }
     } un;
     un.e = e;
+    // Whatever the unmapper really unmapped is applied to the table on EVERY exit path (also the error returns
+    // below), so that a failed sleep never leaves units the table believes mapped but the driver has released.
+    struct ApplyUnmapped {
+        Unmapper* un;
+        fma_engine_t* e;
+        size_t applied = 0;
+        void run() {
+            std::lock_guard<std::mutex> lk(e->mu);
+            for (; applied < un->done.size(); ++applied) {
+                const Range& r = un->done[applied];
+                auto it = e->units.lower_bound(r.va);
+                while (it != e->units.end() && it->first < r.va + r.bytes) {
+                    Arena& a = e->arenas[it->second.arena];
+                    for (auto& z : it->second.zombies) arena_give_back(a, z.first - a.base, z.second);
+                    it = e->units.erase(it);
+                }
+                if (e->ring_attached && e->ring_unit_va >= r.va && e->ring_unit_va < r.va + r.bytes) {
+                    for (int i = 0; i < kMaxRing; ++i) e->ring[i] = nullptr;
+                    e->n_ring = 0; e->ring_slot_bytes = 0; e->ring_attached = false; e->ring_unit_va = 0;
+                }
+                for (Segment& sg : e->segs)
+                    if (sg.va >= r.va && sg.va < r.va + r.bytes) {
+                        sg.mapped = false;
+                        sg.unit_va = 0;
+                    }
+            }
+        }
+        ~ApplyUnmapped() {
+            un->finish();
+            run();
+        }
+    } apply_unmapped{&un, e};
 
     // Units in VA order, split into "discarded" (release now) and "offloaded" (release once the image has their
     // bytes).  image_end = packed offset just past the unit's last live segment.
@@ -1195,16 +1227,9 @@ int do_sleep(fma_engine_t* e, uint64_t offload_mask, int tier, uint32_t flags) {
         s.backup_tier = tier;
         s.packed_off = x.packed_off;
     }
+    apply_unmapped.run();
     {
         std::lock_guard<std::mutex> lk(e->mu);
-        for (const auto& r : un.done) {
-            auto it = e->units.lower_bound(r.va);
-            while (it != e->units.end() && it->first < r.va + r.bytes) {
-                Arena& a = e->arenas[it->second.arena];
-                for (auto& z : it->second.zombies) arena_give_back(a, z.first - a.base, z.second);
-                it = e->units.erase(it);
-            }
-        }
         std::vector<Range> rest;
         for (auto& kv : e->units) add_range(rest, kv.second.va, kv.second.bytes);
         const double a0 = now_s();
