@@ -47,6 +47,7 @@
 
 #include "../../include/fma_engine.h"
 #include "fma_kernels.h"
+#include "fma_layout.h"
 
 namespace {
 
@@ -187,18 +188,8 @@ struct Segment {
     bool digest_valid = false;
 };
 
-// One VA arena per tag: segments of a tag are bump-allocated next to each other, so that after a sleep the
-// whole tag can be re-created with ONE cuMemCreate + cuMemMap + cuMemSetAccess (a "run") instead of three driver
-// calls per segment.  Measured on B200: 15 GiB as 131 pieces = 8 ms map + 17 ms unmap alone, 16 + 22 ms with a
-// second process making VMM calls, and 325 ms inside a 2-rank wake; as one run = 1.4 ms + 5 ms, contention-proof
-// (profiles/vmm_span_probe_r1.json).
-struct Arena {
-    CUdeviceptr base = 0;
-    size_t cap = 0;
-    size_t top = 0;                     // bump pointer
-    int tag = 0;
-    std::map<size_t, size_t> holes;     // freed ranges below top: offset -> length
-};
+using fma_layout::Arena;
+using fma_layout::arena_give_back;
 
 // A live physical mapping: [va, va+bytes).  At load time a unit is one segment; after a wake it is a whole run.
 // The physical handle is released right after cuMemMap (the memory lives until cuMemUnmap), so a unit is just a range.
@@ -335,53 +326,23 @@ int vmm_create_and_map(int device, CUdeviceptr va, size_t bytes) {
 }
 
 // ---- arenas ----------------------------------------------------------------------------------------
-void arena_give_back(Arena& a, size_t off, size_t len) {
-    auto it = a.holes.emplace(off, len).first;
-    if (it != a.holes.begin()) {  // merge with the hole before
-        auto prev = std::prev(it);
-        if (prev->first + prev->second == it->first) {
-            prev->second += it->second;
-            a.holes.erase(it);
-            it = prev;
-        }
-    }
-    auto next = std::next(it);
-    if (next != a.holes.end() && it->first + it->second == next->first) {  // merge with the hole after
-        it->second += next->second;
-        a.holes.erase(next);
-    }
-    if (it->first + it->second == a.top) {  // a hole that touches the bump pointer lowers it
-        a.top = it->first;
-        a.holes.erase(it);
-    }
-}
-
 int arena_take(fma_engine_t* e, int tag, size_t bytes, int* out_arena, CUdeviceptr* out_va) {
     for (size_t i = 0; i < e->arenas.size(); ++i) {
         Arena& a = e->arenas[i];
-        if (a.tag != tag) continue;
-        for (auto it = a.holes.begin(); it != a.holes.end(); ++it) {  // first fit
-            if (it->second < bytes) continue;
-            const size_t off = it->first, len = it->second;
-            a.holes.erase(it);
-            if (len > bytes) a.holes.emplace(off + bytes, len - bytes);
-            *out_arena = (int)i;
-            *out_va = a.base + off;
-            return FMA_OK;
-        }
-        if (a.top + bytes <= a.cap) {
-            *out_arena = (int)i;
-            *out_va = a.base + a.top;
-            a.top += bytes;
-            return FMA_OK;
-        }
+        size_t off = 0;
+        if (a.tag != tag || !fma_layout::arena_take(a, bytes, &off)) continue;  // first fit among holes, else bump
+        *out_arena = (int)i;
+        *out_va = a.base + off;
+        return FMA_OK;
     }
     Arena a;
     a.tag = tag;
     size_t want = std::max<size_t>((size_t)std::max(env_int("FMA_ARENA_GIB", 256), 1) << 30, round_up(bytes, e->gran));
     CUresult r = CUDA_ERROR_OUT_OF_MEMORY;
     while (true) {  // VA is plentiful, but shrink gracefully if a huge reservation is refused
-        r = g_drv.MemAddressReserve(&a.base, want, e->gran, 0, 0);
+        CUdeviceptr base = 0;
+        r = g_drv.MemAddressReserve(&base, want, e->gran, 0, 0);
+        a.base = (uint64_t)base;
         if (r == CUDA_SUCCESS || want <= round_up(bytes, e->gran)) break;
         want = std::max(want / 2, round_up(bytes, e->gran));
     }
@@ -1286,14 +1247,7 @@ int do_wake(fma_engine_t* e, uint64_t tag_mask, uint32_t flags) {
     // Work list: RUNS — maximal VA-contiguous groups of sleeping segments of one arena — so a whole tag is
     // re-created with one cuMemCreate + cuMemMap + cuMemSetAccess.  Runs that have a backup come first, in image
     // order (they gate the copy pipeline); remap-only runs (e.g. kv_cache) are mapped after them.
-    struct Run {
-        CUdeviceptr va = 0;
-        size_t bytes = 0;
-        int arena = -1;
-        bool has_backup = false;
-        uint64_t first_off = 0;       // packed offset of its first segment (ordering key)
-        std::vector<size_t> segs;     // indices into e->segs, ascending VA
-    };
+    using Run = fma_layout::Run;
     std::vector<Run> runs;
     {
         std::vector<size_t> cand;
@@ -1308,25 +1262,12 @@ int do_wake(fma_engine_t* e, uint64_t tag_mask, uint32_t flags) {
             const Segment &x = e->segs[a], &y = e->segs[b];
             return x.arena != y.arena ? x.arena < y.arena : x.va < y.va;
         });
-        const bool merge = env_int("FMA_MERGE_RUNS", 1) != 0;
+        std::vector<fma_layout::SegView> view;
         for (size_t i : cand) {
             const Segment& s = e->segs[i];
-            if (merge && !runs.empty() && runs.back().arena == s.arena && runs.back().va + runs.back().bytes == s.va &&
-                runs.back().has_backup == s.has_backup) {
-                runs.back().bytes += s.bytes;
-                runs.back().segs.push_back(i);
-            } else {
-                Run r;
-                r.va = s.va; r.bytes = s.bytes; r.arena = s.arena; r.has_backup = s.has_backup;
-                r.first_off = s.has_backup ? s.packed_off : kNoOffset;
-                r.segs.push_back(i);
-                runs.push_back(std::move(r));
-            }
+            view.push_back(fma_layout::SegView{i, s.arena, (uint64_t)s.va, s.bytes, s.has_backup, s.packed_off});
         }
-        std::stable_sort(runs.begin(), runs.end(), [](const Run& a, const Run& b) {
-            if (a.has_backup != b.has_backup) return a.has_backup;
-            return a.first_off < b.first_off;
-        });
+        runs = fma_layout::plan_runs(view, env_int("FMA_MERGE_RUNS", 1) != 0);
     }
     const int tier = e->image_tier;
     int mode = resolve_mode(e, tier);
@@ -1351,7 +1292,7 @@ int do_wake(fma_engine_t* e, uint64_t tag_mask, uint32_t flags) {
             const bool at_top = r0.has_backup && (r0.va + r0.bytes == a.base + a.top) && a.top + total <= a.cap;
             if (at_top && env_int("FMA_RING_ATTACH", 1) != 0 && ensure_ring_events(e, ring_slots_for(e)) == FMA_OK) {
                 Run rr;
-                rr.va = r0.va + r0.bytes; rr.bytes = total; rr.arena = r0.arena; rr.has_backup = true; rr.first_off = 0;
+                rr.va = r0.va + r0.bytes; rr.bytes = total; rr.arena = r0.arena; rr.has_backup = true; rr.first_off = 0;  // no segments
                 a.top += total;  // later allocations of this tag land after the ring; the range returns at unmap
                 e->n_ring = ring_slots_for(e);
                 e->ring_slot_bytes = slot;
