@@ -69,13 +69,18 @@ class CuMemAllocator:
             CuMemAllocator.instance = CuMemAllocator()
         return CuMemAllocator.instance
 
-    def __init__(self, device: int | None = None, config: EngineConfig | None = None):
-        import torch
+    def __init__(self, device: int | None = None, config: EngineConfig | None = None, engine: Any = None):
+        """``engine`` may be injected (tests of the host logic); normally the allocator creates its own."""
+        if engine is not None:
+            self.device = 0 if device is None else device
+            self.engine = engine
+        else:
+            import torch
 
-        if not torch.cuda.is_available():
-            raise L.FmaError(L.FMA_ENODRIVER, "CuMemAllocator needs a CUDA device; there is no CPU fallback")
-        self.device = torch.cuda.current_device() if device is None else device
-        self.engine = Engine(self.device, config)
+            if not torch.cuda.is_available():
+                raise L.FmaError(L.FMA_ENODRIVER, "CuMemAllocator needs a CUDA device; there is no CPU fallback")
+            self.device = torch.cuda.current_device() if device is None else device
+            self.engine = Engine(self.device, config)
         self.engine.make_current()
         self.current_tag: str = CuMemAllocator.default_tag
         self.allocator_and_pools: dict[str, Any] = {}
