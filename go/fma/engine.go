@@ -1,0 +1,87 @@
+// Package fma is the cgo binding of the B200 sleep/wake weight-movement engine (include/fma_engine.h).
+//
+// NOT COMPILED OR TESTED IN THIS REPOSITORY'S CI: the build image has no Go toolchain (SURVEY.md §0).  It is the
+// reference-side binding a maintainer of llm-d-fast-model-actuation would add for a Go-hosted engine owner
+// (north_star: "host code in Go calling CUDA through a thin cgo C-ABI"); the same source is shown in INTEGRATION.md §2.
+package fma
+
+/*
+#cgo CFLAGS:  -I${SRCDIR}/../../include
+#cgo LDFLAGS: -L${SRCDIR}/../../llm-d-fast-model-actuation_b200 -lfma_b200 -Wl,-rpath,${SRCDIR}/../../llm-d-fast-model-actuation_b200
+#include <stdlib.h>
+#include "fma_engine.h"
+*/
+import "C"
+
+import (
+	"fmt"
+	"unsafe"
+)
+
+type Engine struct{ h *C.fma_engine_t }
+
+func lastErr(rc C.int) error { return fmt.Errorf("fma: rc=%d: %s", int(rc), C.GoString(C.fma_last_error())) }
+
+// NewEngine replaces the per-process CuMemAllocator singleton (vllm:device_allocator/cumem.py:118-138).
+func NewEngine(device int) (*Engine, error) {
+	var h *C.fma_engine_t
+	if rc := C.fma_engine_create(C.int(device), nil, &h); rc != 0 {
+		return nil, lastErr(rc)
+	}
+	return &Engine{h}, nil
+}
+
+func (e *Engine) Close() { C.fma_engine_destroy(e.h) }
+
+func (e *Engine) Tag(name string) (int, error) {
+	cs := C.CString(name)
+	defer C.free(unsafe.Pointer(cs))
+	id := C.fma_tag_intern(e.h, cs)
+	if id < 0 {
+		return 0, lastErr(id)
+	}
+	return int(id), nil
+}
+
+func (e *Engine) Alloc(bytes uint64, tag int) (uintptr, error) {
+	var p unsafe.Pointer
+	if rc := C.fma_alloc(e.h, C.size_t(bytes), C.int(tag), &p); rc != 0 {
+		return 0, lastErr(rc)
+	}
+	return uintptr(p), nil
+}
+
+// Sleep == POST /sleep?level=1 when offloadMask has the "weights" bit (pkg/controller/dual-pods/inference-server.go:1329-1339).
+func (e *Engine) Sleep(offloadMask uint64, tier int) error {
+	if rc := C.fma_sleep(e.h, C.uint64_t(offloadMask), C.int(tier), 0); rc != 0 {
+		return lastErr(rc)
+	}
+	return nil
+}
+
+// WakeUp == POST /wake_up (inference-server.go:1118-1137); tagMask 0 wakes every tag. Safe to retry.
+func (e *Engine) WakeUp(tagMask uint64) error {
+	if rc := C.fma_wake(e.h, C.uint64_t(tagMask), 0); rc != 0 {
+		return lastErr(rc)
+	}
+	return nil
+}
+
+// IsSleeping backs api.SleepState{IsSleeping} (pkg/api/interface.go:129-133).
+func (e *Engine) IsSleeping() bool { return C.fma_is_sleeping(e.h) == 1 }
+
+// Swap: D2H of the outgoing model overlapped with H2D of the incoming one (BASELINE config 4).
+func Swap(out *Engine, offloadMask uint64, in *Engine, wakeMask uint64) error {
+	if rc := C.fma_swap(out.h, C.uint64_t(offloadMask), C.FMA_TIER_HOST, in.h, C.uint64_t(wakeMask), 0); rc != 0 {
+		return lastErr(rc)
+	}
+	return nil
+}
+
+func (e *Engine) Stats() (C.fma_stats_t, error) {
+	var st C.fma_stats_t
+	if rc := C.fma_stats(e.h, &st); rc != 0 {
+		return st, lastErr(rc)
+	}
+	return st, nil
+}
