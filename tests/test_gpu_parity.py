@@ -445,3 +445,35 @@ def test_peer_tier_roundtrip(engine, oracle, kernel):
     with pytest.raises(FmaError):
         engine.peer_reserve(99, Wb)                                   # not a visible device
     engine.peer_release()
+
+
+# ---- BASELINE full size: size-independent properties (the oracle would take minutes at 15 GiB) -------------------
+def test_full_size_llama3_8b_roundtrip_properties(engine, oracle):
+    """Config[1] at full size (131 segments, 14.96 GiB): K0 fill -> K3 digests -> sleep -> wake; every digest, the
+    checksum of checksums and every device address are unchanged; spot-checked segments match the oracle's bytes."""
+    from fma_b200 import workloads as W
+
+    L = _L()
+    table = W.allocation_table("llama-3-8b")
+    assert W.weight_bytes(table) == 15318 << 20
+    ptrs = [engine.alloc(s.bytes, s.tag) for s in table]
+    first, firsts = 0, []
+    for i, s in enumerate(table):
+        engine.fill(i, 1234, first); firsts.append(first); first += s.bytes // 8
+    before = engine.digest_all(["weights"])
+    assert len(set(before)) == len(before)                          # every segment is distinct (position-dependent stream)
+    small = [i for i, s in enumerate(table) if s.bytes <= (48 << 20)][:3]
+    for i in small:                                                  # oracle bytes for a few segments incl. the 2 MiB one
+        assert before[i] == oracle.digest(oracle.fill(table[i].bytes, 1234, firsts[i]))
+    total = sum(before) % (1 << 64)
+    engine.host_reserve(W.weight_bytes(table))
+    for mode in (L.FMA_MODE_STAGED, L.FMA_MODE_DIRECT):
+        engine.set_option("mode", mode)
+        engine.sleep(["weights"], flags=L.FMA_FLAG_VERIFY)
+        st = engine.stats()
+        assert st["sleep_bytes_offloaded"] == W.weight_bytes(table) and st["hbm_mapped_bytes"] == 0
+        engine.wake(None, flags=L.FMA_FLAG_VERIFY)
+        after = engine.digest_all(["weights"])
+        assert after == before and sum(after) % (1 << 64) == total
+        assert [s.va for s in engine.segments()] == ptrs
+        assert engine.stats()["wake_seconds"] < 5.0                 # the controller's /wake_up timeout (inference-server.go:1699-1702)
