@@ -1,0 +1,114 @@
+// Drives the engine's C-ABI on the host simulation under ThreadSanitizer / AddressSanitizer (built and run by
+// tests/test_engine_hostsim.py).  Scenario: load a table, sleep/wake in every mode, tag-selective wake, free inside a
+// merged unit, hot swap of two engines (sleep and wake concurrently), cold load from a file, failed wake + retry.
+#include <cassert>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "fma_engine.h"
+
+extern "C" unsigned long long hostsim_live_mapped_bytes();
+extern "C" unsigned long long hostsim_live_handles();
+extern "C" void hostsim_fail_create_after(long n);
+
+#define OK(x)                                                                          \
+    do {                                                                               \
+        int _rc = (x);                                                                 \
+        if (_rc != 0) { fprintf(stderr, "%s -> %d: %s\n", #x, _rc, fma_last_error()); abort(); } \
+    } while (0)
+
+static const size_t P = FMA_PAGE_BYTES;
+
+static std::vector<uint64_t> digests(fma_engine_t* e) {
+    int n = fma_segment_count(e);
+    std::vector<uint64_t> d(n > 0 ? n : 1);
+    OK(fma_digest_all(e, 0, d.data(), n));
+    d.resize(n);
+    return d;
+}
+
+int main() {
+    fma_engine_t *a = nullptr, *b = nullptr;
+    OK(fma_engine_create(0, nullptr, &a));
+    OK(fma_engine_create(0, nullptr, &b));
+    int w = fma_tag_intern(a, "weights"), kv = fma_tag_intern(a, "kv_cache");
+    int wb = fma_tag_intern(b, "weights");
+    const size_t sizes[] = {16 * P, 3 * P, P, 24 * P, 6 * P, P, 10 * P};
+    std::vector<void*> pa;
+    for (size_t s : sizes) { void* p; OK(fma_alloc(a, s, w, &p)); pa.push_back(p); }
+    void* pk; OK(fma_alloc(a, 20 * P, kv, &pk));
+    for (int i = 0; i < 7; ++i) OK(fma_fill_segment(a, i, 1234, (uint64_t)i << 24));
+    for (int i = 0; i < 4; ++i) { void* p; OK(fma_alloc(b, 9 * P, wb, &p)); OK(fma_fill_segment(b, i, 99, (uint64_t)i << 20)); }
+    auto da = digests(a), db = digests(b);
+
+    for (int mode : {FMA_MODE_STAGED, FMA_MODE_DIRECT, FMA_MODE_KERNEL}) {
+        OK(fma_set_option(a, "mode", mode));
+        OK(fma_set_option(a, "chunk_bytes", 5 * P));           // ragged ring slots / chunks
+        for (int rep = 0; rep < 2; ++rep) {
+            OK(fma_sleep(a, 1ull << w, FMA_TIER_HOST, FMA_FLAG_VERIFY));
+            assert(fma_is_sleeping(a) == 1);
+            OK(fma_sleep(a, 1ull << w, FMA_TIER_HOST, 0));      // no-op
+            OK(fma_wake(a, 1ull << w, FMA_FLAG_VERIFY));        // weights only
+            assert(fma_is_sleeping(a) == 1);
+            OK(fma_wake(a, 0, 0));                              // the rest
+            OK(fma_wake(a, 0, 0));                              // harmless
+            assert(fma_is_sleeping(a) == 0);
+            auto d = digests(a);
+            for (int i = 0; i < 7; ++i) assert(d[i] == da[i]);
+        }
+    }
+    // local (same-GPU) parking tier: K1/K2 write and read the store themselves
+    OK(fma_set_option(a, "mode", FMA_MODE_AUTO));
+    OK(fma_sleep(a, 1ull << w, FMA_TIER_LOCAL, FMA_FLAG_VERIFY));
+    OK(fma_wake(a, 0, FMA_FLAG_VERIFY));
+    // free inside a merged unit, then another cycle
+    OK(fma_free(a, pa[2]));
+    OK(fma_sleep(a, 1ull << w, FMA_TIER_HOST, FMA_FLAG_VERIFY));
+    OK(fma_wake(a, 0, FMA_FLAG_VERIFY));
+    // hot swap: sleep(a) || wake(b), both directions, twice
+    OK(fma_sleep(b, 1ull << wb, FMA_TIER_HOST, 0));
+    for (int rep = 0; rep < 2; ++rep) {
+        OK(fma_swap(a, 1ull << w, FMA_TIER_HOST, b, 0, FMA_FLAG_VERIFY));
+        assert(fma_is_sleeping(a) == 1 && fma_is_sleeping(b) == 0);
+        OK(fma_swap(b, 1ull << wb, FMA_TIER_HOST, a, 0, FMA_FLAG_VERIFY));
+        assert(fma_is_sleeping(b) == 1 && fma_is_sleeping(a) == 0);
+    }
+    OK(fma_wake(b, 0, 0));
+    auto db2 = digests(b);
+    for (size_t i = 0; i < db.size(); ++i) assert(db2[i] == db[i]);
+
+    // failed wake (cuMemCreate refuses the 2nd allocation) leaves a consistent, retryable state
+    OK(fma_sleep(a, 1ull << w, FMA_TIER_HOST, FMA_FLAG_VERIFY));
+    assert(hostsim_live_mapped_bytes() == 4 * 9 * P + 0 * P || hostsim_live_mapped_bytes() >= 4 * 9 * P);  // only engine b (+ its ring) is mapped
+    hostsim_fail_create_after(1);
+    int rc = fma_wake(a, 0, FMA_FLAG_VERIFY);
+    assert(rc != 0 && fma_is_sleeping(a) == 1);
+    hostsim_fail_create_after(-1);
+    OK(fma_wake(a, 0, FMA_FLAG_VERIFY));                        // the controller's retry
+    assert(fma_is_sleeping(a) == 0);
+
+    // cold load: file -> segments, multi-threaded readers
+    const char* path = "/tmp/fma_hostsim_load.bin";
+    std::vector<unsigned char> blob(40 * P + 4096);
+    for (size_t i = 0; i < blob.size(); ++i) blob[i] = (unsigned char)(i * 2654435761u >> 13);
+    FILE* f = fopen(path, "wb"); fwrite(blob.data(), 1, blob.size(), f); fclose(f);
+    fma_segment_info_t s0, s3;
+    OK(fma_segment_info(a, 0, &s0)); OK(fma_segment_info(a, 2, &s3));   // index 2 is the 24-page segment now
+    fma_load_span_t spans[2] = {{4096, 16 * P, s0.va}, {16 * P + 4096, 24 * P, s3.va}};
+    fma_load_stats_t ls;
+    OK(fma_set_option(a, "load_chunk_bytes", 3 << 20)); OK(fma_set_option(a, "load_threads", 6)); OK(fma_set_option(a, "load_slots", 4));
+    OK(fma_load_file(a, path, spans, 2, 0, &ls));
+    assert(ls.bytes == 40 * P);
+    std::vector<unsigned char> back(16 * P);
+    OK(fma_segment_read(a, 0, 0, back.data(), 16 * P));
+    assert(memcmp(back.data(), blob.data() + 4096, 16 * P) == 0);
+    remove(path);
+
+    OK(fma_engine_destroy(a));
+    OK(fma_engine_destroy(b));
+    assert(hostsim_live_mapped_bytes() == 0 && hostsim_live_handles() == 0);   // nothing leaked: no mapping, no handle
+    puts("engine sanitizer scenario ok");
+    return 0;
+}

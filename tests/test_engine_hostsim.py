@@ -1,0 +1,61 @@
+"""The engine's HOST logic on CPU.  fma_engine.cu is compiled with g++ against a host simulation of the CUDA runtime +
+VMM driver calls (tests/cpp/hostsim/, test infrastructure: mmap-backed VMM with the real map/unmap semantics, eager
+streams) and host stand-ins for the kernel launch wrappers, then
+
+  1. the GPU parity suite (tests/test_gpu_parity.py, everything that does not need torch on a GPU) runs against that
+     library in a subprocess — segment table, arenas, runs, ring, mapper/unmapper threads, modes, tiers incl. the
+     peer tier, swap, cold load, error handling;
+  2. a C++ scenario drives the C-ABI under ThreadSanitizer and under AddressSanitizer+UBSan+LeakSanitizer, including
+     a failed wake (injected cuMemCreate failure) followed by the controller's retry, and checks that destroying the
+     engines leaves no mapping and no handle behind.
+
+The product library contains none of this: without a GPU it refuses to run (tests/test_abi.py)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SIM = os.path.join(ROOT, "tests", "cpp", "hostsim")
+CSRC = os.path.join(ROOT, "llm-d-fast-model-actuation_b200", "csrc")
+INC = ["-I/usr/local/cuda/include", "-I" + CSRC, "-I" + os.path.join(ROOT, "include")]
+SRCS = ["-x", "c++", os.path.join(CSRC, "fma_engine.cu"), "-x", "c++", os.path.join(SIM, "hostsim_cuda.cpp"), os.path.join(SIM, "hostsim_kernels.cpp")]
+
+
+def _have_cuda_headers():
+    return os.path.exists("/usr/local/cuda/include/cuda_runtime.h")
+
+
+@pytest.fixture(scope="module")
+def hostsim_lib(tmp_path_factory):
+    if not _have_cuda_headers():
+        pytest.skip("CUDA headers not installed")
+    out = str(tmp_path_factory.mktemp("hostsim") / "libfma_b200_hostsim.so")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-g", "-shared", "-fPIC", "-fvisibility=hidden", *INC, *SRCS, "-o", out, "-lpthread"])
+    return out
+
+
+def test_parity_suite_against_the_host_simulated_engine(hostsim_lib, oracle):
+    env = dict(os.environ, FMA_B200_LIB=hostsim_lib, FMA_HOSTSIM="1", HOSTSIM_DEVICES="2")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-x", "-q", "-m", "gpu",
+                        "-k", "not shim and not torch_pool and not full_size", "-p", "no:cacheprovider"],
+                       env=env, cwd=ROOT, capture_output=True, text=True, timeout=900)
+    tail = (r.stdout + r.stderr)[-3000:]
+    assert r.returncode == 0, tail
+    assert " passed" in r.stdout and "failed" not in r.stdout, tail
+
+
+@pytest.mark.parametrize("san,flags", [("tsan", ["-fsanitize=thread"]),
+                                        ("asan", ["-fsanitize=address,undefined", "-fno-omit-frame-pointer"])])
+def test_engine_scenario_under_sanitizers(tmp_path, san, flags):
+    if not _have_cuda_headers():
+        pytest.skip("CUDA headers not installed")
+    exe = str(tmp_path / f"engine_{san}")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-g", *flags, *INC, *SRCS, os.path.join(SIM, "engine_sanitizer_test.cpp"),
+                           "-o", exe, "-lpthread"])
+    env = dict(os.environ, ASAN_OPTIONS="detect_leaks=1", TSAN_OPTIONS="halt_on_error=1", HOSTSIM_DEVICES="2")
+    r = subprocess.run([exe], env=env, capture_output=True, text=True, timeout=600)
+    out = r.stdout + r.stderr
+    assert r.returncode == 0 and "engine sanitizer scenario ok" in out, out[-3000:]
+    assert "WARNING: ThreadSanitizer" not in out and "ERROR: AddressSanitizer" not in out and "runtime error:" not in out, out[-3000:]

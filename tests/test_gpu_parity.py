@@ -413,6 +413,8 @@ def test_load_file_rejects_bad_spans(engine, tmp_path):
 
 # ---- peer-HBM parking tier over NVLink (needs >= 2 GPUs; skipped on a 1-GPU box) ------------------------------
 def _n_gpus():
+    if os.environ.get("FMA_HOSTSIM") == "1":            # host simulation of the CUDA APIs (tests/test_engine_hostsim.py)
+        return int(os.environ.get("HOSTSIM_DEVICES", "2"))
     import torch
 
     return torch.cuda.device_count()
