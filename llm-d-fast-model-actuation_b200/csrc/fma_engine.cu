@@ -1159,9 +1159,12 @@ int do_sleep(fma_engine_t* e, uint64_t offload_mask, int tier, uint32_t flags) {
                     RT(cudaEventRecord(e->ev_ring_full[slot], e->ks));
                     RT(cudaStreamWaitEvent(cstream, e->ev_ring_full[slot], 0));
                     RT(cudaMemcpyAsync(store + p0 * FMA_PAGE_BYTES, e->ring[slot], np * FMA_PAGE_BYTES, cudaMemcpyDefault, cstream));
+                    // "slot free" also means "every earlier slot has reached the store" (chained through the previous
+                    // slot's event), so the unmapper below never releases device memory whose bytes are not yet on the host
+                    if (c > 0) RT(cudaStreamWaitEvent(cstream, e->ev_ring_free[(c - 1) % e->n_ring], 0));
                     RT(cudaEventRecord(e->ev_ring_free[slot], cstream));
                     ++copy_ops;
-                    rc = publish_gathered(p0 + np);  // once gathered into the ring the source segments are dead
+                    rc = publish_consumed((uint64_t)(p0 + np) * FMA_PAGE_BYTES, cstream);  // units fully in the store are dead
                     if (rc != FMA_OK) return rc;
                 }
             }
