@@ -1005,6 +1005,8 @@ int do_sleep(fma_engine_t* e, uint64_t offload_mask, int tier, uint32_t flags) {
     struct ApplyUnmapped {
         Unmapper* un;
         fma_engine_t* e;
+        const std::vector<Extent>* ex;   // offloaded extents: a unit is only ever unmapped after its bytes reached the store,
+        int tier;                        // so an unmapped offloaded segment HAS a backup even if the sleep fails later
         size_t applied = 0;
         void run() {
             std::lock_guard<std::mutex> lk(e->mu);
@@ -1025,13 +1027,23 @@ int do_sleep(fma_engine_t* e, uint64_t offload_mask, int tier, uint32_t flags) {
                         sg.mapped = false;
                         sg.unit_va = 0;
                     }
+                for (const Extent& x : *ex)
+                    if (x.va >= r.va && x.va < r.va + r.bytes) {
+                        Segment& sg = e->segs[x.seg_index];
+                        sg.has_backup = true;
+                        sg.backup_tier = tier;
+                        sg.packed_off = x.packed_off;
+                    }
+            }
+            if (!un->done.empty()) {  // even a failed sleep leaves an image a later wake can restore from
+                e->image_tier = tier;
             }
         }
         ~ApplyUnmapped() {
             un->finish();
             run();
         }
-    } apply_unmapped{&un, e};
+    } apply_unmapped{&un, e, &ex, tier};
 
     // Units in VA order, split into "discarded" (release now) and "offloaded" (release once the image has their
     // bytes).  image_end = packed offset just past the unit's last live segment.

@@ -12,6 +12,7 @@
 extern "C" unsigned long long hostsim_live_mapped_bytes();
 extern "C" unsigned long long hostsim_live_handles();
 extern "C" void hostsim_fail_create_after(long n);
+extern "C" void hostsim_fail_memcpy_after(long n);
 
 #define OK(x)                                                                          \
     do {                                                                               \
@@ -88,6 +89,28 @@ int main() {
     hostsim_fail_create_after(-1);
     OK(fma_wake(a, 0, FMA_FLAG_VERIFY));                        // the controller's retry
     assert(fma_is_sleeping(a) == 0);
+
+    // failed SLEEP (a D2H refuses to enqueue after a few slots): whatever was already released has its bytes in the
+    // store, the rest is still mapped -> a wake brings everything back bit-exact, in every mode
+    {
+        auto before = digests(a);
+        for (int mode : {FMA_MODE_STAGED, FMA_MODE_DIRECT}) {
+            OK(fma_set_option(a, "mode", mode));
+            OK(fma_set_option(a, "chunk_bytes", 5 * P));
+            hostsim_fail_memcpy_after(3);
+            int src = fma_sleep(a, 1ull << w, FMA_TIER_HOST, 0);
+            hostsim_fail_memcpy_after(-1);
+            assert(src != 0);
+            OK(fma_wake(a, 0, 0));
+            assert(fma_is_sleeping(a) == 0);
+            auto after = digests(a);
+            for (size_t i = 0; i < before.size(); ++i)
+                if (i != before.size() - 1) assert(after[i] == before[i]);   // the last segment is kv_cache: contents not preserved
+            OK(fma_sleep(a, 1ull << w, FMA_TIER_HOST, FMA_FLAG_VERIFY));     // and the engine still sleeps normally afterwards
+            OK(fma_wake(a, 0, FMA_FLAG_VERIFY));
+        }
+        OK(fma_set_option(a, "mode", FMA_MODE_AUTO));
+    }
 
     // cold load: file -> segments, multi-threaded readers
     const char* path = "/tmp/fma_hostsim_load.bin";

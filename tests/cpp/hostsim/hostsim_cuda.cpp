@@ -36,6 +36,7 @@ std::atomic<unsigned long long> g_next_handle{1};
 thread_local int tl_device = 0;
 thread_local cudaError_t tl_last = cudaSuccess;
 std::atomic<long> g_fail_create_after{-1};                    // fault injection: fail the Nth cuMemCreate from now
+std::atomic<long> g_fail_memcpy_after{-1};                    // fault injection: fail the Nth large cudaMemcpyAsync from now
 
 int device_count() {
     const char* v = getenv("HOSTSIM_DEVICES");
@@ -152,6 +153,7 @@ extern "C" __attribute__((visibility("default"))) unsigned long long hostsim_liv
     return g_handles.size();
 }
 extern "C" __attribute__((visibility("default"))) void hostsim_fail_create_after(long n) { g_fail_create_after.store(n); }
+extern "C" __attribute__((visibility("default"))) void hostsim_fail_memcpy_after(long n) { g_fail_memcpy_after.store(n); }
 
 extern "C" {
 cudaError_t cudaGetDeviceCount(int* n) { *n = device_count(); return cudaSuccess; }
@@ -180,7 +182,14 @@ cudaError_t cudaEventDestroy(cudaEvent_t e) { delete (Event*)e; return cudaSucce
 cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) { ((Event*)e)->t_ms = now_ms(); return cudaSuccess; }
 cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) { *ms = (float)(((Event*)b)->t_ms - ((Event*)a)->t_ms); if (*ms <= 0) *ms = 1e-3f; return cudaSuccess; }
-cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { memcpy(d, s, n); return cudaSuccess; }
+cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) {
+    if (n >= (1u << 20)) {  // only bulk copies (page tables and descriptors are small)
+        long f = g_fail_memcpy_after.load();
+        if (f >= 0 && g_fail_memcpy_after.fetch_sub(1) == 0) return cudaErrorLaunchFailure;
+    }
+    memcpy(d, s, n);
+    return cudaSuccess;
+}
 cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { memcpy(d, s, n); return cudaSuccess; }
 cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { memset(d, v, n); return cudaSuccess; }
 cudaError_t cudaGetDriverEntryPoint(const char* name, void** fn, unsigned long long, cudaDriverEntryPointQueryResult* st) {
