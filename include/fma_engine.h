@@ -218,6 +218,17 @@ FMA_API int  fma_host_store_view(fma_engine_t* e, const void** base, uint64_t* b
 FMA_API int  fma_peer_reserve(fma_engine_t* e, int peer_device, size_t bytes);
 FMA_API int  fma_peer_release(fma_engine_t* e);
 
+/* ---- image hand-over between processes (SURVEY.md §5 checkpoint/resume, §8f-1) ---------------------------------
+ * In the reference the level-1 backup is owned by the sleeping process and dies with it, after which the controller
+ * cold-starts a new instance (pkg/controller/dual-pods/inference-server.go:416-448).  With FMA_HOST_STORE_SHM=1 the host
+ * store is a memfd: a sleeping engine can hand its packed image (data + a descriptor of segment sizes, tags and K3
+ * digests) to another process as a file descriptor, and an engine that has allocated the SAME segment sequence (same
+ * model, freshly created, contents irrelevant) adopts it and is then "asleep with that image": a following fma_wake
+ * restores the weights at PCIe speed instead of re-reading a checkpoint.
+ * Status: exercised on the CUDA host simulation only (tests/test_engine_hostsim.py); not yet run on a B200. */
+FMA_API int  fma_image_export(fma_engine_t* e, int* out_fd);          /* caller owns (closes) the returned fd          */
+FMA_API int  fma_image_adopt(fma_engine_t* e, int fd, uint64_t tag_mask, uint32_t flags);  /* fd stays owned by the caller */
+
 /* ---- integrity (K3) and synthetic data (K0) --------------------------------------- */
 /* 64-bit position-sensitive digest of a mapped segment, computed on the device.
  * Definition: oracle/fma_oracle.h `fma_oracle_digest`. */

@@ -125,6 +125,8 @@ _PROTOTYPES = {
     "fma_scratch_free": (C.c_int, [C.c_void_p, C.c_uint64]),
     "fma_load_file": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(fma_load_span_t), C.c_uint32, C.c_uint32,
                                 C.POINTER(fma_load_stats_t)]),
+    "fma_image_export": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+    "fma_image_adopt": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_uint32]),
     "fma_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
     "fma_stats": (C.c_int, [C.c_void_p, C.POINTER(fma_stats_t)]),
 }

@@ -208,7 +208,28 @@ struct HostStore {
     bool registered = false;    // mmap + cudaHostRegister (else cudaHostAlloc)
     int numa_node = -1;
     double pin_seconds = 0;
+    int fd = -1;                // memfd backing (FMA_HOST_STORE_SHM=1 or an adopted image); -1 = anonymous memory
+    size_t map_bytes = 0;       // bytes mapped at base (cap + descriptor tail for memfd stores)
 };
+
+// Descriptor of a packed image, stored in the last 2 MiB of a memfd-backed store (fma_image_export / fma_image_adopt).
+constexpr uint64_t kImageMagic = 0x31304d49414d46ull;  // "FMAIM01"
+constexpr size_t kImageTail = (size_t)2 << 20;
+struct ImageSegDesc {
+    uint64_t bytes;
+    uint64_t packed_off;
+    uint64_t digest;
+    uint32_t digest_valid;
+    uint32_t tag_len;
+    char tag[32];
+};
+struct ImageHeader {
+    uint64_t magic;
+    uint32_t version;
+    uint32_t n_segments;
+    uint64_t image_bytes;
+};
+constexpr uint32_t kFlagAdopt = 1u << 31;  // internal: "sleep" onto an adopted image without copying
 
 struct ParkStore {  // peer-HBM or local-HBM parking buffer (VMM, P2P mapped)
     CUdeviceptr va = 0;
@@ -519,10 +540,11 @@ void host_store_free(HostStore& h) {
     if (!h.base) return;
     if (h.registered) {
         cudaHostUnregister(h.base);
-        munmap(h.base, h.cap);
+        munmap(h.base, h.map_bytes ? h.map_bytes : h.cap);
     } else {
         cudaFreeHost(h.base);
     }
+    if (h.fd >= 0) close(h.fd);
     cudaGetLastError();
     h = HostStore{};
 }
@@ -537,8 +559,23 @@ int host_store_reserve(fma_engine_t* e, size_t bytes) {
     const int want_bind = e->cfg.numa_bind != 0;  // -1 (default) and 1 both bind
     const int node = want_bind ? gpu_numa_node(e->device) : -1;
     const bool use_register = env_int("FMA_HOST_REGISTER", 1) != 0;
-    if (use_register) {
-        void* p = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    const bool use_shm = env_int("FMA_HOST_STORE_SHM", 0) != 0;
+    if (use_register || use_shm) {
+        void* p = MAP_FAILED;
+        h.map_bytes = bytes;
+        if (use_shm) {  // memfd: the image can be handed to another process (fma_image_export)
+            h.fd = (int)syscall(SYS_memfd_create, "fma-host-store", 1u /* MFD_CLOEXEC */);
+            if (h.fd >= 0 && ftruncate(h.fd, (off_t)(bytes + kImageTail)) == 0) {
+                h.map_bytes = bytes + kImageTail;
+                p = mmap(nullptr, h.map_bytes, PROT_READ | PROT_WRITE, MAP_SHARED, h.fd, 0);
+            }
+            if (p == MAP_FAILED && h.fd >= 0) {
+                close(h.fd);
+                h.fd = -1;
+                h.map_bytes = bytes;
+            }
+        }
+        if (p == MAP_FAILED) p = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
         if (p != MAP_FAILED) {
             madvise(p, bytes, MADV_HUGEPAGE);
             if (node >= 0 && node < 64) {
@@ -556,13 +593,16 @@ int host_store_reserve(fma_engine_t* e, size_t bytes) {
                 th.emplace_back([p, lo, hi] { memset((char*)p + lo, 0, hi - lo); });
             }
             for (auto& t : th) t.join();
-            cudaError_t r = cudaHostRegister(p, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped);
+            cudaError_t r = cudaHostRegister(p, h.map_bytes, cudaHostRegisterPortable | cudaHostRegisterMapped);
             if (r == cudaSuccess) {
                 h.base = p;
                 h.registered = true;
             } else {
                 cudaGetLastError();
-                munmap(p, bytes);
+                munmap(p, h.map_bytes);
+                if (h.fd >= 0) close(h.fd);
+                h.fd = -1;
+                h.map_bytes = 0;
             }
         }
     }
@@ -882,7 +922,7 @@ int do_sleep(fma_engine_t* e, uint64_t offload_mask, int tier, uint32_t flags) {
         }
     }
     int mode = resolve_mode(e, tier);
-    if (W && mode == FMA_MODE_STAGED && ensure_ring(e, W) != FMA_OK) mode = FMA_MODE_DIRECT;  // HBM too full for a ring
+    if (W && !(flags & kFlagAdopt) && mode == FMA_MODE_STAGED && ensure_ring(e, W) != FMA_OK) mode = FMA_MODE_DIRECT;  // HBM too full for a ring
     if (W) {
         if (tier == FMA_TIER_HOST) {
             rc = host_store_reserve(e, W);
@@ -899,7 +939,8 @@ int do_sleep(fma_engine_t* e, uint64_t offload_mask, int tier, uint32_t flags) {
         }
     }
 
-    if ((flags & FMA_FLAG_VERIFY) && W) {
+    const bool adopt = (flags & kFlagAdopt) != 0;  // the store already holds the image: release the device side only
+    if ((flags & FMA_FLAG_VERIFY) && W && !adopt) {
         std::vector<size_t> idx;
         for (const Extent& x : ex) idx.push_back(x.seg_index);
         std::vector<uint64_t> dg;
@@ -1107,7 +1148,9 @@ int do_sleep(fma_engine_t* e, uint64_t offload_mask, int tier, uint32_t flags) {
     KernelTimes kt{e};
     uint32_t copy_ops = 0;
     double copy_s = 0;
-    if (W) {
+    if (W && adopt) {
+        publish_consumed(W, e->ks);  // nothing to copy: every offloaded unit can go at once
+    } else if (W) {
         const size_t chunk = direct_chunk(e);
         char* store = static_cast<char*>(store_copy_base(e, tier));
         rc = timer.begin();
@@ -2225,6 +2268,110 @@ int fma_load_file(fma_engine_t* e, const char* path, const fma_load_span_t* span
         out_stats->bytes = total;
         out_stats->chunks = (uint32_t)items.size();
         out_stats->threads = (uint32_t)n_threads;
+    }
+    return FMA_OK;
+}
+
+int fma_image_export(fma_engine_t* e, int* out_fd) {
+    if (check_engine(e) != FMA_OK) return FMA_EINVAL;
+    if (!out_fd) return fail(FMA_EINVAL, "out_fd is NULL");
+    if (e->host.fd < 0 || !e->host.base) return fail(FMA_ESTATE, "the host store is not shareable (set FMA_HOST_STORE_SHM=1 before the first sleep)");
+    if (e->image_tier != FMA_TIER_HOST) return fail(FMA_ESTATE, "no host-tier image");
+    std::vector<const Segment*> segs;
+    for (const Segment& s : e->segs)
+        if (s.has_backup && s.backup_tier == FMA_TIER_HOST && !s.mapped) segs.push_back(&s);
+    if (segs.empty()) return fail(FMA_ESTATE, "nothing is asleep in the host store");
+    std::sort(segs.begin(), segs.end(), [](const Segment* a, const Segment* b) { return a->packed_off < b->packed_off; });
+    if (sizeof(ImageHeader) + segs.size() * sizeof(ImageSegDesc) > kImageTail) return fail(FMA_ENOMEM, "too many segments for the descriptor");
+    char* tail = static_cast<char*>(e->host.base) + e->host.cap;
+    ImageHeader hd{kImageMagic, 1, (uint32_t)segs.size(), e->image_bytes};
+    memcpy(tail, &hd, sizeof(hd));
+    for (size_t i = 0; i < segs.size(); ++i) {
+        ImageSegDesc d;
+        memset(&d, 0, sizeof(d));
+        d.bytes = segs[i]->bytes;
+        d.packed_off = segs[i]->packed_off;
+        d.digest = segs[i]->digest;
+        d.digest_valid = segs[i]->digest_valid ? 1 : 0;
+        const std::string& t = e->tags[segs[i]->tag];
+        d.tag_len = (uint32_t)std::min<size_t>(t.size(), sizeof(d.tag) - 1);
+        memcpy(d.tag, t.data(), d.tag_len);
+        memcpy(tail + sizeof(hd) + i * sizeof(d), &d, sizeof(d));
+    }
+    int fd = dup(e->host.fd);
+    if (fd < 0) return fail(FMA_ENOMEM, "dup failed: %s", strerror(errno));
+    *out_fd = fd;
+    return FMA_OK;
+}
+
+int fma_image_adopt(fma_engine_t* e, int fd, uint64_t tag_mask, uint32_t flags) {
+    if (check_engine(e) != FMA_OK) return FMA_EINVAL;
+    if (!tag_mask) return fail(FMA_EINVAL, "adopt needs the tag mask the image was slept with");
+    for (const Segment& s : e->segs)
+        if (!s.mapped) return fail(FMA_ESTATE, "adopt needs a fully awake engine");
+    struct stat sb;
+    if (fstat(fd, &sb) != 0 || (size_t)sb.st_size <= kImageTail) return fail(FMA_EINVAL, "not an image fd");
+    const size_t map_bytes = (size_t)sb.st_size, cap = map_bytes - kImageTail;
+    int myfd = dup(fd);
+    if (myfd < 0) return fail(FMA_ENOMEM, "dup failed: %s", strerror(errno));
+    void* p = mmap(nullptr, map_bytes, PROT_READ | PROT_WRITE, MAP_SHARED, myfd, 0);
+    if (p == MAP_FAILED) {
+        close(myfd);
+        return fail(FMA_ENOMEM, "cannot map the image: %s", strerror(errno));
+    }
+    auto bail = [&](int code, const char* why) {
+        munmap(p, map_bytes);
+        close(myfd);
+        return fail(code, "%s", why);
+    };
+    const char* tail = static_cast<const char*>(p) + cap;
+    ImageHeader hd;
+    memcpy(&hd, tail, sizeof(hd));
+    if (hd.magic != kImageMagic || hd.version != 1 || hd.image_bytes > cap) return bail(FMA_EINVAL, "image descriptor missing or corrupt");
+    // the segments this engine would offload for tag_mask, in image order (same rule as fma_sleep)
+    std::vector<size_t> order;
+    for (size_t i = 0; i < e->segs.size(); ++i)
+        if (tag_bit_set(tag_mask, e->segs[i].tag)) order.push_back(i);
+    std::sort(order.begin(), order.end(), [&](size_t a, size_t b) {
+        const Segment &x = e->segs[a], &y = e->segs[b];
+        return x.arena != y.arena ? x.arena < y.arena : x.va < y.va;
+    });
+    if (order.size() != hd.n_segments) return bail(FMA_EINVAL, "image and engine disagree on the number of segments");
+    std::vector<ImageSegDesc> ds(hd.n_segments);
+    uint64_t off = 0;
+    for (size_t i = 0; i < ds.size(); ++i) {
+        memcpy(&ds[i], tail + sizeof(hd) + i * sizeof(ImageSegDesc), sizeof(ImageSegDesc));
+        const Segment& s = e->segs[order[i]];
+        if (ds[i].bytes != s.bytes || ds[i].packed_off != off || std::string(ds[i].tag, ds[i].tag_len) != e->tags[s.tag])
+            return bail(FMA_EINVAL, "image and engine disagree on a segment's size, offset or tag");
+        off += s.bytes;
+    }
+    if (off != hd.image_bytes) return bail(FMA_EINVAL, "image size mismatch");
+    DeviceGuard guard(e->device);
+    cudaDeviceSynchronize();
+    host_store_free(e->host);
+    const double t0 = now_s();
+    cudaError_t r = cudaHostRegister(p, map_bytes, cudaHostRegisterPortable | cudaHostRegisterMapped);
+    if (r != cudaSuccess) {
+        cudaGetLastError();
+        return bail(FMA_ECUDA, "cannot pin the adopted image");
+    }
+    HostStore h;
+    h.base = p; h.cap = cap; h.map_bytes = map_bytes; h.fd = myfd; h.registered = true;
+    void* alias = nullptr;
+    if (cudaHostGetDevicePointer(&alias, p, 0) == cudaSuccess) h.dev_alias = alias;
+    else cudaGetLastError();
+    h.pin_seconds = now_s() - t0;
+    e->host = h;
+    e->st.host_store_bytes = cap;
+    e->st.host_store_pin_seconds = h.pin_seconds;
+    // release the device side exactly as a sleep would, without copying anything out
+    int rc = do_sleep(e, tag_mask, FMA_TIER_HOST, (flags & ~FMA_FLAG_VERIFY) | kFlagAdopt);
+    if (rc != FMA_OK) return rc;
+    for (size_t i = 0; i < ds.size(); ++i) {  // integrity data travels with the image: FMA_FLAG_VERIFY on wake checks it
+        Segment& s = e->segs[order[i]];
+        s.digest = ds[i].digest;
+        s.digest_valid = ds[i].digest_valid != 0;
     }
     return FMA_OK;
 }

@@ -225,6 +225,17 @@ class Engine:
     def scratch_free(self, ptr: int) -> None:
         check(self._lib.fma_scratch_free(self._h, ptr))
 
+    # -- image hand-over ------------------------------------------------------------------
+    def image_export(self) -> int:
+        """File descriptor of the sleeping image (needs FMA_HOST_STORE_SHM=1); the caller closes it."""
+        fd = C.c_int(-1)
+        check(self._lib.fma_image_export(self._h, C.byref(fd)))
+        return int(fd.value)
+
+    def image_adopt(self, fd: int, tags: Sequence[str], flags: int = 0) -> None:
+        """Become 'asleep with that image': this engine must hold the same segment sequence for ``tags``."""
+        check(self._lib.fma_image_adopt(self._h, fd, self.tag_mask(tags), flags))
+
     # -- cold load -------------------------------------------------------------------------
     def load_file(self, path: str, spans: Sequence[tuple[int, int, int]], o_direct: bool = False) -> dict:
         """Stream (file_offset, nbytes, device_address) spans of one file into mapped segments."""

@@ -479,3 +479,69 @@ def test_full_size_llama3_8b_roundtrip_properties(engine, oracle):
         assert after == before and sum(after) % (1 << 64) == total
         assert [s.va for s in engine.segments()] == ptrs
         assert engine.stats()["wake_seconds"] < 5.0                 # the controller's /wake_up timeout (inference-server.go:1699-1702)
+
+
+# ---- image hand-over between processes (memfd host store).  Host-simulation only this round: the feature has not been
+# ---- run on a B200 yet (no GPU budget was left when it was written), so it must not gate the round-end GPU suite.
+_HOSTSIM_ONLY = pytest.mark.skipif(os.environ.get("FMA_HOSTSIM") != "1", reason="image hand-over is validated on the CUDA host simulation only so far")
+
+_ADOPT_CHILD = r"""
+import os, sys, json
+sys.path.insert(0, {root!r})
+import fma_b200
+from fma_b200 import workloads as W, _lib as L
+fd = int(sys.argv[1])
+eng = fma_b200.Engine(0)
+table = W.allocation_table("tiny-llama-test", kv_cache_bytes=32 << 20, kv_tensors=2)
+for s in table: eng.alloc(s.bytes, s.tag)          # same model, nothing loaded: contents are whatever fresh memory holds
+eng.image_adopt(fd, ["weights"])
+assert eng.is_sleeping()
+eng.wake(None, flags=L.FMA_FLAG_VERIFY)            # digests travel with the image
+print(json.dumps(eng.digest_all(["weights"])))
+"""
+
+
+@_HOSTSIM_ONLY
+def test_image_handover_to_another_engine_and_process(engine, oracle, monkeypatch, tmp_path):
+    import subprocess
+    import sys
+
+    import fma_b200
+    from fma_b200 import FmaError
+
+    L = _L()
+    monkeypatch.setenv("FMA_HOST_STORE_SHM", "1")
+    table = _tiny_table()
+    ptrs, ref = _load(engine, oracle, table)
+    want = engine.digest_all(["weights"])
+    with pytest.raises(FmaError):
+        engine.image_export()                                        # awake: nothing to hand over
+    engine.sleep(["weights"], flags=L.FMA_FLAG_VERIFY)
+    fd = engine.image_export()
+    try:
+        # (1) another engine in this process adopts the image
+        with fma_b200.Engine(0) as other:
+            for s in table:
+                other.alloc(s.bytes, s.tag)
+            other.image_adopt(fd, ["weights"])
+            assert other.is_sleeping() and other.stats()["hbm_mapped_bytes"] == 0
+            other.wake(None, flags=L.FMA_FLAG_VERIFY)
+            assert other.digest_all(["weights"]) == want
+            for i in ref:
+                assert other.read(i, table[i].bytes) == ref[i].tobytes()
+        # (2) a different model is refused, and an awake-with-holes engine too
+        with fma_b200.Engine(0) as wrong:
+            wrong.alloc(4 * PAGE, "weights")
+            with pytest.raises(FmaError):
+                wrong.image_adopt(fd, ["weights"])
+            assert not wrong.is_sleeping()
+        # (3) a separate PROCESS inherits the fd, adopts and wakes
+        script = tmp_path / "adopt_child.py"
+        script.write_text(_ADOPT_CHILD.format(root=os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+        r = subprocess.run([sys.executable, str(script), str(fd)], pass_fds=[fd], capture_output=True, text=True, timeout=300, env=dict(os.environ))
+        assert r.returncode == 0, r.stderr[-2000:]
+        assert json.loads(r.stdout.strip().splitlines()[-1]) == want
+    finally:
+        os.close(fd)
+    engine.wake(None, flags=L.FMA_FLAG_VERIFY)                        # the owner still wakes from its own image
+    assert engine.digest_all(["weights"]) == want and [s.va for s in engine.segments()] == ptrs
