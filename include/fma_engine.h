@@ -91,7 +91,9 @@ typedef struct fma_config {
     int32_t  map_threads;       /* host threads doing cuMemCreate/Map on wake (0 = 1)      */
     int32_t  numa_bind;         /* 1 = bind the host store to the GPU's NUMA node (default),
                                    0 = leave placement to the OS, -1 = default             */
-    int32_t  reserved_i32;
+    int32_t  pack;              /* 1 = PACKED host image: bf16 pages are stored in the lossless "FMP4" code
+                                   (csrc/fma_codec.h, 0.758 of their size) by K4 on sleep and decoded by K5 on
+                                   wake; pages that do not code well stay raw.  Host tier + STAGED only; 0 = off */
     uint64_t reserved[6];
 } fma_config_t;
 
@@ -132,7 +134,7 @@ typedef struct fma_stats {
     int32_t  host_store_numa_node;
     int32_t  tier;
     int32_t  mode;
-    int32_t  reserved_i32;
+    int32_t  image_packed;          /* 1 = the sleeping image is in the PACKED form (config.pack) */
     /* lifetime counters */
     uint64_t total_kernel_launches;
     uint64_t total_copy_ops;
@@ -141,7 +143,8 @@ typedef struct fma_stats {
     uint64_t hbm_mapped_bytes;      /* physical HBM behind live mapping units of this engine            */
     uint64_t hbm_aux_bytes;         /* staging ring + page tables + digest scratch on this GPU           */
     uint64_t parked_bytes;          /* parking buffer held in a peer's (or this GPU's) HBM               */
-    uint64_t reserved[1];
+    uint64_t image_store_bytes;     /* bytes the last sleep's image takes in its store: == sleep_bytes_offloaded,
+                                       or less for a PACKED image (these are the bytes that cross PCIe)    */
 } fma_stats_t;
 
 /* ---- library ---------------------------------------------------------------------- */
@@ -243,6 +246,22 @@ FMA_API int  fma_fill_segment(fma_engine_t* e, int index, uint64_t seed, uint64_
 FMA_API int  fma_segment_write(fma_engine_t* e, int index, uint64_t offset, const void* host_src, uint64_t bytes);
 FMA_API int  fma_segment_read(fma_engine_t* e, int index, uint64_t offset, void* host_dst, uint64_t bytes);
 
+/* ---- PACKED host image (config.pack / option "pack"; format: csrc/fma_codec.h) ------------------------------ */
+/* Where each 2 MiB page of the sleeping image lives in the store: page p (= packed_offset / FMA_PAGE_BYTES of the
+ * segment that owns it) occupies out_bytes[p] bytes at out_offsets[p].  Returns the number of image pages (also when
+ * cap is smaller; then only cap entries are written), 0 if nothing sleeps.  For an image that is not packed the
+ * answer is the identity layout (offset p * 2 MiB, 2 MiB each). */
+FMA_API int  fma_image_pages(fma_engine_t* e, uint64_t* out_offsets, uint32_t* out_bytes, uint32_t cap);
+/* K4p / K4 / K5 on caller-provided pages (parity tests, roofline measurement).  K4p: out_stored_bytes[p] = size page p
+ * would take (host array).  K4: device pages -> stored pages laid out back to back from dst_base with the sizes K4p
+ * reports (out_stored_bytes as returned by K4p).  K5: inverse.  *out_ms (optional) = CUDA-event duration. */
+FMA_API int  fma_op_pack_probe(fma_engine_t* e, const uint64_t* pages, uint64_t base, uint32_t n_pages,
+                               uint32_t* out_stored_bytes, float* out_ms);
+FMA_API int  fma_op_pack(fma_engine_t* e, const uint64_t* src_pages, uint64_t src_base, uint64_t dst_base,
+                         const uint32_t* stored_bytes, uint32_t n_pages, float* out_ms);
+FMA_API int  fma_op_unpack(fma_engine_t* e, uint64_t src_base, const uint32_t* stored_bytes, const uint64_t* dst_pages,
+                           uint64_t dst_base, uint32_t n_pages, float* out_ms);
+
 /* ---- raw kernel entry points (parity tests and roofline measurement) -------------- */
 /* K1/K2: copy n_pages pages of FMA_PAGE_BYTES.  src_pages / dst_pages are HOST arrays of
  * device addresses (NULL = contiguous from src_base / dst_base).  Runs on an engine
@@ -288,7 +307,7 @@ FMA_API int  fma_load_file(fma_engine_t* e, const char* path, const fma_load_spa
 
 /* ---- tuning ----------------------------------------------------------------------- */
 /* Change one knob of a live engine (between operations).  Keys: "mode", "kernel",
- * "copy_streams", "chunk_bytes", "ring_slots", "map_threads", "tma_tile_bytes",
+ * "copy_streams", "chunk_bytes", "ring_slots", "map_threads", "pack", "tma_tile_bytes",
  * "tma_stages", "tma_pipes", "tma_ctas_per_sm", "load_threads", "load_chunk_bytes", "load_slots". */
 FMA_API int  fma_set_option(fma_engine_t* e, const char* key, int64_t value);
 

@@ -6,6 +6,7 @@ import os
 
 FMA_ABI_VERSION = 1
 FMA_PAGE_BYTES = 2 << 20
+FMA_PACKED_PAGE_BYTES = (3 << 19) + (16 << 10)   # stored size of a page in the "FMP4" code (csrc/fma_codec.h)
 FMA_MAX_TAGS = 64
 
 FMA_OK, FMA_EINVAL, FMA_ENODRIVER, FMA_ECUDA, FMA_ENOMEM, FMA_ESTATE, FMA_ENOTFOUND, FMA_EINTEGRITY = (
@@ -35,7 +36,7 @@ class fma_config_t(C.Structure):
     _fields_ = [
         ("abi_version", C.c_uint32), ("mode", C.c_int32), ("kernel", C.c_int32), ("copy_streams", C.c_int32),
         ("chunk_bytes", C.c_uint64), ("ring_slots", C.c_int32), ("map_threads", C.c_int32),
-        ("numa_bind", C.c_int32), ("reserved_i32", C.c_int32), ("reserved", C.c_uint64 * 6),
+        ("numa_bind", C.c_int32), ("pack", C.c_int32), ("reserved", C.c_uint64 * 6),
     ]
 
 
@@ -56,10 +57,10 @@ class fma_stats_t(C.Structure):
         ("kernel_seconds", C.c_double), ("kernel_bytes", C.c_uint64), ("kernel_launches", C.c_uint32),
         ("copy_ops", C.c_uint32),
         ("host_store_bytes", C.c_uint64), ("host_store_pin_seconds", C.c_double),
-        ("host_store_numa_node", C.c_int32), ("tier", C.c_int32), ("mode", C.c_int32), ("reserved_i32", C.c_int32),
+        ("host_store_numa_node", C.c_int32), ("tier", C.c_int32), ("mode", C.c_int32), ("image_packed", C.c_int32),
         ("total_kernel_launches", C.c_uint64), ("total_copy_ops", C.c_uint64),
         ("hbm_mapped_bytes", C.c_uint64), ("hbm_aux_bytes", C.c_uint64), ("parked_bytes", C.c_uint64),
-        ("reserved", C.c_uint64 * 1),
+        ("image_store_bytes", C.c_uint64),
     ]
 
     def as_dict(self) -> dict:
@@ -121,6 +122,13 @@ _PROTOTYPES = {
                                    C.c_uint32, C.c_int, C.POINTER(C.c_float)]),
     "fma_op_page_digest": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.c_uint64, C.POINTER(C.c_uint64), C.c_uint32,
                                      C.POINTER(C.c_uint64), C.POINTER(C.c_float)]),
+    "fma_image_pages": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.c_uint32]),
+    "fma_op_pack_probe": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.c_uint64, C.c_uint32, C.POINTER(C.c_uint32),
+                                    C.POINTER(C.c_float)]),
+    "fma_op_pack": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.c_uint64, C.c_uint64, C.POINTER(C.c_uint32), C.c_uint32,
+                              C.POINTER(C.c_float)]),
+    "fma_op_unpack": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.c_uint64, C.c_uint32,
+                                C.POINTER(C.c_float)]),
     "fma_scratch_alloc": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64)]),
     "fma_scratch_free": (C.c_int, [C.c_void_p, C.c_uint64]),
     "fma_load_file": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(fma_load_span_t), C.c_uint32, C.c_uint32,

@@ -260,6 +260,17 @@ struct fma_engine {
     ParkStore park;
     uint64_t image_bytes = 0;  // W of the current packed image
     int image_tier = FMA_TIER_HOST;
+    // PACKED host image (option "pack", fma_codec.h): image page p (= packed_off / 2 MiB) is stored at
+    // img_off[p] in the store and takes img_bytes[p] bytes (FMA_K_PACKED_PAGE_BYTES coded, 2 MiB raw)
+    bool image_packed = false;
+    std::vector<uint64_t> img_off;
+    std::vector<uint32_t> img_bytes;
+    uint64_t image_store_bytes = 0;  // bytes the image occupies in its store (== image_bytes unless packed)
+    fma_k_pack_desc* d_pdesc = nullptr;  // per-page descriptors of K4 / K5
+    fma_k_pack_desc* h_pdesc = nullptr;
+    uint32_t* d_psize = nullptr;         // K4p output; d_psize[pdesc_cap] is the K4/K5 error counter
+    uint32_t* h_psize = nullptr;
+    size_t pdesc_cap = 0;
 
     cudaStream_t cs[kMaxStreams] = {};  // copy-engine streams
     int n_cs = 0;
@@ -441,6 +452,23 @@ int ensure_desc(fma_engine_t* e, size_t n_pages) {
     RT(cudaMalloc(&e->d_dig, cap * sizeof(uint64_t)));
     RT(cudaHostAlloc(&e->h_dig, cap * sizeof(uint64_t), cudaHostAllocDefault));
     e->desc_cap = cap;
+    return FMA_OK;
+}
+
+int ensure_pack_bufs(fma_engine_t* e, size_t n_pages) {
+    if (n_pages <= e->pdesc_cap) return FMA_OK;
+    size_t cap = std::max<size_t>(round_up(n_pages, 4096), 16384);
+    if (e->d_pdesc) cudaFree(e->d_pdesc);
+    if (e->h_pdesc) cudaFreeHost(e->h_pdesc);
+    if (e->d_psize) cudaFree(e->d_psize);
+    if (e->h_psize) cudaFreeHost(e->h_psize);
+    e->d_pdesc = nullptr; e->h_pdesc = nullptr; e->d_psize = nullptr; e->h_psize = nullptr;
+    e->pdesc_cap = 0;
+    RT(cudaMalloc(&e->d_pdesc, cap * sizeof(fma_k_pack_desc)));
+    RT(cudaHostAlloc(&e->h_pdesc, cap * sizeof(fma_k_pack_desc), cudaHostAllocDefault));
+    RT(cudaMalloc(&e->d_psize, (cap + 1) * sizeof(uint32_t)));
+    RT(cudaHostAlloc(&e->h_psize, (cap + 1) * sizeof(uint32_t), cudaHostAllocDefault));
+    e->pdesc_cap = cap;
     return FMA_OK;
 }
 
@@ -807,6 +835,19 @@ struct KernelTimes {  // event pairs around each K1/K2 launch on the kernel stre
         bytes += 2ull * n_pages * FMA_PAGE_BYTES;
         return FMA_OK;
     }
+    // K4 / K5 (packed image): bracket a launch the caller makes itself; `b` = algorithmic bytes (read + write)
+    int begin() {
+        int rc = ensure_event_pool(e, used + 2);
+        if (rc != FMA_OK) return rc;
+        RT(cudaEventRecord(e->ev_pool[used], e->ks));
+        return FMA_OK;
+    }
+    int end(uint64_t b) {
+        RT(cudaEventRecord(e->ev_pool[used + 1], e->ks));
+        used += 2;
+        bytes += b;
+        return FMA_OK;
+    }
     // Called after the streams are synchronised.  Reading ~100s of event pairs costs ~1 ms, so it is
     // deferred to fma_stats() / the next operation instead of sitting inside the wake latency.
     int collect() {
@@ -884,6 +925,44 @@ int digest_segments(fma_engine_t* e, const std::vector<size_t>& idx, std::vector
 }
 
 // ------------------------------------------------------------------------------------
+// PACKED host image: K4p over every page of the image, then the store layout on the host.
+// Stored pages are laid back to back (sizes are multiples of 16 KiB), so every ring slot's D2H / H2D is one
+// contiguous copy.  *packed = false when coding would save < 5 % (fp8 / int / already dense data): the caller then
+// takes the plain path and the probe (one HBM read of the image, ~3 ms per 16 GiB) is all it cost.
+// ------------------------------------------------------------------------------------
+int plan_packed_image(fma_engine_t* e, const std::vector<Extent>& ex, uint64_t W, std::vector<uint64_t>* off,
+                      std::vector<uint32_t>* bytes, uint64_t* stored_total, bool* packed) {
+    *packed = false;
+    *stored_total = W;
+    const size_t n_pages = W / FMA_PAGE_BYTES;
+    int rc = ensure_tables(e, n_pages);
+    if (rc != FMA_OK) return rc;
+    rc = ensure_pack_bufs(e, n_pages);
+    if (rc != FMA_OK) return rc;
+    RT(cudaDeviceSynchronize());  // the caller's streams may still be writing weights (same reason as in do_sleep)
+    build_page_table(ex, e->h_tab);
+    RT(cudaMemcpyAsync(e->d_tab, e->h_tab, n_pages * sizeof(uint64_t), cudaMemcpyHostToDevice, e->ks));
+    RT(fma_k_launch_pack_probe(e->d_tab, (uint32_t)n_pages, e->d_psize, e->ks));
+    RT(cudaMemcpyAsync(e->h_psize, e->d_psize, n_pages * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->ks));
+    RT(cudaStreamSynchronize(e->ks));
+    e->st.total_kernel_launches += 1;
+    off->resize(n_pages);
+    bytes->resize(n_pages);
+    uint64_t total = 0;
+    for (size_t p = 0; p < n_pages; ++p) {
+        const uint32_t b = e->h_psize[p];
+        if (b != FMA_K_PACKED_PAGE_BYTES && b != FMA_PAGE_BYTES) return fail(FMA_ECUDA, "pack probe returned size %u for page %zu", b, p);
+        (*off)[p] = total;
+        (*bytes)[p] = b;
+        total += b;
+    }
+    if (total * 100 > W * 95) return FMA_OK;
+    *stored_total = total;
+    *packed = true;
+    return FMA_OK;
+}
+
+// ------------------------------------------------------------------------------------
 // SLEEP
 // ------------------------------------------------------------------------------------
 int do_sleep(fma_engine_t* e, uint64_t offload_mask, int tier, uint32_t flags) {
@@ -923,9 +1002,25 @@ int do_sleep(fma_engine_t* e, uint64_t offload_mask, int tier, uint32_t flags) {
     }
     int mode = resolve_mode(e, tier);
     if (W && !(flags & kFlagAdopt) && mode == FMA_MODE_STAGED && ensure_ring(e, W) != FMA_OK) mode = FMA_MODE_DIRECT;  // HBM too full for a ring
+    // PACKED image (config.pack): decide per page what its stored form is BEFORE the store is sized
+    bool packed = false;
+    uint64_t Wp = W;
+    {
+        std::vector<uint64_t> pk_off;
+        std::vector<uint32_t> pk_bytes;
+        if (W && e->cfg.pack && !(flags & kFlagAdopt) && tier == FMA_TIER_HOST && mode == FMA_MODE_STAGED) {
+            rc = plan_packed_image(e, ex, W, &pk_off, &pk_bytes, &Wp, &packed);
+            if (rc != FMA_OK) return rc;
+        }
+        e->image_packed = packed;
+        e->image_store_bytes = Wp;
+        e->img_off = packed ? std::move(pk_off) : std::vector<uint64_t>();
+        e->img_bytes = packed ? std::move(pk_bytes) : std::vector<uint32_t>();
+        if (packed) e->image_bytes = W;  // the layout above is indexed by image page: valid from here on, also if the sleep fails
+    }
     if (W) {
         if (tier == FMA_TIER_HOST) {
-            rc = host_store_reserve(e, W);
+            rc = host_store_reserve(e, Wp);
             if (rc != FMA_OK) return rc;
             if (mode == FMA_MODE_KERNEL && !e->host.dev_alias) return fail(FMA_ECUDA, "host store has no device alias for zero-copy mode");
         } else if (tier == FMA_TIER_PEER) {
@@ -1199,6 +1294,51 @@ int do_sleep(fma_engine_t* e, uint64_t offload_mask, int tier, uint32_t flags) {
                     rc = publish_gathered(p0 + np);
                     if (rc != FMA_OK) return rc;
                 }
+            } else if (packed) {  // STAGED + PACKED: K4 gather+encode -> ring slot (stored pages back to back) -> one D2H per slot
+                rc = ensure_ring(e, W);
+                if (rc != FMA_OK) return rc;
+                struct Slot { size_t p0, np; uint64_t bytes; };
+                std::vector<Slot> slots;
+                for (size_t p = 0; p < n_pages;) {
+                    Slot sl{p, 0, 0};
+                    while (p < n_pages && sl.bytes + e->img_bytes[p] <= e->ring_slot_bytes) {
+                        sl.bytes += e->img_bytes[p];
+                        ++sl.np;
+                        ++p;
+                    }
+                    if (!sl.np) return fail(FMA_EINVAL, "ring slot of %zu bytes cannot hold one page", e->ring_slot_bytes);
+                    slots.push_back(sl);
+                }
+                for (size_t c = 0; c < slots.size(); ++c)
+                    for (size_t p = slots[c].p0; p < slots[c].p0 + slots[c].np; ++p) {
+                        fma_k_pack_desc& d = e->h_pdesc[p];
+                        d.src = e->h_tab[p];
+                        d.dst = (uint64_t)(uintptr_t)e->ring[c % e->n_ring] + (e->img_off[p] - e->img_off[slots[c].p0]);
+                        d.mode = e->img_bytes[p] == FMA_PAGE_BYTES ? FMA_K_PACK_RAW : FMA_K_PACK_BF16;
+                        d.pad = 0;
+                    }
+                uint32_t* d_err = e->d_psize + e->pdesc_cap;
+                RT(cudaMemcpyAsync(e->d_pdesc, e->h_pdesc, n_pages * sizeof(fma_k_pack_desc), cudaMemcpyHostToDevice, e->ks));
+                RT(cudaMemsetAsync(d_err, 0, sizeof(uint32_t), e->ks));
+                for (size_t c = 0; c < slots.size(); ++c) {
+                    const Slot& sl = slots[c];
+                    const int slot = (int)(c % e->n_ring);
+                    cudaStream_t cstream = e->cs[c % e->n_cs];
+                    if (c >= (size_t)e->n_ring) RT(cudaStreamWaitEvent(e->ks, e->ev_ring_free[slot], 0));
+                    rc = kt.begin();
+                    if (rc != FMA_OK) return rc;
+                    RT(fma_k_launch_pack(e->d_pdesc + sl.p0, (uint32_t)sl.np, d_err, e->ks));
+                    rc = kt.end((uint64_t)sl.np * FMA_PAGE_BYTES + sl.bytes);
+                    if (rc != FMA_OK) return rc;
+                    RT(cudaEventRecord(e->ev_ring_full[slot], e->ks));
+                    RT(cudaStreamWaitEvent(cstream, e->ev_ring_full[slot], 0));
+                    RT(cudaMemcpyAsync(store + e->img_off[sl.p0], e->ring[slot], sl.bytes, cudaMemcpyDefault, cstream));
+                    if (c > 0) RT(cudaStreamWaitEvent(cstream, e->ev_ring_free[(c - 1) % e->n_ring], 0));  // same chaining as below
+                    RT(cudaEventRecord(e->ev_ring_free[slot], cstream));
+                    ++copy_ops;
+                    rc = publish_consumed((uint64_t)(sl.p0 + sl.np) * FMA_PAGE_BYTES, cstream);
+                    if (rc != FMA_OK) return rc;
+                }
             } else {  // STAGED: K1 gather -> HBM ring slot -> copy engine D2H
                 rc = ensure_ring(e, W);
                 if (rc != FMA_OK) return rc;
@@ -1233,6 +1373,12 @@ int do_sleep(fma_engine_t* e, uint64_t offload_mask, int tier, uint32_t flags) {
         if (rc != FMA_OK) return rc;
         rc = kt.collect();
         if (rc != FMA_OK) return rc;
+        if (packed) {  // K4 counts pages that no longer fit the form the probe chose (weights written during the sleep)
+            RT(cudaMemcpyAsync(e->h_psize + e->pdesc_cap, e->d_psize + e->pdesc_cap, sizeof(uint32_t), cudaMemcpyDeviceToHost, e->ks));
+            RT(cudaStreamSynchronize(e->ks));
+            if (e->h_psize[e->pdesc_cap])
+                return fail(FMA_EINTEGRITY, "%u page(s) changed between the pack probe and the pack: weights were written during sleep", e->h_psize[e->pdesc_cap]);
+        }
         if (env_int("FMA_RING_PERSIST", 0) == 0 || e->ring_attached) release_ring(e);  // while the unmapper finishes its last ranges
     }
     un.finish();
@@ -1329,6 +1475,10 @@ int do_wake(fma_engine_t* e, uint64_t tag_mask, uint32_t flags) {
     }
     const int tier = e->image_tier;
     int mode = resolve_mode(e, tier);
+    // A PACKED image can only be read by K5: through the staging ring, or (no HBM for a ring) straight from the
+    // mapped pinned store.
+    const bool packed = e->image_packed && tier == FMA_TIER_HOST;
+    if (packed) mode = FMA_MODE_STAGED;
 
     // Staging ring.  Steady state: the ring is its OWN small run (2 x 512 MiB) placed right after the first backed-up
     // run at the arena's bump pointer and mapped FIRST — a 1 GiB cuMemCreate/Map/SetAccess costs ~0.2 ms, the H2D
@@ -1489,7 +1639,110 @@ int do_wake(fma_engine_t* e, uint64_t tag_mask, uint32_t flags) {
         if (tier == FMA_TIER_HOST && mode == FMA_MODE_KERNEL && !e->host.dev_alias)
             WAKE_CHECK(fail(FMA_ECUDA, "host store has no device alias for zero-copy mode"));
         WAKE_CHECK(timer.begin());
-        if (mode == FMA_MODE_DIRECT) {
+        if (packed) {
+            // ---- PACKED image: H2D of the stored pages (0.758 of the bytes) -> ring slot -> K5 decode + scatter ----
+            const bool zero_copy = mode != FMA_MODE_STAGED;  // no ring could be had: K5 reads the pinned store over PCIe
+            if (zero_copy && !e->host.dev_alias) WAKE_CHECK(fail(FMA_ENOMEM, "no HBM for a staging ring and the host store has no device alias: a packed image cannot be woken"));
+            struct Dst { uint64_t packed_off; size_t w; };
+            std::vector<Dst> d;
+            for (size_t w = 0; w < with_backup.size(); ++w) d.push_back(Dst{e->segs[with_backup[w]].packed_off, w});
+            std::sort(d.begin(), d.end(), [](const Dst& a, const Dst& b) { return a.packed_off < b.packed_off; });
+            const size_t n_pages = W / FMA_PAGE_BYTES;
+            WAKE_CHECK(ensure_pack_bufs(e, n_pages));
+            std::vector<size_t> need_item(n_pages);
+            std::vector<uint64_t> soff(n_pages), dsts(n_pages);
+            std::vector<uint32_t> sbytes(n_pages);
+            size_t p = 0;
+            for (const Dst& x : d) {
+                const Segment& s = e->segs[with_backup[x.w]];
+                for (size_t o = 0; o < s.bytes; o += FMA_PAGE_BYTES, ++p) {
+                    const size_t lp = (size_t)((s.packed_off + o) / FMA_PAGE_BYTES);
+                    if (lp >= e->img_off.size()) WAKE_CHECK(fail(FMA_ESTATE, "segment at image offset %llu is outside the packed image's page table", (unsigned long long)(s.packed_off + o)));
+                    soff[p] = e->img_off[lp];
+                    sbytes[p] = e->img_bytes[lp];
+                    dsts[p] = (uint64_t)s.va + o;
+                    need_item[p] = seg_run[with_backup[x.w]] + 1;
+                }
+            }
+            uint32_t* d_err = e->d_psize + e->pdesc_cap;
+            WAKE_RT(cudaMemsetAsync(d_err, 0, sizeof(uint32_t), e->ks));
+            if (!zero_copy) {
+                if (ring_run) {
+                    int mrc0 = wait_mapped(1);
+                    if (mrc0 != FMA_OK) WAKE_CHECK(fail(mrc0, "%s", prog.msg));
+                } else {
+                    WAKE_CHECK(ensure_ring(e, W));
+                }
+                struct Slot { size_t p0, np; uint64_t bytes; };
+                std::vector<Slot> slots;  // pages that are adjacent in the store and fit one ring slot
+                for (size_t q = 0; q < n_pages;) {
+                    Slot sl{q, 0, 0};
+                    while (q < n_pages && sl.bytes + sbytes[q] <= e->ring_slot_bytes && (sl.np == 0 || soff[q] == soff[q - 1] + sbytes[q - 1])) {
+                        sl.bytes += sbytes[q];
+                        ++sl.np;
+                        ++q;
+                    }
+                    if (!sl.np) WAKE_CHECK(fail(FMA_EINVAL, "ring slot of %zu bytes cannot hold one page", e->ring_slot_bytes));
+                    slots.push_back(sl);
+                }
+                for (size_t c = 0; c < slots.size(); ++c)
+                    for (size_t q = slots[c].p0; q < slots[c].p0 + slots[c].np; ++q) {
+                        fma_k_pack_desc& pd = e->h_pdesc[q];
+                        pd.src = (uint64_t)(uintptr_t)e->ring[c % e->n_ring] + (soff[q] - soff[slots[c].p0]);
+                        pd.dst = dsts[q];
+                        pd.mode = sbytes[q] == FMA_PAGE_BYTES ? FMA_K_PACK_RAW : FMA_K_PACK_BF16;
+                        pd.pad = 0;
+                    }
+                WAKE_RT(cudaMemcpyAsync(e->d_pdesc, e->h_pdesc, n_pages * sizeof(fma_k_pack_desc), cudaMemcpyHostToDevice, e->ks));
+                for (size_t c = 0; c < slots.size(); ++c) {
+                    const Slot& sl = slots[c];
+                    const int slot = (int)(c % e->n_ring);
+                    cudaStream_t cstream = e->cs[c % e->n_cs];
+                    if (c >= (size_t)e->n_ring) WAKE_RT(cudaStreamWaitEvent(cstream, e->ev_ring_free[slot], 0));
+                    WAKE_RT(cudaMemcpyAsync(e->ring[slot], store + soff[sl.p0], sl.bytes, cudaMemcpyDefault, cstream));
+                    if (!copy_ops) first_copy_delay = now_s() - t_entry;
+                    ++copy_ops;
+                    WAKE_RT(cudaEventRecord(e->ev_ring_full[slot], cstream));
+                    size_t need = 0;
+                    for (size_t q = sl.p0; q < sl.p0 + sl.np; ++q) need = std::max(need, need_item[q]);
+                    int mrc = wait_mapped(need);
+                    if (mrc != FMA_OK) WAKE_CHECK(fail(mrc, "%s", prog.msg));
+                    WAKE_RT(cudaStreamWaitEvent(e->ks, e->ev_ring_full[slot], 0));
+                    WAKE_CHECK(kt.begin());
+                    WAKE_RT(fma_k_launch_unpack(e->d_pdesc + sl.p0, (uint32_t)sl.np, d_err, e->ks));
+                    WAKE_CHECK(kt.end((uint64_t)sl.np * FMA_PAGE_BYTES + sl.bytes));
+                    WAKE_RT(cudaEventRecord(e->ev_ring_free[slot], e->ks));
+                }
+            } else {
+                const uint64_t sbase = (uint64_t)(uintptr_t)e->host.dev_alias;
+                for (size_t q = 0; q < n_pages; ++q) {
+                    fma_k_pack_desc& pd = e->h_pdesc[q];
+                    pd.src = sbase + soff[q];
+                    pd.dst = dsts[q];
+                    pd.mode = sbytes[q] == FMA_PAGE_BYTES ? FMA_K_PACK_RAW : FMA_K_PACK_BF16;
+                    pd.pad = 0;
+                }
+                WAKE_RT(cudaMemcpyAsync(e->d_pdesc, e->h_pdesc, n_pages * sizeof(fma_k_pack_desc), cudaMemcpyHostToDevice, e->ks));
+                const size_t batch_pages = std::max<size_t>(staged_slot(e) / FMA_PAGE_BYTES, 1);
+                for (size_t p0 = 0; p0 < n_pages;) {
+                    const size_t np = std::min(batch_pages, n_pages - p0);
+                    size_t need = 0;
+                    uint64_t stored = 0;
+                    for (size_t q = p0; q < p0 + np; ++q) {
+                        need = std::max(need, need_item[q]);
+                        stored += sbytes[q];
+                    }
+                    int mrc = wait_mapped(need);
+                    if (mrc != FMA_OK) WAKE_CHECK(fail(mrc, "%s", prog.msg));
+                    WAKE_CHECK(kt.begin());
+                    WAKE_RT(fma_k_launch_unpack(e->d_pdesc + p0, (uint32_t)np, d_err, e->ks));
+                    WAKE_CHECK(kt.end((uint64_t)np * FMA_PAGE_BYTES + stored));
+                    if (!copy_ops) first_copy_delay = now_s() - t_entry;
+                    ++copy_ops;
+                    p0 += np;
+                }
+            }
+        } else if (mode == FMA_MODE_DIRECT) {
             int k = 0;
             for (size_t w = 0; w < with_backup.size(); ++w) {
                 int mrc = wait_mapped(seg_run[with_backup[w]] + 1);
@@ -1596,6 +1849,11 @@ int do_wake(fma_engine_t* e, uint64_t tag_mask, uint32_t flags) {
         if (rc != FMA_OK) return rc;
         rc = kt.collect();
         if (rc != FMA_OK) return rc;
+        if (packed) {  // K5 counts stored pages it could not read (bad magic / count): the image is damaged
+            RT(cudaMemcpyAsync(e->h_psize + e->pdesc_cap, e->d_psize + e->pdesc_cap, sizeof(uint32_t), cudaMemcpyDeviceToHost, e->ks));
+            RT(cudaStreamSynchronize(e->ks));
+            if (e->h_psize[e->pdesc_cap]) return fail(FMA_EINTEGRITY, "%u stored page(s) of the packed image are malformed", e->h_psize[e->pdesc_cap]);
+        }
         t_copy_end = now_s();
     }
     if (dbg_t)
@@ -1689,6 +1947,7 @@ int fma_engine_create(int device, const fma_config_t* cfg, fma_engine_t** out) {
     if (!e->cfg.chunk_bytes) e->cfg.chunk_bytes = (uint64_t)env_int("FMA_CHUNK_MIB", 0) << 20;
     if (!e->cfg.ring_slots) e->cfg.ring_slots = env_int("FMA_RING_SLOTS", 0);
     if (!e->cfg.map_threads) e->cfg.map_threads = env_int("FMA_MAP_THREADS", 0);
+    if (!e->cfg.pack) e->cfg.pack = env_int("FMA_PACK", 0);
     e->tma.tile_bytes = (uint32_t)env_int("FMA_TMA_TILE_KIB", (int)(e->tma.tile_bytes >> 10)) << 10;
     e->tma.stages = (uint32_t)env_int("FMA_TMA_STAGES", (int)e->tma.stages);
     e->tma.pipes = (uint32_t)env_int("FMA_TMA_PIPES", (int)e->tma.pipes);
@@ -1741,6 +2000,10 @@ int fma_engine_destroy(fma_engine_t* e) {
     if (e->h_desc) cudaFreeHost(e->h_desc);
     if (e->d_dig) cudaFree(e->d_dig);
     if (e->h_dig) cudaFreeHost(e->h_dig);
+    if (e->d_pdesc) cudaFree(e->d_pdesc);
+    if (e->h_pdesc) cudaFreeHost(e->h_pdesc);
+    if (e->d_psize) cudaFree(e->d_psize);
+    if (e->h_psize) cudaFreeHost(e->h_psize);
     for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
     for (cudaEvent_t ev : e->ev_stage) cudaEventDestroy(ev);
     for (cudaEvent_t ev : e->ev_load) cudaEventDestroy(ev);
@@ -2087,6 +2350,90 @@ int fma_op_page_digest(fma_engine_t* e, const uint64_t* pages, uint64_t base, co
     return FMA_OK;
 }
 
+// ---- PACKED image: page layout query + raw K4p / K4 / K5 ----------------------------------------------------
+int fma_image_pages(fma_engine_t* e, uint64_t* out_offsets, uint32_t* out_bytes, uint32_t cap) {
+    if (check_engine(e) != FMA_OK) return FMA_EINVAL;
+    bool asleep = false;
+    for (const Segment& s : e->segs)
+        if (s.has_backup && !s.mapped) asleep = true;
+    if (!asleep) return 0;
+    const size_t n = e->image_bytes / FMA_PAGE_BYTES;
+    for (size_t p = 0; p < n && p < cap; ++p) {
+        if (out_offsets) out_offsets[p] = e->image_packed ? e->img_off[p] : (uint64_t)p * FMA_PAGE_BYTES;
+        if (out_bytes) out_bytes[p] = e->image_packed ? e->img_bytes[p] : (uint32_t)FMA_PAGE_BYTES;
+    }
+    return (int)n;
+}
+
+int fma_op_pack_probe(fma_engine_t* e, const uint64_t* pages, uint64_t base, uint32_t n_pages, uint32_t* out_stored_bytes, float* out_ms) {
+    if (check_engine(e) != FMA_OK) return FMA_EINVAL;
+    if (!n_pages) return FMA_OK;
+    if (!out_stored_bytes) return fail(FMA_EINVAL, "out is NULL");
+    DeviceGuard guard(e->device);
+    int rc = ensure_tables(e, n_pages);
+    if (rc != FMA_OK) return rc;
+    rc = ensure_pack_bufs(e, n_pages);
+    if (rc != FMA_OK) return rc;
+    for (uint32_t p = 0; p < n_pages; ++p) e->h_tab[p] = pages ? pages[p] : base + (uint64_t)p * FMA_PAGE_BYTES;
+    RT(cudaMemcpyAsync(e->d_tab, e->h_tab, n_pages * sizeof(uint64_t), cudaMemcpyHostToDevice, e->ks));
+    RT(cudaEventRecord(e->ev_start, e->ks));
+    RT(fma_k_launch_pack_probe(e->d_tab, n_pages, e->d_psize, e->ks));
+    RT(cudaEventRecord(e->ev_end, e->ks));
+    RT(cudaMemcpyAsync(e->h_psize, e->d_psize, n_pages * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->ks));
+    RT(cudaStreamSynchronize(e->ks));
+    e->st.total_kernel_launches += 1;
+    memcpy(out_stored_bytes, e->h_psize, n_pages * sizeof(uint32_t));
+    if (out_ms) RT(cudaEventElapsedTime(out_ms, e->ev_start, e->ev_end));
+    return FMA_OK;
+}
+
+// shared by fma_op_pack / fma_op_unpack: stored pages back to back from store_base, device pages from a table or a base
+static int run_pack_op(fma_engine_t* e, bool unpack, const uint64_t* dev_pages, uint64_t dev_base, uint64_t store_base,
+                const uint32_t* stored_bytes, uint32_t n_pages, float* out_ms) {
+    if (check_engine(e) != FMA_OK) return FMA_EINVAL;
+    if (!n_pages) return FMA_OK;
+    if (!stored_bytes) return fail(FMA_EINVAL, "stored_bytes is NULL");
+    DeviceGuard guard(e->device);
+    int rc = ensure_pack_bufs(e, n_pages);
+    if (rc != FMA_OK) return rc;
+    uint64_t off = 0;
+    for (uint32_t p = 0; p < n_pages; ++p) {
+        if (stored_bytes[p] != FMA_K_PACKED_PAGE_BYTES && stored_bytes[p] != FMA_PAGE_BYTES)
+            return fail(FMA_EINVAL, "stored size %u of page %u is neither packed nor raw", stored_bytes[p], p);
+        const uint64_t dev = dev_pages ? dev_pages[p] : dev_base + (uint64_t)p * FMA_PAGE_BYTES;
+        fma_k_pack_desc& d = e->h_pdesc[p];
+        d.src = unpack ? store_base + off : dev;
+        d.dst = unpack ? dev : store_base + off;
+        d.mode = stored_bytes[p] == FMA_PAGE_BYTES ? FMA_K_PACK_RAW : FMA_K_PACK_BF16;
+        d.pad = 0;
+        off += stored_bytes[p];
+    }
+    uint32_t* d_err = e->d_psize + e->pdesc_cap;
+    RT(cudaMemcpyAsync(e->d_pdesc, e->h_pdesc, n_pages * sizeof(fma_k_pack_desc), cudaMemcpyHostToDevice, e->ks));
+    RT(cudaMemsetAsync(d_err, 0, sizeof(uint32_t), e->ks));
+    RT(cudaEventRecord(e->ev_start, e->ks));
+    if (unpack) RT(fma_k_launch_unpack(e->d_pdesc, n_pages, d_err, e->ks));
+    else RT(fma_k_launch_pack(e->d_pdesc, n_pages, d_err, e->ks));
+    RT(cudaEventRecord(e->ev_end, e->ks));
+    RT(cudaMemcpyAsync(e->h_psize + e->pdesc_cap, d_err, sizeof(uint32_t), cudaMemcpyDeviceToHost, e->ks));
+    RT(cudaStreamSynchronize(e->ks));
+    e->st.total_kernel_launches += 1;
+    if (out_ms) RT(cudaEventElapsedTime(out_ms, e->ev_start, e->ev_end));
+    if (e->h_psize[e->pdesc_cap])
+        return fail(FMA_EINTEGRITY, "%u page(s) could not be %s", e->h_psize[e->pdesc_cap], unpack ? "decoded (malformed stored page)" : "coded (more exceptions than the probe saw)");
+    return FMA_OK;
+}
+
+int fma_op_pack(fma_engine_t* e, const uint64_t* src_pages, uint64_t src_base, uint64_t dst_base, const uint32_t* stored_bytes,
+                uint32_t n_pages, float* out_ms) {
+    return run_pack_op(e, false, src_pages, src_base, dst_base, stored_bytes, n_pages, out_ms);
+}
+
+int fma_op_unpack(fma_engine_t* e, uint64_t src_base, const uint32_t* stored_bytes, const uint64_t* dst_pages, uint64_t dst_base,
+                  uint32_t n_pages, float* out_ms) {
+    return run_pack_op(e, true, dst_pages, dst_base, src_base, stored_bytes, n_pages, out_ms);
+}
+
 int fma_scratch_alloc(fma_engine_t* e, size_t bytes, uint64_t* out_dev_ptr) {
     if (check_engine(e) != FMA_OK) return FMA_EINVAL;
     if (!out_dev_ptr) return fail(FMA_EINVAL, "out is NULL");
@@ -2277,6 +2624,7 @@ int fma_image_export(fma_engine_t* e, int* out_fd) {
     if (!out_fd) return fail(FMA_EINVAL, "out_fd is NULL");
     if (e->host.fd < 0 || !e->host.base) return fail(FMA_ESTATE, "the host store is not shareable (set FMA_HOST_STORE_SHM=1 before the first sleep)");
     if (e->image_tier != FMA_TIER_HOST) return fail(FMA_ESTATE, "no host-tier image");
+    if (e->image_packed) return fail(FMA_ESTATE, "a PACKED image cannot be exported yet (its page table is not part of the descriptor)");
     std::vector<const Segment*> segs;
     for (const Segment& s : e->segs)
         if (s.has_backup && s.backup_tier == FMA_TIER_HOST && !s.mapped) segs.push_back(&s);
@@ -2399,6 +2747,9 @@ int fma_set_option(fma_engine_t* e, const char* key, int64_t value) {
     } else if (k == "map_threads") {
         if (value < 1 || value > 8) return fail(FMA_EINVAL, "map_threads must be 1..8");
         e->cfg.map_threads = (int32_t)value;
+    } else if (k == "pack") {
+        if (value != 0 && value != 1) return fail(FMA_EINVAL, "pack must be 0 or 1");
+        e->cfg.pack = (int32_t)value;
     } else if (k == "tma_tile_bytes") {
         if (value < 1024 || (FMA_PAGE_BYTES % (size_t)value) != 0 || value % 16) return fail(FMA_EINVAL, "bad tma tile %lld", (long long)value);
         e->tma.tile_bytes = (uint32_t)value;
@@ -2439,8 +2790,11 @@ int fma_stats(fma_engine_t* e, fma_stats_t* out) {
         out->hbm_mapped_bytes = mapped;
     }
     out->hbm_aux_bytes = (e->ring_attached ? 0 : (uint64_t)e->n_ring * e->ring_slot_bytes) + 2 * e->d_tab_cap * sizeof(uint64_t) +
-                         e->desc_cap * (sizeof(fma_k_page_desc) + sizeof(uint64_t));
+                         e->desc_cap * (sizeof(fma_k_page_desc) + sizeof(uint64_t)) +
+                         e->pdesc_cap * (sizeof(fma_k_pack_desc) + sizeof(uint32_t));
     out->parked_bytes = e->park.cap;
+    out->image_packed = e->image_packed ? 1 : 0;
+    out->image_store_bytes = e->image_store_bytes;
     return FMA_OK;
 }
 

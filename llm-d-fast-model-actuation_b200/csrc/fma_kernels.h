@@ -30,3 +30,21 @@ cudaError_t fma_k_launch_page_digest(const fma_k_page_desc* pages, uint32_t n_pa
                                      cudaStream_t stream);
 // K0
 cudaError_t fma_k_launch_fill(const fma_k_page_desc* pages, uint32_t n_pages, uint64_t seed, cudaStream_t stream);
+
+// ---- PACKED host image (fma_pack_kernels.cu; format in fma_codec.h) -------------------------------------------
+#define FMA_K_PACK_RAW 0     // page stored verbatim (2 MiB)
+#define FMA_K_PACK_BF16 1    // page stored in the "FMP4" code (fma_codec::kPackedBytes)
+#define FMA_K_PACKED_PAGE_BYTES ((3u << 19) + (16u << 10))
+
+struct fma_k_pack_desc {
+    uint64_t src;   // K4: device address of the 2 MiB page          K5: address of the stored page (ring slot / store alias)
+    uint64_t dst;   // K4: where the stored page goes (ring slot)    K5: device address of the 2 MiB page
+    uint32_t mode;  // FMA_K_PACK_*
+    uint32_t pad;
+};
+
+// K4p: out_bytes[p] = stored size of page p (FMA_K_PACKED_PAGE_BYTES, or FMA_K_PAGE_BYTES when it has to stay raw)
+cudaError_t fma_k_launch_pack_probe(const uint64_t* src_tab, uint32_t n_pages, uint32_t* out_bytes, cudaStream_t stream);
+// K4 / K5: *err_count (device, zeroed by the caller) counts pages that could not be coded / decoded
+cudaError_t fma_k_launch_pack(const fma_k_pack_desc* descs, uint32_t n_pages, uint32_t* err_count, cudaStream_t stream);
+cudaError_t fma_k_launch_unpack(const fma_k_pack_desc* descs, uint32_t n_pages, uint32_t* err_count, cudaStream_t stream);

@@ -18,6 +18,7 @@ class EngineConfig:
     ring_slots: int = 0
     map_threads: int = 0
     numa_bind: int = -1
+    pack: int = 0            # 1 = PACKED host image (lossless bf16 page code, csrc/fma_codec.h)
 
     def to_c(self) -> L.fma_config_t:
         c = L.fma_config_t()
@@ -25,6 +26,7 @@ class EngineConfig:
         c.mode, c.kernel, c.copy_streams = self.mode, self.kernel, self.copy_streams
         c.chunk_bytes, c.ring_slots, c.map_threads, c.numa_bind = (
             self.chunk_bytes, self.ring_slots, self.map_threads, self.numa_bind)
+        c.pack = self.pack
         return c
 
 
@@ -216,6 +218,35 @@ class Engine:
         ms = C.c_float()
         check(self._lib.fma_op_page_digest(self._h, pp, base, fw, n_pages, out, C.byref(ms)))
         return [int(x) for x in out], float(ms.value)
+
+    # -- PACKED image ---------------------------------------------------------------------
+    def image_pages(self) -> tuple[list[int], list[int]]:
+        """(store offset, stored bytes) of every 2 MiB page of the sleeping image, in image order."""
+        n = check(self._lib.fma_image_pages(self._h, None, None, 0))
+        off, nb = (C.c_uint64 * max(n, 1))(), (C.c_uint32 * max(n, 1))()
+        check(self._lib.fma_image_pages(self._h, off, nb, n))
+        return [int(off[i]) for i in range(n)], [int(nb[i]) for i in range(n)]
+
+    def op_pack_probe(self, n_pages: int, pages: Sequence[int] | None = None, base: int = 0) -> tuple[list[int], float]:
+        pp = (C.c_uint64 * n_pages)(*pages) if pages is not None else None
+        out = (C.c_uint32 * n_pages)()
+        ms = C.c_float()
+        check(self._lib.fma_op_pack_probe(self._h, pp, base, n_pages, out, C.byref(ms)))
+        return [int(x) for x in out], float(ms.value)
+
+    def op_pack(self, stored_bytes: Sequence[int], dst_base: int, src_pages: Sequence[int] | None = None, src_base: int = 0) -> float:
+        n = len(stored_bytes)
+        sp = (C.c_uint64 * n)(*src_pages) if src_pages is not None else None
+        ms = C.c_float()
+        check(self._lib.fma_op_pack(self._h, sp, src_base, dst_base, (C.c_uint32 * n)(*stored_bytes), n, C.byref(ms)))
+        return float(ms.value)
+
+    def op_unpack(self, stored_bytes: Sequence[int], src_base: int, dst_pages: Sequence[int] | None = None, dst_base: int = 0) -> float:
+        n = len(stored_bytes)
+        dp = (C.c_uint64 * n)(*dst_pages) if dst_pages is not None else None
+        ms = C.c_float()
+        check(self._lib.fma_op_unpack(self._h, src_base, (C.c_uint32 * n)(*stored_bytes), dp, dst_base, n, C.byref(ms)))
+        return float(ms.value)
 
     def scratch_alloc(self, nbytes: int) -> int:
         out = C.c_uint64()

@@ -14,6 +14,9 @@
  *   - packed-image page gather / scatter (K1/K2)                      -> fma_oracle_gather/scatter
  *   - splitmix64 counter-based fill (K0)                              -> fma_oracle_fill
  *   - position-sensitive 64-bit digest (K3)                           -> fma_oracle_digest
+ *   - the "FMP4" page code of packed host images (K4/K5; format spec in
+ *     llm-d-fast-model-actuation_b200/csrc/fma_codec.h, restated here value by value,
+ *     independently of that header)                                   -> fma_oracle_pack_page/unpack_page
  *
  * PARITY PINNING: the reference's own tests hold no golden vector for this path (SURVEY.md
  * §8c: vLLM is MagicMock'ed, test_launcher.py:32-38).  Pins used instead:
@@ -42,6 +45,14 @@ uint64_t fma_oracle_digest(const void* src, uint64_t n_bytes, uint64_t first_wor
 /* K1: dst + p*PAGE <- src_pages[p]  ;  K2: dst_pages[p] <- src + p*PAGE. */
 void fma_oracle_gather(const void* const* src_pages, uint32_t n_pages, void* dst);
 void fma_oracle_scatter(const void* src, void* const* dst_pages, uint32_t n_pages);
+
+/* "FMP4" page code.  pack: 2 MiB page -> stored page; returns the stored size: FMA_ORACLE_PACKED_BYTES, or
+ * FMA_ORACLE_PAGE_BYTES when the page needs more than 2048 exceptions and is stored verbatim.  Exceptions are
+ * emitted in increasing index order; bytes of the stored page the format leaves unspecified are zero.
+ * unpack: inverse; returns 0, or -1 if the stored page is malformed (bad size / magic / count). */
+#define FMA_ORACLE_PACKED_BYTES ((size_t)((3u << 19) + (16u << 10)))
+uint32_t fma_oracle_pack_page(const void* page, void* stored);
+int      fma_oracle_unpack_page(const void* stored, uint32_t stored_bytes, void* page);
 
 /* ---- restatement of the reference hot loops over a CPU stand-in for device memory ---- */
 typedef struct fma_oracle_seg {

@@ -48,8 +48,40 @@ def lib() -> C.CDLL:
         l.fma_oracle_sleep.argtypes = [C.POINTER(seg_t), C.c_uint32, C.c_uint64]
         l.fma_oracle_wake.restype = C.c_uint64
         l.fma_oracle_wake.argtypes = [C.POINTER(seg_t), C.c_uint32, C.c_uint64, C.c_uint8]
+        l.fma_oracle_pack_page.restype = C.c_uint32
+        l.fma_oracle_pack_page.argtypes = [C.c_void_p, C.c_void_p]
+        l.fma_oracle_unpack_page.restype = C.c_int
+        l.fma_oracle_unpack_page.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
         _lib = l
     return _lib
+
+
+PACKED_PAGE = (3 << 19) + (16 << 10)   # stored size of a page in the "FMP4" code (csrc/fma_codec.h)
+
+
+def pack_page(page: np.ndarray) -> np.ndarray:
+    """Stored form of one 2 MiB page: PACKED_PAGE bytes in the FMP4 code, or the page verbatim (PAGE bytes)."""
+    b = np.ascontiguousarray(page).view(np.uint8)
+    assert b.size == PAGE
+    out = np.empty(PAGE, dtype=np.uint8)
+    n = int(lib().fma_oracle_pack_page(b.ctypes.data, out.ctypes.data))
+    return out[:n].copy()
+
+
+def unpack_page(stored: np.ndarray) -> np.ndarray:
+    b = np.ascontiguousarray(stored).view(np.uint8)
+    out = np.empty(PAGE, dtype=np.uint8)
+    if lib().fma_oracle_unpack_page(b.ctypes.data, b.size, out.ctypes.data) != 0:
+        raise ValueError("malformed stored page")
+    return out
+
+
+def bf16_weights(n_values: int, seed: int, scale: float = 1e-3) -> np.ndarray:
+    """uint16 bit patterns of bf16 values ~ U(-scale, scale) (what vLLM's dummy loader fills parameters with,
+    vllm:model_executor/model_loader/weight_utils.py:1451-1471), truncated from float32."""
+    rng = np.random.default_rng(seed)
+    f = rng.uniform(-scale, scale, n_values).astype(np.float32)
+    return (f.view(np.uint32) >> 16).astype(np.uint16)
 
 
 def splitmix64(seed: int, k: int) -> int:

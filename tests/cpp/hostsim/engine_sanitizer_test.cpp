@@ -1,6 +1,7 @@
 // Drives the engine's C-ABI on the host simulation under ThreadSanitizer / AddressSanitizer (built and run by
 // tests/test_engine_hostsim.py).  Scenario: load a table, sleep/wake in every mode, tag-selective wake, free inside a
-// merged unit, hot swap of two engines (sleep and wake concurrently), cold load from a file, failed wake + retry.
+// merged unit, hot swap of two engines (sleep and wake concurrently), cold load from a file, failed wake + retry,
+// PACKED host images (sleep/wake, failed sleep, swap).
 #include <cassert>
 #include <cstdio>
 #include <cstdlib>
@@ -109,6 +110,53 @@ int main() {
             OK(fma_sleep(a, 1ull << w, FMA_TIER_HOST, FMA_FLAG_VERIFY));     // and the engine still sleeps normally afterwards
             OK(fma_wake(a, 0, FMA_FLAG_VERIFY));
         }
+        OK(fma_set_option(a, "mode", FMA_MODE_AUTO));
+    }
+
+    // PACKED host image: bf16-looking weights in segments 0/1 (packable), the others stay splitmix noise (raw pages);
+    // sleep/wake with the option on, a failed packed sleep (D2H refuses) followed by a wake, and a hot swap of a packed image
+    {
+        std::vector<uint16_t> vals(16 * P / 2);
+        uint32_t x = 12345;
+        for (size_t i = 0; i < vals.size(); ++i) {
+            x = x * 1664525u + 1013904223u;
+            vals[i] = (uint16_t)(((x >> 31) << 15) | ((118u + ((x >> 8) % 9u)) << 7) | ((x >> 16) & 0x7F));   // exponents 118..126
+        }
+        vals[77] = 0; vals[1000] = 0x0085;                                  // a zero and a far-below-range value (exception)
+        OK(fma_segment_write(a, 0, 0, vals.data(), 16 * P));
+        OK(fma_segment_write(a, 1, 0, vals.data(), 3 * P));
+        auto before = digests(a);
+        OK(fma_set_option(a, "mode", FMA_MODE_STAGED));
+        OK(fma_set_option(a, "chunk_bytes", 5 * P));
+        OK(fma_set_option(a, "pack", 1));
+        fma_stats_t st;
+        for (int rep = 0; rep < 2; ++rep) {
+            OK(fma_sleep(a, 1ull << w, FMA_TIER_HOST, FMA_FLAG_VERIFY));
+            OK(fma_stats(a, &st));
+            assert(st.image_packed == 1 && st.image_store_bytes < st.sleep_bytes_offloaded);
+            OK(fma_wake(a, 1ull << w, FMA_FLAG_VERIFY));
+            OK(fma_wake(a, 0, 0));
+            auto d = digests(a);
+            for (size_t i = 0; i + 1 < before.size(); ++i) assert(d[i] == before[i]);
+        }
+        hostsim_fail_memcpy_after(4);                                       // descriptor upload + a few slots, then a D2H fails
+        int src = fma_sleep(a, 1ull << w, FMA_TIER_HOST, 0);
+        hostsim_fail_memcpy_after(-1);
+        assert(src != 0);
+        OK(fma_wake(a, 0, 0));
+        {
+            auto d = digests(a);
+            for (size_t i = 0; i + 1 < before.size(); ++i) assert(d[i] == before[i]);
+        }
+        OK(fma_sleep(b, 1ull << wb, FMA_TIER_HOST, 0));
+        OK(fma_swap(a, 1ull << w, FMA_TIER_HOST, b, 0, FMA_FLAG_VERIFY));   // a sleeps packed while b wakes plain
+        OK(fma_swap(b, 1ull << wb, FMA_TIER_HOST, a, 0, FMA_FLAG_VERIFY));
+        OK(fma_wake(b, 0, 0));
+        {
+            auto d = digests(a);
+            for (size_t i = 0; i + 1 < before.size(); ++i) assert(d[i] == before[i]);
+        }
+        OK(fma_set_option(a, "pack", 0));
         OK(fma_set_option(a, "mode", FMA_MODE_AUTO));
     }
 
