@@ -16,6 +16,7 @@
 // tests run, and restated in oracle/fma_oracle.c.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 #include "fma_codec.h"
 #include "fma_kernels.h"
 
@@ -27,6 +28,10 @@ constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr int kU = 4;  // tiles in flight per warp
 
+// Streaming loads / stores: the image is touched once, so nothing is allocated in L1.  FMA_CUDA_EMU (tests/cpp/cuda_emu/,
+// test infrastructure) runs this file on a CPU and replaces the PTX by plain accesses; the launch macro likewise.
+#if !defined(FMA_CUDA_EMU)
+#define FMA_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 __device__ __forceinline__ uint4 ld_stream16(const void* p) {
     uint4 v;
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
@@ -51,6 +56,14 @@ __device__ __forceinline__ void st_stream8(void* p, uint32_t a, uint32_t b) {
 __device__ __forceinline__ void st_stream4(void* p, uint32_t a) {
     asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" ::"l"(p), "r"(a) : "memory");
 }
+#else
+inline uint4 ld_stream16(const void* p) { uint4 v; memcpy(&v, p, 16); return v; }
+inline uint2 ld_stream8(const void* p) { uint2 v; memcpy(&v, p, 8); return v; }
+inline uint32_t ld_stream4(const void* p) { uint32_t v; memcpy(&v, p, 4); return v; }
+inline void st_stream16(void* p, const uint4& v) { memcpy(p, &v, 16); }
+inline void st_stream8(void* p, uint32_t a, uint32_t b) { uint32_t t[2] = {a, b}; memcpy(p, t, 8); }
+inline void st_stream4(void* p, uint32_t a) { memcpy(p, &a, 4); }
+#endif
 
 // tile handled by (iteration, warp, u): consecutive warps take consecutive groups of kU tiles
 __device__ __forceinline__ uint32_t tile_of(uint32_t it, uint32_t warp, uint32_t u) { return (it * kWarps + warp) * kU + u; }
@@ -220,18 +233,18 @@ unsigned pack_grid(uint32_t n_pages) {
 
 cudaError_t fma_k_launch_pack_probe(const uint64_t* src_tab, uint32_t n_pages, uint32_t* out_bytes, cudaStream_t stream) {
     if (n_pages == 0) return cudaSuccess;
-    fma_k_pack_probe<<<pack_grid(n_pages), kThreads, 0, stream>>>(src_tab, n_pages, out_bytes);
+    FMA_LAUNCH(fma_k_pack_probe, pack_grid(n_pages), kThreads, 0, stream, src_tab, n_pages, out_bytes);
     return cudaGetLastError();
 }
 
 cudaError_t fma_k_launch_pack(const fma_k_pack_desc* descs, uint32_t n_pages, uint32_t* err_count, cudaStream_t stream) {
     if (n_pages == 0) return cudaSuccess;
-    fma_k_pack<<<pack_grid(n_pages), kThreads, 0, stream>>>(descs, n_pages, err_count);
+    FMA_LAUNCH(fma_k_pack, pack_grid(n_pages), kThreads, 0, stream, descs, n_pages, err_count);
     return cudaGetLastError();
 }
 
 cudaError_t fma_k_launch_unpack(const fma_k_pack_desc* descs, uint32_t n_pages, uint32_t* err_count, cudaStream_t stream) {
     if (n_pages == 0) return cudaSuccess;
-    fma_k_unpack<<<pack_grid(n_pages), kThreads, 0, stream>>>(descs, n_pages, err_count);
+    FMA_LAUNCH(fma_k_unpack, pack_grid(n_pages), kThreads, 0, stream, descs, n_pages, err_count);
     return cudaGetLastError();
 }

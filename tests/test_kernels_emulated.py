@@ -1,0 +1,29 @@
+"""The ACTUAL kernel source of the packed-image path (csrc/fma_pack_kernels.cu: K4p, K4, K5) executed on a CPU model of
+the CUDA execution hierarchy (tests/cpp/cuda_emu/cuda_emu.h: a CTA = blockDim OS threads, __syncthreads = barrier, warp
+collectives = warp barrier + scratch line, __shared__ = static) and compared with the oracle page by page.  Under
+ThreadSanitizer a missing __syncthreads() shows up as a data race (checked by mutation when this was written).
+
+Test infrastructure only; nothing here ships.  What it cannot show — the PTX load/store wrappers, coalescing, speed —
+is what the -m gpu tests and the ncu profiles are for."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMU = os.path.join(ROOT, "tests", "cpp", "cuda_emu")
+CSRC = os.path.join(ROOT, "llm-d-fast-model-actuation_b200", "csrc")
+
+
+@pytest.mark.parametrize("san,flags", [("plain", ["-O2"]), ("tsan", ["-O1", "-fsanitize=thread"])])
+def test_pack_kernels_source_on_the_cpu_execution_model(tmp_path, san, flags):
+    if not os.path.exists("/usr/local/cuda/include/cuda_runtime.h"):
+        pytest.skip("CUDA headers not installed")
+    exe = str(tmp_path / f"pack_emu_{san}")
+    subprocess.check_call(["g++", "-std=c++17", "-g", *flags, "-DFMA_CUDA_EMU", "-include", os.path.join(EMU, "cuda_emu.h"),
+                           "-I/usr/local/cuda/include", "-I" + CSRC, os.path.join(EMU, "pack_kernels_emu_test.cpp"),
+                           os.path.join(ROOT, "oracle", "fma_oracle.c"), "-o", exe, "-lpthread"])
+    r = subprocess.run([exe], env=dict(os.environ, TSAN_OPTIONS="halt_on_error=1"), capture_output=True, text=True, timeout=900)
+    out = r.stdout + r.stderr
+    assert r.returncode == 0 and "pack kernels (emulated) ok" in out, out[-3000:]
+    assert "WARNING: ThreadSanitizer" not in out, out[-3000:]
