@@ -138,18 +138,15 @@ def run_ours(args) -> None:
     mode = {"auto": L.FMA_MODE_AUTO, "direct": L.FMA_MODE_DIRECT, "staged": L.FMA_MODE_STAGED, "kernel": L.FMA_MODE_KERNEL}[args.mode]
     kernel = {"tma": L.FMA_KERNEL_TMA, "ldg": L.FMA_KERNEL_LDG}[args.kernel]
     cfg = fma_b200.EngineConfig(mode=mode, kernel=kernel, copy_streams=args.copy_streams,
-                                chunk_bytes=args.chunk_mib << 20, ring_slots=args.ring_slots, map_threads=args.map_threads)
+                                chunk_bytes=args.chunk_mib << 20, ring_slots=args.ring_slots, map_threads=args.map_threads,
+                                pack=args.pack)
     eng = fma_b200.Engine(local_rank, cfg)
     workload = workload_for(args.gpus, args.workload)
     table = W.allocation_table(workload, kv_cache_bytes=int(args.kv_gib * GiB))
     for s in table:
         eng.alloc(s.bytes, s.tag)
     Wb = W.weight_bytes(table)
-    first = 0
-    for i, s in enumerate(table):
-        if s.tag == "weights":
-            eng.fill(i, ranks.shard_seed(rank), first)   # K0, device side
-            first += s.bytes // 8
+    fill_weights(eng, table, ranks.shard_seed(rank), args.contents, torch)
     before = eng.digest_all(["weights"])    # K3
     if tier == L.FMA_TIER_HOST:
         eng.host_reserve(Wb)                # pre-pin off the critical path (the engine's load-time hook does this)
@@ -204,6 +201,7 @@ def run_ours(args) -> None:
     map_s = max_over_ranks(mean([r[1]["wake_map_seconds"] for r in rows]))
     unmap_s = max_over_ranks(mean([r[0]["sleep_unmap_seconds"] for r in rows]))
     st = eng.stats()
+    sum_store = sum_over_ranks(float(rows[-1][0]["image_store_bytes"]))   # bytes that crossed PCIe per step (== W unless packed)
 
     # Plain pinned cudaMemcpyAsync on THIS box/slot (nothing of ours): boxes of the pool differ by several GB/s, so at
     # N=1 the fraction of this ceiling says more about the engine than the fraction of the nominal 64 GB/s.
@@ -241,6 +239,8 @@ def run_ours(args) -> None:
                        "weights_gib_per_rank": round(Wb / GiB, 3), "kv_cache_gib_per_rank": args.kv_gib,
                        "segments_per_rank": len(table), "mode": ["auto", "direct", "staged", "kernel"][st["mode"]],
                        "kernel": args.kernel, "chunk_mib": args.chunk_mib or "default", "copy_streams": args.copy_streams or "default",
+                       "contents": "splitmix64 bytes (incompressible)" if args.contents == "prng" else "bf16 U(-1e-3, 1e-3) (vLLM dummy weights)",
+                       "pack": bool(st["image_packed"]) if args.pack else False,
                        "l2": "working set >> 126 MB L2 (no flush needed)", "parallelism": f"{world} independent ranks"},
             "wake_latency_s": round(wake_wall_m, 5), "wake_latency_s_median": round(wake_wall_med, 5),
             "e2e_median_gbs": round(W_total / wake_wall_med / 1e9, 3),   # value/e2e use the MEAN over the K steps
@@ -251,6 +251,7 @@ def run_ours(args) -> None:
             "bit_exact": bool(all_exact),
             "e2e": {"value": round(e2e_gbs, 3), "unit": "GB/s", "h2d_bytes_per_step": int(W_total),
                     "d2h_bytes_per_step": int(W_total),
+                    "link_bytes_per_step": int(sum_store),
                     "api": "fma_wake() through the C-ABI: VMM remap of weights+kv_cache, H2D from the pinned host store, K2, sync"},
             "gpu_launches": launches_total,
             "roofline": {"bound": "hbm", "kernel": "fma_k_page_copy_tma (K2 scatter, wake)" if args.kernel == "tma" else "fma_k_page_copy_ldg (K2)",
@@ -273,9 +274,104 @@ def run_ours(args) -> None:
             out["peer_tier"] = peer
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = reference_sample(args, workload)
+        if world == 1 and args.packed_extra and not args.pack and tier == L.FMA_TIER_HOST:
+            out["packed_image"] = packed_image_extra(args, workload)
         print(json.dumps(out), flush=True)
     eng.close()
     group.close()
+
+
+def fill_weights(eng, table, seed: int, contents: str, torch) -> None:
+    """Synthetic weights.  "prng": counter-based splitmix64 bytes (K0, on the device) — incompressible, the default.
+    "bf16": bf16 values ~ U(-1e-3, 1e-3), what vLLM's --load-format dummy fills parameters with
+    (vllm:model_executor/model_loader/weight_utils.py:1451-1471); one 1 GiB block generated on the GPU is written to
+    every segment at a rotating offset (contents repeat across segments: irrelevant for bandwidth, digests still bite)."""
+    first = 0
+    if contents == "prng":
+        for i, s in enumerate(table):
+            if s.tag == "weights":
+                eng.fill(i, seed, first)
+                first += s.bytes // 8
+        return
+    n = 512 << 20
+    gen = torch.Generator(device="cuda"); gen.manual_seed(seed)
+    src = torch.empty(n, dtype=torch.bfloat16, device="cuda").uniform_(-1e-3, 1e-3, generator=gen)
+    host = torch.empty(n, dtype=torch.bfloat16, pin_memory=True).copy_(src)
+    del src
+    blk = n * 2
+    for i, s in enumerate(table):
+        if s.tag != "weights":
+            continue
+        o = 0
+        while o < s.bytes:
+            start = ((i * 7919 + o // (2 << 20)) * (2 << 20)) % blk
+            m = min(s.bytes - o, blk - start)
+            eng.write_ptr(i, host.data_ptr() + start, m, offset=o)
+            o += m
+    del host
+
+
+def packed_image_extra(args, workload: str) -> dict:
+    """Extra evidence at N=1 (like peer_tier at N>1; never fails the main line): the same table filled with bf16 dummy
+    weights, slept and woken with the PACKED host image (config.pack: K4 encodes, K5 decodes, 0.758 of the bytes cross
+    PCIe).  Runs in its OWN process with a timeout so that nothing it does can disturb the numbers above."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--packed-child", "--workload", workload, "--kv-gib", str(args.kv_gib),
+           "--steps", "5", "--warmup", "3"]
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=dict(os.environ, FMA_BENCH_NO_CLOCKS="1"))
+        for line in reversed(r.stdout.strip().splitlines()):
+            if line.startswith("{"):
+                return json.loads(line)
+        return {"error": f"no result (rc {r.returncode}): {(r.stderr or r.stdout)[-300:]}"}
+    except subprocess.TimeoutExpired:
+        return {"error": "timed out after 240 s"}
+    except Exception as e:
+        return {"error": str(e)[:200]}
+
+
+def run_packed_child(args) -> None:
+    import torch
+
+    import fma_b200
+    from fma_b200 import _lib as L
+    from fma_b200 import workloads as W
+
+    torch.cuda.set_device(0)
+    eng = fma_b200.Engine(0, fma_b200.EngineConfig(pack=1))
+    workload = workload_for(1, args.workload)
+    table = W.allocation_table(workload, kv_cache_bytes=int(args.kv_gib * GiB))
+    for s in table:
+        eng.alloc(s.bytes, s.tag)
+    Wb = W.weight_bytes(table)
+    fill_weights(eng, table, 1234, "bf16", torch)
+    before = eng.digest_all(["weights"])
+    eng.host_reserve(Wb)
+    rows = []
+    for i in range(args.warmup + args.steps):
+        eng.sleep(["weights"]); s1 = eng.stats()
+        eng.wake(None); s2 = eng.stats()
+        if i >= args.warmup:
+            rows.append((s1, s2))
+    ok = eng.digest_all(["weights"]) == before
+    mean = lambda xs: sum(xs) / len(xs)
+    wake = mean([r[1]["wake_seconds"] for r in rows]); wake_dev = mean([r[1]["wake_copy_seconds"] for r in rows])
+    sleep = mean([r[0]["sleep_seconds"] for r in rows])
+    stored = rows[-1][0]["image_store_bytes"]
+    k5_s = sum(r[1]["kernel_seconds"] for r in rows); k5_b = sum(r[1]["kernel_bytes"] for r in rows)
+    k4_s = sum(r[0]["kernel_seconds"] for r in rows); k4_b = sum(r[0]["kernel_bytes"] for r in rows)
+    peak, _ = hbm_peak()
+    print(json.dumps({
+        "contents": "bf16 U(-1e-3, 1e-3) (vLLM dummy weights)", "image_packed": bool(rows[-1][0]["image_packed"]),
+        "bit_exact": bool(ok), "weights_gib": round(Wb / GiB, 3), "stored_gib": round(stored / GiB, 3), "stored_frac": round(stored / Wb, 4),
+        "wake_latency_s": round(wake, 5), "wake_latency_s_median": round(statistics.median([r[1]["wake_seconds"] for r in rows]), 5),
+        "sleep_latency_s": round(sleep, 5),
+        "e2e_effective_gbs": round(Wb / wake / 1e9, 3), "e2e_link_gbs": round(stored / wake / 1e9, 3),
+        "device_effective_gbs": round(Wb / wake_dev / 1e9, 3),
+        "k5_unpack_gbs": round(k5_b / k5_s / 1e9, 1) if k5_s > 0 else None, "k5_frac_of_hbm_peak": round(k5_b / k5_s / 1e9 / peak, 4) if k5_s > 0 else None,
+        "k4_pack_gbs": round(k4_b / k4_s / 1e9, 1) if k4_s > 0 else None,
+        "steps": args.steps, "warmup": args.warmup,
+        "note": "effective = weight bytes restored / time; link = bytes that crossed PCIe / time (bounded by the link)"}), flush=True)
+    eng.close()
 
 
 def pcie_ceiling_gbs(torch, nbytes: int = 2 << 30, reps: int = 3) -> float:
@@ -496,7 +592,14 @@ def main() -> None:
     ap.add_argument("--map-threads", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--peer-extra", type=int, default=1, help="at N>1 also measure the NVLink peer-HBM tier (reported under peer_tier)")
+    ap.add_argument("--contents", choices=["prng", "bf16"], default="prng", help="synthetic weights: incompressible bytes (default) or bf16 dummy weights")
+    ap.add_argument("--pack", type=int, default=0, help="1 = PACKED host image (lossless bf16 page code; pays off with --contents bf16)")
+    ap.add_argument("--packed-extra", type=int, default=1, help="at N=1 also measure the PACKED image on bf16 dummy weights in a child process (reported under packed_image)")
+    ap.add_argument("--packed-child", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.packed_child:
+        run_packed_child(args)
+        return
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3  # timing rules: >= 3 warm-up steps
     if args.impl == "reference":

@@ -59,3 +59,18 @@ def test_engine_scenario_under_sanitizers(tmp_path, san, flags):
     out = r.stdout + r.stderr
     assert r.returncode == 0 and "engine sanitizer scenario ok" in out, out[-3000:]
     assert "WARNING: ThreadSanitizer" not in out and "ERROR: AddressSanitizer" not in out and "runtime error:" not in out, out[-3000:]
+
+
+def test_bench_packed_image_child_runs_against_the_host_simulated_engine(hostsim_lib, oracle):
+    """bench.py's packed-image extra (its own process at N=1): fill with bf16 dummy weights, sleep/wake with config.pack,
+    digests before == after, 0.758 of the bytes stored.  torch is replaced by tests/stubs/torch (numpy)."""
+    import json
+
+    env = dict(os.environ, FMA_B200_LIB=hostsim_lib, FMA_HOSTSIM="1", HOSTSIM_DEVICES="1",
+               PYTHONPATH=os.path.join(ROOT, "tests", "stubs") + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--packed-child", "--workload", "tiny-llama-test",
+                        "--kv-gib", "0.03125", "--steps", "2", "--warmup", "1"], env=env, cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    assert out["bit_exact"] is True and out["image_packed"] is True
+    assert 0.75 < out["stored_frac"] < 0.80 and out["e2e_effective_gbs"] > out["e2e_link_gbs"] > 0
