@@ -293,7 +293,7 @@ def fill_weights(eng, table, seed: int, contents: str, torch) -> None:
                 eng.fill(i, seed, first)
                 first += s.bytes // 8
         return
-    n = 512 << 20
+    n = min(512 << 20, max(1 << 20, max(s.bytes for s in table if s.tag == "weights") // 2))   # values in the block (<= 1 GiB)
     gen = torch.Generator(device="cuda"); gen.manual_seed(seed)
     src = torch.empty(n, dtype=torch.bfloat16, device="cuda").uniform_(-1e-3, 1e-3, generator=gen)
     host = torch.empty(n, dtype=torch.bfloat16, pin_memory=True).copy_(src)

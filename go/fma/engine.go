@@ -78,6 +78,72 @@ func Swap(out *Engine, offloadMask uint64, in *Engine, wakeMask uint64) error {
 	return nil
 }
 
+// SetOption changes one knob of a live engine between operations ("mode", "pack", "chunk_bytes", ...: fma_set_option).
+// SetOption("pack", 1) turns on the PACKED host image: bf16 weight pages cross PCIe in a lossless 0.758x code.
+func (e *Engine) SetOption(key string, value int64) error {
+	cs := C.CString(key)
+	defer C.free(unsafe.Pointer(cs))
+	if rc := C.fma_set_option(e.h, cs, C.int64_t(value)); rc != 0 {
+		return lastErr(rc)
+	}
+	return nil
+}
+
+// HostReserve pins the host store ahead of the first sleep, off the critical path (the reference pins one buffer per
+// segment inside its sleep loop, vllm:device_allocator/cumem.py:204-209).
+func (e *Engine) HostReserve(bytes uint64) error {
+	if rc := C.fma_host_reserve(e.h, C.size_t(bytes)); rc != 0 {
+		return lastErr(rc)
+	}
+	return nil
+}
+
+// PeerReserve prepares a parking buffer in another GPU's HBM for the NVLink tier (BASELINE config 5).
+func (e *Engine) PeerReserve(peerDevice int, bytes uint64) error {
+	if rc := C.fma_peer_reserve(e.h, C.int(peerDevice), C.size_t(bytes)); rc != 0 {
+		return lastErr(rc)
+	}
+	return nil
+}
+
+// Free releases one segment (my_free of the pluggable allocator).
+func (e *Engine) Free(ptr uintptr) error {
+	if rc := C.fma_free(e.h, unsafe.Pointer(ptr)); rc != 0 {
+		return lastErr(rc)
+	}
+	return nil
+}
+
+// CurrentUsage mirrors CuMemAllocator.get_current_usage (cumem.py:310-318): bytes of all live segments.
+func (e *Engine) CurrentUsage() uint64 { return uint64(C.fma_current_usage(e.h)) }
+
+// LoadSpan is one byte range of a checkpoint file and the device address it lands at.
+type LoadSpan struct {
+	FileOffset, Bytes uint64
+	Dst               uintptr
+}
+
+// LoadFile streams byte ranges of one file into mapped segments through the pinned bounce ring and the copy engines
+// (the cold "load_model" path, SURVEY.md §8f-3).
+func (e *Engine) LoadFile(path string, spans []LoadSpan) (seconds float64, err error) {
+	if len(spans) == 0 {
+		return 0, nil
+	}
+	cs := C.CString(path)
+	defer C.free(unsafe.Pointer(cs))
+	cspans := make([]C.fma_load_span_t, len(spans))
+	for i, s := range spans {
+		cspans[i].file_offset = C.uint64_t(s.FileOffset)
+		cspans[i].bytes = C.uint64_t(s.Bytes)
+		cspans[i].dst = C.uint64_t(s.Dst)
+	}
+	var st C.fma_load_stats_t
+	if rc := C.fma_load_file(e.h, cs, &cspans[0], C.uint32_t(len(spans)), 0, &st); rc != 0 {
+		return 0, lastErr(rc)
+	}
+	return float64(st.seconds), nil
+}
+
 func (e *Engine) Stats() (C.fma_stats_t, error) {
 	var st C.fma_stats_t
 	if rc := C.fma_stats(e.h, &st); rc != 0 {

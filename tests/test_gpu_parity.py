@@ -483,7 +483,8 @@ def test_full_size_llama3_8b_roundtrip_properties(engine, oracle):
 
 # ---- image hand-over between processes (memfd host store).  Host-simulation only this round: the feature has not been
 # ---- run on a B200 yet (no GPU budget was left when it was written), so it must not gate the round-end GPU suite.
-_HOSTSIM_ONLY = pytest.mark.skipif(os.environ.get("FMA_HOSTSIM") != "1", reason="image hand-over is validated on the CUDA host simulation only so far")
+_HOSTSIM_ONLY = pytest.mark.skipif(os.environ.get("FMA_HOSTSIM") != "1" and os.environ.get("FMA_TEST_IMAGE_ON_GPU") != "1",
+                                   reason="image hand-over is validated on the CUDA host simulation only so far (set FMA_TEST_IMAGE_ON_GPU=1)")
 
 _ADOPT_CHILD = r"""
 import os, sys, json
