@@ -14,6 +14,7 @@ extern "C" unsigned long long hostsim_live_mapped_bytes();
 extern "C" unsigned long long hostsim_live_handles();
 extern "C" void hostsim_fail_create_after(long n);
 extern "C" void hostsim_fail_memcpy_after(long n);
+extern "C" void hostsim_malloc_limit(long long bytes);
 
 #define OK(x)                                                                          \
     do {                                                                               \
@@ -144,6 +145,19 @@ int main() {
         hostsim_fail_memcpy_after(-1);
         assert(src != 0);
         OK(fma_wake(a, 0, 0));
+        {
+            auto d = digests(a);
+            for (size_t i = 0; i + 1 < before.size(); ++i) assert(d[i] == before[i]);
+        }
+        // HBM too full for a staging ring at wake time: K5 reads the packed image straight from the mapped host store
+        OK(fma_sleep(a, 1ull << w, FMA_TIER_HOST, FMA_FLAG_VERIFY));
+        setenv("FMA_RING_ATTACH", "0", 1);
+        hostsim_malloc_limit(1 << 20);
+        OK(fma_wake(a, 0, FMA_FLAG_VERIFY));
+        OK(fma_stats(a, &st));
+        assert(st.mode != FMA_MODE_STAGED);
+        hostsim_malloc_limit(0);
+        unsetenv("FMA_RING_ATTACH");
         {
             auto d = digests(a);
             for (size_t i = 0; i + 1 < before.size(); ++i) assert(d[i] == before[i]);

@@ -154,6 +154,8 @@ extern "C" __attribute__((visibility("default"))) unsigned long long hostsim_liv
 }
 extern "C" __attribute__((visibility("default"))) void hostsim_fail_create_after(long n) { g_fail_create_after.store(n); }
 extern "C" __attribute__((visibility("default"))) void hostsim_fail_memcpy_after(long n) { g_fail_memcpy_after.store(n); }
+static std::atomic<long long> g_malloc_limit{0};  // > 0: cudaMalloc of more bytes fails ("HBM full": no staging ring)
+extern "C" __attribute__((visibility("default"))) void hostsim_malloc_limit(long long bytes) { g_malloc_limit.store(bytes); }
 
 extern "C" {
 cudaError_t cudaGetDeviceCount(int* n) { *n = device_count(); return cudaSuccess; }
@@ -165,7 +167,7 @@ cudaError_t cudaDeviceSynchronize(void) { return cudaSuccess; }
 cudaError_t cudaDeviceGetPCIBusId(char* buf, int len, int dev) { snprintf(buf, len, "0000:%02x:00.0", 0x10 + dev); return cudaSuccess; }
 cudaError_t cudaDeviceCanAccessPeer(int* can, int a, int b) { *can = (a != b && a < device_count() && b < device_count()); return cudaSuccess; }
 cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr, int) { *v = 148; return cudaSuccess; }
-cudaError_t cudaMalloc(void** p, size_t n) { *p = aligned_alloc(2u << 20, ((n + (2u << 20) - 1) / (2u << 20)) * (2u << 20)); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+cudaError_t cudaMalloc(void** p, size_t n) { if (g_malloc_limit.load() > 0 && (long long)n > g_malloc_limit.load()) { *p = nullptr; tl_last = cudaErrorMemoryAllocation; return cudaErrorMemoryAllocation; } *p = aligned_alloc(2u << 20, ((n + (2u << 20) - 1) / (2u << 20)) * (2u << 20)); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
 cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
 cudaError_t cudaHostAlloc(void** p, size_t n, unsigned) { *p = aligned_alloc(4096, ((n + 4095) / 4096) * 4096); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
 cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
