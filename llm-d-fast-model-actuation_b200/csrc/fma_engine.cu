@@ -1019,7 +1019,9 @@ int do_sleep(fma_engine_t* e, uint64_t offload_mask, int tier, uint32_t flags) {
         if (packed) e->image_bytes = W;  // the layout above is indexed by image page: valid from here on, also if the sleep fails
     }
     if (W) {
-        if (tier == FMA_TIER_HOST) {
+        if (tier == FMA_TIER_HOST && (flags & kFlagAdopt)) {
+            if (!e->host.base) return fail(FMA_ESTATE, "adopt without a store");  // the adopted store IS the image: never re-sized
+        } else if (tier == FMA_TIER_HOST) {
             rc = host_store_reserve(e, Wp);
             if (rc != FMA_OK) return rc;
             if (mode == FMA_MODE_KERNEL && !e->host.dev_alias) return fail(FMA_ECUDA, "host store has no device alias for zero-copy mode");
@@ -2624,15 +2626,17 @@ int fma_image_export(fma_engine_t* e, int* out_fd) {
     if (!out_fd) return fail(FMA_EINVAL, "out_fd is NULL");
     if (e->host.fd < 0 || !e->host.base) return fail(FMA_ESTATE, "the host store is not shareable (set FMA_HOST_STORE_SHM=1 before the first sleep)");
     if (e->image_tier != FMA_TIER_HOST) return fail(FMA_ESTATE, "no host-tier image");
-    if (e->image_packed) return fail(FMA_ESTATE, "a PACKED image cannot be exported yet (its page table is not part of the descriptor)");
     std::vector<const Segment*> segs;
     for (const Segment& s : e->segs)
         if (s.has_backup && s.backup_tier == FMA_TIER_HOST && !s.mapped) segs.push_back(&s);
     if (segs.empty()) return fail(FMA_ESTATE, "nothing is asleep in the host store");
     std::sort(segs.begin(), segs.end(), [](const Segment* a, const Segment* b) { return a->packed_off < b->packed_off; });
-    if (sizeof(ImageHeader) + segs.size() * sizeof(ImageSegDesc) > kImageTail) return fail(FMA_ENOMEM, "too many segments for the descriptor");
+    // version 2 = PACKED image: the per-page stored sizes follow the segment descriptors (offsets are their prefix sums)
+    const size_t n_img_pages = e->image_packed ? e->img_bytes.size() : 0;
+    if (sizeof(ImageHeader) + segs.size() * sizeof(ImageSegDesc) + sizeof(uint32_t) * (1 + n_img_pages) > kImageTail)
+        return fail(FMA_ENOMEM, "too many segments / pages for the descriptor");
     char* tail = static_cast<char*>(e->host.base) + e->host.cap;
-    ImageHeader hd{kImageMagic, 1, (uint32_t)segs.size(), e->image_bytes};
+    ImageHeader hd{kImageMagic, e->image_packed ? 2u : 1u, (uint32_t)segs.size(), e->image_bytes};
     memcpy(tail, &hd, sizeof(hd));
     for (size_t i = 0; i < segs.size(); ++i) {
         ImageSegDesc d;
@@ -2645,6 +2649,12 @@ int fma_image_export(fma_engine_t* e, int* out_fd) {
         d.tag_len = (uint32_t)std::min<size_t>(t.size(), sizeof(d.tag) - 1);
         memcpy(d.tag, t.data(), d.tag_len);
         memcpy(tail + sizeof(hd) + i * sizeof(d), &d, sizeof(d));
+    }
+    if (e->image_packed) {
+        char* pt = tail + sizeof(hd) + segs.size() * sizeof(ImageSegDesc);
+        const uint32_t np = (uint32_t)n_img_pages;
+        memcpy(pt, &np, sizeof(np));
+        memcpy(pt + sizeof(np), e->img_bytes.data(), n_img_pages * sizeof(uint32_t));
     }
     int fd = dup(e->host.fd);
     if (fd < 0) return fail(FMA_ENOMEM, "dup failed: %s", strerror(errno));
@@ -2675,7 +2685,28 @@ int fma_image_adopt(fma_engine_t* e, int fd, uint64_t tag_mask, uint32_t flags) 
     const char* tail = static_cast<const char*>(p) + cap;
     ImageHeader hd;
     memcpy(&hd, tail, sizeof(hd));
-    if (hd.magic != kImageMagic || hd.version != 1 || hd.image_bytes > cap) return bail(FMA_EINVAL, "image descriptor missing or corrupt");
+    if (hd.magic != kImageMagic || (hd.version != 1 && hd.version != 2) || (hd.version == 1 && hd.image_bytes > cap) ||
+        sizeof(ImageHeader) + (size_t)hd.n_segments * sizeof(ImageSegDesc) + sizeof(uint32_t) > kImageTail)
+        return bail(FMA_EINVAL, "image descriptor missing or corrupt");
+    std::vector<uint64_t> adopt_off;   // version 2: the PACKED image's page table
+    std::vector<uint32_t> adopt_bytes;
+    if (hd.version == 2) {
+        const char* pt = tail + sizeof(hd) + (size_t)hd.n_segments * sizeof(ImageSegDesc);
+        uint32_t np = 0;
+        memcpy(&np, pt, sizeof(np));
+        if ((uint64_t)np * FMA_PAGE_BYTES != hd.image_bytes || sizeof(ImageHeader) + (size_t)hd.n_segments * sizeof(ImageSegDesc) + sizeof(uint32_t) * (1 + (size_t)np) > kImageTail)
+            return bail(FMA_EINVAL, "packed image: page table does not match the image size");
+        adopt_bytes.resize(np);
+        adopt_off.resize(np);
+        memcpy(adopt_bytes.data(), pt + sizeof(np), (size_t)np * sizeof(uint32_t));
+        uint64_t total = 0;
+        for (uint32_t q = 0; q < np; ++q) {
+            if (adopt_bytes[q] != FMA_K_PACKED_PAGE_BYTES && adopt_bytes[q] != FMA_PAGE_BYTES) return bail(FMA_EINVAL, "packed image: bad stored page size");
+            adopt_off[q] = total;
+            total += adopt_bytes[q];
+        }
+        if (total > cap) return bail(FMA_EINVAL, "packed image: stored pages exceed the store");
+    }
     // the segments this engine would offload for tag_mask, in image order (same rule as fma_sleep)
     std::vector<size_t> order;
     for (size_t i = 0; i < e->segs.size(); ++i)
@@ -2716,6 +2747,12 @@ int fma_image_adopt(fma_engine_t* e, int fd, uint64_t tag_mask, uint32_t flags) 
     // release the device side exactly as a sleep would, without copying anything out
     int rc = do_sleep(e, tag_mask, FMA_TIER_HOST, (flags & ~FMA_FLAG_VERIFY) | kFlagAdopt);
     if (rc != FMA_OK) return rc;
+    if (hd.version == 2) {  // wake through K5 with the exporter's page table
+        e->image_packed = true;
+        e->image_store_bytes = adopt_off.empty() ? 0 : adopt_off.back() + adopt_bytes.back();
+        e->img_off = std::move(adopt_off);
+        e->img_bytes = std::move(adopt_bytes);
+    }
     for (size_t i = 0; i < ds.size(); ++i) {  // integrity data travels with the image: FMA_FLAG_VERIFY on wake checks it
         Segment& s = e->segs[order[i]];
         s.digest = ds[i].digest;

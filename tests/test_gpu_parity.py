@@ -503,7 +503,8 @@ print(json.dumps(eng.digest_all(["weights"])))
 
 
 @_HOSTSIM_ONLY
-def test_image_handover_to_another_engine_and_process(engine, oracle, monkeypatch, tmp_path):
+@pytest.mark.parametrize("pack", [0, 1])
+def test_image_handover_to_another_engine_and_process(engine, oracle, monkeypatch, tmp_path, pack):
     import subprocess
     import sys
 
@@ -514,10 +515,17 @@ def test_image_handover_to_another_engine_and_process(engine, oracle, monkeypatc
     monkeypatch.setenv("FMA_HOST_STORE_SHM", "1")
     table = _tiny_table()
     ptrs, ref = _load(engine, oracle, table)
+    if pack:                                                         # bf16-looking weights, handed over in the PACKED form
+        engine.set_option("mode", L.FMA_MODE_STAGED)
+        engine.set_option("pack", 1)
+        for k, i in enumerate(sorted(ref)):
+            ref[i] = np.resize(oracle.bf16_weights(1 << 20, 100 + k).view(np.uint8), table[i].bytes)
+            engine.write(i, ref[i].tobytes())
     want = engine.digest_all(["weights"])
     with pytest.raises(FmaError):
         engine.image_export()                                        # awake: nothing to hand over
     engine.sleep(["weights"], flags=L.FMA_FLAG_VERIFY)
+    assert engine.stats()["image_packed"] == pack
     fd = engine.image_export()
     try:
         # (1) another engine in this process adopts the image
@@ -525,7 +533,7 @@ def test_image_handover_to_another_engine_and_process(engine, oracle, monkeypatc
             for s in table:
                 other.alloc(s.bytes, s.tag)
             other.image_adopt(fd, ["weights"])
-            assert other.is_sleeping() and other.stats()["hbm_mapped_bytes"] == 0
+            assert other.is_sleeping() and other.stats()["hbm_mapped_bytes"] == 0 and other.stats()["image_packed"] == pack
             other.wake(None, flags=L.FMA_FLAG_VERIFY)
             assert other.digest_all(["weights"]) == want
             for i in ref:
