@@ -17,3 +17,11 @@ def register() -> None:
     from fma_b200 import cumem
 
     cumem.install_into_vllm()
+    try:                                   # --load-format fma: checkpoint files -> HBM through the engine's mover
+        from fma_b200 import vllm_loader
+
+        vllm_loader.register()
+    except Exception as e:                 # a vLLM without the loader registry: sleep/wake still works
+        import logging
+
+        logging.getLogger("fma_b200").warning("--load-format fma not registered: %s", e)

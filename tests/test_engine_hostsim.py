@@ -74,3 +74,43 @@ def test_bench_packed_image_child_runs_against_the_host_simulated_engine(hostsim
     out = json.loads(r.stdout.strip().splitlines()[-1])
     assert out["bit_exact"] is True and out["image_packed"] is True
     assert 0.75 < out["stored_frac"] < 0.80 and out["e2e_effective_gbs"] > out["e2e_link_gbs"] > 0
+
+
+def test_vllm_loader_streaming_core_against_the_host_simulated_engine(hostsim_lib, tmp_path):
+    """stream_tensors(): two safetensors files, small windows, a staging segment that grows, views that alias it, and a
+    drain() before every reuse — every tensor arrives with the file's bytes, in file order."""
+    code = r"""
+import ctypes, json, os, sys
+import numpy as np
+sys.path.insert(0, %r)
+import fma_b200
+from fma_b200 import loader, vllm_loader
+rng = np.random.default_rng(3)
+files, want = [], {}
+for f in range(2):
+    tensors = []
+    for i, n in enumerate([1000, 70000, 3 << 20, 12, 0, 5 << 20, 4096]):
+        name = f"f{f}.t{i}"
+        raw = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        tensors.append((name, "U8", (n,), raw)); want[name] = raw
+    path = os.path.join(%r, f"m-{f}.safetensors")
+    loader.write_safetensors(path, tensors); files.append(path)
+eng = fma_b200.Engine(0)
+drains, live = [0], []
+def view(ptr, off, t):
+    return (ptr + off, t.nbytes)
+def drain():
+    drains[0] += 1
+stats = {}
+got = {}
+for name, (addr, n) in vllm_loader.stream_tensors(eng, files, view, drain=drain, window_bytes=4 << 20, stats=stats):
+    got[name] = ctypes.string_at(addr, n)            # host simulation: device memory is host memory; consume before the next window
+assert list(got) == [k for k in want if len(want[k])], list(got)
+assert all(got[k] == want[k] for k in got)
+assert stats["windows"] >= 4 and drains[0] == stats["windows"] + 1 and stats["bytes"] >= sum(len(v) for v in want.values())
+assert eng.segment_count() == 0                      # the staging segment is gone
+print("ok")
+""" % (ROOT, str(tmp_path))
+    env = dict(os.environ, FMA_B200_LIB=hostsim_lib, FMA_HOSTSIM="1", HOSTSIM_DEVICES="1")
+    r = subprocess.run([sys.executable, "-c", code], env=env, cwd=ROOT, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, (r.stdout + r.stderr)[-3000:]
