@@ -93,7 +93,9 @@ typedef struct fma_config {
                                    0 = leave placement to the OS, -1 = default             */
     int32_t  pack;              /* 1 = PACKED host image: bf16 pages are stored in the lossless "FMP4" code
                                    (csrc/fma_codec.h, 0.758 of their size) by K4 on sleep and decoded by K5 on
-                                   wake; pages that do not code well stay raw.  Host tier + STAGED only; 0 = off */
+                                   wake; pages that do not code well stay raw.  Host tier: through the staging ring
+                                   (STAGED); peer / local tiers: K4 / K5 write / read the parking store themselves;
+                                   0 = off */
     uint64_t reserved[6];
 } fma_config_t;
 

@@ -1008,7 +1008,9 @@ int do_sleep(fma_engine_t* e, uint64_t offload_mask, int tier, uint32_t flags) {
     {
         std::vector<uint64_t> pk_off;
         std::vector<uint32_t> pk_bytes;
-        if (W && e->cfg.pack && !(flags & kFlagAdopt) && tier == FMA_TIER_HOST && mode == FMA_MODE_STAGED) {
+        // host tier: through the staging ring (STAGED); parking tiers (peer / local HBM): K4 writes the store itself (KERNEL)
+        const bool pack_path = (tier == FMA_TIER_HOST && mode == FMA_MODE_STAGED) || (tier != FMA_TIER_HOST && mode == FMA_MODE_KERNEL);
+        if (W && e->cfg.pack && !(flags & kFlagAdopt) && pack_path) {
             rc = plan_packed_image(e, ex, W, &pk_off, &pk_bytes, &Wp, &packed);
             if (rc != FMA_OK) return rc;
         }
@@ -1026,10 +1028,10 @@ int do_sleep(fma_engine_t* e, uint64_t offload_mask, int tier, uint32_t flags) {
             if (rc != FMA_OK) return rc;
             if (mode == FMA_MODE_KERNEL && !e->host.dev_alias) return fail(FMA_ECUDA, "host store has no device alias for zero-copy mode");
         } else if (tier == FMA_TIER_PEER) {
-            if (!e->park.va || e->park.cap < W || e->park.device == e->device)
-                return fail(FMA_ESTATE, "peer tier needs fma_peer_reserve(peer_device, >= %llu bytes) first", (unsigned long long)W);
+            if (!e->park.va || e->park.cap < Wp || e->park.device == e->device)
+                return fail(FMA_ESTATE, "peer tier needs fma_peer_reserve(peer_device, >= %llu bytes) first", (unsigned long long)Wp);
         } else if (tier == FMA_TIER_LOCAL) {
-            rc = park_reserve(e, e->device, W);
+            rc = park_reserve(e, e->device, Wp);
             if (rc != FMA_OK) return rc;
         } else {
             return fail(FMA_EINVAL, "unknown tier %d", tier);
@@ -1283,7 +1285,37 @@ int do_sleep(fma_engine_t* e, uint64_t offload_mask, int tier, uint32_t flags) {
             build_page_table(ex, e->h_tab);
             RT(cudaMemcpyAsync(e->d_tab, e->h_tab, n_pages * sizeof(uint64_t), cudaMemcpyHostToDevice, e->ks));
             auto publish_gathered = [&](size_t pages_done) -> int { return publish_consumed((uint64_t)pages_done * FMA_PAGE_BYTES, e->ks); };
-            if (mode == FMA_MODE_KERNEL) {
+            if (mode == FMA_MODE_KERNEL && packed) {
+                // PACKED image in a parking tier: K4 encodes straight into the peer / local HBM store (0.758 of the bytes
+                // over NVLink and of the parking GPU's HBM), batches as below
+                rc = ensure_pack_bufs(e, n_pages);
+                if (rc != FMA_OK) return rc;
+                const uint64_t dbase = store_dev_base(e, tier);
+                for (size_t p = 0; p < n_pages; ++p) {
+                    fma_k_pack_desc& d = e->h_pdesc[p];
+                    d.src = e->h_tab[p];
+                    d.dst = dbase + e->img_off[p];
+                    d.mode = e->img_bytes[p] == FMA_PAGE_BYTES ? FMA_K_PACK_RAW : FMA_K_PACK_BF16;
+                    d.pad = 0;
+                }
+                uint32_t* d_err = e->d_psize + e->pdesc_cap;
+                RT(cudaMemcpyAsync(e->d_pdesc, e->h_pdesc, n_pages * sizeof(fma_k_pack_desc), cudaMemcpyHostToDevice, e->ks));
+                RT(cudaMemsetAsync(d_err, 0, sizeof(uint32_t), e->ks));
+                const size_t batch = std::max<size_t>(staged_slot(e) / FMA_PAGE_BYTES, 1);
+                for (size_t p0 = 0; p0 < n_pages; p0 += batch) {
+                    const size_t np = std::min(batch, n_pages - p0);
+                    uint64_t stored = 0;
+                    for (size_t q = p0; q < p0 + np; ++q) stored += e->img_bytes[q];
+                    rc = kt.begin();
+                    if (rc != FMA_OK) return rc;
+                    RT(fma_k_launch_pack(e->d_pdesc + p0, (uint32_t)np, d_err, e->ks));
+                    rc = kt.end((uint64_t)np * FMA_PAGE_BYTES + stored);
+                    if (rc != FMA_OK) return rc;
+                    ++copy_ops;
+                    rc = publish_gathered(p0 + np);
+                    if (rc != FMA_OK) return rc;
+                }
+            } else if (mode == FMA_MODE_KERNEL) {
                 // K1 writes the store itself: mapped pinned host memory (PCIe posted writes) or peer/local HBM;
                 // launched in slot-sized batches so finished segments can be released while later ones still move
                 const size_t batch = std::max<size_t>(staged_slot(e) / FMA_PAGE_BYTES, 1);
@@ -1479,8 +1511,8 @@ int do_wake(fma_engine_t* e, uint64_t tag_mask, uint32_t flags) {
     int mode = resolve_mode(e, tier);
     // A PACKED image can only be read by K5: through the staging ring, or (no HBM for a ring) straight from the
     // mapped pinned store.
-    const bool packed = e->image_packed && tier == FMA_TIER_HOST;
-    if (packed) mode = FMA_MODE_STAGED;
+    const bool packed = e->image_packed;
+    if (packed && tier == FMA_TIER_HOST) mode = FMA_MODE_STAGED;
 
     // Staging ring.  Steady state: the ring is its OWN small run (2 x 512 MiB) placed right after the first backed-up
     // run at the arena's bump pointer and mapped FIRST — a 1 GiB cuMemCreate/Map/SetAccess costs ~0.2 ms, the H2D
@@ -1643,8 +1675,10 @@ int do_wake(fma_engine_t* e, uint64_t tag_mask, uint32_t flags) {
         WAKE_CHECK(timer.begin());
         if (packed) {
             // ---- PACKED image: H2D of the stored pages (0.758 of the bytes) -> ring slot -> K5 decode + scatter ----
-            const bool zero_copy = mode != FMA_MODE_STAGED;  // no ring could be had: K5 reads the pinned store over PCIe
-            if (zero_copy && !e->host.dev_alias) WAKE_CHECK(fail(FMA_ENOMEM, "no HBM for a staging ring and the host store has no device alias: a packed image cannot be woken"));
+            // K5 reads the store itself when it is peer / local HBM, or when no ring could be had (then over PCIe)
+            const bool zero_copy = mode != FMA_MODE_STAGED;
+            if (zero_copy && tier == FMA_TIER_HOST && !e->host.dev_alias)
+                WAKE_CHECK(fail(FMA_ENOMEM, "no HBM for a staging ring and the host store has no device alias: a packed image cannot be woken"));
             struct Dst { uint64_t packed_off; size_t w; };
             std::vector<Dst> d;
             for (size_t w = 0; w < with_backup.size(); ++w) d.push_back(Dst{e->segs[with_backup[w]].packed_off, w});
@@ -1716,7 +1750,7 @@ int do_wake(fma_engine_t* e, uint64_t tag_mask, uint32_t flags) {
                     WAKE_RT(cudaEventRecord(e->ev_ring_free[slot], e->ks));
                 }
             } else {
-                const uint64_t sbase = (uint64_t)(uintptr_t)e->host.dev_alias;
+                const uint64_t sbase = store_dev_base(e, tier);
                 for (size_t q = 0; q < n_pages; ++q) {
                     fma_k_pack_desc& pd = e->h_pdesc[q];
                     pd.src = sbase + soff[q];

@@ -149,6 +149,13 @@ int main() {
             auto d = digests(a);
             for (size_t i = 0; i + 1 < before.size(); ++i) assert(d[i] == before[i]);
         }
+        // the same image parked in local HBM: K4 / K5 write / read the store themselves
+        OK(fma_set_option(a, "mode", FMA_MODE_AUTO));
+        OK(fma_sleep(a, 1ull << w, FMA_TIER_LOCAL, FMA_FLAG_VERIFY));
+        OK(fma_stats(a, &st));
+        assert(st.image_packed == 1 && st.mode == FMA_MODE_KERNEL);
+        OK(fma_wake(a, 0, FMA_FLAG_VERIFY));
+        OK(fma_set_option(a, "mode", FMA_MODE_STAGED));
         // HBM too full for a staging ring at wake time: K5 reads the packed image straight from the mapped host store
         OK(fma_sleep(a, 1ull << w, FMA_TIER_HOST, FMA_FLAG_VERIFY));
         setenv("FMA_RING_ATTACH", "0", 1);

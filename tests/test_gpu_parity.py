@@ -691,3 +691,34 @@ def test_packed_sleep_falls_back_to_plain_for_incompressible_weights(engine, ora
     engine.wake(None)
     for i in ref:
         assert engine.read(i, table[i].bytes) == ref[i].tobytes()
+
+
+@_PACK
+@pytest.mark.parametrize("tier", ["local", "peer"])
+def test_packed_image_in_a_parking_tier(engine, oracle, tier):
+    """PACKED image parked in HBM (local: same GPU; peer: another GPU over NVLink): K4 writes and K5 reads the store
+    themselves, the parking buffer only needs the stored bytes."""
+    L = _L()
+    if tier == "peer" and _n_gpus() < 2:
+        pytest.skip("peer tier needs a second GPU")
+    pages = _pack_pages(oracle)
+    blobs = [np.concatenate(pages[0:4]), np.concatenate(pages[4:9]), np.concatenate(pages[9:11])]
+    ptrs = [engine.alloc(b.size, "weights") for b in blobs] + [engine.alloc(2 * PAGE, "kv_cache")]
+    for i, b in enumerate(blobs):
+        engine.write(i, b.tobytes())
+    W = sum(b.size for b in blobs)
+    stored = sum(oracle.pack_page(b[o:o + PAGE]).size for b in blobs for o in range(0, b.size, PAGE))
+    engine.set_option("pack", 1)
+    engine.set_option("chunk_bytes", 6 << 20)
+    t = L.FMA_TIER_LOCAL if tier == "local" else L.FMA_TIER_PEER
+    if tier == "peer":
+        engine.peer_reserve(1, stored + PAGE)                          # less than W: only the stored bytes are parked
+    for flags in (L.FMA_FLAG_VERIFY, 0):
+        engine.sleep(["weights"], tier=t, flags=flags)
+        st = engine.stats()
+        assert st["image_packed"] == 1 and st["image_store_bytes"] == stored < W and st["mode"] == L.FMA_MODE_KERNEL
+        engine.wake(["weights"], flags=flags)
+        engine.wake(None)
+        for i, b in enumerate(blobs):
+            assert engine.read(i, b.size) == b.tobytes()
+    assert [s.va for s in engine.segments()] == ptrs
