@@ -8,6 +8,9 @@ out=gpurun_out/round2
 mkdir -p "$out"
 export FMA_TEST_PACK_ON_GPU=1
 
+# 0. the kernels alone (managed memory, no engine, no Python): pinpoints a device-side mismatch by page
+timeout 120 tests/cpp/cuda_emu/pack_kernels_gpu_test > "$out/pack_kernels_gpu_test.log" 2>&1; echo "kernel test rc=$?" | tee "$out/status0.txt"
+
 # 1. parity of the PACKED image kernels and engine path against the oracle, then the whole GPU suite
 timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "pack" > "$out/pytest_pack.log" 2>&1; echo "pytest pack rc=$?" | tee "$out/status.txt"
 timeout 600 python -m pytest tests -m gpu -x -q > "$out/pytest_gpu.log" 2>&1; echo "pytest gpu rc=$?" | tee -a "$out/status.txt"

@@ -2,6 +2,11 @@
 // checks it against the oracle (oracle/fma_oracle.c) page by page: probe decisions, stored bytes (exceptions compared
 // as sets), decode, gather/scatter through descriptor tables, the error counter.  Built by tests/test_kernels_emulated.py
 // with g++ -DFMA_CUDA_EMU -include cuda_emu.h, plain and under ThreadSanitizer (missing barriers = data races).
+//
+// The SAME file is the GPU-side kernel test: `nvcc -x cu -DFMA_GPU_TEST ...` (tests/cpp/cuda_emu/Makefile ->
+// tests/cpp/cuda_emu/pack_kernels_gpu_test, run on a B200 by scripts/round2_first_call.sh) compiles the real kernels and
+// keeps every buffer in managed memory, so a mismatch on the device is reported with the page it happened in,
+// without the engine in the way.
 #include <algorithm>
 #include <cassert>
 #include <cstdio>
@@ -9,10 +14,28 @@
 #include <cstring>
 #include <vector>
 
+#if defined(FMA_GPU_TEST)
+#include <cuda_runtime.h>
+#include <new>
+template <class T>
+struct DevAlloc {  // managed memory: the host-side checks read what the kernels wrote
+    typedef T value_type;
+    DevAlloc() = default;
+    template <class U> DevAlloc(const DevAlloc<U>&) {}
+    T* allocate(size_t n) { void* p = nullptr; if (cudaMallocManaged(&p, n * sizeof(T)) != cudaSuccess) throw std::bad_alloc(); return static_cast<T*>(p); }
+    void deallocate(T* p, size_t) { cudaFree(p); }
+    template <class U> bool operator==(const DevAlloc<U>&) const { return true; }
+    template <class U> bool operator!=(const DevAlloc<U>&) const { return false; }
+};
+#define DEVICE_SYNC() do { cudaError_t _e = cudaDeviceSynchronize(); if (_e != cudaSuccess) { fprintf(stderr, "CUDA error: %s\n", cudaGetErrorString(_e)); return 2; } } while (0)
+#else
 // the runtime calls the launch wrappers make
 extern "C" cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
 extern "C" cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr, int) { *v = 3; return cudaSuccess; }  // 3 "SMs": grid-stride loops get exercised
 extern "C" cudaError_t cudaGetLastError(void) { return cudaSuccess; }
+template <class T> using DevAlloc = std::allocator<T>;
+#define DEVICE_SYNC() do { } while (0)
+#endif
 
 #include "../../../llm-d-fast-model-actuation_b200/csrc/fma_pack_kernels.cu"
 
@@ -25,7 +48,9 @@ static const size_t PAGE = 2u << 20, N = 1u << 20, PACKED = FMA_K_PACKED_PAGE_BY
 static uint32_t rng_state = 2463534242u;
 static uint32_t rnd() { rng_state ^= rng_state << 13; rng_state ^= rng_state >> 17; rng_state ^= rng_state << 5; return rng_state; }
 
-typedef std::vector<uint16_t> Page;
+typedef std::vector<uint16_t, DevAlloc<uint16_t>> Page;   // device-visible
+typedef std::vector<unsigned char, DevAlloc<unsigned char>> Bytes;
+template <class T> using DVec = std::vector<T, DevAlloc<T>>;
 static Page weights(uint32_t e_lo, uint32_t span) {  // bf16 values with exponents e_lo .. e_lo+span-1
     Page p(N);
     for (auto& v : p) { uint32_t x = rnd(); v = (uint16_t)(((x >> 31) << 15) | ((e_lo + (x >> 8) % span) << 7) | ((x >> 16) & 0x7F)); }
@@ -57,11 +82,12 @@ int main() {
     const uint32_t n = (uint32_t)pages.size();
 
     // K4p vs oracle
-    std::vector<uint64_t> tab(n);
+    DVec<uint64_t> tab(n);
     for (uint32_t p = 0; p < n; ++p) tab[p] = (uint64_t)(uintptr_t)pages[p].data();
-    std::vector<uint32_t> sizes(n, 0);
+    DVec<uint32_t> sizes(n, 0);
     assert(fma_k_launch_pack_probe(tab.data(), n, sizes.data(), nullptr) == cudaSuccess);
-    std::vector<std::vector<unsigned char>> want(n, std::vector<unsigned char>(PAGE));
+    DEVICE_SYNC();
+    std::vector<Bytes> want(n, Bytes(PAGE));
     uint32_t n_raw = 0;
     for (uint32_t p = 0; p < n; ++p) {
         const uint32_t w = fma_oracle_pack_page(pages[p].data(), want[p].data());
@@ -74,8 +100,8 @@ int main() {
     std::vector<uint32_t> perm = {3, 0, 7, 5, 1, 6, 2, 4};
     uint64_t total = 0;
     for (uint32_t p : perm) total += sizes[p];
-    std::vector<unsigned char> store(total, 0xEE);
-    std::vector<fma_k_pack_desc> d(n);
+    Bytes store(total, 0xEE);
+    DVec<fma_k_pack_desc> d(n);
     std::vector<uint64_t> off(n);
     uint64_t o = 0;
     for (uint32_t k = 0; k < n; ++k) {
@@ -84,19 +110,26 @@ int main() {
         d[k] = fma_k_pack_desc{tab[p], (uint64_t)(uintptr_t)(store.data() + o), sizes[p] == PAGE ? (uint32_t)FMA_K_PACK_RAW : (uint32_t)FMA_K_PACK_BF16, 0};
         o += sizes[p];
     }
-    uint32_t err = 0;
-    assert(fma_k_launch_pack(d.data(), n, &err, nullptr) == cudaSuccess && err == 0);
+    DVec<uint32_t> errv(1, 0);
+    uint32_t& err = errv[0];
+    assert(fma_k_launch_pack(d.data(), n, &err, nullptr) == cudaSuccess);
+    DEVICE_SYNC();
+    assert(err == 0);
     for (uint32_t k = 0; k < n; ++k)
         if (!same_stored(store.data() + off[k], want[perm[k]].data(), sizes[perm[k]])) { fprintf(stderr, "stored page %u differs from the oracle's\n", perm[k]); return 1; }
 
     // K5: scatter back to fresh pages; also decode the ORACLE's stored pages with the kernel
     std::vector<Page> back(n, Page(N, 0xABCD));
     for (uint32_t k = 0; k < n; ++k) { d[k].src = (uint64_t)(uintptr_t)(store.data() + off[k]); d[k].dst = (uint64_t)(uintptr_t)back[perm[k]].data(); }
-    assert(fma_k_launch_unpack(d.data(), n, &err, nullptr) == cudaSuccess && err == 0);
+    assert(fma_k_launch_unpack(d.data(), n, &err, nullptr) == cudaSuccess);
+    DEVICE_SYNC();
+    assert(err == 0);
     for (uint32_t p = 0; p < n; ++p)
         if (back[p] != pages[p]) { fprintf(stderr, "page %u does not survive the round trip\n", p); return 1; }
     for (uint32_t k = 0; k < n; ++k) { d[k].src = (uint64_t)(uintptr_t)want[perm[k]].data(); std::fill(back[perm[k]].begin(), back[perm[k]].end(), 0x1234); }
-    assert(fma_k_launch_unpack(d.data(), n, &err, nullptr) == cudaSuccess && err == 0);
+    assert(fma_k_launch_unpack(d.data(), n, &err, nullptr) == cudaSuccess);
+    DEVICE_SYNC();
+    assert(err == 0);
     for (uint32_t p = 0; p < n; ++p) assert(back[p] == pages[p]);
     // and the oracle decodes the kernel's stored pages
     for (uint32_t k = 0; k < n; ++k) {
@@ -105,15 +138,23 @@ int main() {
     }
 
     // error counters: a page forced into the coded form although it overflows; a damaged header
-    fma_k_pack_desc bad{tab[4], (uint64_t)(uintptr_t)store.data(), FMA_K_PACK_BF16, 0};
+    DVec<fma_k_pack_desc> bad(1, fma_k_pack_desc{tab[4], (uint64_t)(uintptr_t)store.data(), FMA_K_PACK_BF16, 0});
     err = 0;
-    assert(fma_k_launch_pack(&bad, 1, &err, nullptr) == cudaSuccess && err == 1);
-    std::vector<unsigned char> dmg(want[0].begin(), want[0].begin() + PACKED);
+    assert(fma_k_launch_pack(bad.data(), 1, &err, nullptr) == cudaSuccess);
+    DEVICE_SYNC();
+    assert(err == 1);
+    Bytes dmg(want[0].begin(), want[0].begin() + PACKED);
     dmg[fma_codec::kHdrOff] ^= 0xFF;
     Page sink(N);
-    fma_k_pack_desc bad2{(uint64_t)(uintptr_t)dmg.data(), (uint64_t)(uintptr_t)sink.data(), FMA_K_PACK_BF16, 0};
+    bad[0] = fma_k_pack_desc{(uint64_t)(uintptr_t)dmg.data(), (uint64_t)(uintptr_t)sink.data(), FMA_K_PACK_BF16, 0};
     err = 0;
-    assert(fma_k_launch_unpack(&bad2, 1, &err, nullptr) == cudaSuccess && err == 1);
+    assert(fma_k_launch_unpack(bad.data(), 1, &err, nullptr) == cudaSuccess);
+    DEVICE_SYNC();
+    assert(err == 1);
+#if defined(FMA_GPU_TEST)
+    puts("pack kernels (GPU) ok");
+#else
     puts("pack kernels (emulated) ok");
+#endif
     return 0;
 }
