@@ -1,0 +1,150 @@
+// fma_image.cu — image hand-over: a sleeping model's host image outlives its engine / process (memfd store + descriptor)
+// Part of the host engine (see fma_internal.h for the map of translation units; C-ABI in include/fma_engine.h).
+#include "fma_internal.h"
+
+using namespace fma_impl;
+
+extern "C" {
+
+int fma_image_export(fma_engine_t* e, int* out_fd) {
+    if (check_engine(e) != FMA_OK) return FMA_EINVAL;
+    if (!out_fd) return fail(FMA_EINVAL, "out_fd is NULL");
+    if (e->host.fd < 0 || !e->host.base) return fail(FMA_ESTATE, "the host store is not shareable (set FMA_HOST_STORE_SHM=1 before the first sleep)");
+    if (e->image_tier != FMA_TIER_HOST) return fail(FMA_ESTATE, "no host-tier image");
+    std::vector<const Segment*> segs;
+    for (const Segment& s : e->segs)
+        if (s.has_backup && s.backup_tier == FMA_TIER_HOST && !s.mapped) segs.push_back(&s);
+    if (segs.empty()) return fail(FMA_ESTATE, "nothing is asleep in the host store");
+    std::sort(segs.begin(), segs.end(), [](const Segment* a, const Segment* b) { return a->packed_off < b->packed_off; });
+    // version 2 = PACKED image: the per-page stored sizes follow the segment descriptors (offsets are their prefix sums)
+    const size_t n_img_pages = e->image_packed ? e->img_bytes.size() : 0;
+    if (sizeof(ImageHeader) + segs.size() * sizeof(ImageSegDesc) + sizeof(uint32_t) * (1 + n_img_pages) > kImageTail)
+        return fail(FMA_ENOMEM, "too many segments / pages for the descriptor");
+    char* tail = static_cast<char*>(e->host.base) + e->host.cap;
+    ImageHeader hd{kImageMagic, e->image_packed ? 2u : 1u, (uint32_t)segs.size(), e->image_bytes};
+    memcpy(tail, &hd, sizeof(hd));
+    for (size_t i = 0; i < segs.size(); ++i) {
+        ImageSegDesc d;
+        memset(&d, 0, sizeof(d));
+        d.bytes = segs[i]->bytes;
+        d.packed_off = segs[i]->packed_off;
+        d.digest = segs[i]->digest;
+        d.digest_valid = segs[i]->digest_valid ? 1 : 0;
+        const std::string& t = e->tags[segs[i]->tag];
+        d.tag_len = (uint32_t)std::min<size_t>(t.size(), sizeof(d.tag) - 1);
+        memcpy(d.tag, t.data(), d.tag_len);
+        memcpy(tail + sizeof(hd) + i * sizeof(d), &d, sizeof(d));
+    }
+    if (e->image_packed) {
+        char* pt = tail + sizeof(hd) + segs.size() * sizeof(ImageSegDesc);
+        const uint32_t np = (uint32_t)n_img_pages;
+        memcpy(pt, &np, sizeof(np));
+        memcpy(pt + sizeof(np), e->img_bytes.data(), n_img_pages * sizeof(uint32_t));
+    }
+    int fd = dup(e->host.fd);
+    if (fd < 0) return fail(FMA_ENOMEM, "dup failed: %s", strerror(errno));
+    *out_fd = fd;
+    return FMA_OK;
+}
+
+int fma_image_adopt(fma_engine_t* e, int fd, uint64_t tag_mask, uint32_t flags) {
+    if (check_engine(e) != FMA_OK) return FMA_EINVAL;
+    if (!tag_mask) return fail(FMA_EINVAL, "adopt needs the tag mask the image was slept with");
+    for (const Segment& s : e->segs)
+        if (!s.mapped) return fail(FMA_ESTATE, "adopt needs a fully awake engine");
+    struct stat sb;
+    if (fstat(fd, &sb) != 0 || (size_t)sb.st_size <= kImageTail) return fail(FMA_EINVAL, "not an image fd");
+    const size_t map_bytes = (size_t)sb.st_size, cap = map_bytes - kImageTail;
+    int myfd = dup(fd);
+    if (myfd < 0) return fail(FMA_ENOMEM, "dup failed: %s", strerror(errno));
+    void* p = mmap(nullptr, map_bytes, PROT_READ | PROT_WRITE, MAP_SHARED, myfd, 0);
+    if (p == MAP_FAILED) {
+        close(myfd);
+        return fail(FMA_ENOMEM, "cannot map the image: %s", strerror(errno));
+    }
+    auto bail = [&](int code, const char* why) {
+        munmap(p, map_bytes);
+        close(myfd);
+        return fail(code, "%s", why);
+    };
+    const char* tail = static_cast<const char*>(p) + cap;
+    ImageHeader hd;
+    memcpy(&hd, tail, sizeof(hd));
+    if (hd.magic != kImageMagic || (hd.version != 1 && hd.version != 2) || (hd.version == 1 && hd.image_bytes > cap) ||
+        sizeof(ImageHeader) + (size_t)hd.n_segments * sizeof(ImageSegDesc) + sizeof(uint32_t) > kImageTail)
+        return bail(FMA_EINVAL, "image descriptor missing or corrupt");
+    std::vector<uint64_t> adopt_off;   // version 2: the PACKED image's page table
+    std::vector<uint32_t> adopt_bytes;
+    if (hd.version == 2) {
+        const char* pt = tail + sizeof(hd) + (size_t)hd.n_segments * sizeof(ImageSegDesc);
+        uint32_t np = 0;
+        memcpy(&np, pt, sizeof(np));
+        if ((uint64_t)np * FMA_PAGE_BYTES != hd.image_bytes || sizeof(ImageHeader) + (size_t)hd.n_segments * sizeof(ImageSegDesc) + sizeof(uint32_t) * (1 + (size_t)np) > kImageTail)
+            return bail(FMA_EINVAL, "packed image: page table does not match the image size");
+        adopt_bytes.resize(np);
+        adopt_off.resize(np);
+        memcpy(adopt_bytes.data(), pt + sizeof(np), (size_t)np * sizeof(uint32_t));
+        uint64_t total = 0;
+        for (uint32_t q = 0; q < np; ++q) {
+            if (adopt_bytes[q] != FMA_K_PACKED_PAGE_BYTES && adopt_bytes[q] != FMA_PAGE_BYTES) return bail(FMA_EINVAL, "packed image: bad stored page size");
+            adopt_off[q] = total;
+            total += adopt_bytes[q];
+        }
+        if (total > cap) return bail(FMA_EINVAL, "packed image: stored pages exceed the store");
+    }
+    // the segments this engine would offload for tag_mask, in image order (same rule as fma_sleep)
+    std::vector<size_t> order;
+    for (size_t i = 0; i < e->segs.size(); ++i)
+        if (tag_bit_set(tag_mask, e->segs[i].tag)) order.push_back(i);
+    std::sort(order.begin(), order.end(), [&](size_t a, size_t b) {
+        const Segment &x = e->segs[a], &y = e->segs[b];
+        return x.arena != y.arena ? x.arena < y.arena : x.va < y.va;
+    });
+    if (order.size() != hd.n_segments) return bail(FMA_EINVAL, "image and engine disagree on the number of segments");
+    std::vector<ImageSegDesc> ds(hd.n_segments);
+    uint64_t off = 0;
+    for (size_t i = 0; i < ds.size(); ++i) {
+        memcpy(&ds[i], tail + sizeof(hd) + i * sizeof(ImageSegDesc), sizeof(ImageSegDesc));
+        const Segment& s = e->segs[order[i]];
+        if (ds[i].bytes != s.bytes || ds[i].packed_off != off || std::string(ds[i].tag, ds[i].tag_len) != e->tags[s.tag])
+            return bail(FMA_EINVAL, "image and engine disagree on a segment's size, offset or tag");
+        off += s.bytes;
+    }
+    if (off != hd.image_bytes) return bail(FMA_EINVAL, "image size mismatch");
+    DeviceGuard guard(e->device);
+    cudaDeviceSynchronize();
+    host_store_free(e->host);
+    const double t0 = now_s();
+    cudaError_t r = cudaHostRegister(p, map_bytes, cudaHostRegisterPortable | cudaHostRegisterMapped);
+    if (r != cudaSuccess) {
+        cudaGetLastError();
+        return bail(FMA_ECUDA, "cannot pin the adopted image");
+    }
+    HostStore h;
+    h.base = p; h.cap = cap; h.map_bytes = map_bytes; h.fd = myfd; h.registered = true;
+    void* alias = nullptr;
+    if (cudaHostGetDevicePointer(&alias, p, 0) == cudaSuccess) h.dev_alias = alias;
+    else cudaGetLastError();
+    h.pin_seconds = now_s() - t0;
+    e->host = h;
+    e->st.host_store_bytes = cap;
+    e->st.host_store_pin_seconds = h.pin_seconds;
+    // release the device side exactly as a sleep would, without copying anything out
+    int rc = do_sleep(e, tag_mask, FMA_TIER_HOST, (flags & ~FMA_FLAG_VERIFY) | kFlagAdopt);
+    if (rc != FMA_OK) return rc;
+    if (hd.version == 2) {  // wake through K5 with the exporter's page table
+        e->image_packed = true;
+        e->image_store_bytes = adopt_off.empty() ? 0 : adopt_off.back() + adopt_bytes.back();
+        e->img_off = std::move(adopt_off);
+        e->img_bytes = std::move(adopt_bytes);
+    }
+    for (size_t i = 0; i < ds.size(); ++i) {  // integrity data travels with the image: FMA_FLAG_VERIFY on wake checks it
+        Segment& s = e->segs[order[i]];
+        s.digest = ds[i].digest;
+        s.digest_valid = ds[i].digest_valid != 0;
+    }
+    return FMA_OK;
+}
+
+
+}  // extern "C"

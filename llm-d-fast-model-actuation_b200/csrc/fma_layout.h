@@ -1,6 +1,6 @@
 // fma_layout.h — pure host logic of the engine's address-space layout (no CUDA): VA arenas with first-fit hole reuse,
 // and grouping of sleeping segments into runs.  Header-only so that tests/test_layout_cpu.py can compile and exercise
-// it with g++ on a machine without a GPU; fma_engine.cu uses exactly these functions.
+// it with g++ on a machine without a GPU; the engine (fma_engine.cu, fma_wake.cu) uses exactly these functions.
 #pragma once
 #include <stddef.h>
 #include <stdint.h>

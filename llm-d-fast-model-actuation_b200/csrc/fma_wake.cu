@@ -1,0 +1,484 @@
+// fma_wake.cu — WAKE: vllm:device_allocator/cumem.py:227-249 -> do_wake
+// Part of the host engine (see fma_internal.h for the map of translation units; C-ABI in include/fma_engine.h).
+#include "fma_internal.h"
+
+namespace fma_impl {
+
+// ------------------------------------------------------------------------------------
+// WAKE
+// ------------------------------------------------------------------------------------
+struct MapProgress {
+    std::mutex mu;
+    std::condition_variable cv;
+    size_t done = 0;      // number of work items fully mapped (prefix)
+    int error = FMA_OK;
+    char msg[512] = "";
+};
+
+int do_wake(fma_engine_t* e, uint64_t tag_mask, uint32_t flags) {
+    DeviceGuard guard(e->device);
+    int rc = flush_kernel_times(e);
+    if (rc != FMA_OK) return rc;
+    const double t_entry = now_s();
+    rc = ensure_streams(e);
+    if (rc != FMA_OK) return rc;
+
+    // Work list: RUNS — maximal VA-contiguous groups of sleeping segments of one arena — so a whole tag is
+    // re-created with one cuMemCreate + cuMemMap + cuMemSetAccess.  Runs that have a backup come first, in image
+    // order (they gate the copy pipeline); remap-only runs (e.g. kv_cache) are mapped after them.
+    using Run = fma_layout::Run;
+    std::vector<Run> runs;
+    {
+        std::vector<size_t> cand;
+        for (size_t i = 0; i < e->segs.size(); ++i) {
+            const Segment& s = e->segs[i];
+            if (s.mapped) continue;                                  // idempotent: already awake
+            if (tag_mask && !tag_bit_set(tag_mask, s.tag)) continue;  // tags is None or data.tag in tags (cumem.py:238)
+            cand.push_back(i);
+        }
+        if (cand.empty()) return FMA_OK;
+        std::sort(cand.begin(), cand.end(), [&](size_t a, size_t b) {
+            const Segment &x = e->segs[a], &y = e->segs[b];
+            return x.arena != y.arena ? x.arena < y.arena : x.va < y.va;
+        });
+        std::vector<fma_layout::SegView> view;
+        for (size_t i : cand) {
+            const Segment& s = e->segs[i];
+            view.push_back(fma_layout::SegView{i, s.arena, (uint64_t)s.va, s.bytes, s.has_backup, s.packed_off});
+        }
+        runs = fma_layout::plan_runs(view, env_int("FMA_MERGE_RUNS", 1) != 0);
+    }
+    const int tier = e->image_tier;
+    int mode = resolve_mode(e, tier);
+    // A PACKED image can only be read by K5: through the staging ring, or (no HBM for a ring) straight from the
+    // mapped pinned store.
+    const bool packed = e->image_packed;
+    if (packed && tier == FMA_TIER_HOST) mode = FMA_MODE_STAGED;
+
+    // Staging ring.  Steady state: the ring is its OWN small run (2 x 512 MiB) placed right after the first backed-up
+    // run at the arena's bump pointer and mapped FIRST — a 1 GiB cuMemCreate/Map/SetAccess costs ~0.2 ms, the H2D
+    // stream starts as soon as it exists, and the big weights run (whose mapping takes 1.4 ms alone but tens of ms
+    // when 8 ranks wake at once) keeps the ring's ~19 ms of slack.  At the next sleep the ring goes with a cuMemUnmap
+    // like every other unit: no cudaMalloc / cudaFree anywhere (a cudaFree of 1 GiB stalls 0.8-300 ms on these hosts).
+    // Needs the run to end at its arena's bump pointer; otherwise (or FMA_RING_ATTACH=0) one cudaMalloc provides it.
+    // Either way the ring must exist BEFORE the other runs start taking HBM.
+    bool ring_run = false;
+    {
+        uint64_t w_bytes = 0;
+        for (const Run& r : runs)
+            if (r.has_backup) w_bytes += r.bytes;
+        if (w_bytes && mode == FMA_MODE_STAGED && !e->n_ring) {
+            const Run& r0 = runs[0];
+            Arena& a = e->arenas[r0.arena];
+            const size_t slot = ring_slot_for(e, w_bytes);
+            const size_t total = slot * ring_slots_for(e);
+            const bool at_top = r0.has_backup && (r0.va + r0.bytes == a.base + a.top) && a.top + total <= a.cap;
+            if (at_top && env_int("FMA_RING_ATTACH", 1) != 0 && ensure_ring_events(e, ring_slots_for(e)) == FMA_OK) {
+                Run rr;
+                rr.va = r0.va + r0.bytes; rr.bytes = total; rr.arena = r0.arena; rr.has_backup = true; rr.first_off = 0;  // no segments
+                a.top += total;  // later allocations of this tag land after the ring; the range returns at unmap
+                e->n_ring = ring_slots_for(e);
+                e->ring_slot_bytes = slot;
+                e->ring_attached = true;
+                e->ring_unit_va = rr.va;
+                for (int i = 0; i < e->n_ring; ++i) e->ring[i] = reinterpret_cast<void*>(rr.va + (size_t)i * slot);
+                runs.insert(runs.begin(), std::move(rr));
+                ring_run = true;
+            } else if (ensure_ring(e, w_bytes) != FMA_OK) {
+                mode = FMA_MODE_DIRECT;  // HBM too full for a ring: copy engines go straight into the runs
+            }
+        } else if (w_bytes && mode == FMA_MODE_STAGED && ensure_ring(e, w_bytes) != FMA_OK) {
+            mode = FMA_MODE_DIRECT;
+        }
+    }
+
+    std::vector<size_t> with_backup, remap_only;  // segment indices, image order
+    std::vector<size_t> seg_run(e->segs.size(), 0);  // segment -> index of its run in `runs`
+    size_t n_backup_runs = 0;
+    for (size_t r = 0; r < runs.size(); ++r) {
+        if (runs[r].has_backup) ++n_backup_runs;
+        for (size_t i : runs[r].segs) {
+            seg_run[i] = r;
+            (runs[r].has_backup ? with_backup : remap_only).push_back(i);
+        }
+    }
+    const bool dbg_t = env_int("FMA_DEBUG_TIMING", 0) != 0;
+    const double t_ring = now_s();
+    double remap_delay_s;
+    {
+        uint64_t w_bytes = 0;
+        for (size_t i : with_backup) w_bytes += e->segs[i].bytes;
+        // a fifth of the expected host-tier copy time (55 GB/s), half of the NVLink one (600 GB/s): far below the slack
+        const double expected = (double)w_bytes / (tier == FMA_TIER_HOST ? 55e9 : 600e9);
+        const int forced = env_int("FMA_REMAP_DELAY_MS", -1);
+        remap_delay_s = forced >= 0 ? forced * 1e-3 : expected * (tier == FMA_TIER_HOST ? 0.2 : 0.5);
+    }
+
+    // ---- mapper thread(s): one create + map + set-access per run, in `runs` order ----------------------
+    MapProgress prog;
+    std::vector<char> item_done(runs.size(), 0);
+    std::atomic<size_t> next_item{0};
+    std::atomic<uint64_t> map_ns{0};
+    const int n_map = std::max(1, std::min(e->cfg.map_threads > 0 ? e->cfg.map_threads : 1, 8));
+    auto mapper = [&]() {
+        cudaSetDevice(e->device);
+        for (;;) {
+            const size_t k = next_item.fetch_add(1);
+            if (k >= runs.size()) break;
+            {
+                std::lock_guard<std::mutex> lk(prog.mu);
+                if (prog.error != FMA_OK) break;
+            }
+            const Run& run = runs[k];
+            if (!run.has_backup && n_backup_runs && remap_delay_s > 0) {
+                // Remap-only runs (kv_cache) have the whole copy time as slack, the weights run only the ring's worth
+                // (~19 ms).  Driver VMM calls of ALL processes on the host serialise, so a rank that maps its kv early
+                // delays another rank's weights mapping: give every rank's weights a head start.
+                const double wait = t_entry + remap_delay_s - now_s();
+                if (wait > 0) std::this_thread::sleep_for(std::chrono::duration<double>(wait));
+            }
+            const bool is_ring = ring_run && k == 0;
+            const double t0 = now_s();
+            int r = vmm_create_and_map(e->device, run.va, run.bytes);
+            map_ns.fetch_add((uint64_t)((now_s() - t0) * 1e9));
+            std::lock_guard<std::mutex> lk(prog.mu);
+            if (r != FMA_OK) {
+                prog.error = r;
+                snprintf(prog.msg, sizeof(prog.msg), "%s", tl_err);
+                if (is_ring) {  // the ring never came to exist
+                    arena_give_back(e->arenas[run.arena], run.va - e->arenas[run.arena].base, run.bytes);
+                    release_ring(e);
+                }
+            } else {
+                Unit u;
+                u.va = run.va; u.bytes = run.bytes; u.arena = run.arena;
+                if (is_ring) u.zombies.emplace_back(run.va, run.bytes);  // ring VA returns to the arena when the unit is unmapped
+                for (size_t i : run.segs) {
+                    u.live_bytes += e->segs[i].bytes;
+                    e->segs[i].mapped = true;
+                    e->segs[i].unit_va = run.va;
+                }
+                // holes inside a run cannot exist (runs are VA-contiguous live segments), so bytes == live_bytes
+                e->units[run.va] = u;
+                item_done[k] = 1;
+                while (prog.done < runs.size() && item_done[prog.done]) ++prog.done;
+            }
+            prog.cv.notify_all();
+        }
+    };
+    std::vector<std::thread> mappers;
+    for (int t = 0; t < n_map; ++t) mappers.emplace_back(mapper);
+    auto join_mappers = [&]() {
+        for (auto& t : mappers)
+            if (t.joinable()) t.join();
+    };
+    auto wait_mapped = [&](size_t upto) -> int {  // wait until items [0, upto) are mapped
+        std::unique_lock<std::mutex> lk(prog.mu);
+        prog.cv.wait(lk, [&] { return prog.done >= upto || prog.error != FMA_OK; });
+        return prog.error;
+    };
+    auto mapped_now = [&]() -> size_t {
+        std::lock_guard<std::mutex> lk(prog.mu);
+        return prog.done;
+    };
+#define WAKE_CHECK(x)                     \
+    do {                                  \
+        int _rc = (x);                    \
+        if (_rc != FMA_OK) {              \
+            {                             \
+                std::lock_guard<std::mutex> lk(prog.mu); \
+                if (prog.error == FMA_OK) prog.error = _rc; \
+            }                             \
+            join_mappers();               \
+            cudaDeviceSynchronize();      \
+            return _rc;                   \
+        }                                 \
+    } while (0)
+#define WAKE_RT(call)                                                                              \
+    do {                                                                                           \
+        cudaError_t _e = (call);                                                                   \
+        if (_e != cudaSuccess) WAKE_CHECK(fail(FMA_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__)); \
+    } while (0)
+
+    // ---- copy pipeline --------------------------------------------------------------------------
+    uint64_t W = 0;
+    for (size_t i : with_backup) W += e->segs[i].bytes;
+    CopyTimer timer{e};
+    KernelTimes kt{e};
+    uint32_t copy_ops = 0;
+    double copy_s = 0, first_copy_delay = 0;
+    if (W) {
+        const size_t chunk = direct_chunk(e);
+        const char* store = static_cast<const char*>(store_copy_base(e, tier));
+        if (!store) WAKE_CHECK(fail(FMA_ESTATE, "backup store of tier %d is gone", tier));
+        if (tier == FMA_TIER_HOST && mode == FMA_MODE_KERNEL && !e->host.dev_alias)
+            WAKE_CHECK(fail(FMA_ECUDA, "host store has no device alias for zero-copy mode"));
+        WAKE_CHECK(timer.begin());
+        if (packed) {
+            // ---- PACKED image: H2D of the stored pages (0.758 of the bytes) -> ring slot -> K5 decode + scatter ----
+            // K5 reads the store itself when it is peer / local HBM, or when no ring could be had (then over PCIe)
+            const bool zero_copy = mode != FMA_MODE_STAGED;
+            if (zero_copy && tier == FMA_TIER_HOST && !e->host.dev_alias)
+                WAKE_CHECK(fail(FMA_ENOMEM, "no HBM for a staging ring and the host store has no device alias: a packed image cannot be woken"));
+            struct Dst { uint64_t packed_off; size_t w; };
+            std::vector<Dst> d;
+            for (size_t w = 0; w < with_backup.size(); ++w) d.push_back(Dst{e->segs[with_backup[w]].packed_off, w});
+            std::sort(d.begin(), d.end(), [](const Dst& a, const Dst& b) { return a.packed_off < b.packed_off; });
+            const size_t n_pages = W / FMA_PAGE_BYTES;
+            WAKE_CHECK(ensure_pack_bufs(e, n_pages));
+            std::vector<size_t> need_item(n_pages);
+            std::vector<uint64_t> soff(n_pages), dsts(n_pages);
+            std::vector<uint32_t> sbytes(n_pages);
+            size_t p = 0;
+            for (const Dst& x : d) {
+                const Segment& s = e->segs[with_backup[x.w]];
+                for (size_t o = 0; o < s.bytes; o += FMA_PAGE_BYTES, ++p) {
+                    const size_t lp = (size_t)((s.packed_off + o) / FMA_PAGE_BYTES);
+                    if (lp >= e->img_off.size()) WAKE_CHECK(fail(FMA_ESTATE, "segment at image offset %llu is outside the packed image's page table", (unsigned long long)(s.packed_off + o)));
+                    soff[p] = e->img_off[lp];
+                    sbytes[p] = e->img_bytes[lp];
+                    dsts[p] = (uint64_t)s.va + o;
+                    need_item[p] = seg_run[with_backup[x.w]] + 1;
+                }
+            }
+            uint32_t* d_err = e->d_psize + e->pdesc_cap;
+            WAKE_RT(cudaMemsetAsync(d_err, 0, sizeof(uint32_t), e->ks));
+            if (!zero_copy) {
+                if (ring_run) {
+                    int mrc0 = wait_mapped(1);
+                    if (mrc0 != FMA_OK) WAKE_CHECK(fail(mrc0, "%s", prog.msg));
+                } else {
+                    WAKE_CHECK(ensure_ring(e, W));
+                }
+                struct Slot { size_t p0, np; uint64_t bytes; };
+                std::vector<Slot> slots;  // pages that are adjacent in the store and fit one ring slot
+                for (size_t q = 0; q < n_pages;) {
+                    Slot sl{q, 0, 0};
+                    while (q < n_pages && sl.bytes + sbytes[q] <= e->ring_slot_bytes && (sl.np == 0 || soff[q] == soff[q - 1] + sbytes[q - 1])) {
+                        sl.bytes += sbytes[q];
+                        ++sl.np;
+                        ++q;
+                    }
+                    if (!sl.np) WAKE_CHECK(fail(FMA_EINVAL, "ring slot of %zu bytes cannot hold one page", e->ring_slot_bytes));
+                    slots.push_back(sl);
+                }
+                for (size_t c = 0; c < slots.size(); ++c)
+                    for (size_t q = slots[c].p0; q < slots[c].p0 + slots[c].np; ++q) {
+                        fma_k_pack_desc& pd = e->h_pdesc[q];
+                        pd.src = (uint64_t)(uintptr_t)e->ring[c % e->n_ring] + (soff[q] - soff[slots[c].p0]);
+                        pd.dst = dsts[q];
+                        pd.mode = sbytes[q] == FMA_PAGE_BYTES ? FMA_K_PACK_RAW : FMA_K_PACK_BF16;
+                        pd.pad = 0;
+                    }
+                WAKE_RT(cudaMemcpyAsync(e->d_pdesc, e->h_pdesc, n_pages * sizeof(fma_k_pack_desc), cudaMemcpyHostToDevice, e->ks));
+                for (size_t c = 0; c < slots.size(); ++c) {
+                    const Slot& sl = slots[c];
+                    const int slot = (int)(c % e->n_ring);
+                    cudaStream_t cstream = e->cs[c % e->n_cs];
+                    if (c >= (size_t)e->n_ring) WAKE_RT(cudaStreamWaitEvent(cstream, e->ev_ring_free[slot], 0));
+                    WAKE_RT(cudaMemcpyAsync(e->ring[slot], store + soff[sl.p0], sl.bytes, cudaMemcpyDefault, cstream));
+                    if (!copy_ops) first_copy_delay = now_s() - t_entry;
+                    ++copy_ops;
+                    WAKE_RT(cudaEventRecord(e->ev_ring_full[slot], cstream));
+                    size_t need = 0;
+                    for (size_t q = sl.p0; q < sl.p0 + sl.np; ++q) need = std::max(need, need_item[q]);
+                    int mrc = wait_mapped(need);
+                    if (mrc != FMA_OK) WAKE_CHECK(fail(mrc, "%s", prog.msg));
+                    WAKE_RT(cudaStreamWaitEvent(e->ks, e->ev_ring_full[slot], 0));
+                    WAKE_CHECK(kt.begin());
+                    WAKE_RT(fma_k_launch_unpack(e->d_pdesc + sl.p0, (uint32_t)sl.np, d_err, e->ks));
+                    WAKE_CHECK(kt.end((uint64_t)sl.np * FMA_PAGE_BYTES + sl.bytes));
+                    WAKE_RT(cudaEventRecord(e->ev_ring_free[slot], e->ks));
+                }
+            } else {
+                const uint64_t sbase = store_dev_base(e, tier);
+                for (size_t q = 0; q < n_pages; ++q) {
+                    fma_k_pack_desc& pd = e->h_pdesc[q];
+                    pd.src = sbase + soff[q];
+                    pd.dst = dsts[q];
+                    pd.mode = sbytes[q] == FMA_PAGE_BYTES ? FMA_K_PACK_RAW : FMA_K_PACK_BF16;
+                    pd.pad = 0;
+                }
+                WAKE_RT(cudaMemcpyAsync(e->d_pdesc, e->h_pdesc, n_pages * sizeof(fma_k_pack_desc), cudaMemcpyHostToDevice, e->ks));
+                const size_t batch_pages = std::max<size_t>(staged_slot(e) / FMA_PAGE_BYTES, 1);
+                for (size_t p0 = 0; p0 < n_pages;) {
+                    const size_t np = std::min(batch_pages, n_pages - p0);
+                    size_t need = 0;
+                    uint64_t stored = 0;
+                    for (size_t q = p0; q < p0 + np; ++q) {
+                        need = std::max(need, need_item[q]);
+                        stored += sbytes[q];
+                    }
+                    int mrc = wait_mapped(need);
+                    if (mrc != FMA_OK) WAKE_CHECK(fail(mrc, "%s", prog.msg));
+                    WAKE_CHECK(kt.begin());
+                    WAKE_RT(fma_k_launch_unpack(e->d_pdesc + p0, (uint32_t)np, d_err, e->ks));
+                    WAKE_CHECK(kt.end((uint64_t)np * FMA_PAGE_BYTES + stored));
+                    if (!copy_ops) first_copy_delay = now_s() - t_entry;
+                    ++copy_ops;
+                    p0 += np;
+                }
+            }
+        } else if (mode == FMA_MODE_DIRECT) {
+            int k = 0;
+            for (size_t w = 0; w < with_backup.size(); ++w) {
+                int mrc = wait_mapped(seg_run[with_backup[w]] + 1);
+                if (mrc != FMA_OK) WAKE_CHECK(fail(mrc, "%s", prog.msg));
+                const Segment& s = e->segs[with_backup[w]];
+                for (size_t o = 0; o < s.bytes; o += chunk, ++k) {
+                    const size_t n = std::min(chunk, s.bytes - o);
+                    WAKE_RT(cudaMemcpyAsync(reinterpret_cast<void*>(s.va + o), store + s.packed_off + o, n, cudaMemcpyDefault,
+                                            e->cs[k % e->n_cs]));
+                    if (!copy_ops) first_copy_delay = now_s() - t_entry;
+                    ++copy_ops;
+                }
+            }
+        } else {
+            // page table of the DESTINATIONS, ordered by packed offset (== with_backup order by construction
+            // only if every backed-up segment is woken; build explicitly from packed offsets to stay general)
+            struct Dst { uint64_t packed_off; size_t w; };
+            std::vector<Dst> d;
+            for (size_t w = 0; w < with_backup.size(); ++w) d.push_back(Dst{e->segs[with_backup[w]].packed_off, w});
+            std::sort(d.begin(), d.end(), [](const Dst& a, const Dst& b) { return a.packed_off < b.packed_off; });
+            // runs of pages: (image page index, destination address), plus the latest work item each page needs
+            size_t n_pages = W / FMA_PAGE_BYTES;
+            WAKE_CHECK(ensure_tables(e, n_pages));
+            uint64_t* dst_tab = e->h_tab;                 // destination page addresses
+            uint64_t* src_tab = e->h_tab + e->d_tab_cap;  // source page addresses inside the store (may be sparse)
+            std::vector<size_t> need_item(n_pages);
+            const uint64_t sbase = store_dev_base(e, tier);
+            size_t p = 0;
+            for (const Dst& x : d) {
+                const Segment& s = e->segs[with_backup[x.w]];
+                for (size_t o = 0; o < s.bytes; o += FMA_PAGE_BYTES, ++p) {
+                    dst_tab[p] = (uint64_t)s.va + o;
+                    src_tab[p] = sbase + s.packed_off + o;
+                    need_item[p] = seg_run[with_backup[x.w]] + 1;
+                }
+            }
+            WAKE_RT(cudaMemcpyAsync(e->d_tab, dst_tab, n_pages * sizeof(uint64_t), cudaMemcpyHostToDevice, e->ks));
+            WAKE_RT(cudaMemcpyAsync(e->d_tab + e->d_tab_cap, src_tab, n_pages * sizeof(uint64_t), cudaMemcpyHostToDevice, e->ks));
+            const uint64_t* d_dst = e->d_tab;
+            const uint64_t* d_src = e->d_tab + e->d_tab_cap;
+            if (mode == FMA_MODE_KERNEL) {
+                // K2 reads the store itself (zero-copy PCIe reads, or NVLink/HBM loads); launch batches as the
+                // mapper makes progress so the scatter overlaps cuMemCreate/Map of later segments
+                const size_t batch_pages = std::max<size_t>(staged_slot(e) / FMA_PAGE_BYTES, 1);
+                size_t p0 = 0;
+                while (p0 < n_pages) {
+                    size_t np = std::min(batch_pages, n_pages - p0);
+                    size_t need = 0;
+                    for (size_t q = p0; q < p0 + np; ++q) need = std::max(need, need_item[q]);
+                    int mrc = wait_mapped(need);
+                    if (mrc != FMA_OK) WAKE_CHECK(fail(mrc, "%s", prog.msg));
+                    // opportunistically extend the batch over everything already mapped
+                    const size_t have = mapped_now();
+                    while (p0 + np < n_pages && need_item[p0 + np] <= have) ++np;
+                    WAKE_CHECK(kt.launch(d_src + p0, 0, d_dst + p0, 0, (uint32_t)np));
+                    if (!copy_ops) first_copy_delay = now_s() - t_entry;
+                    ++copy_ops;
+                    p0 += np;
+                }
+            } else {  // STAGED: copy engine H2D store -> ring slot (starts at t=0), K2 scatter once the targets are mapped
+                if (ring_run) {  // the ring is run 0 (1 GiB, ~0.2 ms to map): wait for it before the first H2D
+                    int mrc0 = wait_mapped(1);
+                    if (mrc0 != FMA_OK) WAKE_CHECK(fail(mrc0, "%s", prog.msg));
+                } else {
+                    WAKE_CHECK(ensure_ring(e, W));
+                }
+                const size_t slot_pages = e->ring_slot_bytes / FMA_PAGE_BYTES;
+                // the store image may be only partially woken; H2D works on runs that are contiguous in the store
+                size_t c = 0;
+                size_t p0 = 0;
+                while (p0 < n_pages) {
+                    size_t np = 1;
+                    while (np < slot_pages && p0 + np < n_pages && src_tab[p0 + np] == src_tab[p0 + np - 1] + FMA_PAGE_BYTES) ++np;
+                    const int slot = (int)(c % e->n_ring);
+                    cudaStream_t cstream = e->cs[c % e->n_cs];
+                    if (c >= (size_t)e->n_ring) WAKE_RT(cudaStreamWaitEvent(cstream, e->ev_ring_free[slot], 0));
+                    WAKE_RT(cudaMemcpyAsync(e->ring[slot], store + (src_tab[p0] - sbase), np * FMA_PAGE_BYTES, cudaMemcpyDefault, cstream));
+                    if (!copy_ops) first_copy_delay = now_s() - t_entry;
+                    ++copy_ops;
+                    WAKE_RT(cudaEventRecord(e->ev_ring_full[slot], cstream));
+                    size_t need = 0;
+                    for (size_t q = p0; q < p0 + np; ++q) need = std::max(need, need_item[q]);
+                    int mrc = wait_mapped(need);
+                    if (mrc != FMA_OK) WAKE_CHECK(fail(mrc, "%s", prog.msg));
+                    WAKE_RT(cudaStreamWaitEvent(e->ks, e->ev_ring_full[slot], 0));
+                    WAKE_CHECK(kt.launch(nullptr, (uint64_t)(uintptr_t)e->ring[slot], d_dst + p0, 0, (uint32_t)np));
+                    WAKE_RT(cudaEventRecord(e->ev_ring_free[slot], e->ks));
+                    p0 += np;
+                    ++c;
+                }
+            }
+        }
+    }
+    // every requested segment must be mapped before wake returns (cumem.py:237-240)
+    {
+        int mrc = wait_mapped(runs.size());
+        if (mrc != FMA_OK) WAKE_CHECK(fail(mrc, "%s", prog.msg));
+    }
+    join_mappers();
+    const double t_joined = now_s();
+    double t_copy_end = t_joined;
+    if (W) {
+        rc = timer.end(&copy_s);
+        if (rc != FMA_OK) return rc;
+        rc = kt.collect();
+        if (rc != FMA_OK) return rc;
+        if (packed) {  // K5 counts stored pages it could not read (bad magic / count): the image is damaged
+            RT(cudaMemcpyAsync(e->h_psize + e->pdesc_cap, e->d_psize + e->pdesc_cap, sizeof(uint32_t), cudaMemcpyDeviceToHost, e->ks));
+            RT(cudaStreamSynchronize(e->ks));
+            if (e->h_psize[e->pdesc_cap]) return fail(FMA_EINTEGRITY, "%u stored page(s) of the packed image are malformed", e->h_psize[e->pdesc_cap]);
+        }
+        t_copy_end = now_s();
+    }
+    if (dbg_t)
+        fprintf(stderr, "[fma] wake phases: plan+ring %.1f ms | enqueue+map-wait %.1f ms | drain %.1f ms | ring free %.1f ms | runs %zu\n",
+                (t_ring - t_entry) * 1e3, (t_joined - t_ring) * 1e3, (t_copy_end - t_joined) * 1e3, (now_s() - t_copy_end) * 1e3, runs.size());
+#undef WAKE_CHECK
+#undef WAKE_RT
+
+    uint64_t remapped_only = 0;
+    for (size_t i : remap_only) remapped_only += e->segs[i].bytes;
+
+    int verify_rc = FMA_OK;
+    if ((flags & FMA_FLAG_VERIFY) && W) {
+        std::vector<size_t> idx;
+        for (size_t i : with_backup)
+            if (e->segs[i].digest_valid) idx.push_back(i);
+        std::vector<uint64_t> dg;
+        rc = digest_segments(e, idx, &dg);
+        if (rc != FMA_OK) return rc;
+        for (size_t k = 0; k < idx.size(); ++k)
+            if (dg[k] != e->segs[idx[k]].digest)
+                verify_rc = fail(FMA_EINTEGRITY, "segment %zu (va 0x%llx): digest %016llx after wake != %016llx before sleep", idx[k],
+                                 (unsigned long long)e->segs[idx[k]].va, (unsigned long long)dg[k],
+                                 (unsigned long long)e->segs[idx[k]].digest);
+    }
+    if (!(flags & FMA_FLAG_KEEP_BACKUP))
+        for (size_t i : with_backup) {  // data.cpu_backup_tensor = None (cumem.py:249)
+            e->segs[i].has_backup = false;
+            e->segs[i].packed_off = kNoOffset;
+        }
+
+    e->st.wake_seconds = now_s() - t_entry;
+    e->st.wake_copy_seconds = copy_s;
+    e->st.wake_map_seconds = map_ns.load() * 1e-9;
+    e->st.wake_first_copy_delay = first_copy_delay;
+    e->st.wake_bytes_restored = W;
+    e->st.wake_bytes_remapped_only = remapped_only;
+    e->st.copy_ops = copy_ops;
+    e->st.total_copy_ops += copy_ops;
+    e->st.tier = tier;
+    e->st.mode = mode;
+    if (!W) {
+        e->pending_events = 0;
+        e->st.kernel_seconds = 0;
+        e->st.kernel_bytes = 0;
+        e->st.kernel_launches = 0;
+    }
+    return verify_rc;
+}
+
+}  // namespace fma_impl

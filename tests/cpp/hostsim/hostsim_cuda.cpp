@@ -1,6 +1,7 @@
 // hostsim_cuda.cpp — HOST SIMULATION of the CUDA runtime + VMM driver calls the engine uses.  TEST INFRASTRUCTURE ONLY.
 //
-// Purpose: run fma_engine.cu's host logic (segment table, arenas, runs, ring, mapper/unmapper threads, stage events,
+// Purpose: run the host engine's logic (csrc/fma_engine.cu, fma_sleep.cu, fma_wake.cu, fma_load.cu, fma_image.cu:
+// segment table, arenas, runs, ring, mapper/unmapper threads, stage events,
 // error paths) on a machine without a GPU, under ASan/TSan if wanted.  It is linked ONLY into
 // tests/cpp/hostsim/libfma_b200_hostsim.so by tests/test_engine_hostsim.py; the product library
 // (llm-d-fast-model-actuation_b200/libfma_b200.so) contains none of this and refuses to run without a GPU.

@@ -1,4 +1,5 @@
-"""The engine's HOST logic on CPU.  fma_engine.cu is compiled with g++ against a host simulation of the CUDA runtime +
+"""The engine's HOST logic on CPU.  The host translation units (csrc/fma_engine.cu, fma_sleep.cu, fma_wake.cu, fma_load.cu,
+fma_image.cu) are compiled with g++ against a host simulation of the CUDA runtime +
 VMM driver calls (tests/cpp/hostsim/, test infrastructure: mmap-backed VMM with the real map/unmap semantics, eager
 streams) and host stand-ins for the kernel launch wrappers, then
 
@@ -20,7 +21,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SIM = os.path.join(ROOT, "tests", "cpp", "hostsim")
 CSRC = os.path.join(ROOT, "llm-d-fast-model-actuation_b200", "csrc")
 INC = ["-I/usr/local/cuda/include", "-I" + CSRC, "-I" + os.path.join(ROOT, "include")]
-SRCS = ["-x", "c++", os.path.join(CSRC, "fma_engine.cu"), "-x", "c++", os.path.join(SIM, "hostsim_cuda.cpp"), os.path.join(SIM, "hostsim_kernels.cpp")]
+HOST_TUS = ["fma_engine.cu", "fma_sleep.cu", "fma_wake.cu", "fma_load.cu", "fma_image.cu"]   # the host engine (no kernels): csrc/Makefile HOST_SRCS
+SRCS = ["-x", "c++", *[os.path.join(CSRC, f) for f in HOST_TUS], os.path.join(SIM, "hostsim_cuda.cpp"), os.path.join(SIM, "hostsim_kernels.cpp")]
 
 
 def _have_cuda_headers():

@@ -1,5 +1,5 @@
 """The engine's address-space layout logic (VA arenas with first-fit reuse, run planning) is plain C++ in
-csrc/fma_layout.h and is what fma_engine.cu compiles in; exercised here on CPU with g++ (incl. a 20k-step randomised
+csrc/fma_layout.h and is what the engine (csrc/fma_engine.cu, fma_wake.cu) compiles in; exercised here on CPU with g++ (incl. a 20k-step randomised
 alloc/free invariant check)."""
 import os
 import subprocess
@@ -17,5 +17,6 @@ def test_layout_logic(tmp_path):
 
 
 def test_engine_uses_the_tested_header():
-    src = open(os.path.join(ROOT, "llm-d-fast-model-actuation_b200", "csrc", "fma_engine.cu")).read()
+    csrc = os.path.join(ROOT, "llm-d-fast-model-actuation_b200", "csrc")
+    src = "".join(open(os.path.join(csrc, f)).read() for f in ("fma_internal.h", "fma_engine.cu", "fma_wake.cu"))
     assert '#include "fma_layout.h"' in src and "fma_layout::plan_runs(" in src and "fma_layout::arena_take(" in src
