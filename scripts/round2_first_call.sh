@@ -27,6 +27,9 @@ timeout 600 python bench.py --steps 10 --warmup 3 > "$out/bench_default.json" 2>
 timeout 400 python bench.py --steps 10 --warmup 3 --contents bf16 --pack 0 --no-cpu-baseline --packed-extra 0 > "$out/bench_bf16_plain.json" 2>> "$out/bench_default.err"
 timeout 400 python bench.py --steps 10 --warmup 3 --contents bf16 --pack 1 --no-cpu-baseline --packed-extra 0 > "$out/bench_bf16_packed.json" 2>> "$out/bench_default.err"; echo "bench packed rc=$?" | tee -a "$out/status.txt"
 
+# 4b. VMM granularity / VA alignment probe (seconds)
+timeout 120 python scripts/gran_probe.py > "$out/gran_probe.log" 2>&1
+
 # 5. ncu: launch list of the packed bench, then one full capture of K5 and K4
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$out/launches_packed.csv" \
     python bench.py --steps 2 --warmup 3 --contents bf16 --pack 1 --no-cpu-baseline --packed-extra 0 > "$out/ncu_launches.log" 2>&1
