@@ -19,6 +19,47 @@ cfg = dict(architectures=["LlamaForCausalLM"], model_type="llama", hidden_act="s
 json.dump(cfg, open(f"{mdir}/config.json", "w"))
 OUT = os.path.join(ROOT, "gpurun_out", "e2e"); os.makedirs(OUT, exist_ok=True)
 LPORT, VPORT = 8001, 8005
+# Arms (E2E_ARMS=comma list).  Default: vLLM's allocator vs the engine, dummy weights.  Extra arms:
+#   fma_b200_packed  the engine with the PACKED host image (FMA_PACK=1; dummy weights are bf16 U(-1e-3, 1e-3): they code)
+#   ckpt_default / ckpt_fma   a synthetic safetensors checkpoint of the same shape, loaded by vLLM's own loader vs
+#                             --load-format fma (the engine's file -> HBM stream); both must generate the same tokens
+ARMS = os.environ.get("E2E_ARMS", "reference,fma_b200").split(",")
+ARM_ENV = {"reference": {}, "fma_b200": {"FMA_B200": "1"}, "fma_b200_packed": {"FMA_B200": "1", "FMA_PACK": "1"},
+           "ckpt_default": {"FMA_B200": "1"}, "ckpt_fma": {"FMA_B200": "1"}}
+ARM_LOAD = {"ckpt_default": "auto", "ckpt_fma": "fma"}
+
+
+def write_checkpoint(path):
+    """Random bf16 LlamaForCausalLM checkpoint (HF tensor names) in one safetensors file, written by the repo's own writer."""
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    import fma_b200  # noqa: F401
+    from fma_b200 import loader
+    c = CFGS[MODEL]; h, inter, L, nh, nkv, v = c["hidden_size"], c["intermediate_size"], c["num_hidden_layers"], c["num_attention_heads"], c["num_key_value_heads"], c["vocab_size"]
+    hd = h // nh
+    rng = np.random.default_rng(1234)
+    def t(name, *shape, ones=False):
+        n = int(np.prod(shape))
+        if ones:
+            a = np.full(n, 0x3F80, np.uint16)
+        else:
+            a = (rng.normal(0, 0.02, n).astype(np.float32).view(np.uint32) >> 16).astype(np.uint16)
+        return (name, "BF16", tuple(shape), a.tobytes())
+    def tensors():
+        yield t("model.embed_tokens.weight", v, h)
+        for i in range(L):
+            p = f"model.layers.{i}."
+            yield t(p + "self_attn.q_proj.weight", nh * hd, h); yield t(p + "self_attn.k_proj.weight", nkv * hd, h)
+            yield t(p + "self_attn.v_proj.weight", nkv * hd, h); yield t(p + "self_attn.o_proj.weight", h, nh * hd)
+            yield t(p + "mlp.gate_proj.weight", inter, h); yield t(p + "mlp.up_proj.weight", inter, h); yield t(p + "mlp.down_proj.weight", h, inter)
+            yield t(p + "input_layernorm.weight", h, ones=True); yield t(p + "post_attention_layernorm.weight", h, ones=True)
+        yield t("model.norm.weight", h, ones=True)
+        yield t("lm_head.weight", v, h)
+    loader.write_safetensors(path, tensors())
+
+
+if any(a in ARM_LOAD for a in ARMS) and not os.path.exists(f"{mdir}/model.safetensors"):
+    t0 = time.time(); write_checkpoint(f"{mdir}/model.safetensors"); print(f"checkpoint written in {time.time() - t0:.1f} s", flush=True)
 
 def http(method, url, body=None, timeout=600):
     data = json.dumps(body).encode() if body is not None else (b"" if method in ("POST", "PUT") else None)
@@ -46,9 +87,11 @@ try:
     options = (f"--model {mdir} --load-format dummy --skip-tokenizer-init --enable-sleep-mode --port {VPORT} --host 127.0.0.1 "
                f"--enforce-eager --max-model-len 2048 --gpu-memory-utilization 0.30 --no-enable-prefix-caching"
                + (f" --tensor-parallel-size {TP}" if TP > 1 else ""))
-    for arm, extra_env in (("reference", {}), ("fma_b200", {"FMA_B200": "1"})):
+    for arm in ARMS:
+        extra_env = ARM_ENV[arm]
         iid = f"e2e-{arm}"
-        body = {"options": options, "env_vars": {"VLLM_SERVER_DEV_MODE": "1", **extra_env}, "annotations": {"isc-name": "e2e", "inference-port": str(VPORT)}}
+        arm_options = options.replace("--load-format dummy", f"--load-format {ARM_LOAD[arm]}") if arm in ARM_LOAD else options
+        body = {"options": arm_options, "env_vars": {"VLLM_SERVER_DEV_MODE": "1", **extra_env}, "annotations": {"isc-name": "e2e", "inference-port": str(VPORT)}}
         st, txt, _ = http("PUT", f"http://127.0.0.1:{LPORT}/v2/vllm/instances/{iid}", body)
         assert st == 201, (st, txt)
         t0 = time.time(); up = False
@@ -80,13 +123,15 @@ try:
         after = gen()
         log = http("GET", f"http://127.0.0.1:{LPORT}/v2/vllm/instances/{iid}/log")[1]
         open(f"{OUT}/{arm}_vllm.log", "w").write(log)
-        lines = [l for l in log.splitlines() if "It took" in l or "sleep freed" in l or "fma_b200" in l]
+        lines = [l for l in log.splitlines() if "It took" in l or "sleep freed" in l or "fma_b200" in l or "Loading weights took" in l]
         results[arm] = dict(load_s=load_s, rows=rows, tokens_before=before, tokens_after=after, same_tokens=before == after,
                             uses_fma=any("fma_b200" in l for l in lines), vllm_log_lines=lines[-12:])
         print(arm, json.dumps(results[arm])[:1800], flush=True)
         st, _, _ = http("DELETE", f"http://127.0.0.1:{LPORT}/v2/vllm/instances/{iid}")
         time.sleep(8)
 finally:
+    if "ckpt_default" in results and "ckpt_fma" in results and "tokens_before" in results["ckpt_default"] and "tokens_before" in results["ckpt_fma"]:
+        results["ckpt_loaders_agree"] = results["ckpt_default"]["tokens_before"] == results["ckpt_fma"]["tokens_before"]
     json.dump(results, open(f"{OUT}/e2e_launcher_vllm_{MODEL}_tp{TP}.json", "w"), indent=1)
     launcher.terminate()
     try: launcher.wait(timeout=20)

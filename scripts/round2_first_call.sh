@@ -37,4 +37,7 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:fma_
     python bench.py --steps 1 --warmup 3 --contents bf16 --pack 1 --no-cpu-baseline --packed-extra 0 > "$out/ncu_k5.log" 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:fma_k_pack$ -c 1 -o "$out/k4_full" \
     python bench.py --steps 1 --warmup 3 --contents bf16 --pack 1 --no-cpu-baseline --packed-extra 0 > "$out/ncu_k4.log" 2>&1
+# 6. end to end through the unmodified reference launcher + real vLLM: packed image over HTTP, and --load-format fma
+timeout 900 env E2E_ARMS=fma_b200,fma_b200_packed python scripts/e2e_launcher_vllm.py llama-3-8b > "$out/e2e_packed.log" 2>&1; echo "e2e packed rc=$?" | tee -a "$out/status.txt"
+timeout 900 env E2E_ARMS=ckpt_default,ckpt_fma python scripts/e2e_launcher_vllm.py llama-1b > "$out/e2e_ckpt.log" 2>&1; echo "e2e ckpt rc=$?" | tee -a "$out/status.txt"
 cat "$out/status.txt"
