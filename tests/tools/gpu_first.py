@@ -1,7 +1,7 @@
 """First GPU contact: correctness of K0/K1/K2/K3 + every sleep/wake mode vs the oracle, then timings.
 Writes gpurun_out/first/*.json.  Exploratory (not the bench, not a test)."""
 import ctypes as C, json, os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))  # repo root
 import numpy as np
 import fma_b200
 from fma_b200 import workloads as W, _lib as L

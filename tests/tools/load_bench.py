@@ -1,7 +1,7 @@
 """Cold load, file -> HBM: fma_load_file vs the loaders vLLM's default path builds on (safetensors' own GPU load and a
 vLLM-style per-tensor safe_open + copy_), Llama-3-8B-shaped synthetic safetensors file in the page cache."""
 import os, sys, json, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))  # repo root
 import numpy as np, torch
 import fma_b200
 from fma_b200 import workloads as W, loader, _lib as L
