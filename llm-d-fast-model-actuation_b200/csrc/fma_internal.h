@@ -21,6 +21,7 @@
 #include <cstdlib>
 #include <cerrno>
 #include <cstring>
+#include <functional>
 #include <iterator>
 #include <map>
 #include <mutex>

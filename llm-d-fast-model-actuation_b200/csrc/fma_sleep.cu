@@ -42,6 +42,371 @@ int plan_packed_image(fma_engine_t* e, const std::vector<Extent>& ex, uint64_t W
     return FMA_OK;
 }
 
+namespace {
+
+// ---- unmapper thread: cuMemUnmap runs UNDER the copy pipeline instead of after it -----------------------
+// (cumem.py:213 unmaps each segment right after its blocking copy.)  The thread only issues driver calls on
+// ranges planned here; the table is updated by this thread after it has been joined.  Adjacent units are
+// unmapped with ONE spanning cuMemUnmap (allowed across whole mappings, scripts/vmm_span_probe.py).
+struct Range {
+    CUdeviceptr va;
+    size_t bytes;
+};
+struct Stage {
+    cudaEvent_t ev;
+    std::vector<Range> ranges;
+};
+struct Unmapper {
+    fma_engine_t* e;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<Stage> stages;
+    bool closed = false;
+    int error = FMA_OK;
+    char msg[512] = "";
+    double seconds = 0;
+    std::vector<Range> first;  // ranges with nothing to wait for (discarded tags)
+    std::vector<Range> done;   // ranges actually unmapped
+    std::thread th;
+    void unmap_range(const Range& r, bool dbg) {
+        const double a = now_s();
+        CUresult r1 = g_drv.MemUnmap(r.va, r.bytes);
+        const double b = now_s();
+        seconds += b - a;
+        if (r1 != CUDA_SUCCESS) {
+            std::lock_guard<std::mutex> lk(mu);
+            if (error == FMA_OK) {
+                error = FMA_ECUDA;
+                snprintf(msg, sizeof(msg), "cuMemUnmap(%zu bytes) failed: %s", r.bytes, cu_err(r1));
+            }
+            return;
+        }
+        if (dbg && (b - a) > 5e-3)
+            fprintf(stderr, "[fma] slow unmap va=0x%llx bytes=%zu unmap=%.1f ms\n", (unsigned long long)r.va, r.bytes, (b - a) * 1e3);
+        done.push_back(r);
+    }
+    void run() {
+        cudaSetDevice(e->device);
+        const bool dbg = env_int("FMA_DEBUG_VMM", 0) != 0;
+        for (const Range& r : first) unmap_range(r, dbg);
+        size_t k = 0;
+        for (;;) {
+            Stage st;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return stages.size() > k || closed; });
+                if (k >= stages.size()) break;
+                st = stages[k];
+            }
+            cudaError_t r = cudaEventSynchronize(st.ev);
+            if (r != cudaSuccess) {
+                std::lock_guard<std::mutex> lk(mu);
+                if (error == FMA_OK) {
+                    error = FMA_ECUDA;
+                    snprintf(msg, sizeof(msg), "cudaEventSynchronize(stage) failed: %s", cudaGetErrorString(r));
+                }
+                break;  // never unmap memory whose copy may not have finished
+            }
+            for (const Range& rg : st.ranges) unmap_range(rg, dbg);
+            ++k;
+        }
+    }
+    void publish(Stage&& st) {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            stages.push_back(std::move(st));
+        }
+        cv.notify_all();
+    }
+    void finish() {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            closed = true;
+        }
+        cv.notify_all();
+        if (th.joinable()) th.join();
+    }
+    ~Unmapper() { finish(); }
+};
+
+// Whatever the unmapper really unmapped is applied to the table on EVERY exit path (also the error returns
+// below), so that a failed sleep never leaves units the table believes mapped but the driver has released.
+struct ApplyUnmapped {
+    Unmapper* un;
+    fma_engine_t* e;
+    const std::vector<Extent>* ex;   // offloaded extents: a unit is only ever unmapped after its bytes reached the store,
+    int tier;                        // so an unmapped offloaded segment HAS a backup even if the sleep fails later
+    size_t applied = 0;
+    void run() {
+        std::lock_guard<std::mutex> lk(e->mu);
+        for (; applied < un->done.size(); ++applied) {
+            const Range& r = un->done[applied];
+            auto it = e->units.lower_bound(r.va);
+            while (it != e->units.end() && it->first < r.va + r.bytes) {
+                Arena& a = e->arenas[it->second.arena];
+                for (auto& z : it->second.zombies) arena_give_back(a, z.first - a.base, z.second);
+                it = e->units.erase(it);
+            }
+            if (e->ring_attached && e->ring_unit_va >= r.va && e->ring_unit_va < r.va + r.bytes) {
+                for (int i = 0; i < kMaxRing; ++i) e->ring[i] = nullptr;
+                e->n_ring = 0; e->ring_slot_bytes = 0; e->ring_attached = false; e->ring_unit_va = 0;
+            }
+            for (Segment& sg : e->segs)
+                if (sg.va >= r.va && sg.va < r.va + r.bytes) {
+                    sg.mapped = false;
+                    sg.unit_va = 0;
+                }
+            for (const Extent& x : *ex)
+                if (x.va >= r.va && x.va < r.va + r.bytes) {
+                    Segment& sg = e->segs[x.seg_index];
+                    sg.has_backup = true;
+                    sg.backup_tier = tier;
+                    sg.packed_off = x.packed_off;
+                }
+        }
+        if (!un->done.empty()) {  // even a failed sleep leaves an image a later wake can restore from
+            e->image_tier = tier;
+        }
+    }
+    ~ApplyUnmapped() {
+        un->finish();
+        run();
+    }
+};
+
+// Units in VA order, split into "discarded" (release now) and "offloaded" (release once the image has their
+// bytes).  image_end = packed offset just past the unit's last live segment.
+struct PlannedUnit {
+    CUdeviceptr va;
+    size_t bytes;
+    uint64_t image_end;
+};
+
+// What the copy pipelines of one sleep share.  Each pipeline enqueues the work that moves image[0, W) into the store
+// and tells the unmapper, through publish_consumed(image_done, stream), which units are dead once `stream` gets there.
+struct SleepPipe {
+    fma_engine_t* e;
+    const std::vector<Extent>& ex;
+    uint64_t W;
+    int tier;
+    char* store;           // host pointer of the store (copy-engine target), or the parking buffer
+    KernelTimes& kt;
+    uint32_t& copy_ops;
+    std::function<int(uint64_t, cudaStream_t)> publish_consumed;
+    int publish_gathered(size_t pages_done) { return publish_consumed((uint64_t)pages_done * FMA_PAGE_BYTES, e->ks); }
+    // page table of the image (device addresses of its pages, in order) -> e->h_tab / e->d_tab
+    int upload_page_table(size_t* n_pages) {
+        *n_pages = W / FMA_PAGE_BYTES;
+        int rc = ensure_tables(e, *n_pages);
+        if (rc != FMA_OK) return rc;
+        build_page_table(ex, e->h_tab);
+        RT(cudaMemcpyAsync(e->d_tab, e->h_tab, *n_pages * sizeof(uint64_t), cudaMemcpyHostToDevice, e->ks));
+        return FMA_OK;
+    }
+};
+
+// DIRECT: copy engines move each segment chunk straight into the packed image
+int sleep_direct(SleepPipe& pipe) {
+    fma_engine_t* e = pipe.e;
+    const std::vector<Extent>& ex = pipe.ex;
+    uint32_t& copy_ops = pipe.copy_ops;
+    char* store = pipe.store;
+    auto publish_consumed = [&](uint64_t done, cudaStream_t s) { return pipe.publish_consumed(done, s); };
+    int rc = FMA_OK;
+    const size_t chunk = direct_chunk(e);
+    // copy engines straight from the segments into the packed image, chunks round-robin over the streams;
+    // every `slot` bytes of image the streams are joined so that one event marks the units behind it dead
+    const size_t slot = staged_slot(e);
+    uint64_t next_join = slot;
+    int k = 0;
+    for (const Extent& x : ex) {
+        for (size_t o = 0; o < x.bytes; o += chunk, ++k) {
+            const size_t n = std::min(chunk, x.bytes - o);
+            RT(cudaMemcpyAsync(store + x.packed_off + o, reinterpret_cast<void*>(x.va + o), n, cudaMemcpyDefault,
+                               e->cs[k % e->n_cs]));
+            ++copy_ops;
+        }
+        const uint64_t image_done = x.packed_off + x.bytes;
+        if (image_done >= next_join || &x == &ex.back()) {
+            for (int i = 1; i < e->n_cs; ++i) {  // stream 0 waits for the others
+                RT(cudaEventRecord(e->ev_cs[i], e->cs[i]));
+                RT(cudaStreamWaitEvent(e->cs[0], e->ev_cs[i], 0));
+            }
+            rc = publish_consumed(image_done, e->cs[0]);
+            if (rc != FMA_OK) return rc;
+            next_join = image_done + slot;
+        }
+    }
+    return rc;
+}
+
+// KERNEL + PACKED (parking tiers): K4 encodes straight into the peer / local HBM store
+int sleep_kernel_packed(SleepPipe& pipe) {
+    fma_engine_t* e = pipe.e;
+    KernelTimes& kt = pipe.kt;
+    uint32_t& copy_ops = pipe.copy_ops;
+    const int tier = pipe.tier;
+    auto publish_gathered = [&](size_t pages) { return pipe.publish_gathered(pages); };
+    int rc = FMA_OK;
+    size_t n_pages = 0;
+    rc = pipe.upload_page_table(&n_pages);
+    if (rc != FMA_OK) return rc;
+    // PACKED image in a parking tier: K4 encodes straight into the peer / local HBM store (0.758 of the bytes
+    // over NVLink and of the parking GPU's HBM), batches as below
+    rc = ensure_pack_bufs(e, n_pages);
+    if (rc != FMA_OK) return rc;
+    const uint64_t dbase = store_dev_base(e, tier);
+    for (size_t p = 0; p < n_pages; ++p) {
+        fma_k_pack_desc& d = e->h_pdesc[p];
+        d.src = e->h_tab[p];
+        d.dst = dbase + e->img_off[p];
+        d.mode = e->img_bytes[p] == FMA_PAGE_BYTES ? FMA_K_PACK_RAW : FMA_K_PACK_BF16;
+        d.pad = 0;
+    }
+    uint32_t* d_err = e->d_psize + e->pdesc_cap;
+    RT(cudaMemcpyAsync(e->d_pdesc, e->h_pdesc, n_pages * sizeof(fma_k_pack_desc), cudaMemcpyHostToDevice, e->ks));
+    RT(cudaMemsetAsync(d_err, 0, sizeof(uint32_t), e->ks));
+    const size_t batch = std::max<size_t>(staged_slot(e) / FMA_PAGE_BYTES, 1);
+    for (size_t p0 = 0; p0 < n_pages; p0 += batch) {
+        const size_t np = std::min(batch, n_pages - p0);
+        uint64_t stored = 0;
+        for (size_t q = p0; q < p0 + np; ++q) stored += e->img_bytes[q];
+        rc = kt.begin();
+        if (rc != FMA_OK) return rc;
+        RT(fma_k_launch_pack(e->d_pdesc + p0, (uint32_t)np, d_err, e->ks));
+        rc = kt.end((uint64_t)np * FMA_PAGE_BYTES + stored);
+        if (rc != FMA_OK) return rc;
+        ++copy_ops;
+        rc = publish_gathered(p0 + np);
+        if (rc != FMA_OK) return rc;
+    }
+    return rc;
+}
+
+// KERNEL: K1 writes the store itself (mapped pinned host memory, peer or local HBM)
+int sleep_kernel(SleepPipe& pipe) {
+    fma_engine_t* e = pipe.e;
+    KernelTimes& kt = pipe.kt;
+    uint32_t& copy_ops = pipe.copy_ops;
+    const int tier = pipe.tier;
+    auto publish_gathered = [&](size_t pages) { return pipe.publish_gathered(pages); };
+    int rc = FMA_OK;
+    size_t n_pages = 0;
+    rc = pipe.upload_page_table(&n_pages);
+    if (rc != FMA_OK) return rc;
+    // K1 writes the store itself: mapped pinned host memory (PCIe posted writes) or peer/local HBM;
+    // launched in slot-sized batches so finished segments can be released while later ones still move
+    const size_t batch = std::max<size_t>(staged_slot(e) / FMA_PAGE_BYTES, 1);
+    const uint64_t dbase = store_dev_base(e, tier);
+    for (size_t p0 = 0; p0 < n_pages; p0 += batch) {
+        const size_t np = std::min(batch, n_pages - p0);
+        rc = kt.launch(e->d_tab + p0, 0, nullptr, dbase + p0 * FMA_PAGE_BYTES, (uint32_t)np);
+        if (rc != FMA_OK) return rc;
+        ++copy_ops;
+        rc = publish_gathered(p0 + np);
+        if (rc != FMA_OK) return rc;
+    }
+    return rc;
+}
+
+// STAGED + PACKED: K4 gather + encode -> ring slot (stored pages back to back) -> one D2H per slot
+int sleep_staged_packed(SleepPipe& pipe) {
+    fma_engine_t* e = pipe.e;
+    KernelTimes& kt = pipe.kt;
+    uint32_t& copy_ops = pipe.copy_ops;
+    char* store = pipe.store;
+    const uint64_t W = pipe.W;
+    auto publish_consumed = [&](uint64_t done, cudaStream_t s) { return pipe.publish_consumed(done, s); };
+    int rc = FMA_OK;
+    size_t n_pages = 0;
+    rc = pipe.upload_page_table(&n_pages);
+    if (rc != FMA_OK) return rc;
+    rc = ensure_ring(e, W);
+    if (rc != FMA_OK) return rc;
+    struct Slot { size_t p0, np; uint64_t bytes; };
+    std::vector<Slot> slots;
+    for (size_t p = 0; p < n_pages;) {
+        Slot sl{p, 0, 0};
+        while (p < n_pages && sl.bytes + e->img_bytes[p] <= e->ring_slot_bytes) {
+            sl.bytes += e->img_bytes[p];
+            ++sl.np;
+            ++p;
+        }
+        if (!sl.np) return fail(FMA_EINVAL, "ring slot of %zu bytes cannot hold one page", e->ring_slot_bytes);
+        slots.push_back(sl);
+    }
+    for (size_t c = 0; c < slots.size(); ++c)
+        for (size_t p = slots[c].p0; p < slots[c].p0 + slots[c].np; ++p) {
+            fma_k_pack_desc& d = e->h_pdesc[p];
+            d.src = e->h_tab[p];
+            d.dst = (uint64_t)(uintptr_t)e->ring[c % e->n_ring] + (e->img_off[p] - e->img_off[slots[c].p0]);
+            d.mode = e->img_bytes[p] == FMA_PAGE_BYTES ? FMA_K_PACK_RAW : FMA_K_PACK_BF16;
+            d.pad = 0;
+        }
+    uint32_t* d_err = e->d_psize + e->pdesc_cap;
+    RT(cudaMemcpyAsync(e->d_pdesc, e->h_pdesc, n_pages * sizeof(fma_k_pack_desc), cudaMemcpyHostToDevice, e->ks));
+    RT(cudaMemsetAsync(d_err, 0, sizeof(uint32_t), e->ks));
+    for (size_t c = 0; c < slots.size(); ++c) {
+        const Slot& sl = slots[c];
+        const int slot = (int)(c % e->n_ring);
+        cudaStream_t cstream = e->cs[c % e->n_cs];
+        if (c >= (size_t)e->n_ring) RT(cudaStreamWaitEvent(e->ks, e->ev_ring_free[slot], 0));
+        rc = kt.begin();
+        if (rc != FMA_OK) return rc;
+        RT(fma_k_launch_pack(e->d_pdesc + sl.p0, (uint32_t)sl.np, d_err, e->ks));
+        rc = kt.end((uint64_t)sl.np * FMA_PAGE_BYTES + sl.bytes);
+        if (rc != FMA_OK) return rc;
+        RT(cudaEventRecord(e->ev_ring_full[slot], e->ks));
+        RT(cudaStreamWaitEvent(cstream, e->ev_ring_full[slot], 0));
+        RT(cudaMemcpyAsync(store + e->img_off[sl.p0], e->ring[slot], sl.bytes, cudaMemcpyDefault, cstream));
+        if (c > 0) RT(cudaStreamWaitEvent(cstream, e->ev_ring_free[(c - 1) % e->n_ring], 0));  // same chaining as below
+        RT(cudaEventRecord(e->ev_ring_free[slot], cstream));
+        ++copy_ops;
+        rc = publish_consumed((uint64_t)(sl.p0 + sl.np) * FMA_PAGE_BYTES, cstream);
+        if (rc != FMA_OK) return rc;
+    }
+    return rc;
+}
+
+// STAGED: K1 gather -> HBM ring slot -> one large D2H per slot
+int sleep_staged(SleepPipe& pipe) {
+    fma_engine_t* e = pipe.e;
+    KernelTimes& kt = pipe.kt;
+    uint32_t& copy_ops = pipe.copy_ops;
+    char* store = pipe.store;
+    const uint64_t W = pipe.W;
+    auto publish_consumed = [&](uint64_t done, cudaStream_t s) { return pipe.publish_consumed(done, s); };
+    int rc = FMA_OK;
+    size_t n_pages = 0;
+    rc = pipe.upload_page_table(&n_pages);
+    if (rc != FMA_OK) return rc;
+    rc = ensure_ring(e, W);
+    if (rc != FMA_OK) return rc;
+    const size_t slot_pages = e->ring_slot_bytes / FMA_PAGE_BYTES;
+    size_t c = 0;
+    for (size_t p0 = 0; p0 < n_pages; p0 += slot_pages, ++c) {
+        const int slot = (int)(c % e->n_ring);
+        const size_t np = std::min(slot_pages, n_pages - p0);
+        cudaStream_t cstream = e->cs[c % e->n_cs];
+        if (c >= (size_t)e->n_ring) RT(cudaStreamWaitEvent(e->ks, e->ev_ring_free[slot], 0));
+        rc = kt.launch(e->d_tab + p0, 0, nullptr, (uint64_t)(uintptr_t)e->ring[slot], (uint32_t)np);
+        if (rc != FMA_OK) return rc;
+        RT(cudaEventRecord(e->ev_ring_full[slot], e->ks));
+        RT(cudaStreamWaitEvent(cstream, e->ev_ring_full[slot], 0));
+        RT(cudaMemcpyAsync(store + p0 * FMA_PAGE_BYTES, e->ring[slot], np * FMA_PAGE_BYTES, cudaMemcpyDefault, cstream));
+        // "slot free" also means "every earlier slot has reached the store" (chained through the previous
+        // slot's event), so the unmapper below never releases device memory whose bytes are not yet on the host
+        if (c > 0) RT(cudaStreamWaitEvent(cstream, e->ev_ring_free[(c - 1) % e->n_ring], 0));
+        RT(cudaEventRecord(e->ev_ring_free[slot], cstream));
+        ++copy_ops;
+        rc = publish_consumed((uint64_t)(p0 + np) * FMA_PAGE_BYTES, cstream);  // units fully in the store are dead
+        if (rc != FMA_OK) return rc;
+    }
+    return rc;
+}
+
+}  // namespace
+
 // ------------------------------------------------------------------------------------
 // SLEEP
 // ------------------------------------------------------------------------------------
@@ -135,143 +500,11 @@ int do_sleep(fma_engine_t* e, uint64_t offload_mask, int tier, uint32_t flags) {
     // reference's blocking cudaMemcpy on the legacy stream implicitly does.
     RT(cudaDeviceSynchronize());
 
-    // ---- unmapper thread: cuMemUnmap runs UNDER the copy pipeline instead of after it -----------------------
-    // (cumem.py:213 unmaps each segment right after its blocking copy.)  The thread only issues driver calls on
-    // ranges planned here; the table is updated by this thread after it has been joined.  Adjacent units are
-    // unmapped with ONE spanning cuMemUnmap (allowed across whole mappings, scripts/vmm_span_probe.py).
-    struct Range {
-        CUdeviceptr va;
-        size_t bytes;
-    };
-    struct Stage {
-        cudaEvent_t ev;
-        std::vector<Range> ranges;
-    };
-    struct Unmapper {
-        fma_engine_t* e;
-        std::mutex mu;
-        std::condition_variable cv;
-        std::vector<Stage> stages;
-        bool closed = false;
-        int error = FMA_OK;
-        char msg[512] = "";
-        double seconds = 0;
-        std::vector<Range> first;  // ranges with nothing to wait for (discarded tags)
-        std::vector<Range> done;   // ranges actually unmapped
-        std::thread th;
-        void unmap_range(const Range& r, bool dbg) {
-            const double a = now_s();
-            CUresult r1 = g_drv.MemUnmap(r.va, r.bytes);
-            const double b = now_s();
-            seconds += b - a;
-            if (r1 != CUDA_SUCCESS) {
-                std::lock_guard<std::mutex> lk(mu);
-                if (error == FMA_OK) {
-                    error = FMA_ECUDA;
-                    snprintf(msg, sizeof(msg), "cuMemUnmap(%zu bytes) failed: %s", r.bytes, cu_err(r1));
-                }
-                return;
-            }
-            if (dbg && (b - a) > 5e-3)
-                fprintf(stderr, "[fma] slow unmap va=0x%llx bytes=%zu unmap=%.1f ms\n", (unsigned long long)r.va, r.bytes, (b - a) * 1e3);
-            done.push_back(r);
-        }
-        void run() {
-            cudaSetDevice(e->device);
-            const bool dbg = env_int("FMA_DEBUG_VMM", 0) != 0;
-            for (const Range& r : first) unmap_range(r, dbg);
-            size_t k = 0;
-            for (;;) {
-                Stage st;
-                {
-                    std::unique_lock<std::mutex> lk(mu);
-                    cv.wait(lk, [&] { return stages.size() > k || closed; });
-                    if (k >= stages.size()) break;
-                    st = stages[k];
-                }
-                cudaError_t r = cudaEventSynchronize(st.ev);
-                if (r != cudaSuccess) {
-                    std::lock_guard<std::mutex> lk(mu);
-                    if (error == FMA_OK) {
-                        error = FMA_ECUDA;
-                        snprintf(msg, sizeof(msg), "cudaEventSynchronize(stage) failed: %s", cudaGetErrorString(r));
-                    }
-                    break;  // never unmap memory whose copy may not have finished
-                }
-                for (const Range& rg : st.ranges) unmap_range(rg, dbg);
-                ++k;
-            }
-        }
-        void publish(Stage&& st) {
-            {
-                std::lock_guard<std::mutex> lk(mu);
-                stages.push_back(std::move(st));
-            }
-            cv.notify_all();
-        }
-        void finish() {
-            {
-                std::lock_guard<std::mutex> lk(mu);
-                closed = true;
-            }
-            cv.notify_all();
-            if (th.joinable()) th.join();
-        }
-        ~Unmapper() { finish(); }
-    } un;
+    // ---- unmapper thread (types above): cuMemUnmap runs UNDER the copy pipeline instead of after it ----
+    Unmapper un;
     un.e = e;
-    // Whatever the unmapper really unmapped is applied to the table on EVERY exit path (also the error returns
-    // below), so that a failed sleep never leaves units the table believes mapped but the driver has released.
-    struct ApplyUnmapped {
-        Unmapper* un;
-        fma_engine_t* e;
-        const std::vector<Extent>* ex;   // offloaded extents: a unit is only ever unmapped after its bytes reached the store,
-        int tier;                        // so an unmapped offloaded segment HAS a backup even if the sleep fails later
-        size_t applied = 0;
-        void run() {
-            std::lock_guard<std::mutex> lk(e->mu);
-            for (; applied < un->done.size(); ++applied) {
-                const Range& r = un->done[applied];
-                auto it = e->units.lower_bound(r.va);
-                while (it != e->units.end() && it->first < r.va + r.bytes) {
-                    Arena& a = e->arenas[it->second.arena];
-                    for (auto& z : it->second.zombies) arena_give_back(a, z.first - a.base, z.second);
-                    it = e->units.erase(it);
-                }
-                if (e->ring_attached && e->ring_unit_va >= r.va && e->ring_unit_va < r.va + r.bytes) {
-                    for (int i = 0; i < kMaxRing; ++i) e->ring[i] = nullptr;
-                    e->n_ring = 0; e->ring_slot_bytes = 0; e->ring_attached = false; e->ring_unit_va = 0;
-                }
-                for (Segment& sg : e->segs)
-                    if (sg.va >= r.va && sg.va < r.va + r.bytes) {
-                        sg.mapped = false;
-                        sg.unit_va = 0;
-                    }
-                for (const Extent& x : *ex)
-                    if (x.va >= r.va && x.va < r.va + r.bytes) {
-                        Segment& sg = e->segs[x.seg_index];
-                        sg.has_backup = true;
-                        sg.backup_tier = tier;
-                        sg.packed_off = x.packed_off;
-                    }
-            }
-            if (!un->done.empty()) {  // even a failed sleep leaves an image a later wake can restore from
-                e->image_tier = tier;
-            }
-        }
-        ~ApplyUnmapped() {
-            un->finish();
-            run();
-        }
-    } apply_unmapped{&un, e, &ex, tier};
+    ApplyUnmapped apply_unmapped{&un, e, &ex, tier};
 
-    // Units in VA order, split into "discarded" (release now) and "offloaded" (release once the image has their
-    // bytes).  image_end = packed offset just past the unit's last live segment.
-    struct PlannedUnit {
-        CUdeviceptr va;
-        size_t bytes;
-        uint64_t image_end;
-    };
     std::vector<PlannedUnit> off_units;  // same order as the image
     auto add_range = [](std::vector<Range>& v, CUdeviceptr va, size_t bytes) {
         if (!v.empty() && v.back().va + v.back().bytes == va) v.back().bytes += bytes;  // VA-adjacent: one driver call
@@ -330,154 +563,14 @@ int do_sleep(fma_engine_t* e, uint64_t offload_mask, int tier, uint32_t flags) {
     if (W && adopt) {
         publish_consumed(W, e->ks);  // nothing to copy: every offloaded unit can go at once
     } else if (W) {
-        const size_t chunk = direct_chunk(e);
         char* store = static_cast<char*>(store_copy_base(e, tier));
         rc = timer.begin();
         if (rc != FMA_OK) return rc;
-        if (mode == FMA_MODE_DIRECT) {
-            // copy engines straight from the segments into the packed image, chunks round-robin over the streams;
-            // every `slot` bytes of image the streams are joined so that one event marks the units behind it dead
-            const size_t slot = staged_slot(e);
-            uint64_t next_join = slot;
-            int k = 0;
-            for (const Extent& x : ex) {
-                for (size_t o = 0; o < x.bytes; o += chunk, ++k) {
-                    const size_t n = std::min(chunk, x.bytes - o);
-                    RT(cudaMemcpyAsync(store + x.packed_off + o, reinterpret_cast<void*>(x.va + o), n, cudaMemcpyDefault,
-                                       e->cs[k % e->n_cs]));
-                    ++copy_ops;
-                }
-                const uint64_t image_done = x.packed_off + x.bytes;
-                if (image_done >= next_join || &x == &ex.back()) {
-                    for (int i = 1; i < e->n_cs; ++i) {  // stream 0 waits for the others
-                        RT(cudaEventRecord(e->ev_cs[i], e->cs[i]));
-                        RT(cudaStreamWaitEvent(e->cs[0], e->ev_cs[i], 0));
-                    }
-                    rc = publish_consumed(image_done, e->cs[0]);
-                    if (rc != FMA_OK) return rc;
-                    next_join = image_done + slot;
-                }
-            }
-        } else {
-            const size_t n_pages = W / FMA_PAGE_BYTES;
-            rc = ensure_tables(e, n_pages);
-            if (rc != FMA_OK) return rc;
-            build_page_table(ex, e->h_tab);
-            RT(cudaMemcpyAsync(e->d_tab, e->h_tab, n_pages * sizeof(uint64_t), cudaMemcpyHostToDevice, e->ks));
-            auto publish_gathered = [&](size_t pages_done) -> int { return publish_consumed((uint64_t)pages_done * FMA_PAGE_BYTES, e->ks); };
-            if (mode == FMA_MODE_KERNEL && packed) {
-                // PACKED image in a parking tier: K4 encodes straight into the peer / local HBM store (0.758 of the bytes
-                // over NVLink and of the parking GPU's HBM), batches as below
-                rc = ensure_pack_bufs(e, n_pages);
-                if (rc != FMA_OK) return rc;
-                const uint64_t dbase = store_dev_base(e, tier);
-                for (size_t p = 0; p < n_pages; ++p) {
-                    fma_k_pack_desc& d = e->h_pdesc[p];
-                    d.src = e->h_tab[p];
-                    d.dst = dbase + e->img_off[p];
-                    d.mode = e->img_bytes[p] == FMA_PAGE_BYTES ? FMA_K_PACK_RAW : FMA_K_PACK_BF16;
-                    d.pad = 0;
-                }
-                uint32_t* d_err = e->d_psize + e->pdesc_cap;
-                RT(cudaMemcpyAsync(e->d_pdesc, e->h_pdesc, n_pages * sizeof(fma_k_pack_desc), cudaMemcpyHostToDevice, e->ks));
-                RT(cudaMemsetAsync(d_err, 0, sizeof(uint32_t), e->ks));
-                const size_t batch = std::max<size_t>(staged_slot(e) / FMA_PAGE_BYTES, 1);
-                for (size_t p0 = 0; p0 < n_pages; p0 += batch) {
-                    const size_t np = std::min(batch, n_pages - p0);
-                    uint64_t stored = 0;
-                    for (size_t q = p0; q < p0 + np; ++q) stored += e->img_bytes[q];
-                    rc = kt.begin();
-                    if (rc != FMA_OK) return rc;
-                    RT(fma_k_launch_pack(e->d_pdesc + p0, (uint32_t)np, d_err, e->ks));
-                    rc = kt.end((uint64_t)np * FMA_PAGE_BYTES + stored);
-                    if (rc != FMA_OK) return rc;
-                    ++copy_ops;
-                    rc = publish_gathered(p0 + np);
-                    if (rc != FMA_OK) return rc;
-                }
-            } else if (mode == FMA_MODE_KERNEL) {
-                // K1 writes the store itself: mapped pinned host memory (PCIe posted writes) or peer/local HBM;
-                // launched in slot-sized batches so finished segments can be released while later ones still move
-                const size_t batch = std::max<size_t>(staged_slot(e) / FMA_PAGE_BYTES, 1);
-                const uint64_t dbase = store_dev_base(e, tier);
-                for (size_t p0 = 0; p0 < n_pages; p0 += batch) {
-                    const size_t np = std::min(batch, n_pages - p0);
-                    rc = kt.launch(e->d_tab + p0, 0, nullptr, dbase + p0 * FMA_PAGE_BYTES, (uint32_t)np);
-                    if (rc != FMA_OK) return rc;
-                    ++copy_ops;
-                    rc = publish_gathered(p0 + np);
-                    if (rc != FMA_OK) return rc;
-                }
-            } else if (packed) {  // STAGED + PACKED: K4 gather+encode -> ring slot (stored pages back to back) -> one D2H per slot
-                rc = ensure_ring(e, W);
-                if (rc != FMA_OK) return rc;
-                struct Slot { size_t p0, np; uint64_t bytes; };
-                std::vector<Slot> slots;
-                for (size_t p = 0; p < n_pages;) {
-                    Slot sl{p, 0, 0};
-                    while (p < n_pages && sl.bytes + e->img_bytes[p] <= e->ring_slot_bytes) {
-                        sl.bytes += e->img_bytes[p];
-                        ++sl.np;
-                        ++p;
-                    }
-                    if (!sl.np) return fail(FMA_EINVAL, "ring slot of %zu bytes cannot hold one page", e->ring_slot_bytes);
-                    slots.push_back(sl);
-                }
-                for (size_t c = 0; c < slots.size(); ++c)
-                    for (size_t p = slots[c].p0; p < slots[c].p0 + slots[c].np; ++p) {
-                        fma_k_pack_desc& d = e->h_pdesc[p];
-                        d.src = e->h_tab[p];
-                        d.dst = (uint64_t)(uintptr_t)e->ring[c % e->n_ring] + (e->img_off[p] - e->img_off[slots[c].p0]);
-                        d.mode = e->img_bytes[p] == FMA_PAGE_BYTES ? FMA_K_PACK_RAW : FMA_K_PACK_BF16;
-                        d.pad = 0;
-                    }
-                uint32_t* d_err = e->d_psize + e->pdesc_cap;
-                RT(cudaMemcpyAsync(e->d_pdesc, e->h_pdesc, n_pages * sizeof(fma_k_pack_desc), cudaMemcpyHostToDevice, e->ks));
-                RT(cudaMemsetAsync(d_err, 0, sizeof(uint32_t), e->ks));
-                for (size_t c = 0; c < slots.size(); ++c) {
-                    const Slot& sl = slots[c];
-                    const int slot = (int)(c % e->n_ring);
-                    cudaStream_t cstream = e->cs[c % e->n_cs];
-                    if (c >= (size_t)e->n_ring) RT(cudaStreamWaitEvent(e->ks, e->ev_ring_free[slot], 0));
-                    rc = kt.begin();
-                    if (rc != FMA_OK) return rc;
-                    RT(fma_k_launch_pack(e->d_pdesc + sl.p0, (uint32_t)sl.np, d_err, e->ks));
-                    rc = kt.end((uint64_t)sl.np * FMA_PAGE_BYTES + sl.bytes);
-                    if (rc != FMA_OK) return rc;
-                    RT(cudaEventRecord(e->ev_ring_full[slot], e->ks));
-                    RT(cudaStreamWaitEvent(cstream, e->ev_ring_full[slot], 0));
-                    RT(cudaMemcpyAsync(store + e->img_off[sl.p0], e->ring[slot], sl.bytes, cudaMemcpyDefault, cstream));
-                    if (c > 0) RT(cudaStreamWaitEvent(cstream, e->ev_ring_free[(c - 1) % e->n_ring], 0));  // same chaining as below
-                    RT(cudaEventRecord(e->ev_ring_free[slot], cstream));
-                    ++copy_ops;
-                    rc = publish_consumed((uint64_t)(sl.p0 + sl.np) * FMA_PAGE_BYTES, cstream);
-                    if (rc != FMA_OK) return rc;
-                }
-            } else {  // STAGED: K1 gather -> HBM ring slot -> copy engine D2H
-                rc = ensure_ring(e, W);
-                if (rc != FMA_OK) return rc;
-                const size_t slot_pages = e->ring_slot_bytes / FMA_PAGE_BYTES;
-                size_t c = 0;
-                for (size_t p0 = 0; p0 < n_pages; p0 += slot_pages, ++c) {
-                    const int slot = (int)(c % e->n_ring);
-                    const size_t np = std::min(slot_pages, n_pages - p0);
-                    cudaStream_t cstream = e->cs[c % e->n_cs];
-                    if (c >= (size_t)e->n_ring) RT(cudaStreamWaitEvent(e->ks, e->ev_ring_free[slot], 0));
-                    rc = kt.launch(e->d_tab + p0, 0, nullptr, (uint64_t)(uintptr_t)e->ring[slot], (uint32_t)np);
-                    if (rc != FMA_OK) return rc;
-                    RT(cudaEventRecord(e->ev_ring_full[slot], e->ks));
-                    RT(cudaStreamWaitEvent(cstream, e->ev_ring_full[slot], 0));
-                    RT(cudaMemcpyAsync(store + p0 * FMA_PAGE_BYTES, e->ring[slot], np * FMA_PAGE_BYTES, cudaMemcpyDefault, cstream));
-                    // "slot free" also means "every earlier slot has reached the store" (chained through the previous
-                    // slot's event), so the unmapper below never releases device memory whose bytes are not yet on the host
-                    if (c > 0) RT(cudaStreamWaitEvent(cstream, e->ev_ring_free[(c - 1) % e->n_ring], 0));
-                    RT(cudaEventRecord(e->ev_ring_free[slot], cstream));
-                    ++copy_ops;
-                    rc = publish_consumed((uint64_t)(p0 + np) * FMA_PAGE_BYTES, cstream);  // units fully in the store are dead
-                    if (rc != FMA_OK) return rc;
-                }
-            }
-        }
+        SleepPipe pipe{e, ex, W, tier, store, kt, copy_ops, publish_consumed};
+        if (mode == FMA_MODE_DIRECT) rc = sleep_direct(pipe);
+        else if (mode == FMA_MODE_KERNEL) rc = packed ? sleep_kernel_packed(pipe) : sleep_kernel(pipe);
+        else rc = packed ? sleep_staged_packed(pipe) : sleep_staged(pipe);
+        if (rc != FMA_OK) return rc;
         {
             std::lock_guard<std::mutex> lk(un.mu);
             un.closed = true;

@@ -4,6 +4,284 @@
 
 namespace fma_impl {
 
+namespace {
+
+// What the copy pipelines of one wake share.  A pipeline enqueues the work that brings the backed-up segments'
+// bytes from the store into their (re-)mapped runs; wait_mapped(n) blocks until the mapper thread has mapped work
+// items [0, n) (or failed: the error code comes back, its text is in map_msg).
+struct WakePipe {
+    fma_engine_t* e;
+    const std::vector<size_t>& with_backup;   // segment indices that have a backup, image order
+    const std::vector<size_t>& seg_run;       // segment -> index of its run in the mapper's work list
+    uint64_t W;
+    int tier;
+    int mode;
+    bool ring_run;                             // the staging ring is work item 0
+    const char* store;
+    KernelTimes& kt;
+    uint32_t& copy_ops;
+    double& first_copy_delay;
+    double t_entry;
+    std::function<int(size_t)> wait_mapped;
+    std::function<size_t()> mapped_now;
+    const char* map_msg;
+};
+
+#define PIPE_CHECK(x)                 \
+    do {                              \
+        int _rc = (x);                \
+        if (_rc != FMA_OK) return _rc; \
+    } while (0)
+
+// PACKED image: H2D of the stored pages (0.758 of the bytes) -> ring slot -> K5 decode + scatter; or K5 reads the store itself
+int wake_packed(WakePipe& pipe) {
+    fma_engine_t* e = pipe.e;
+    const std::vector<size_t>& with_backup = pipe.with_backup;
+    const std::vector<size_t>& seg_run = pipe.seg_run;
+    KernelTimes& kt = pipe.kt;
+    uint32_t& copy_ops = pipe.copy_ops;
+    double& first_copy_delay = pipe.first_copy_delay;
+    const double t_entry = pipe.t_entry;
+    const int tier = pipe.tier;
+    const int mode = pipe.mode;
+    const bool ring_run = pipe.ring_run;
+    const char* store = pipe.store;
+    const uint64_t W = pipe.W;
+    auto wait_mapped = [&](size_t upto) { return pipe.wait_mapped(upto); };
+    // ---- PACKED image: H2D of the stored pages (0.758 of the bytes) -> ring slot -> K5 decode + scatter ----
+    // K5 reads the store itself when it is peer / local HBM, or when no ring could be had (then over PCIe)
+    const bool zero_copy = mode != FMA_MODE_STAGED;
+    if (zero_copy && tier == FMA_TIER_HOST && !e->host.dev_alias)
+        PIPE_CHECK(fail(FMA_ENOMEM, "no HBM for a staging ring and the host store has no device alias: a packed image cannot be woken"));
+    struct Dst { uint64_t packed_off; size_t w; };
+    std::vector<Dst> d;
+    for (size_t w = 0; w < with_backup.size(); ++w) d.push_back(Dst{e->segs[with_backup[w]].packed_off, w});
+    std::sort(d.begin(), d.end(), [](const Dst& a, const Dst& b) { return a.packed_off < b.packed_off; });
+    const size_t n_pages = W / FMA_PAGE_BYTES;
+    PIPE_CHECK(ensure_pack_bufs(e, n_pages));
+    std::vector<size_t> need_item(n_pages);
+    std::vector<uint64_t> soff(n_pages), dsts(n_pages);
+    std::vector<uint32_t> sbytes(n_pages);
+    size_t p = 0;
+    for (const Dst& x : d) {
+        const Segment& s = e->segs[with_backup[x.w]];
+        for (size_t o = 0; o < s.bytes; o += FMA_PAGE_BYTES, ++p) {
+            const size_t lp = (size_t)((s.packed_off + o) / FMA_PAGE_BYTES);
+            if (lp >= e->img_off.size()) PIPE_CHECK(fail(FMA_ESTATE, "segment at image offset %llu is outside the packed image's page table", (unsigned long long)(s.packed_off + o)));
+            soff[p] = e->img_off[lp];
+            sbytes[p] = e->img_bytes[lp];
+            dsts[p] = (uint64_t)s.va + o;
+            need_item[p] = seg_run[with_backup[x.w]] + 1;
+        }
+    }
+    uint32_t* d_err = e->d_psize + e->pdesc_cap;
+    RT(cudaMemsetAsync(d_err, 0, sizeof(uint32_t), e->ks));
+    if (!zero_copy) {
+        if (ring_run) {
+            int mrc0 = wait_mapped(1);
+            if (mrc0 != FMA_OK) PIPE_CHECK(fail(mrc0, "%s", pipe.map_msg));
+        } else {
+            PIPE_CHECK(ensure_ring(e, W));
+        }
+        struct Slot { size_t p0, np; uint64_t bytes; };
+        std::vector<Slot> slots;  // pages that are adjacent in the store and fit one ring slot
+        for (size_t q = 0; q < n_pages;) {
+            Slot sl{q, 0, 0};
+            while (q < n_pages && sl.bytes + sbytes[q] <= e->ring_slot_bytes && (sl.np == 0 || soff[q] == soff[q - 1] + sbytes[q - 1])) {
+                sl.bytes += sbytes[q];
+                ++sl.np;
+                ++q;
+            }
+            if (!sl.np) PIPE_CHECK(fail(FMA_EINVAL, "ring slot of %zu bytes cannot hold one page", e->ring_slot_bytes));
+            slots.push_back(sl);
+        }
+        for (size_t c = 0; c < slots.size(); ++c)
+            for (size_t q = slots[c].p0; q < slots[c].p0 + slots[c].np; ++q) {
+                fma_k_pack_desc& pd = e->h_pdesc[q];
+                pd.src = (uint64_t)(uintptr_t)e->ring[c % e->n_ring] + (soff[q] - soff[slots[c].p0]);
+                pd.dst = dsts[q];
+                pd.mode = sbytes[q] == FMA_PAGE_BYTES ? FMA_K_PACK_RAW : FMA_K_PACK_BF16;
+                pd.pad = 0;
+            }
+        RT(cudaMemcpyAsync(e->d_pdesc, e->h_pdesc, n_pages * sizeof(fma_k_pack_desc), cudaMemcpyHostToDevice, e->ks));
+        for (size_t c = 0; c < slots.size(); ++c) {
+            const Slot& sl = slots[c];
+            const int slot = (int)(c % e->n_ring);
+            cudaStream_t cstream = e->cs[c % e->n_cs];
+            if (c >= (size_t)e->n_ring) RT(cudaStreamWaitEvent(cstream, e->ev_ring_free[slot], 0));
+            RT(cudaMemcpyAsync(e->ring[slot], store + soff[sl.p0], sl.bytes, cudaMemcpyDefault, cstream));
+            if (!copy_ops) first_copy_delay = now_s() - t_entry;
+            ++copy_ops;
+            RT(cudaEventRecord(e->ev_ring_full[slot], cstream));
+            size_t need = 0;
+            for (size_t q = sl.p0; q < sl.p0 + sl.np; ++q) need = std::max(need, need_item[q]);
+            int mrc = wait_mapped(need);
+            if (mrc != FMA_OK) PIPE_CHECK(fail(mrc, "%s", pipe.map_msg));
+            RT(cudaStreamWaitEvent(e->ks, e->ev_ring_full[slot], 0));
+            PIPE_CHECK(kt.begin());
+            RT(fma_k_launch_unpack(e->d_pdesc + sl.p0, (uint32_t)sl.np, d_err, e->ks));
+            PIPE_CHECK(kt.end((uint64_t)sl.np * FMA_PAGE_BYTES + sl.bytes));
+            RT(cudaEventRecord(e->ev_ring_free[slot], e->ks));
+        }
+    } else {
+        const uint64_t sbase = store_dev_base(e, tier);
+        for (size_t q = 0; q < n_pages; ++q) {
+            fma_k_pack_desc& pd = e->h_pdesc[q];
+            pd.src = sbase + soff[q];
+            pd.dst = dsts[q];
+            pd.mode = sbytes[q] == FMA_PAGE_BYTES ? FMA_K_PACK_RAW : FMA_K_PACK_BF16;
+            pd.pad = 0;
+        }
+        RT(cudaMemcpyAsync(e->d_pdesc, e->h_pdesc, n_pages * sizeof(fma_k_pack_desc), cudaMemcpyHostToDevice, e->ks));
+        const size_t batch_pages = std::max<size_t>(staged_slot(e) / FMA_PAGE_BYTES, 1);
+        for (size_t p0 = 0; p0 < n_pages;) {
+            const size_t np = std::min(batch_pages, n_pages - p0);
+            size_t need = 0;
+            uint64_t stored = 0;
+            for (size_t q = p0; q < p0 + np; ++q) {
+                need = std::max(need, need_item[q]);
+                stored += sbytes[q];
+            }
+            int mrc = wait_mapped(need);
+            if (mrc != FMA_OK) PIPE_CHECK(fail(mrc, "%s", pipe.map_msg));
+            PIPE_CHECK(kt.begin());
+            RT(fma_k_launch_unpack(e->d_pdesc + p0, (uint32_t)np, d_err, e->ks));
+            PIPE_CHECK(kt.end((uint64_t)np * FMA_PAGE_BYTES + stored));
+            if (!copy_ops) first_copy_delay = now_s() - t_entry;
+            ++copy_ops;
+            p0 += np;
+        }
+    }
+    return FMA_OK;
+}
+
+// DIRECT: copy engines move each chunk of the image straight into its segment as soon as the segment is mapped
+int wake_direct(WakePipe& pipe) {
+    fma_engine_t* e = pipe.e;
+    const std::vector<size_t>& with_backup = pipe.with_backup;
+    const std::vector<size_t>& seg_run = pipe.seg_run;
+    uint32_t& copy_ops = pipe.copy_ops;
+    double& first_copy_delay = pipe.first_copy_delay;
+    const double t_entry = pipe.t_entry;
+    const char* store = pipe.store;
+    auto wait_mapped = [&](size_t upto) { return pipe.wait_mapped(upto); };
+    const size_t chunk = direct_chunk(e);
+    int k = 0;
+    for (size_t w = 0; w < with_backup.size(); ++w) {
+        int mrc = wait_mapped(seg_run[with_backup[w]] + 1);
+        if (mrc != FMA_OK) PIPE_CHECK(fail(mrc, "%s", pipe.map_msg));
+        const Segment& s = e->segs[with_backup[w]];
+        for (size_t o = 0; o < s.bytes; o += chunk, ++k) {
+            const size_t n = std::min(chunk, s.bytes - o);
+            RT(cudaMemcpyAsync(reinterpret_cast<void*>(s.va + o), store + s.packed_off + o, n, cudaMemcpyDefault,
+                                    e->cs[k % e->n_cs]));
+            if (!copy_ops) first_copy_delay = now_s() - t_entry;
+            ++copy_ops;
+        }
+    }
+    return FMA_OK;
+}
+
+// KERNEL / STAGED: page-table driven — K2 reads the store itself, or H2D -> ring slot -> K2 scatter
+int wake_paged(WakePipe& pipe) {
+    fma_engine_t* e = pipe.e;
+    const std::vector<size_t>& with_backup = pipe.with_backup;
+    const std::vector<size_t>& seg_run = pipe.seg_run;
+    KernelTimes& kt = pipe.kt;
+    uint32_t& copy_ops = pipe.copy_ops;
+    double& first_copy_delay = pipe.first_copy_delay;
+    const double t_entry = pipe.t_entry;
+    const int tier = pipe.tier;
+    const int mode = pipe.mode;
+    const bool ring_run = pipe.ring_run;
+    const char* store = pipe.store;
+    const uint64_t W = pipe.W;
+    auto wait_mapped = [&](size_t upto) { return pipe.wait_mapped(upto); };
+    auto mapped_now = [&]() { return pipe.mapped_now(); };
+    // page table of the DESTINATIONS, ordered by packed offset (== with_backup order by construction
+    // only if every backed-up segment is woken; build explicitly from packed offsets to stay general)
+    struct Dst { uint64_t packed_off; size_t w; };
+    std::vector<Dst> d;
+    for (size_t w = 0; w < with_backup.size(); ++w) d.push_back(Dst{e->segs[with_backup[w]].packed_off, w});
+    std::sort(d.begin(), d.end(), [](const Dst& a, const Dst& b) { return a.packed_off < b.packed_off; });
+    // runs of pages: (image page index, destination address), plus the latest work item each page needs
+    size_t n_pages = W / FMA_PAGE_BYTES;
+    PIPE_CHECK(ensure_tables(e, n_pages));
+    uint64_t* dst_tab = e->h_tab;                 // destination page addresses
+    uint64_t* src_tab = e->h_tab + e->d_tab_cap;  // source page addresses inside the store (may be sparse)
+    std::vector<size_t> need_item(n_pages);
+    const uint64_t sbase = store_dev_base(e, tier);
+    size_t p = 0;
+    for (const Dst& x : d) {
+        const Segment& s = e->segs[with_backup[x.w]];
+        for (size_t o = 0; o < s.bytes; o += FMA_PAGE_BYTES, ++p) {
+            dst_tab[p] = (uint64_t)s.va + o;
+            src_tab[p] = sbase + s.packed_off + o;
+            need_item[p] = seg_run[with_backup[x.w]] + 1;
+        }
+    }
+    RT(cudaMemcpyAsync(e->d_tab, dst_tab, n_pages * sizeof(uint64_t), cudaMemcpyHostToDevice, e->ks));
+    RT(cudaMemcpyAsync(e->d_tab + e->d_tab_cap, src_tab, n_pages * sizeof(uint64_t), cudaMemcpyHostToDevice, e->ks));
+    const uint64_t* d_dst = e->d_tab;
+    const uint64_t* d_src = e->d_tab + e->d_tab_cap;
+    if (mode == FMA_MODE_KERNEL) {
+        // K2 reads the store itself (zero-copy PCIe reads, or NVLink/HBM loads); launch batches as the
+        // mapper makes progress so the scatter overlaps cuMemCreate/Map of later segments
+        const size_t batch_pages = std::max<size_t>(staged_slot(e) / FMA_PAGE_BYTES, 1);
+        size_t p0 = 0;
+        while (p0 < n_pages) {
+            size_t np = std::min(batch_pages, n_pages - p0);
+            size_t need = 0;
+            for (size_t q = p0; q < p0 + np; ++q) need = std::max(need, need_item[q]);
+            int mrc = wait_mapped(need);
+            if (mrc != FMA_OK) PIPE_CHECK(fail(mrc, "%s", pipe.map_msg));
+            // opportunistically extend the batch over everything already mapped
+            const size_t have = mapped_now();
+            while (p0 + np < n_pages && need_item[p0 + np] <= have) ++np;
+            PIPE_CHECK(kt.launch(d_src + p0, 0, d_dst + p0, 0, (uint32_t)np));
+            if (!copy_ops) first_copy_delay = now_s() - t_entry;
+            ++copy_ops;
+            p0 += np;
+        }
+    } else {  // STAGED: copy engine H2D store -> ring slot (starts at t=0), K2 scatter once the targets are mapped
+        if (ring_run) {  // the ring is run 0 (1 GiB, ~0.2 ms to map): wait for it before the first H2D
+            int mrc0 = wait_mapped(1);
+            if (mrc0 != FMA_OK) PIPE_CHECK(fail(mrc0, "%s", pipe.map_msg));
+        } else {
+            PIPE_CHECK(ensure_ring(e, W));
+        }
+        const size_t slot_pages = e->ring_slot_bytes / FMA_PAGE_BYTES;
+        // the store image may be only partially woken; H2D works on runs that are contiguous in the store
+        size_t c = 0;
+        size_t p0 = 0;
+        while (p0 < n_pages) {
+            size_t np = 1;
+            while (np < slot_pages && p0 + np < n_pages && src_tab[p0 + np] == src_tab[p0 + np - 1] + FMA_PAGE_BYTES) ++np;
+            const int slot = (int)(c % e->n_ring);
+            cudaStream_t cstream = e->cs[c % e->n_cs];
+            if (c >= (size_t)e->n_ring) RT(cudaStreamWaitEvent(cstream, e->ev_ring_free[slot], 0));
+            RT(cudaMemcpyAsync(e->ring[slot], store + (src_tab[p0] - sbase), np * FMA_PAGE_BYTES, cudaMemcpyDefault, cstream));
+            if (!copy_ops) first_copy_delay = now_s() - t_entry;
+            ++copy_ops;
+            RT(cudaEventRecord(e->ev_ring_full[slot], cstream));
+            size_t need = 0;
+            for (size_t q = p0; q < p0 + np; ++q) need = std::max(need, need_item[q]);
+            int mrc = wait_mapped(need);
+            if (mrc != FMA_OK) PIPE_CHECK(fail(mrc, "%s", pipe.map_msg));
+            RT(cudaStreamWaitEvent(e->ks, e->ev_ring_full[slot], 0));
+            PIPE_CHECK(kt.launch(nullptr, (uint64_t)(uintptr_t)e->ring[slot], d_dst + p0, 0, (uint32_t)np));
+            RT(cudaEventRecord(e->ev_ring_free[slot], e->ks));
+            p0 += np;
+            ++c;
+        }
+    }
+    return FMA_OK;
+}
+
+#undef PIPE_CHECK
+
+}  // namespace
+
 // ------------------------------------------------------------------------------------
 // WAKE
 // ------------------------------------------------------------------------------------
@@ -208,210 +486,15 @@ int do_wake(fma_engine_t* e, uint64_t tag_mask, uint32_t flags) {
     uint32_t copy_ops = 0;
     double copy_s = 0, first_copy_delay = 0;
     if (W) {
-        const size_t chunk = direct_chunk(e);
         const char* store = static_cast<const char*>(store_copy_base(e, tier));
         if (!store) WAKE_CHECK(fail(FMA_ESTATE, "backup store of tier %d is gone", tier));
         if (tier == FMA_TIER_HOST && mode == FMA_MODE_KERNEL && !e->host.dev_alias)
             WAKE_CHECK(fail(FMA_ECUDA, "host store has no device alias for zero-copy mode"));
         WAKE_CHECK(timer.begin());
-        if (packed) {
-            // ---- PACKED image: H2D of the stored pages (0.758 of the bytes) -> ring slot -> K5 decode + scatter ----
-            // K5 reads the store itself when it is peer / local HBM, or when no ring could be had (then over PCIe)
-            const bool zero_copy = mode != FMA_MODE_STAGED;
-            if (zero_copy && tier == FMA_TIER_HOST && !e->host.dev_alias)
-                WAKE_CHECK(fail(FMA_ENOMEM, "no HBM for a staging ring and the host store has no device alias: a packed image cannot be woken"));
-            struct Dst { uint64_t packed_off; size_t w; };
-            std::vector<Dst> d;
-            for (size_t w = 0; w < with_backup.size(); ++w) d.push_back(Dst{e->segs[with_backup[w]].packed_off, w});
-            std::sort(d.begin(), d.end(), [](const Dst& a, const Dst& b) { return a.packed_off < b.packed_off; });
-            const size_t n_pages = W / FMA_PAGE_BYTES;
-            WAKE_CHECK(ensure_pack_bufs(e, n_pages));
-            std::vector<size_t> need_item(n_pages);
-            std::vector<uint64_t> soff(n_pages), dsts(n_pages);
-            std::vector<uint32_t> sbytes(n_pages);
-            size_t p = 0;
-            for (const Dst& x : d) {
-                const Segment& s = e->segs[with_backup[x.w]];
-                for (size_t o = 0; o < s.bytes; o += FMA_PAGE_BYTES, ++p) {
-                    const size_t lp = (size_t)((s.packed_off + o) / FMA_PAGE_BYTES);
-                    if (lp >= e->img_off.size()) WAKE_CHECK(fail(FMA_ESTATE, "segment at image offset %llu is outside the packed image's page table", (unsigned long long)(s.packed_off + o)));
-                    soff[p] = e->img_off[lp];
-                    sbytes[p] = e->img_bytes[lp];
-                    dsts[p] = (uint64_t)s.va + o;
-                    need_item[p] = seg_run[with_backup[x.w]] + 1;
-                }
-            }
-            uint32_t* d_err = e->d_psize + e->pdesc_cap;
-            WAKE_RT(cudaMemsetAsync(d_err, 0, sizeof(uint32_t), e->ks));
-            if (!zero_copy) {
-                if (ring_run) {
-                    int mrc0 = wait_mapped(1);
-                    if (mrc0 != FMA_OK) WAKE_CHECK(fail(mrc0, "%s", prog.msg));
-                } else {
-                    WAKE_CHECK(ensure_ring(e, W));
-                }
-                struct Slot { size_t p0, np; uint64_t bytes; };
-                std::vector<Slot> slots;  // pages that are adjacent in the store and fit one ring slot
-                for (size_t q = 0; q < n_pages;) {
-                    Slot sl{q, 0, 0};
-                    while (q < n_pages && sl.bytes + sbytes[q] <= e->ring_slot_bytes && (sl.np == 0 || soff[q] == soff[q - 1] + sbytes[q - 1])) {
-                        sl.bytes += sbytes[q];
-                        ++sl.np;
-                        ++q;
-                    }
-                    if (!sl.np) WAKE_CHECK(fail(FMA_EINVAL, "ring slot of %zu bytes cannot hold one page", e->ring_slot_bytes));
-                    slots.push_back(sl);
-                }
-                for (size_t c = 0; c < slots.size(); ++c)
-                    for (size_t q = slots[c].p0; q < slots[c].p0 + slots[c].np; ++q) {
-                        fma_k_pack_desc& pd = e->h_pdesc[q];
-                        pd.src = (uint64_t)(uintptr_t)e->ring[c % e->n_ring] + (soff[q] - soff[slots[c].p0]);
-                        pd.dst = dsts[q];
-                        pd.mode = sbytes[q] == FMA_PAGE_BYTES ? FMA_K_PACK_RAW : FMA_K_PACK_BF16;
-                        pd.pad = 0;
-                    }
-                WAKE_RT(cudaMemcpyAsync(e->d_pdesc, e->h_pdesc, n_pages * sizeof(fma_k_pack_desc), cudaMemcpyHostToDevice, e->ks));
-                for (size_t c = 0; c < slots.size(); ++c) {
-                    const Slot& sl = slots[c];
-                    const int slot = (int)(c % e->n_ring);
-                    cudaStream_t cstream = e->cs[c % e->n_cs];
-                    if (c >= (size_t)e->n_ring) WAKE_RT(cudaStreamWaitEvent(cstream, e->ev_ring_free[slot], 0));
-                    WAKE_RT(cudaMemcpyAsync(e->ring[slot], store + soff[sl.p0], sl.bytes, cudaMemcpyDefault, cstream));
-                    if (!copy_ops) first_copy_delay = now_s() - t_entry;
-                    ++copy_ops;
-                    WAKE_RT(cudaEventRecord(e->ev_ring_full[slot], cstream));
-                    size_t need = 0;
-                    for (size_t q = sl.p0; q < sl.p0 + sl.np; ++q) need = std::max(need, need_item[q]);
-                    int mrc = wait_mapped(need);
-                    if (mrc != FMA_OK) WAKE_CHECK(fail(mrc, "%s", prog.msg));
-                    WAKE_RT(cudaStreamWaitEvent(e->ks, e->ev_ring_full[slot], 0));
-                    WAKE_CHECK(kt.begin());
-                    WAKE_RT(fma_k_launch_unpack(e->d_pdesc + sl.p0, (uint32_t)sl.np, d_err, e->ks));
-                    WAKE_CHECK(kt.end((uint64_t)sl.np * FMA_PAGE_BYTES + sl.bytes));
-                    WAKE_RT(cudaEventRecord(e->ev_ring_free[slot], e->ks));
-                }
-            } else {
-                const uint64_t sbase = store_dev_base(e, tier);
-                for (size_t q = 0; q < n_pages; ++q) {
-                    fma_k_pack_desc& pd = e->h_pdesc[q];
-                    pd.src = sbase + soff[q];
-                    pd.dst = dsts[q];
-                    pd.mode = sbytes[q] == FMA_PAGE_BYTES ? FMA_K_PACK_RAW : FMA_K_PACK_BF16;
-                    pd.pad = 0;
-                }
-                WAKE_RT(cudaMemcpyAsync(e->d_pdesc, e->h_pdesc, n_pages * sizeof(fma_k_pack_desc), cudaMemcpyHostToDevice, e->ks));
-                const size_t batch_pages = std::max<size_t>(staged_slot(e) / FMA_PAGE_BYTES, 1);
-                for (size_t p0 = 0; p0 < n_pages;) {
-                    const size_t np = std::min(batch_pages, n_pages - p0);
-                    size_t need = 0;
-                    uint64_t stored = 0;
-                    for (size_t q = p0; q < p0 + np; ++q) {
-                        need = std::max(need, need_item[q]);
-                        stored += sbytes[q];
-                    }
-                    int mrc = wait_mapped(need);
-                    if (mrc != FMA_OK) WAKE_CHECK(fail(mrc, "%s", prog.msg));
-                    WAKE_CHECK(kt.begin());
-                    WAKE_RT(fma_k_launch_unpack(e->d_pdesc + p0, (uint32_t)np, d_err, e->ks));
-                    WAKE_CHECK(kt.end((uint64_t)np * FMA_PAGE_BYTES + stored));
-                    if (!copy_ops) first_copy_delay = now_s() - t_entry;
-                    ++copy_ops;
-                    p0 += np;
-                }
-            }
-        } else if (mode == FMA_MODE_DIRECT) {
-            int k = 0;
-            for (size_t w = 0; w < with_backup.size(); ++w) {
-                int mrc = wait_mapped(seg_run[with_backup[w]] + 1);
-                if (mrc != FMA_OK) WAKE_CHECK(fail(mrc, "%s", prog.msg));
-                const Segment& s = e->segs[with_backup[w]];
-                for (size_t o = 0; o < s.bytes; o += chunk, ++k) {
-                    const size_t n = std::min(chunk, s.bytes - o);
-                    WAKE_RT(cudaMemcpyAsync(reinterpret_cast<void*>(s.va + o), store + s.packed_off + o, n, cudaMemcpyDefault,
-                                            e->cs[k % e->n_cs]));
-                    if (!copy_ops) first_copy_delay = now_s() - t_entry;
-                    ++copy_ops;
-                }
-            }
-        } else {
-            // page table of the DESTINATIONS, ordered by packed offset (== with_backup order by construction
-            // only if every backed-up segment is woken; build explicitly from packed offsets to stay general)
-            struct Dst { uint64_t packed_off; size_t w; };
-            std::vector<Dst> d;
-            for (size_t w = 0; w < with_backup.size(); ++w) d.push_back(Dst{e->segs[with_backup[w]].packed_off, w});
-            std::sort(d.begin(), d.end(), [](const Dst& a, const Dst& b) { return a.packed_off < b.packed_off; });
-            // runs of pages: (image page index, destination address), plus the latest work item each page needs
-            size_t n_pages = W / FMA_PAGE_BYTES;
-            WAKE_CHECK(ensure_tables(e, n_pages));
-            uint64_t* dst_tab = e->h_tab;                 // destination page addresses
-            uint64_t* src_tab = e->h_tab + e->d_tab_cap;  // source page addresses inside the store (may be sparse)
-            std::vector<size_t> need_item(n_pages);
-            const uint64_t sbase = store_dev_base(e, tier);
-            size_t p = 0;
-            for (const Dst& x : d) {
-                const Segment& s = e->segs[with_backup[x.w]];
-                for (size_t o = 0; o < s.bytes; o += FMA_PAGE_BYTES, ++p) {
-                    dst_tab[p] = (uint64_t)s.va + o;
-                    src_tab[p] = sbase + s.packed_off + o;
-                    need_item[p] = seg_run[with_backup[x.w]] + 1;
-                }
-            }
-            WAKE_RT(cudaMemcpyAsync(e->d_tab, dst_tab, n_pages * sizeof(uint64_t), cudaMemcpyHostToDevice, e->ks));
-            WAKE_RT(cudaMemcpyAsync(e->d_tab + e->d_tab_cap, src_tab, n_pages * sizeof(uint64_t), cudaMemcpyHostToDevice, e->ks));
-            const uint64_t* d_dst = e->d_tab;
-            const uint64_t* d_src = e->d_tab + e->d_tab_cap;
-            if (mode == FMA_MODE_KERNEL) {
-                // K2 reads the store itself (zero-copy PCIe reads, or NVLink/HBM loads); launch batches as the
-                // mapper makes progress so the scatter overlaps cuMemCreate/Map of later segments
-                const size_t batch_pages = std::max<size_t>(staged_slot(e) / FMA_PAGE_BYTES, 1);
-                size_t p0 = 0;
-                while (p0 < n_pages) {
-                    size_t np = std::min(batch_pages, n_pages - p0);
-                    size_t need = 0;
-                    for (size_t q = p0; q < p0 + np; ++q) need = std::max(need, need_item[q]);
-                    int mrc = wait_mapped(need);
-                    if (mrc != FMA_OK) WAKE_CHECK(fail(mrc, "%s", prog.msg));
-                    // opportunistically extend the batch over everything already mapped
-                    const size_t have = mapped_now();
-                    while (p0 + np < n_pages && need_item[p0 + np] <= have) ++np;
-                    WAKE_CHECK(kt.launch(d_src + p0, 0, d_dst + p0, 0, (uint32_t)np));
-                    if (!copy_ops) first_copy_delay = now_s() - t_entry;
-                    ++copy_ops;
-                    p0 += np;
-                }
-            } else {  // STAGED: copy engine H2D store -> ring slot (starts at t=0), K2 scatter once the targets are mapped
-                if (ring_run) {  // the ring is run 0 (1 GiB, ~0.2 ms to map): wait for it before the first H2D
-                    int mrc0 = wait_mapped(1);
-                    if (mrc0 != FMA_OK) WAKE_CHECK(fail(mrc0, "%s", prog.msg));
-                } else {
-                    WAKE_CHECK(ensure_ring(e, W));
-                }
-                const size_t slot_pages = e->ring_slot_bytes / FMA_PAGE_BYTES;
-                // the store image may be only partially woken; H2D works on runs that are contiguous in the store
-                size_t c = 0;
-                size_t p0 = 0;
-                while (p0 < n_pages) {
-                    size_t np = 1;
-                    while (np < slot_pages && p0 + np < n_pages && src_tab[p0 + np] == src_tab[p0 + np - 1] + FMA_PAGE_BYTES) ++np;
-                    const int slot = (int)(c % e->n_ring);
-                    cudaStream_t cstream = e->cs[c % e->n_cs];
-                    if (c >= (size_t)e->n_ring) WAKE_RT(cudaStreamWaitEvent(cstream, e->ev_ring_free[slot], 0));
-                    WAKE_RT(cudaMemcpyAsync(e->ring[slot], store + (src_tab[p0] - sbase), np * FMA_PAGE_BYTES, cudaMemcpyDefault, cstream));
-                    if (!copy_ops) first_copy_delay = now_s() - t_entry;
-                    ++copy_ops;
-                    WAKE_RT(cudaEventRecord(e->ev_ring_full[slot], cstream));
-                    size_t need = 0;
-                    for (size_t q = p0; q < p0 + np; ++q) need = std::max(need, need_item[q]);
-                    int mrc = wait_mapped(need);
-                    if (mrc != FMA_OK) WAKE_CHECK(fail(mrc, "%s", prog.msg));
-                    WAKE_RT(cudaStreamWaitEvent(e->ks, e->ev_ring_full[slot], 0));
-                    WAKE_CHECK(kt.launch(nullptr, (uint64_t)(uintptr_t)e->ring[slot], d_dst + p0, 0, (uint32_t)np));
-                    WAKE_RT(cudaEventRecord(e->ev_ring_free[slot], e->ks));
-                    p0 += np;
-                    ++c;
-                }
-            }
-        }
+        WakePipe pipe{e, with_backup, seg_run, W, tier, mode, ring_run, store, kt, copy_ops, first_copy_delay, t_entry, wait_mapped, mapped_now, prog.msg};
+        if (packed) WAKE_CHECK(wake_packed(pipe));
+        else if (mode == FMA_MODE_DIRECT) WAKE_CHECK(wake_direct(pipe));
+        else WAKE_CHECK(wake_paged(pipe));
     }
     // every requested segment must be mapped before wake returns (cumem.py:237-240)
     {
