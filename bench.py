@@ -419,7 +419,7 @@ def measure_peer(eng, L, Wb, local_rank, world, barrier, max_over_ranks, before,
 # --------------------------------------------------------------------------------------------------
 # reference arm: vLLM's own CuMemAllocator (vllm:device_allocator/cumem.py:177-249), unmodified
 # --------------------------------------------------------------------------------------------------
-def reference_cycle_worker(gpu: int, workload: str, kv_gib: float, steps: int, warmup: int, conn, start_barrier=None):
+def reference_cycle_worker(gpu: int, workload: str, kv_gib: float, steps: int, warmup: int, conn, start_barrier=None, contents: str = "prng"):
     """Runs in its own process: one GPU, the same allocation table, vLLM's allocator moving the bytes."""
     os.environ["CUDA_VISIBLE_DEVICES"] = str(gpu)
     try:
@@ -441,7 +441,10 @@ def reference_cycle_worker(gpu: int, workload: str, kv_gib: float, steps: int, w
         with alloc.use_memory_pool(tag="kv_cache"):
             kv = [torch.empty(s.bytes, dtype=torch.uint8, device="cuda") for s in table if s.tag == "kv_cache"]
         for t in tensors:
-            t.view(torch.int64).random_(generator=gen)
+            if contents == "bf16":     # what vLLM's dummy loader fills parameters with (weight_utils.py:1451-1471)
+                t.view(torch.bfloat16).uniform_(-1e-3, 1e-3, generator=gen)
+            else:
+                t.view(torch.int64).random_(generator=gen)
         sums = [int(t.view(torch.int64).sum().item()) for t in tensors[:8]]
         Wb = sum(t.numel() for t in tensors)
         torch.cuda.synchronize()
@@ -462,7 +465,7 @@ def reference_cycle_worker(gpu: int, workload: str, kv_gib: float, steps: int, w
         conn.send({"error": f"{type(e).__name__}: {e}"[:300]})
 
 
-def run_reference_workers(n_gpus: int, workload: str, kv_gib: float, steps: int, warmup: int):
+def run_reference_workers(n_gpus: int, workload: str, kv_gib: float, steps: int, warmup: int, contents: str = "prng"):
     import multiprocessing as mp
 
     ctx = mp.get_context("spawn")
@@ -470,7 +473,7 @@ def run_reference_workers(n_gpus: int, workload: str, kv_gib: float, steps: int,
     procs, conns = [], []
     for g in range(n_gpus):
         pc, cc = ctx.Pipe()
-        p = ctx.Process(target=reference_cycle_worker, args=(g, workload, kv_gib, steps, warmup, cc, bar))
+        p = ctx.Process(target=reference_cycle_worker, args=(g, workload, kv_gib, steps, warmup, cc, bar, contents))
         p.start()
         procs.append(p); conns.append(pc)
     results = [c.recv() for c in conns]
@@ -495,7 +498,7 @@ def reference_sample(args, workload) -> dict:
     """cpu_baseline: the reference data path timed on this box in the same run (bounded: 1 warm-up + 2 cycles)."""
     cores = os.cpu_count()
     try:
-        res = run_reference_workers(1, workload, args.kv_gib, steps=2, warmup=1)
+        res = run_reference_workers(1, workload, args.kv_gib, steps=2, warmup=1, contents=args.contents)
         summ, err = summarise_reference(res, 2)
         if err:
             raise RuntimeError(err)
@@ -547,7 +550,7 @@ def run_reference(args) -> None:
     workload = workload_for(args.gpus, args.workload)
     t0 = time.perf_counter()
     try:
-        res = run_reference_workers(args.gpus, workload, args.kv_gib, args.steps, args.warmup)
+        res = run_reference_workers(args.gpus, workload, args.kv_gib, args.steps, args.warmup, contents=args.contents)
         summ, err = summarise_reference(res, args.steps)
         if err:
             raise RuntimeError(err)
