@@ -722,3 +722,18 @@ def test_packed_image_in_a_parking_tier(engine, oracle, tier):
         for i, b in enumerate(blobs):
             assert engine.read(i, b.size) == b.tobytes()
     assert [s.va for s in engine.segments()] == ptrs
+
+
+@_PACK
+def test_pack_kernels_binary_on_the_device():
+    """tests/cpp/cuda_emu/pack_kernels_gpu_test: the kernel-level test (same source as the CPU-emulated one) with managed
+    memory on the real device — no engine, no Python in the way."""
+    if os.environ.get("FMA_HOSTSIM") == "1":
+        pytest.skip("a device binary: nothing to run on the host simulation")
+    import subprocess
+
+    exe = os.path.join(os.path.dirname(__file__), "cpp", "cuda_emu", "pack_kernels_gpu_test")
+    if not os.path.exists(exe):
+        pytest.skip("not built (make -C tests/cpp/cuda_emu)")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "pack kernels (GPU) ok" in r.stdout, (r.stdout + r.stderr)[-2000:]
