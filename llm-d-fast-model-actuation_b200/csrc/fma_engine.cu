@@ -1227,6 +1227,9 @@ int fma_set_option(fma_engine_t* e, const char* key, int64_t value) {
     } else if (k == "pack") {
         if (value != 0 && value != 1) return fail(FMA_EINVAL, "pack must be 0 or 1");
         e->cfg.pack = (int32_t)value;
+    } else if (k == "pack_kernel") {  // process-wide: 0 = LDG/STG kernels, 1 = TMA-pipelined kernels (K4 / K5)
+        if (value != FMA_K_PACK_VARIANT_LDG && value != FMA_K_PACK_VARIANT_TMA) return fail(FMA_EINVAL, "pack_kernel must be 0 or 1");
+        fma_k_set_pack_variant((int)value);
     } else if (k == "tma_tile_bytes") {
         if (value < 1024 || (FMA_PAGE_BYTES % (size_t)value) != 0 || value % 16) return fail(FMA_EINVAL, "bad tma tile %lld", (long long)value);
         e->tma.tile_bytes = (uint32_t)value;

@@ -48,3 +48,11 @@ cudaError_t fma_k_launch_pack_probe(const uint64_t* src_tab, uint32_t n_pages, u
 // K4 / K5: *err_count (device, zeroed by the caller) counts pages that could not be coded / decoded
 cudaError_t fma_k_launch_pack(const fma_k_pack_desc* descs, uint32_t n_pages, uint32_t* err_count, cudaStream_t stream);
 cudaError_t fma_k_launch_unpack(const fma_k_pack_desc* descs, uint32_t n_pages, uint32_t* err_count, cudaStream_t stream);
+// TMA-pipelined variants of K4 / K5 (fma_pack_tma_kernels.cu); fma_k_launch_pack / _unpack dispatch to them when the
+// process-wide variant is 1 (fma_k_set_pack_variant; default from FMA_PACK_KERNEL)
+#define FMA_K_PACK_VARIANT_LDG 0
+#define FMA_K_PACK_VARIANT_TMA 1
+void fma_k_set_pack_variant(int variant);
+int fma_k_pack_variant();
+cudaError_t fma_k_launch_pack_tma(const fma_k_pack_desc* descs, uint32_t n_pages, uint32_t* err_count, cudaStream_t stream);
+cudaError_t fma_k_launch_unpack_tma(const fma_k_pack_desc* descs, uint32_t n_pages, uint32_t* err_count, cudaStream_t stream);

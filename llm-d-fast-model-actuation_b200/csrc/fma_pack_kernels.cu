@@ -16,6 +16,7 @@
 // tests run, and restated in oracle/fma_oracle.c.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 #include "fma_codec.h"
 #include "fma_kernels.h"
@@ -231,6 +232,17 @@ unsigned pack_grid(uint32_t n_pages) {
 
 }  // namespace
 
+// process-wide choice between the LDG/STG kernels of this file and the TMA-pipelined ones (fma_pack_tma_kernels.cu)
+static int g_pack_variant = -1;
+void fma_k_set_pack_variant(int variant) { g_pack_variant = variant == FMA_K_PACK_VARIANT_TMA ? FMA_K_PACK_VARIANT_TMA : FMA_K_PACK_VARIANT_LDG; }
+int fma_k_pack_variant() {
+    if (g_pack_variant < 0) {
+        const char* v = getenv("FMA_PACK_KERNEL");
+        g_pack_variant = (v && atoi(v) == 1) ? FMA_K_PACK_VARIANT_TMA : FMA_K_PACK_VARIANT_LDG;
+    }
+    return g_pack_variant;
+}
+
 cudaError_t fma_k_launch_pack_probe(const uint64_t* src_tab, uint32_t n_pages, uint32_t* out_bytes, cudaStream_t stream) {
     if (n_pages == 0) return cudaSuccess;
     FMA_LAUNCH(fma_k_pack_probe, pack_grid(n_pages), kThreads, 0, stream, src_tab, n_pages, out_bytes);
@@ -239,12 +251,14 @@ cudaError_t fma_k_launch_pack_probe(const uint64_t* src_tab, uint32_t n_pages, u
 
 cudaError_t fma_k_launch_pack(const fma_k_pack_desc* descs, uint32_t n_pages, uint32_t* err_count, cudaStream_t stream) {
     if (n_pages == 0) return cudaSuccess;
+    if (fma_k_pack_variant() == FMA_K_PACK_VARIANT_TMA) return fma_k_launch_pack_tma(descs, n_pages, err_count, stream);
     FMA_LAUNCH(fma_k_pack, pack_grid(n_pages), kThreads, 0, stream, descs, n_pages, err_count);
     return cudaGetLastError();
 }
 
 cudaError_t fma_k_launch_unpack(const fma_k_pack_desc* descs, uint32_t n_pages, uint32_t* err_count, cudaStream_t stream) {
     if (n_pages == 0) return cudaSuccess;
+    if (fma_k_pack_variant() == FMA_K_PACK_VARIANT_TMA) return fma_k_launch_unpack_tma(descs, n_pages, err_count, stream);
     FMA_LAUNCH(fma_k_unpack, pack_grid(n_pages), kThreads, 0, stream, descs, n_pages, err_count);
     return cudaGetLastError();
 }

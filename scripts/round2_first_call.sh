@@ -26,6 +26,7 @@ timeout 300 env FMA_TEST_IMAGE_ON_GPU=1 python -m pytest tests/test_gpu_parity.p
 timeout 600 python bench.py --steps 10 --warmup 3 > "$out/bench_default.json" 2> "$out/bench_default.err"; echo "bench default rc=$?" | tee -a "$out/status.txt"
 timeout 400 python bench.py --steps 10 --warmup 3 --contents bf16 --pack 0 --no-cpu-baseline --packed-extra 0 > "$out/bench_bf16_plain.json" 2>> "$out/bench_default.err"
 timeout 400 python bench.py --steps 10 --warmup 3 --contents bf16 --pack 1 --no-cpu-baseline --packed-extra 0 > "$out/bench_bf16_packed.json" 2>> "$out/bench_default.err"; echo "bench packed rc=$?" | tee -a "$out/status.txt"
+timeout 400 env FMA_PACK_KERNEL=1 python bench.py --steps 10 --warmup 3 --contents bf16 --pack 1 --no-cpu-baseline --packed-extra 0 > "$out/bench_bf16_packed_tma.json" 2>> "$out/bench_default.err"; echo "bench packed (TMA kernels) rc=$?" | tee -a "$out/status.txt"
 
 # 4b. VMM granularity / VA alignment probe (seconds)
 timeout 120 python scripts/gran_probe.py > "$out/gran_probe.log" 2>&1

@@ -12,7 +12,12 @@
 #include <pthread.h>
 #include <stdint.h>
 
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
 #include <functional>
+#include <map>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -34,11 +39,14 @@ struct Tls {
 inline thread_local Tls tls;
 inline dim3 g_block_dim, g_grid_dim;
 
+inline void reset_bars();
+inline void thread_exit_check();
 inline void launch(unsigned grid, unsigned block, const std::function<void()>& body) {
     g_block_dim = dim3(block, 1, 1);
     g_grid_dim = dim3(grid, 1, 1);
     for (unsigned b = 0; b < grid; ++b) {  // CTAs one after the other: statics stand in for __shared__
         Cta cta;
+        reset_bars();
         pthread_barrier_init(&cta.bar, nullptr, block);
         cta.warps = std::vector<Warp>((block + 31) / 32);
         for (size_t w = 0; w < cta.warps.size(); ++w) {
@@ -52,6 +60,7 @@ inline void launch(unsigned grid, unsigned block, const std::function<void()>& b
                 tls.bid = uint3{b, 0, 0};
                 tls.cta = &cta;
                 body();
+                thread_exit_check();
             });
         for (auto& x : th) x.join();
         for (auto& w : cta.warps) pthread_barrier_destroy(&w.bar);
@@ -73,8 +82,92 @@ inline uint32_t warp_reduce(uint32_t v, Op op) {
     return r;
 }
 
+inline void syncwarp() { pthread_barrier_wait(&tls.cta->warps[tls.tid.x >> 5].bar); }
+
+// ---- the async proxy, LAZILY: bulk copies do not happen when they are issued but when somebody legitimately waits for
+// them.  A kernel that reads a shared-memory buffer before waiting on its mbarrier sees stale bytes, one that overwrites
+// a buffer a bulk store has not finished reading (no wait_group.read) ships the wrong bytes, one that exits without
+// wait_group 0 loses its last stores — all of which the comparison with the oracle then catches. ----
+struct Copy { void* dst; const void* src; uint32_t bytes; };
+struct MBar {
+    std::mutex mu;
+    uint32_t phase = 0;      // completed phases
+    uint32_t expected = 0;   // bytes announced by arrive.expect_tx for the current phase
+    uint32_t have = 0;       // bytes of the loads issued against the current phase
+    std::vector<Copy> pending;
+};
+inline std::mutex g_bars_mu;
+inline std::map<const void*, MBar*> g_bars;   // one emulated mbarrier per shared-memory address; reset at every CTA start
+inline MBar& bar_of(const void* addr) {
+    std::lock_guard<std::mutex> lk(g_bars_mu);
+    MBar*& b = g_bars[addr];
+    if (!b) b = new MBar();
+    return *b;
+}
+inline void reset_bars() {
+    std::lock_guard<std::mutex> lk(g_bars_mu);
+    for (auto& kv : g_bars) delete kv.second;
+    g_bars.clear();
+}
+inline void mbar_init(uint64_t* bar, uint32_t count) {
+    if (count != 1) { fprintf(stderr, "cuda_emu: only arrival count 1 is modelled\n"); abort(); }
+    MBar& b = bar_of(bar);
+    std::lock_guard<std::mutex> lk(b.mu);
+    b.phase = 0; b.expected = 0; b.have = 0; b.pending.clear();
+}
+inline void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    MBar& b = bar_of(bar);
+    std::lock_guard<std::mutex> lk(b.mu);
+    if (b.expected) { fprintf(stderr, "cuda_emu: second arrive.expect_tx on a phase that is still open\n"); abort(); }
+    b.expected = bytes;
+}
+inline void bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+    if (bytes % 16 || (uintptr_t)dst_smem % 16 || (uintptr_t)src % 16) { fprintf(stderr, "cuda_emu: cp.async.bulk needs 16-byte size and alignment\n"); abort(); }
+    MBar& b = bar_of(bar);
+    std::lock_guard<std::mutex> lk(b.mu);
+    b.pending.push_back(Copy{dst_smem, src, bytes});
+    b.have += bytes;
+}
+inline void mbar_wait(uint64_t* bar, uint32_t parity) {
+    MBar& b = bar_of(bar);
+    for (int spins = 0;; ++spins) {
+        {
+            std::lock_guard<std::mutex> lk(b.mu);
+            if ((b.phase & 1u) != parity) return;                       // that phase has completed
+            if (b.expected && b.have == b.expected) {                    // every announced byte was issued: the phase completes NOW
+                for (const Copy& c : b.pending) memcpy(c.dst, c.src, c.bytes);
+                b.pending.clear(); b.expected = 0; b.have = 0; ++b.phase;
+                return;
+            }
+            if (b.have > b.expected && b.expected) { fprintf(stderr, "cuda_emu: more bytes copied than expect_tx announced\n"); abort(); }
+        }
+        if (spins > 2000000) { fprintf(stderr, "cuda_emu: mbarrier wait would hang (parity %u never completes)\n", parity); abort(); }
+        std::this_thread::yield();
+    }
+}
+struct StoreQueue { std::vector<Copy> open; std::vector<std::vector<Copy>> groups; };
+inline thread_local StoreQueue tl_stores;
+inline void bulk_s2g(void* dst, const void* src_smem, uint32_t bytes) {
+    if (bytes % 16 || (uintptr_t)dst % 16 || (uintptr_t)src_smem % 16) { fprintf(stderr, "cuda_emu: cp.async.bulk needs 16-byte size and alignment\n"); abort(); }
+    tl_stores.open.push_back(Copy{dst, src_smem, bytes});
+}
+inline void bulk_commit() { tl_stores.groups.push_back(std::move(tl_stores.open)); tl_stores.open.clear(); }
+inline void bulk_wait_keep(size_t n) {  // wait_group[.read] n: all but the newest n groups are performed
+    while (tl_stores.groups.size() > n) {
+        for (const Copy& c : tl_stores.groups.front()) memcpy(c.dst, c.src, c.bytes);
+        tl_stores.groups.erase(tl_stores.groups.begin());
+    }
+}
+inline void thread_exit_check() {
+    if (!tl_stores.open.empty() || !tl_stores.groups.empty()) {
+        fprintf(stderr, "cuda_emu: a thread exited with bulk stores it never waited for (they would race with the CTA's exit)\n");
+        abort();
+    }
+}
+
 }  // namespace fma_emu
 
+#define __syncwarp() fma_emu::syncwarp()
 #undef __shared__
 #define __shared__ static
 #undef __global__
@@ -88,6 +181,14 @@ inline uint32_t warp_reduce(uint32_t v, Op op) {
 #define __syncthreads() fma_emu::syncthreads()
 inline uint32_t __reduce_max_sync(unsigned, uint32_t v) { return fma_emu::warp_reduce(v, [](uint32_t a, uint32_t b) { return a > b ? a : b; }); }
 inline uint32_t __reduce_add_sync(unsigned, uint32_t v) { return fma_emu::warp_reduce(v, [](uint32_t a, uint32_t b) { return a + b; }); }
+inline uint32_t __shfl_sync(unsigned, uint32_t v, uint32_t src_lane) {
+    fma_emu::Warp& w = fma_emu::tls.cta->warps[fma_emu::tls.tid.x >> 5];
+    w.scratch[fma_emu::tls.tid.x & 31] = v;
+    pthread_barrier_wait(&w.bar);
+    const uint32_t r = w.scratch[src_lane & 31];
+    pthread_barrier_wait(&w.bar);
+    return r;
+}
 inline uint32_t atomicAdd(uint32_t* p, uint32_t v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 template <class T> inline T __ldg(const T* p) { return *p; }
 template <class T> inline T __ldcg(const T* p) { return *p; }

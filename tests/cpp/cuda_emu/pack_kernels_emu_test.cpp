@@ -1,4 +1,5 @@
-// Runs the ACTUAL kernel source csrc/fma_pack_kernels.cu (K4p / K4 / K5) on the CPU execution model of cuda_emu.h and
+// Runs the ACTUAL kernel sources csrc/fma_pack_kernels.cu (K4p / K4 / K5) and csrc/fma_pack_tma_kernels.cu (their
+// TMA-pipelined variants) on the CPU execution model of cuda_emu.h and
 // checks it against the oracle (oracle/fma_oracle.c) page by page: probe decisions, stored bytes (exceptions compared
 // as sets), decode, gather/scatter through descriptor tables, the error counter.  Built by tests/test_kernels_emulated.py
 // with g++ -DFMA_CUDA_EMU -include cuda_emu.h, plain and under ThreadSanitizer (missing barriers = data races).
@@ -38,6 +39,7 @@ template <class T> using DevAlloc = std::allocator<T>;
 #endif
 
 #include "../../../llm-d-fast-model-actuation_b200/csrc/fma_pack_kernels.cu"
+#include "../../../llm-d-fast-model-actuation_b200/csrc/fma_pack_tma_kernels.cu"   // the TMA-pipelined K4 / K5 (variant 1)
 
 extern "C" {
 uint32_t fma_oracle_pack_page(const void* page, void* stored);
@@ -69,7 +71,8 @@ static bool same_stored(const unsigned char* a, const unsigned char* b, uint32_t
     return ea == eb;
 }
 
-int main() {
+static int run_variant(int variant) {
+    fma_k_set_pack_variant(variant);
     std::vector<Page> pages;
     pages.push_back(weights(110, 12));                                  // well inside 13 binades
     pages.push_back(weights(100, 27));                                  // wide: many exceptions -> probably raw
@@ -79,6 +82,7 @@ int main() {
     { Page p(N); for (auto& v : p) v = (uint16_t)rnd(); pages.push_back(p); }                                                   // noise -> raw
     pages.push_back(Page(N, 0));                                        // zeros
     { Page p = weights(120, 6); p[5] = 0x7F80; p[300000] = 0xFFC1; p[N - 1] = 0x0001; pages.push_back(p); }                    // inf / nan / denormal at the edges
+    if (getenv("FMA_EMU_FAST")) pages.resize(5);                        // sanitizer runs: the first five pages cover every branch but noise / inf
     const uint32_t n = (uint32_t)pages.size();
 
     // K4p vs oracle
@@ -94,10 +98,11 @@ int main() {
         if (w != sizes[p]) { fprintf(stderr, "page %u: probe says %u, oracle %u\n", p, sizes[p], w); return 1; }
         n_raw += w == PAGE;
     }
-    assert(n_raw >= 2 && n_raw <= 3);
+    assert(n_raw >= 1 && n_raw <= 3);
 
     // K4: gather in a permuted order into one contiguous store
-    std::vector<uint32_t> perm = {3, 0, 7, 5, 1, 6, 2, 4};
+    std::vector<uint32_t> perm(n);
+    for (uint32_t k = 0; k < n; ++k) perm[k] = (3 * k + 3) % n;          // a permutation for n = 5 and n = 8
     uint64_t total = 0;
     for (uint32_t p : perm) total += sizes[p];
     Bytes store(total, 0xEE);
@@ -151,6 +156,15 @@ int main() {
     assert(fma_k_launch_unpack(bad.data(), 1, &err, nullptr) == cudaSuccess);
     DEVICE_SYNC();
     assert(err == 1);
+    printf("variant %d (%s) ok\n", variant, variant ? "TMA-pipelined" : "LDG/STG");
+    return 0;
+}
+
+int main() {
+    for (int variant = 0; variant < 2; ++variant) {
+        const int rc = run_variant(variant);
+        if (rc) return rc;
+    }
 #if defined(FMA_GPU_TEST)
     puts("pack kernels (GPU) ok");
 #else

@@ -52,6 +52,10 @@ cudaError_t fma_k_launch_fill(const fma_k_page_desc* pages, uint32_t n_pages, ui
 #include "fma_codec.h"
 namespace fc = fma_codec;
 
+static int g_variant = 0;  // the stand-ins below serve both kernel variants: same bytes by contract
+void fma_k_set_pack_variant(int v) { g_variant = v; }
+int fma_k_pack_variant() { return g_variant; }
+
 static void load_lane(const unsigned char* src, uint32_t tile, uint32_t lane, uint32_t w[4]) { memcpy(w, src + tile * 512u + lane * 16u, 16); }
 
 static uint32_t tile_emax(const unsigned char* src, uint32_t tile) {

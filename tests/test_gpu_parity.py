@@ -597,8 +597,17 @@ def _same_stored_page(a: np.ndarray, b: np.ndarray) -> bool:
                 and np.array_equal(a[hdr:hdr + 4], b[hdr:hdr + 4]))
 
 
+@pytest.fixture()
+def pack_kernel(request, engine):
+    """K4 / K5 variant for a test: 0 = LDG/STG kernels, 1 = TMA-pipelined kernels (process-wide switch, reset afterwards)."""
+    engine.set_option("pack_kernel", request.param)
+    yield request.param
+    engine.set_option("pack_kernel", 0)
+
+
 @_PACK
-def test_pack_kernels_match_oracle_page_by_page(engine, oracle):
+@pytest.mark.parametrize("pack_kernel", [0, 1], indirect=True)
+def test_pack_kernels_match_oracle_page_by_page(engine, oracle, pack_kernel):
     L = _L()
     pages = _pack_pages(oracle)
     n = len(pages)
@@ -624,8 +633,9 @@ def test_pack_kernels_match_oracle_page_by_page(engine, oracle):
 
 
 @_PACK
+@pytest.mark.parametrize("pack_kernel", [0, 1], indirect=True)
 @pytest.mark.parametrize("chunk_mib,slots", [(6, 2), (2, 2), (512, 2), (4, 3)])
-def test_packed_sleep_wake_roundtrip_and_image_match_oracle(engine, oracle, chunk_mib, slots):
+def test_packed_sleep_wake_roundtrip_and_image_match_oracle(engine, oracle, chunk_mib, slots, pack_kernel):
     L = _L()
     pages = _pack_pages(oracle)
     rng = np.random.default_rng(5)
