@@ -111,6 +111,7 @@ fma_k_pack_tma(const fma_k_pack_desc* __restrict__ descs, uint32_t n_pages, uint
     if (lane == 0) {
         for (int s = 0; s < kStages; ++s) tma_mbar_init(&full_bar[warp][s], 1);
         tma_fence_mbar_init();
+        tma_fence_proxy_async();  // the initialised barriers are visible to the bulk-copy engine (same sequence as K1/K2)
     }
     __syncwarp();
     uint32_t g0 = 0;  // chunks this warp has pipelined so far (over all pages): stage = g % kStages, parity = (g / kStages) & 1
@@ -193,6 +194,7 @@ fma_k_unpack_tma(const fma_k_pack_desc* __restrict__ descs, uint32_t n_pages, ui
     if (lane == 0) {
         for (int s = 0; s < kStages; ++s) tma_mbar_init(&full_bar[warp][s], 1);
         tma_fence_mbar_init();
+        tma_fence_proxy_async();  // the initialised barriers are visible to the bulk-copy engine (same sequence as K1/K2)
     }
     __syncwarp();
     uint32_t g0 = 0;
