@@ -38,7 +38,7 @@ int main() {
     OK(fma_engine_create(0, nullptr, &b));
     int w = fma_tag_intern(a, "weights"), kv = fma_tag_intern(a, "kv_cache");
     int wb = fma_tag_intern(b, "weights");
-    const size_t sizes[] = {16 * P, 3 * P, P, 24 * P, 6 * P, P, 10 * P};
+    const size_t sizes[] = {8 * P, 3 * P, P, 12 * P, 6 * P, P, 5 * P};
     std::vector<void*> pa;
     for (size_t s : sizes) { void* p; OK(fma_alloc(a, s, w, &p)); pa.push_back(p); }
     void* pk; OK(fma_alloc(a, 20 * P, kv, &pk));
@@ -117,14 +117,14 @@ int main() {
     // PACKED host image: bf16-looking weights in segments 0/1 (packable), the others stay splitmix noise (raw pages);
     // sleep/wake with the option on, a failed packed sleep (D2H refuses) followed by a wake, and a hot swap of a packed image
     {
-        std::vector<uint16_t> vals(16 * P / 2);
+        std::vector<uint16_t> vals(8 * P / 2);
         uint32_t x = 12345;
         for (size_t i = 0; i < vals.size(); ++i) {
             x = x * 1664525u + 1013904223u;
             vals[i] = (uint16_t)(((x >> 31) << 15) | ((118u + ((x >> 8) % 9u)) << 7) | ((x >> 16) & 0x7F));   // exponents 118..126
         }
         vals[77] = 0; vals[1000] = 0x0085;                                  // a zero and a far-below-range value (exception)
-        OK(fma_segment_write(a, 0, 0, vals.data(), 16 * P));
+        OK(fma_segment_write(a, 0, 0, vals.data(), 8 * P));
         OK(fma_segment_write(a, 1, 0, vals.data(), 3 * P));
         auto before = digests(a);
         OK(fma_set_option(a, "mode", FMA_MODE_STAGED));
@@ -183,19 +183,19 @@ int main() {
 
     // cold load: file -> segments, multi-threaded readers
     const char* path = "/tmp/fma_hostsim_load.bin";
-    std::vector<unsigned char> blob(40 * P + 4096);
+    std::vector<unsigned char> blob(20 * P + 4096);
     for (size_t i = 0; i < blob.size(); ++i) blob[i] = (unsigned char)(i * 2654435761u >> 13);
     FILE* f = fopen(path, "wb"); fwrite(blob.data(), 1, blob.size(), f); fclose(f);
     fma_segment_info_t s0, s3;
-    OK(fma_segment_info(a, 0, &s0)); OK(fma_segment_info(a, 2, &s3));   // index 2 is the 24-page segment now
-    fma_load_span_t spans[2] = {{4096, 16 * P, s0.va}, {16 * P + 4096, 24 * P, s3.va}};
+    OK(fma_segment_info(a, 0, &s0)); OK(fma_segment_info(a, 2, &s3));   // index 2 is the 12-page segment now
+    fma_load_span_t spans[2] = {{4096, 8 * P, s0.va}, {8 * P + 4096, 12 * P, s3.va}};
     fma_load_stats_t ls;
     OK(fma_set_option(a, "load_chunk_bytes", 3 << 20)); OK(fma_set_option(a, "load_threads", 6)); OK(fma_set_option(a, "load_slots", 4));
     OK(fma_load_file(a, path, spans, 2, 0, &ls));
-    assert(ls.bytes == 40 * P);
-    std::vector<unsigned char> back(16 * P);
-    OK(fma_segment_read(a, 0, 0, back.data(), 16 * P));
-    assert(memcmp(back.data(), blob.data() + 4096, 16 * P) == 0);
+    assert(ls.bytes == 20 * P);
+    std::vector<unsigned char> back(8 * P);
+    OK(fma_segment_read(a, 0, 0, back.data(), 8 * P));
+    assert(memcmp(back.data(), blob.data() + 4096, 8 * P) == 0);
     remove(path);
 
     OK(fma_engine_destroy(a));
