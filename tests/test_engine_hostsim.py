@@ -116,3 +116,24 @@ print("ok")
     env = dict(os.environ, FMA_B200_LIB=hostsim_lib, FMA_HOSTSIM="1", HOSTSIM_DEVICES="1")
     r = subprocess.run([sys.executable, "-c", code], env=env, cwd=ROOT, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "ok" in r.stdout, (r.stdout + r.stderr)[-3000:]
+
+
+def test_bench_main_flow_runs_against_the_host_simulated_engine(hostsim_lib, oracle):
+    """The whole of bench.py's own arm at N=1 — table, fill, digests, timed cycles, JSON line with every contract key,
+    cpu_baseline fallback (the oracle port: vLLM's allocator cannot load here) and the packed_image child — with torch
+    replaced by tests/stubs/torch.  Numbers are meaningless here; the flow and the keys are what is checked."""
+    import json
+
+    env = dict(os.environ, FMA_B200_LIB=hostsim_lib, FMA_HOSTSIM="1", HOSTSIM_DEVICES="1",
+               PYTHONPATH=os.path.join(ROOT, "tests", "stubs") + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", "tiny-llama-test", "--kv-gib", "0.03125",
+                        "--steps", "2", "--warmup", "3"], env=env, cwd=ROOT, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+                "data", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks", "packed_image"):
+        assert key in out, key
+    assert out["bit_exact"] is True and out["n_gpus"] == 1 and out["gpu_launches"] > 0
+    assert out["e2e"]["link_bytes_per_step"] == out["e2e"]["h2d_bytes_per_step"]          # not packed: every weight byte crosses the link
+    assert out["cpu_baseline"]["kind"] == "port"
+    assert out["packed_image"].get("bit_exact") is True and out["packed_image"]["image_packed"] is True
