@@ -137,3 +137,11 @@ def test_bench_main_flow_runs_against_the_host_simulated_engine(hostsim_lib, ora
     assert out["e2e"]["link_bytes_per_step"] == out["e2e"]["h2d_bytes_per_step"]          # not packed: every weight byte crosses the link
     assert out["cpu_baseline"]["kind"] == "port"
     assert out["packed_image"].get("bit_exact") is True and out["packed_image"]["image_packed"] is True
+
+
+def test_smoke_entry_point_runs_against_the_host_simulated_engine(hostsim_lib, oracle):
+    """__graft_entry__.smoke() — what the driver runs on cuda:0 — with the host-simulated engine: its checks (digests, packed
+    host image == oracle gather, addresses, bytes) hold in all three modes."""
+    env = dict(os.environ, FMA_B200_LIB=hostsim_lib, FMA_HOSTSIM="1", HOSTSIM_DEVICES="1")
+    r = subprocess.run([sys.executable, "-c", "import __graft_entry__ as g; g.smoke()"], env=env, cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "smoke ok" in r.stdout, (r.stdout + r.stderr)[-3000:]
