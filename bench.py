@@ -272,6 +272,8 @@ def run_ours(args) -> None:
         }
         if peer:
             out["peer_tier"] = peer
+        if world == 1:
+            eng.close()   # everything above is measured: give the HBM and the pinned store back before the baseline / extra processes run
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = reference_sample(args, workload)
         if world == 1 and args.packed_extra and not args.pack and tier == L.FMA_TIER_HOST:
