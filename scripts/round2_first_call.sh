@@ -28,6 +28,9 @@ timeout 400 python bench.py --steps 10 --warmup 3 --contents bf16 --pack 0 --no-
 timeout 400 python bench.py --steps 10 --warmup 3 --contents bf16 --pack 1 --no-cpu-baseline --packed-extra 0 > "$out/bench_bf16_packed.json" 2>> "$out/bench_default.err"; echo "bench packed rc=$?" | tee -a "$out/status.txt"
 timeout 400 env FMA_PACK_KERNEL=1 python bench.py --steps 10 --warmup 3 --contents bf16 --pack 1 --no-cpu-baseline --packed-extra 0 > "$out/bench_bf16_packed_tma.json" 2>> "$out/bench_default.err"; echo "bench packed (TMA kernels) rc=$?" | tee -a "$out/status.txt"
 
+# 4a. isolated K4p / K4 / K5 throughput, both variants (under timeout: the TMA variant has never run on a GPU)
+timeout 300 python scripts/pack_sweep.py > "$out/pack_sweep.log" 2>&1; echo "pack sweep rc=$?" | tee -a "$out/status.txt"
+
 # 4b. VMM granularity / VA alignment probe (seconds)
 timeout 120 python scripts/gran_probe.py > "$out/gran_probe.log" 2>&1
 
