@@ -12,8 +12,9 @@ export FMA_TEST_PACK_ON_GPU=1
 timeout 120 tests/cpp/cuda_emu/pack_kernels_gpu_test > "$out/pack_kernels_gpu_test.log" 2>&1; echo "kernel test rc=$?" | tee "$out/status0.txt"
 
 # 1. parity of the PACKED image kernels and engine path against the oracle, then the whole GPU suite
-timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "pack" > "$out/pytest_pack.log" 2>&1; echo "pytest pack rc=$?" | tee "$out/status.txt"
-timeout 600 python -m pytest tests -m gpu -x -q > "$out/pytest_gpu.log" 2>&1; echo "pytest gpu rc=$?" | tee -a "$out/status.txt"
+timeout 300 env FMA_TEST_PACK_KERNELS=0 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "pack" > "$out/pytest_pack.log" 2>&1; echo "pytest pack (LDG/STG kernels) rc=$?" | tee "$out/status.txt"
+timeout 300 env FMA_TEST_PACK_KERNELS=1 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "pack and not binary" > "$out/pytest_pack_tma.log" 2>&1; echo "pytest pack (TMA kernels) rc=$?" | tee -a "$out/status.txt"
+timeout 600 env FMA_TEST_PACK_KERNELS=0 python -m pytest tests -m gpu -x -q > "$out/pytest_gpu.log" 2>&1; echo "pytest gpu rc=$?" | tee -a "$out/status.txt"
 
 # 2. memcheck + racecheck over the pack tests (small tables)
 timeout 600 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "pack_kernels_match" > "$out/sanitizer_memcheck_pack.log" 2>&1; echo "memcheck rc=$?" | tee -a "$out/status.txt"
