@@ -229,7 +229,9 @@ FMA_API int  fma_peer_release(fma_engine_t* e);
  * store is a memfd: a sleeping engine can hand its packed image (data + a descriptor of segment sizes, tags and K3
  * digests) to another process as a file descriptor, and an engine that has allocated the SAME segment sequence (same
  * model, freshly created, contents irrelevant) adopts it and is then "asleep with that image": a following fma_wake
- * restores the weights at PCIe speed instead of re-reading a checkpoint.
+ * restores the weights at PCIe speed instead of re-reading a checkpoint.  The fd may also be a regular FILE holding
+ * the same bytes (Engine.image_save / image_load in the Python binding): if its mapping cannot be pinned in place the
+ * image is copied once into an anonymous pinned store.  A PACKED image travels with its page table (descriptor v2).
  * Status: exercised on the CUDA host simulation only (tests/test_engine_hostsim.py); not yet run on a B200. */
 FMA_API int  fma_image_export(fma_engine_t* e, int* out_fd);          /* caller owns (closes) the returned fd          */
 FMA_API int  fma_image_adopt(fma_engine_t* e, int fd, uint64_t tag_mask, uint32_t flags);  /* fd stays owned by the caller */

@@ -116,12 +116,33 @@ int fma_image_adopt(fma_engine_t* e, int fd, uint64_t tag_mask, uint32_t flags) 
     host_store_free(e->host);
     const double t0 = now_s();
     cudaError_t r = cudaHostRegister(p, map_bytes, cudaHostRegisterPortable | cudaHostRegisterMapped);
-    if (r != cudaSuccess) {
-        cudaGetLastError();
-        return bail(FMA_ECUDA, "cannot pin the adopted image");
-    }
     HostStore h;
-    h.base = p; h.cap = cap; h.map_bytes = map_bytes; h.fd = myfd; h.registered = true;
+    if (r != cudaSuccess) {
+        // The mapping cannot be pinned in place (e.g. an image FILE on a filesystem whose pages the driver will not lock):
+        // copy it once into an anonymous pinned store — a load from the page cache, several threads — and let go of the fd.
+        cudaGetLastError();
+        void* q = nullptr;
+        r = cudaHostAlloc(&q, map_bytes, cudaHostAllocPortable | cudaHostAllocMapped);
+        if (r != cudaSuccess) {
+            cudaGetLastError();
+            return bail(FMA_ENOMEM, "cannot pin the adopted image, in place or as a copy");
+        }
+        const int nt = std::max(1, std::min(env_int("FMA_TOUCH_THREADS", 8), 32));
+        const size_t per = round_up((map_bytes + nt - 1) / nt, FMA_PAGE_BYTES);
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; ++t) {
+            const size_t lo = (size_t)t * per, hi = std::min(map_bytes, lo + per);
+            if (lo >= hi) break;
+            th.emplace_back([p, q, lo, hi] { memcpy(static_cast<char*>(q) + lo, static_cast<const char*>(p) + lo, hi - lo); });
+        }
+        for (auto& t : th) t.join();
+        munmap(p, map_bytes);
+        close(myfd);
+        h.base = q; h.cap = cap; h.map_bytes = 0; h.fd = -1; h.registered = false;
+        p = q;
+    } else {
+        h.base = p; h.cap = cap; h.map_bytes = map_bytes; h.fd = myfd; h.registered = true;
+    }
     void* alias = nullptr;
     if (cudaHostGetDevicePointer(&alias, p, 0) == cudaSuccess) h.dev_alias = alias;
     else cudaGetLastError();

@@ -267,6 +267,32 @@ class Engine:
         """Become 'asleep with that image': this engine must hold the same segment sequence for ``tags``."""
         check(self._lib.fma_image_adopt(self._h, fd, self.tag_mask(tags), flags))
 
+    def image_save(self, path: str) -> int:
+        """Persist the sleeping image (store + descriptor) as a file; a later process with the same segment table can
+        ``image_load`` it instead of loading weights.  Needs FMA_HOST_STORE_SHM=1.  Returns the bytes written."""
+        import os
+        import shutil
+
+        fd = self.image_export()
+        try:
+            with os.fdopen(os.dup(fd), "rb") as src, open(path + ".tmp", "wb") as dst:
+                shutil.copyfileobj(src, dst, length=64 << 20)
+                n = dst.tell()
+            os.replace(path + ".tmp", path)
+            return n
+        finally:
+            os.close(fd)
+
+    def image_load(self, path: str, tags: Sequence[str], flags: int = 0) -> None:
+        """``image_adopt`` from a file written by ``image_save``: afterwards this engine is asleep with that image."""
+        import os
+
+        fd = os.open(path, os.O_RDWR)
+        try:
+            self.image_adopt(fd, tags, flags)
+        finally:
+            os.close(fd)
+
     # -- cold load -------------------------------------------------------------------------
     def load_file(self, path: str, spans: Sequence[tuple[int, int, int]], o_direct: bool = False) -> dict:
         """Stream (file_offset, nbytes, device_address) spans of one file into mapped segments."""

@@ -172,7 +172,10 @@ cudaError_t cudaMalloc(void** p, size_t n) { if (g_malloc_limit.load() > 0 && (l
 cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
 cudaError_t cudaHostAlloc(void** p, size_t n, unsigned) { *p = aligned_alloc(4096, ((n + 4095) / 4096) * 4096); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
 cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
-cudaError_t cudaHostRegister(void*, size_t, unsigned) { return cudaSuccess; }
+cudaError_t cudaHostRegister(void*, size_t, unsigned) {
+    if (getenv("HOSTSIM_FAIL_HOST_REGISTER")) { tl_last = cudaErrorInvalidValue; return cudaErrorInvalidValue; }   // "this mapping cannot be pinned"
+    return cudaSuccess;
+}
 cudaError_t cudaHostUnregister(void*) { return cudaSuccess; }
 cudaError_t cudaHostGetDevicePointer(void** d, void* h, unsigned) { *d = h; return cudaSuccess; }
 cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = (cudaStream_t) new Stream(); return cudaSuccess; }

@@ -556,6 +556,45 @@ def test_image_handover_to_another_engine_and_process(engine, oracle, monkeypatc
     assert engine.digest_all(["weights"]) == want and [s.va for s in engine.segments()] == ptrs
 
 
+@_HOSTSIM_ONLY
+@pytest.mark.parametrize("pack,pin_in_place", [(0, True), (1, True), (1, False)])
+def test_image_saved_to_a_file_and_loaded_by_a_fresh_engine(engine, oracle, monkeypatch, tmp_path, pack, pin_in_place):
+    """A sleeping model's image persisted as a file (image_save) and adopted by a fresh engine with the same segment table
+    (image_load): digests travel with it; when the file mapping cannot be pinned in place it is copied into a pinned store."""
+    import fma_b200
+
+    L = _L()
+    monkeypatch.setenv("FMA_HOST_STORE_SHM", "1")
+    table = _tiny_table()
+    _, ref = _load(engine, oracle, table)
+    if pack:
+        engine.set_option("mode", L.FMA_MODE_STAGED)
+        engine.set_option("pack", 1)
+        for k, i in enumerate(sorted(ref)):
+            ref[i] = np.resize(oracle.bf16_weights(1 << 20, 200 + k).view(np.uint8), table[i].bytes)
+            engine.write(i, ref[i].tobytes())
+    want = engine.digest_all(["weights"])
+    engine.sleep(["weights"], flags=L.FMA_FLAG_VERIFY)
+    path = str(tmp_path / "model.fmaimage")
+    n = engine.image_save(path)
+    assert n == os.path.getsize(path) > engine.stats()["image_store_bytes"]
+    engine.wake(None)
+    if not pin_in_place:
+        if os.environ.get("FMA_HOSTSIM") != "1":
+            pytest.skip("the pin failure is injected into the host simulation")
+        monkeypatch.setenv("HOSTSIM_FAIL_HOST_REGISTER", "1")
+    with fma_b200.Engine(0) as fresh:
+        for s in table:
+            fresh.alloc(s.bytes, s.tag)
+        fresh.image_load(path, ["weights"])
+        assert fresh.is_sleeping() and fresh.stats()["image_packed"] == pack
+        monkeypatch.delenv("HOSTSIM_FAIL_HOST_REGISTER", raising=False)
+        fresh.wake(None, flags=L.FMA_FLAG_VERIFY)
+        assert fresh.digest_all(["weights"]) == want
+        for i in ref:
+            assert fresh.read(i, table[i].bytes) == ref[i].tobytes()
+
+
 # ---- PACKED host image (K4p / K4 / K5, csrc/fma_codec.h) ------------------------------------------------------
 # Written in a round that had no GPU minutes left: validated against the oracle on the CUDA host simulation (which runs
 # the SAME per-lane codec arithmetic as the kernels); the first GPU call of the next round flips this switch.
