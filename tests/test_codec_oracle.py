@@ -83,3 +83,26 @@ def test_compression_ratio_on_dummy_and_gaussian_weights(oracle):
                  _page(np.random.default_rng(4).normal(0, 0.02, N).astype(np.float32).view(np.uint32) >> 16)):
         assert oracle.pack_page(page).size == PACKED
     assert abs(PACKED / PAGE - 0.7578125) < 1e-12
+
+
+def test_format_is_pinned_by_the_golden_fixture(oracle):
+    """tests/golden/fmp4_pages.json (tests/golden/make_fmp4_golden.py): SHA-256 of the stored form of seeded pages.  The oracle
+    zero-fills what the format leaves unspecified and emits exceptions in index order, so its stored pages are canonical."""
+    import hashlib
+    import importlib.util
+    import json
+    import os
+
+    here = os.path.dirname(__file__)
+    spec = importlib.util.spec_from_file_location("make_fmp4_golden", os.path.join(here, "golden", "make_fmp4_golden.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    want = {p["name"]: p for p in json.load(open(os.path.join(here, "golden", "fmp4_pages.json")))["pages"]}
+    seen = 0
+    for name, page in gen.pages():
+        w = want[name]
+        assert hashlib.sha256(page.tobytes()).hexdigest() == w["input_sha256"], f"{name}: the generator's input changed"
+        stored = oracle.pack_page(page)
+        assert stored.size == w["stored_bytes"] and hashlib.sha256(stored.tobytes()).hexdigest() == w["stored_sha256"], name
+        seen += 1
+    assert seen == len(want) == 7
