@@ -21,6 +21,11 @@
 #include "fma_kernels.h"
 
 #define FMA_GOLDEN 0x9E3779B97F4A7C15ull
+// FMA_CUDA_EMU (tests/cpp/cuda_emu/, test infrastructure) runs this file's kernels on a CPU model of the execution hierarchy;
+// it brings its own FMA_LAUNCH and replaces the PTX wrappers below.  The nvcc build is unaffected (same SASS).
+#if !defined(FMA_CUDA_EMU) && !defined(FMA_LAUNCH)
+#define FMA_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#endif
 
 namespace {
 
@@ -30,6 +35,7 @@ __device__ __forceinline__ uint64_t fmix64(uint64_t z) {
     return z ^ (z >> 31);
 }
 
+#if !defined(FMA_CUDA_EMU)
 // ------------------------------------------------------------------------------------
 // PTX wrappers (sm_90+/sm_100a bulk async copy + mbarrier)
 // ------------------------------------------------------------------------------------
@@ -78,6 +84,22 @@ __device__ __forceinline__ void bulk_wait_read() {
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+#else  // FMA_CUDA_EMU: the same names on the CPU execution model (tests/cpp/cuda_emu/cuda_emu.h, test infrastructure)
+inline uint32_t smem_u32(const void* p) { return fma_emu::handle_of(p); }
+inline void mbar_init(uint32_t bar, uint32_t count) { fma_emu::mbar_init(static_cast<uint64_t*>(fma_emu::ptr_of(bar)), count); }
+inline void mbar_expect_tx(uint32_t bar, uint32_t bytes) { fma_emu::mbar_expect_tx(static_cast<uint64_t*>(fma_emu::ptr_of(bar)), bytes); }
+inline void mbar_wait(uint32_t bar, uint32_t parity) { fma_emu::mbar_wait(static_cast<uint64_t*>(fma_emu::ptr_of(bar)), parity); }
+inline uint64_t policy_evict_first() { return 0; }
+inline void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar, uint64_t) {
+    fma_emu::bulk_g2s(fma_emu::ptr_of(dst_smem), src, bytes, static_cast<uint64_t*>(fma_emu::ptr_of(bar)));
+}
+inline void bulk_s2g(void* dst, uint32_t src_smem, uint32_t bytes, uint64_t) { fma_emu::bulk_s2g(dst, fma_emu::ptr_of(src_smem), bytes); }
+inline void bulk_commit() { fma_emu::bulk_commit(); }
+template <int N> inline void bulk_wait_read() { fma_emu::bulk_wait_keep(N); }
+inline void bulk_wait_all() { fma_emu::bulk_wait_keep(0); }
+inline void fence_proxy_async() {}
+inline void fence_mbar_init() {}
+#endif
 
 __device__ __forceinline__ uint64_t page_addr(const uint64_t* __restrict__ tab, uint64_t base, uint32_t p) {
     return tab ? __ldg(tab + p) : base + (uint64_t)p * FMA_K_PAGE_BYTES;
@@ -98,7 +120,11 @@ constexpr int kMaxPipes = 4;  // warps per CTA
 __global__ void __launch_bounds__(32 * kMaxPipes, 1)
 fma_k_page_copy_tma(const uint64_t* __restrict__ src_tab, uint64_t src_base, const uint64_t* __restrict__ dst_tab,
                     uint64_t dst_base, uint32_t n_pages, uint32_t tile_bytes, uint32_t stages) {
+#if !defined(FMA_CUDA_EMU)
     extern __shared__ __align__(128) unsigned char smem_raw[];
+#else
+    alignas(128) static unsigned char smem_raw[227u * 1024u];  // CTAs run one after the other on the CPU model
+#endif
     __shared__ __align__(8) uint64_t full_bar[kMaxPipes][kMaxStages];
 
     if ((threadIdx.x & 31) != 0) return;  // one elected thread per warp; no block-wide sync is used below
@@ -160,6 +186,7 @@ fma_k_page_copy_tma(const uint64_t* __restrict__ src_tab, uint64_t src_base, con
 // 256-bit streaming load/store (sm_100: LDG.E.256 / STG.E.256); the L2::evict_first qualifier is only
 // accepted by ptxas on the .v4.b64 / .v8.b32 forms.
 struct __align__(32) u64x4 { uint64_t a, b, c, d; };
+#if !defined(FMA_CUDA_EMU)
 __device__ __forceinline__ u64x4 ld_stream(const u64x4* p) {
     u64x4 v;
     asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.b64 {%0,%1,%2,%3}, [%4];"
@@ -170,6 +197,10 @@ __device__ __forceinline__ void st_stream(u64x4* p, const u64x4& v) {
     asm volatile("st.global.L1::no_allocate.L2::evict_first.v4.b64 [%0], {%1,%2,%3,%4};" ::"l"(p), "l"(v.a), "l"(v.b),
                  "l"(v.c), "l"(v.d) : "memory");
 }
+#else
+inline u64x4 ld_stream(const u64x4* p) { return *p; }
+inline void st_stream(u64x4* p, const u64x4& v) { *p = v; }
+#endif
 
 template <int UNROLL>
 __global__ void __launch_bounds__(256)
@@ -304,21 +335,23 @@ cudaError_t fma_k_launch_page_copy(const uint64_t* src_tab, uint64_t src_base, c
             return cudaErrorInvalidValue;
         const size_t smem = (size_t)c.pipes * c.stages * c.tile_bytes + 128;
         if (smem > 227u * 1024u) return cudaErrorInvalidValue;
+#if !defined(FMA_CUDA_EMU)
         cudaError_t err = cudaFuncSetAttribute(fma_k_page_copy_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return err;
+#endif
         const uint64_t n_tiles = (uint64_t)n_pages * (FMA_K_PAGE_BYTES / c.tile_bytes);
         uint64_t grid = (uint64_t)sm_count() * c.ctas_per_sm;
         const uint64_t need = (n_tiles + c.pipes - 1) / c.pipes;
         if (grid > need) grid = need;
-        fma_k_page_copy_tma<<<(unsigned)grid, 32 * c.pipes, smem, stream>>>(src_tab, src_base, dst_tab, dst_base,
-                                                                           n_pages, c.tile_bytes, c.stages);
+        FMA_LAUNCH(fma_k_page_copy_tma, (unsigned)grid, 32 * c.pipes, smem, stream, src_tab, src_base, dst_tab, dst_base, n_pages,
+                   c.tile_bytes, c.stages);
         return cudaGetLastError();
     } else if (variant == FMA_K_VARIANT_LDG) {
         constexpr int U = 4;
         const uint64_t n_tiles = (uint64_t)n_pages * (FMA_K_PAGE_BYTES / (256u * 32u * U));
         uint64_t grid = (uint64_t)sm_count() * 4;
         if (grid > n_tiles) grid = n_tiles;
-        fma_k_page_copy_ldg<U><<<(unsigned)grid, 256, 0, stream>>>(src_tab, src_base, dst_tab, dst_base, n_pages);
+        FMA_LAUNCH(fma_k_page_copy_ldg<U>, (unsigned)grid, 256, 0, stream, src_tab, src_base, dst_tab, dst_base, n_pages);
         return cudaGetLastError();
     }
     return cudaErrorInvalidValue;
@@ -330,7 +363,7 @@ cudaError_t fma_k_launch_page_digest(const fma_k_page_desc* pages, uint32_t n_pa
     const uint64_t n_tiles = (uint64_t)n_pages * (FMA_K_PAGE_BYTES / (256u * 32u * kDigUnroll));
     uint64_t grid = (uint64_t)sm_count() * 8;
     if (grid > n_tiles) grid = n_tiles;
-    fma_k_page_digest<<<(unsigned)grid, 256, 0, stream>>>(pages, n_pages, reinterpret_cast<unsigned long long*>(out_zeroed));
+    FMA_LAUNCH(fma_k_page_digest, (unsigned)grid, 256, 0, stream, pages, n_pages, reinterpret_cast<unsigned long long*>(out_zeroed));
     return cudaGetLastError();
 }
 
@@ -339,6 +372,6 @@ cudaError_t fma_k_launch_fill(const fma_k_page_desc* pages, uint32_t n_pages, ui
     const uint64_t n_tiles = (uint64_t)n_pages * (FMA_K_PAGE_BYTES / (256u * 32u * 4));
     uint64_t grid = (uint64_t)sm_count() * 8;
     if (grid > n_tiles) grid = n_tiles;
-    fma_k_fill<<<(unsigned)grid, 256, 0, stream>>>(pages, n_pages, seed);
+    FMA_LAUNCH(fma_k_fill, (unsigned)grid, 256, 0, stream, pages, n_pages, seed);
     return cudaGetLastError();
 }

@@ -12,6 +12,7 @@
 #include <pthread.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -81,6 +82,17 @@ inline uint32_t warp_reduce(uint32_t v, Op op) {
     pthread_barrier_wait(&w.bar);  // nobody overwrites the scratch line before everybody has read it
     return r;
 }
+
+// 32-bit "shared window" addresses (kernels that do address arithmetic on __cvta_generic_to_shared values): the CPU model's
+// shared memory is static storage of the test binary, which lies inside one 4 GiB-aligned region
+inline std::atomic<uintptr_t> g_smem_hi{0};
+inline uint32_t handle_of(const void* p) {
+    const uintptr_t a = (uintptr_t)p, hi = (a & ~(uintptr_t)0xFFFFFFFFull) | 1;   // | 1: "set", also when the high bits are zero
+    uintptr_t seen = 0;
+    if (!g_smem_hi.compare_exchange_strong(seen, hi) && seen != hi) { fprintf(stderr, "cuda_emu: shared objects straddle a 4 GiB boundary\n"); abort(); }
+    return (uint32_t)a;
+}
+inline void* ptr_of(uint32_t h) { return (void*)((g_smem_hi.load() & ~(uintptr_t)1) | (uintptr_t)h); }
 
 inline void syncwarp() { pthread_barrier_wait(&tls.cta->warps[tls.tid.x >> 5].bar); }
 
@@ -189,6 +201,22 @@ inline uint32_t __shfl_sync(unsigned, uint32_t v, uint32_t src_lane) {
     pthread_barrier_wait(&w.bar);
     return r;
 }
+inline unsigned long long __shfl_down_sync(unsigned, unsigned long long v, unsigned delta) {
+    static thread_local int dummy; (void)dummy;
+    fma_emu::Warp& w = fma_emu::tls.cta->warps[fma_emu::tls.tid.x >> 5];
+    static_assert(sizeof(w.scratch) >= 32 * sizeof(uint32_t), "scratch line");
+    // 64-bit values: two rounds over the 32-bit scratch line
+    const unsigned lane = fma_emu::tls.tid.x & 31, src = lane + delta;
+    uint32_t parts[2];
+    for (int h = 0; h < 2; ++h) {
+        w.scratch[lane] = (uint32_t)(v >> (32 * h));
+        pthread_barrier_wait(&w.bar);
+        parts[h] = src < 32 ? w.scratch[src] : (uint32_t)(v >> (32 * h));
+        pthread_barrier_wait(&w.bar);
+    }
+    return ((unsigned long long)parts[1] << 32) | parts[0];
+}
+inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 inline uint32_t atomicAdd(uint32_t* p, uint32_t v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 template <class T> inline T __ldg(const T* p) { return *p; }
 template <class T> inline T __ldcg(const T* p) { return *p; }

@@ -32,3 +32,20 @@ def test_pack_kernels_source_on_the_cpu_execution_model(tmp_path, san, flags):
     out = r.stdout + r.stderr
     assert r.returncode == 0 and "pack kernels (emulated) ok" in out, out[-3000:]
     assert "WARNING: ThreadSanitizer" not in out, out[-3000:]
+
+
+@pytest.mark.parametrize("san,flags", [("plain", ["-O2"]), ("tsan", ["-O1", "-fsanitize=thread"])])
+def test_hot_path_kernels_source_on_the_cpu_execution_model(tmp_path, san, flags):
+    """csrc/fma_kernels.cu — K0 fill, K1/K2 page copy (TMA pipeline in five shapes + LDG variant), K3 digest — the exact source
+    that is validated on B200 hardware, here against the oracle on the CPU model (its nvcc build is byte-identical SASS with and
+    without the emulation guards: checked when they were added)."""
+    if not os.path.exists("/usr/local/cuda/include/cuda_runtime.h"):
+        pytest.skip("CUDA headers not installed")
+    exe = str(tmp_path / f"kernels_emu_{san}")
+    subprocess.check_call(["g++", "-std=c++17", "-g", *flags, "-DFMA_CUDA_EMU", "-include", os.path.join(EMU, "cuda_emu.h"),
+                           "-I/usr/local/cuda/include", "-I" + CSRC, os.path.join(EMU, "kernels_emu_test.cpp"),
+                           os.path.join(ROOT, "oracle", "fma_oracle.c"), "-o", exe, "-lpthread"])
+    r = subprocess.run([exe], env=dict(os.environ, TSAN_OPTIONS="halt_on_error=1"), capture_output=True, text=True, timeout=900)
+    out = r.stdout + r.stderr
+    assert r.returncode == 0 and "kernels (emulated) ok" in out, out[-3000:]
+    assert "WARNING: ThreadSanitizer" not in out, out[-3000:]
