@@ -789,3 +789,34 @@ def test_pack_kernels_binary_on_the_device():
         pytest.skip("not built (make -C tests/cpp/cuda_emu)")
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "pack kernels (GPU) ok" in r.stdout, (r.stdout + r.stderr)[-2000:]
+
+
+@_PACK
+def test_packed_image_with_two_offloaded_tags_woken_separately(engine, oracle):
+    """Two offloaded tags whose segments alternate in the image: waking one tag reads stored pages that are NOT adjacent in
+    the store (each gap starts a new ring slot), the other tag follows later; a discarded tag sits in between."""
+    L = _L()
+    pages = _pack_pages(oracle)
+    a = [np.concatenate(pages[0:2]), np.concatenate(pages[5:8])]          # tag "weights": 2 + 3 pages (one raw)
+    b = [np.concatenate(pages[2:5]), pages[9].copy()]                      # tag "adapters": 3 pages + 1 raw page
+    order = [("weights", a[0]), ("adapters", b[0]), ("kv_cache", None), ("weights", a[1]), ("adapters", b[1])]
+    for tag, blob in order:
+        engine.alloc(blob.size if blob is not None else 2 * PAGE, tag)
+    for i, (tag, blob) in enumerate(order):
+        if blob is not None:
+            engine.write(i, blob.tobytes())
+    engine.set_option("mode", L.FMA_MODE_STAGED)
+    engine.set_option("pack", 1)
+    engine.set_option("chunk_bytes", 4 << 20)
+    engine.sleep(["weights", "adapters"], flags=L.FMA_FLAG_VERIFY)
+    assert engine.stats()["image_packed"] == 1
+    engine.wake(["adapters"], flags=L.FMA_FLAG_VERIFY)
+    segs = engine.segments()
+    assert [s.mapped for s in segs] == [False, True, False, False, True] and engine.is_sleeping()
+    for i in (1, 4):
+        assert engine.read(i, order[i][1].size) == order[i][1].tobytes()
+    engine.wake(["weights"], flags=L.FMA_FLAG_VERIFY)
+    for i in (0, 3):
+        assert engine.read(i, order[i][1].size) == order[i][1].tobytes()
+    engine.wake(None)
+    assert not engine.is_sleeping()
