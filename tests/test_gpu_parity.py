@@ -820,3 +820,55 @@ def test_packed_image_with_two_offloaded_tags_woken_separately(engine, oracle):
         assert engine.read(i, order[i][1].size) == order[i][1].tobytes()
     engine.wake(None)
     assert not engine.is_sleeping()
+
+
+@_PACK
+@pytest.mark.parametrize("seed", list(range(1, 17)))
+def test_packed_random_tables_and_wake_orders(built, oracle, seed):
+    """Seeded random tables (sizes, tags, page kinds), ring shapes and wake orders: whatever the plan, every offloaded byte
+    comes back, discarded tags come back mapped, addresses do not move, and the stored size is what the oracle's per-page
+    decisions add up to (or the plain size when packing would save < 5 %)."""
+    import fma_b200
+
+    L = _L()
+    rng = np.random.default_rng(seed)
+    pool = _pack_pages(oracle)
+    stored_size = [oracle.pack_page(p).size for p in pool]
+    with fma_b200.Engine(0) as eng:
+        segs, tags = [], ["weights", "adapters", "kv_cache", "scratch"]
+        for _ in range(int(rng.integers(3, 9))):
+            tag = tags[int(rng.integers(0, len(tags)))]
+            kinds = [int(k) for k in rng.integers(0, len(pool), int(rng.integers(1, 5)))]
+            ptr = eng.alloc(len(kinds) * PAGE, tag)
+            segs.append((tag, kinds, ptr))
+        for i, (tag, kinds, _) in enumerate(segs):
+            eng.write(i, b"".join(pool[k].tobytes() for k in kinds))
+        offload = [t for t in ("weights", "adapters") if rng.random() < 0.8] or ["weights"]
+        eng.set_option("mode", L.FMA_MODE_STAGED)
+        eng.set_option("pack", 1)
+        eng.set_option("chunk_bytes", int(rng.choice([2, 4, 6, 512])) << 20)
+        eng.set_option("ring_slots", int(rng.integers(2, 5)))
+        for cycle in range(2):
+            eng.sleep(offload, flags=L.FMA_FLAG_VERIFY if cycle == 0 else 0)
+            st = eng.stats()
+            W = sum(len(k) * PAGE for t, k, _ in segs if t in offload)
+            packed_total = sum(stored_size[x] for t, k, _ in segs if t in offload for x in k)
+            assert st["sleep_bytes_offloaded"] == W
+            if W and packed_total * 100 <= W * 95:
+                assert st["image_packed"] == 1 and st["image_store_bytes"] == packed_total
+            else:
+                assert st["image_packed"] == 0 and st["image_store_bytes"] == W
+            order = [t for t in tags if any(s[0] == t for s in segs)]
+            rng.shuffle(order)
+            for t in order[:-1]:
+                eng.wake([t], flags=L.FMA_FLAG_VERIFY if cycle == 0 else 0)
+                eng.wake([t])                                           # retried: harmless
+            eng.wake(None)
+            assert not eng.is_sleeping()
+            info = eng.segments()
+            assert [s.va for s in info] == [p for _, _, p in segs]
+            for i, (tag, kinds, _) in enumerate(segs):
+                if tag in offload:
+                    assert eng.read(i, len(kinds) * PAGE) == b"".join(pool[k].tobytes() for k in kinds), (seed, cycle, i)
+                else:                                                   # discarded: mapped again, contents undefined -> rewrite
+                    eng.write(i, b"".join(pool[k].tobytes() for k in kinds))
