@@ -823,7 +823,7 @@ def test_packed_image_with_two_offloaded_tags_woken_separately(engine, oracle):
 
 
 @_PACK
-@pytest.mark.parametrize("seed", list(range(1, 17)))
+@pytest.mark.parametrize("seed", list(range(1, int(os.environ.get("FMA_TEST_SEEDS", "17")))))
 def test_packed_random_tables_and_wake_orders(built, oracle, seed):
     """Seeded random tables (sizes, tags, page kinds), ring shapes and wake orders: whatever the plan, every offloaded byte
     comes back, discarded tags come back mapped, addresses do not move, and the stored size is what the oracle's per-page
@@ -872,3 +872,78 @@ def test_packed_random_tables_and_wake_orders(built, oracle, seed):
                     assert eng.read(i, len(kinds) * PAGE) == b"".join(pool[k].tobytes() for k in kinds), (seed, cycle, i)
                 else:                                                   # discarded: mapped again, contents undefined -> rewrite
                     eng.write(i, b"".join(pool[k].tobytes() for k in kinds))
+
+
+_NEW_THIS_ROUND = pytest.mark.skipif(os.environ.get("FMA_HOSTSIM") != "1" and os.environ.get("FMA_TEST_NEW_ON_GPU") != "1",
+                                     reason="written after the round's GPU minutes were spent: host simulation only until its first GPU run (FMA_TEST_NEW_ON_GPU=1)")
+
+
+@_NEW_THIS_ROUND
+@pytest.mark.parametrize("seed", list(range(1, int(os.environ.get("FMA_TEST_SEEDS", "13")))))
+def test_random_alloc_free_sleep_wake_sequences(built, oracle, seed):
+    """The default (unpacked) path under seeded random histories: allocations of several tags, frees while awake and while
+    asleep, re-allocations into freed holes, sleeps in every mode on the host / local tier with random ring shapes,
+    partial and retried wakes.  Invariants after every step: offloaded segments keep their bytes and their addresses,
+    is_sleeping matches the model, accounting adds up."""
+    import fma_b200
+
+    L = _L()
+    rng = np.random.default_rng(1000 + seed)
+    tags = ["weights", "kv_cache", "adapters"]
+    with fma_b200.Engine(0) as eng:
+        live = {}                                                      # ptr -> (tag, bytes or None if contents undefined)
+        def alloc():
+            tag = tags[int(rng.integers(0, len(tags)))]
+            n = int(rng.integers(1, 6)) * PAGE
+            ptr = eng.alloc(n, tag)
+            assert ptr not in live
+            data = rng.integers(0, 256, n, dtype=np.uint8)
+            eng.write(eng.find(ptr), data.tobytes())
+            live[ptr] = (tag, data)
+        def check_contents():
+            for ptr, (tag, data) in live.items():
+                i = eng.find(ptr)
+                s = eng.segment(i)
+                assert s.va == ptr and s.mapped
+                if data is not None:
+                    assert eng.read(i, data.size) == data.tobytes(), (seed, hex(ptr), tag)
+        for _ in range(int(rng.integers(3, 8))):
+            alloc()
+        for step in range(6):
+            for _ in range(int(rng.integers(0, 3))):                   # churn while awake
+                if live and rng.random() < 0.5:
+                    ptr = list(live)[int(rng.integers(0, len(live)))]
+                    eng.free(ptr); del live[ptr]
+                else:
+                    alloc()
+            if not live:
+                alloc()
+            mode = [L.FMA_MODE_DIRECT, L.FMA_MODE_STAGED, L.FMA_MODE_KERNEL][int(rng.integers(0, 3))]
+            tier = L.FMA_TIER_HOST if rng.random() < 0.7 else L.FMA_TIER_LOCAL
+            eng.set_option("mode", mode)
+            eng.set_option("chunk_bytes", int(rng.choice([2, 4, 6, 32])) << 20)
+            eng.set_option("ring_slots", int(rng.integers(2, 5)))
+            offload = [t for t in ("weights", "adapters") if rng.random() < 0.8]
+            eng.sleep(offload, tier=tier, flags=L.FMA_FLAG_VERIFY if rng.random() < 0.5 else 0)
+            st = eng.stats()
+            assert st["sleep_bytes_offloaded"] == sum(d.size if d is not None else 0 for t, d in live.values() if t in offload) or \
+                st["sleep_bytes_offloaded"] == sum(eng.segment(eng.find(p)).bytes for p, (t, _) in live.items() if t in offload)
+            assert eng.is_sleeping() and st["hbm_mapped_bytes"] == 0
+            for ptr, (tag, data) in list(live.items()):                 # what is not offloaded loses its contents (cumem.py:240-249)
+                if tag not in offload:
+                    live[ptr] = (tag, None)
+            if rng.random() < 0.4 and live:                             # free a sleeping segment
+                ptr = list(live)[int(rng.integers(0, len(live)))]
+                eng.free(ptr); del live[ptr]
+            order = list(tags); rng.shuffle(order)
+            for t in order[:int(rng.integers(0, 3))]:
+                eng.wake([t]); eng.wake([t])
+            eng.wake(None, flags=L.FMA_FLAG_VERIFY)
+            assert not eng.is_sleeping()
+            check_contents()
+            for ptr, (tag, data) in list(live.items()):                 # give discarded segments defined contents again
+                if data is None:
+                    i = eng.find(ptr)
+                    d = rng.integers(0, 256, eng.segment(i).bytes, dtype=np.uint8)
+                    eng.write(i, d.tobytes()); live[ptr] = (tag, d)
+            assert eng.current_usage() == sum(eng.segment(eng.find(p)).bytes for p in live)
