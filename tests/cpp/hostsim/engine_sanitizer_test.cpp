@@ -1,7 +1,7 @@
 // Drives the engine's C-ABI on the host simulation under ThreadSanitizer / AddressSanitizer (built and run by
 // tests/test_engine_hostsim.py).  Scenario: load a table, sleep/wake in every mode, tag-selective wake, free inside a
 // merged unit, hot swap of two engines (sleep and wake concurrently), cold load from a file, failed wake + retry,
-// PACKED host images (sleep/wake, failed sleep, swap).
+// PACKED host images (sleep/wake, failed sleep, swap), then seeded random histories on a third engine.
 #include <cassert>
 #include <cstdio>
 #include <cstdlib>
@@ -197,6 +197,56 @@ int main() {
     OK(fma_segment_read(a, 0, 0, back.data(), 8 * P));
     assert(memcmp(back.data(), blob.data() + 4096, 8 * P) == 0);
     remove(path);
+
+    // seeded random histories on a third engine: allocations of three tags, frees while awake and asleep, every mode, host and
+    // local tier, packed or not, partial + retried wakes — digests of offloaded segments must survive (memory errors and races
+    // in rarely taken paths are what the sanitizers are for)
+    {
+        fma_engine_t* c = nullptr;
+        OK(fma_engine_create(0, nullptr, &c));
+        const int tw = fma_tag_intern(c, "weights"), tk = fma_tag_intern(c, "kv_cache"), ta = fma_tag_intern(c, "adapters");
+        const int tag_of[3] = {tw, tk, ta};
+        uint32_t x = 2463534242u;
+        auto rnd = [&](uint32_t n) { x ^= x << 13; x ^= x >> 17; x ^= x << 5; return x % n; };
+        struct Live { void* p; int tag; uint64_t digest; bool defined; };
+        std::vector<Live> live;
+        auto index_of = [&](void* p) { int i = fma_segment_find(c, p); assert(i >= 0); return i; };
+        auto alloc_one = [&]() {
+            Live l{nullptr, tag_of[rnd(3)], 0, true};
+            OK(fma_alloc(c, (1 + rnd(4)) * P, l.tag, &l.p));
+            OK(fma_fill_segment(c, index_of(l.p), 77 + rnd(1000), rnd(1u << 20)));
+            OK(fma_digest_segment(c, index_of(l.p), &l.digest));
+            live.push_back(l);
+        };
+        for (int i = 0; i < 4; ++i) alloc_one();
+        for (int step = 0; step < 24; ++step) {
+            for (uint32_t k = rnd(3); k > 0; --k) {
+                if (!live.empty() && rnd(2)) { size_t j = rnd((uint32_t)live.size()); OK(fma_free(c, live[j].p)); live.erase(live.begin() + j); }
+                else alloc_one();
+            }
+            if (live.empty()) alloc_one();
+            const int modes[3] = {FMA_MODE_DIRECT, FMA_MODE_STAGED, FMA_MODE_KERNEL};
+            OK(fma_set_option(c, "mode", modes[rnd(3)]));
+            OK(fma_set_option(c, "chunk_bytes", (int64_t)(1 + rnd(3)) * 2 * P));
+            OK(fma_set_option(c, "ring_slots", 2 + rnd(3)));
+            OK(fma_set_option(c, "pack", rnd(2)));
+            uint64_t mask = 0;
+            if (rnd(5)) mask |= 1ull << tw;
+            if (rnd(5)) mask |= 1ull << ta;
+            OK(fma_sleep(c, mask, rnd(3) ? FMA_TIER_HOST : FMA_TIER_LOCAL, rnd(2) ? FMA_FLAG_VERIFY : 0));
+            for (Live& l : live) if (!((mask >> l.tag) & 1)) l.defined = false;
+            if (!live.empty() && rnd(3) == 0) { size_t j = rnd((uint32_t)live.size()); OK(fma_free(c, live[j].p)); live.erase(live.begin() + j); }
+            if (rnd(2)) { uint64_t m1 = 1ull << tag_of[rnd(3)]; OK(fma_wake(c, m1, 0)); OK(fma_wake(c, m1, 0)); }
+            OK(fma_wake(c, 0, FMA_FLAG_VERIFY));
+            assert(fma_is_sleeping(c) == 0);
+            for (Live& l : live) {
+                const int i = index_of(l.p);
+                if (l.defined) { uint64_t d = 0; OK(fma_digest_segment(c, i, &d)); assert(d == l.digest); }
+                else { OK(fma_fill_segment(c, i, 5 + rnd(100), 0)); OK(fma_digest_segment(c, i, &l.digest)); l.defined = true; }
+            }
+        }
+        OK(fma_engine_destroy(c));
+    }
 
     OK(fma_engine_destroy(a));
     OK(fma_engine_destroy(b));
