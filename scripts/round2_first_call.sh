@@ -45,4 +45,6 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:fma_
 # 6. end to end through the unmodified reference launcher + real vLLM: packed image over HTTP, and --load-format fma
 timeout 900 env E2E_ARMS=fma_b200,fma_b200_packed python scripts/e2e_launcher_vllm.py llama-3-8b > "$out/e2e_packed.log" 2>&1; echo "e2e packed rc=$?" | tee -a "$out/status.txt"
 timeout 900 env E2E_ARMS=ckpt_default,ckpt_fma python scripts/e2e_launcher_vllm.py llama-1b > "$out/e2e_ckpt.log" 2>&1; echo "e2e ckpt rc=$?" | tee -a "$out/status.txt"
+# 7. the compiled host side over HTTP (no vLLM, no Python in the serving process)
+timeout 300 python scripts/native_server_e2e.py llama-3-8b 1 0 > "$out/native_server.log" 2>&1; echo "native server rc=$?" | tee -a "$out/status.txt"
 cat "$out/status.txt"

@@ -145,3 +145,64 @@ def test_smoke_entry_point_runs_against_the_host_simulated_engine(hostsim_lib, o
     env = dict(os.environ, FMA_B200_LIB=hostsim_lib, FMA_HOSTSIM="1", HOSTSIM_DEVICES="1")
     r = subprocess.run([sys.executable, "-c", "import __graft_entry__ as g; g.smoke()"], env=env, cwd=ROOT, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "smoke ok" in r.stdout, (r.stdout + r.stderr)[-3000:]
+
+
+def test_native_server_speaks_the_controller_contract_over_the_host_simulated_engine(hostsim_lib, tmp_path):
+    """csrc/fma_served.cpp — the compiled host side: the reference's cmd/test-server (main.go:56-91) with the atomic bool
+    replaced by engines.  Built against the host-simulated library, two ranks; the controller's sequence, idempotence and
+    retries, level / tag-selective wake, wrong methods, and bit-identity of the weights (K3 digests) across sleep -> wake."""
+    import json
+    import time
+    import urllib.error
+    import urllib.request
+
+    exe = str(tmp_path / "fma_served")
+    libdir = os.path.dirname(hostsim_lib)
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-g", "-Wall", "-Wextra", os.path.join(CSRC, "fma_served.cpp"), "-o", exe,
+                           "-L" + libdir, "-l:" + os.path.basename(hostsim_lib), "-Wl,-rpath," + libdir, "-lpthread"])
+    env = dict(os.environ, HOSTSIM_DEVICES="2")
+    p = subprocess.Popen([exe, "--port", "0", "--device", "0", "--device", "1", "--seg", "weights:6", "--seg", "weights:2", "--seg", "kv_cache:8",
+                          "--seg", "weights:4"], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    try:
+        line = p.stdout.readline()
+        assert line.startswith("listening on "), line + p.stderr.read()
+        base = f"http://127.0.0.1:{int(line.split()[-1])}"
+
+        def call(method, path):
+            req = urllib.request.Request(base + path, data=b"" if method == "POST" else None, method=method, headers={"Content-Type": "application/json"})
+            try:
+                with urllib.request.urlopen(req, timeout=60) as r:
+                    return r.status, r.read()
+            except urllib.error.HTTPError as e:
+                return e.code, e.read()
+
+        assert call("GET", "/health") == (200, b"OK\n")
+        assert json.loads(call("GET", "/is_sleeping")[1]) == {"is_sleeping": False}
+        st, before = call("GET", "/digests")
+        assert st == 200 and len(json.loads(before)) == 2 and len(json.loads(before)[0]) == 3
+        # the controller's sequence (inference-server.go:1329-1339, 1595-1607, 1118-1137)
+        assert call("POST", "/sleep") == (200, b"")
+        assert json.loads(call("GET", "/is_sleeping")[1]) == {"is_sleeping": True}
+        assert call("GET", "/digests")[0] == 409
+        stats = json.loads(call("GET", "/stats")[1])
+        assert [r["sleep_bytes_offloaded"] for r in stats["ranks"]] == [12 << 20] * 2 and all(r["hbm_mapped_bytes"] == 0 for r in stats["ranks"])
+        assert call("POST", "/sleep") == (200, b"")                       # twice: harmless
+        assert call("POST", "/wake_up") == (200, b"") and call("POST", "/wake_up") == (200, b"")   # retried by the controller
+        assert json.loads(call("GET", "/is_sleeping")[1]) == {"is_sleeping": False}
+        assert call("GET", "/digests") == (200, before)                   # weights bit-identical on every rank
+        # level 2 + tag-selective wake (vLLM API compatibility)
+        assert call("POST", "/sleep?level=2&mode=abort")[0] == 200
+        assert call("POST", "/wake_up?tags=weights")[0] == 200 and json.loads(call("GET", "/is_sleeping")[1])["is_sleeping"] is True
+        assert call("POST", "/wake_up?tags=bogus")[0] == 200 and json.loads(call("GET", "/is_sleeping")[1])["is_sleeping"] is True
+        assert call("POST", "/wake_up?tags=kv_cache")[0] == 200 and json.loads(call("GET", "/is_sleeping")[1])["is_sleeping"] is False
+        assert json.loads(call("GET", "/stats")[1])["ranks"][0]["wake_bytes_restored"] == 0      # level 2 offloads nothing
+        # errors
+        assert call("GET", "/sleep")[0] == 405 and call("POST", "/is_sleeping")[0] == 405 and call("GET", "/nope")[0] == 404
+        assert call("POST", "/sleep?level=x")[0] == 422
+    finally:
+        p.terminate()
+        try:
+            p.wait(timeout=30)
+        except subprocess.TimeoutExpired:
+            p.kill()
+    assert p.returncode == 0, p.stderr.read()[-2000:]
