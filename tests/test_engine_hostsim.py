@@ -147,7 +147,8 @@ def test_smoke_entry_point_runs_against_the_host_simulated_engine(hostsim_lib, o
     assert r.returncode == 0 and "smoke ok" in r.stdout, (r.stdout + r.stderr)[-3000:]
 
 
-def test_native_server_speaks_the_controller_contract_over_the_host_simulated_engine(hostsim_lib, tmp_path):
+@pytest.mark.parametrize("build", ["linked", "tsan"])
+def test_native_server_speaks_the_controller_contract_over_the_host_simulated_engine(hostsim_lib, tmp_path, build):
     """csrc/fma_served.cpp — the compiled host side: the reference's cmd/test-server (main.go:56-91) with the atomic bool
     replaced by engines.  Built against the host-simulated library, two ranks; the controller's sequence, idempotence and
     retries, level / tag-selective wake, wrong methods, and bit-identity of the weights (K3 digests) across sleep -> wake."""
@@ -158,9 +159,12 @@ def test_native_server_speaks_the_controller_contract_over_the_host_simulated_en
 
     exe = str(tmp_path / "fma_served")
     libdir = os.path.dirname(hostsim_lib)
-    subprocess.check_call(["g++", "-std=c++17", "-O1", "-g", "-Wall", "-Wextra", os.path.join(CSRC, "fma_served.cpp"), "-o", exe,
-                           "-L" + libdir, "-l:" + os.path.basename(hostsim_lib), "-Wl,-rpath," + libdir, "-lpthread"])
-    env = dict(os.environ, HOSTSIM_DEVICES="2")
+    if build == "linked":      # against the shared library, as the product binary is
+        subprocess.check_call(["g++", "-std=c++17", "-O1", "-g", "-Wall", "-Wextra", os.path.join(CSRC, "fma_served.cpp"), "-o", exe,
+                               "-L" + libdir, "-l:" + os.path.basename(hostsim_lib), "-Wl,-rpath," + libdir, "-lpthread"])
+    else:                      # server + engine + simulation in one ThreadSanitizer build: connection threads vs rank threads vs engine threads
+        subprocess.check_call(["g++", "-std=c++17", "-O1", "-g", "-fsanitize=thread", *INC, *SRCS, os.path.join(CSRC, "fma_served.cpp"), "-o", exe, "-lpthread"])
+    env = dict(os.environ, HOSTSIM_DEVICES="2", TSAN_OPTIONS="halt_on_error=1")
     p = subprocess.Popen([exe, "--port", "0", "--device", "0", "--device", "1", "--seg", "weights:6", "--seg", "weights:2", "--seg", "kv_cache:8",
                           "--seg", "weights:4"], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     try:
@@ -205,4 +209,5 @@ def test_native_server_speaks_the_controller_contract_over_the_host_simulated_en
             p.wait(timeout=30)
         except subprocess.TimeoutExpired:
             p.kill()
-    assert p.returncode == 0, p.stderr.read()[-2000:]
+    err = p.stderr.read()
+    assert p.returncode == 0 and "WARNING: ThreadSanitizer" not in err, err[-3000:]
