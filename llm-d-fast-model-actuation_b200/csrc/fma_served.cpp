@@ -152,7 +152,7 @@ void respond(int fd, int code, const char* reason, const char* ctype, const std:
 std::string url_decode(const std::string& s) {
     std::string o;
     for (size_t i = 0; i < s.size(); ++i) {
-        if (s[i] == '%' && i + 2 < s.size() + 0 && isxdigit((unsigned char)s[i + 1]) && isxdigit((unsigned char)s[i + 2])) {
+        if (s[i] == '%' && i + 2 < s.size() && isxdigit((unsigned char)s[i + 1]) && isxdigit((unsigned char)s[i + 2])) {
             o += (char)strtol(s.substr(i + 1, 2).c_str(), nullptr, 16);
             i += 2;
         } else if (s[i] == '+') {
