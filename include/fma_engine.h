@@ -250,7 +250,10 @@ FMA_API int  fma_fill_segment(fma_engine_t* e, int index, uint64_t seed, uint64_
 FMA_API int  fma_segment_write(fma_engine_t* e, int index, uint64_t offset, const void* host_src, uint64_t bytes);
 FMA_API int  fma_segment_read(fma_engine_t* e, int index, uint64_t offset, void* host_dst, uint64_t bytes);
 
-/* ---- PACKED host image (config.pack / option "pack"; format: csrc/fma_codec.h) ------------------------------ */
+/* ---- PACKED host image (config.pack / option "pack"; format: csrc/fma_codec.h) ------------------------------
+ * No counterpart in the reference: vLLM's sleep copies every segment verbatim (vllm:device_allocator/cumem.py:198-213).
+ * These entry points only expose the image's layout and the three kernels for tests and measurement; the feature itself
+ * rides inside fma_sleep / fma_wake. */
 /* Where each 2 MiB page of the sleeping image lives in the store: page p (= packed_offset / FMA_PAGE_BYTES of the
  * segment that owns it) occupies out_bytes[p] bytes at out_offsets[p].  Returns the number of image pages (also when
  * cap is smaller; then only cap entries are written), 0 if nothing sleeps.  For an image that is not packed the
