@@ -126,6 +126,9 @@ class CuMemAllocator:
         if st["sleep_copy_seconds"] > 0:
             logger.info("fma_b200: sleep %.3f s, D2H %.1f GB/s", st["sleep_seconds"],
                         st["sleep_bytes_offloaded"] / st["sleep_copy_seconds"] / 1e9)
+        if st.get("image_packed"):
+            logger.info("fma_b200: packed image: %.2f GiB stored for %.2f GiB of weights (%.3f)", st["image_store_bytes"] / 1024**3,
+                        st["sleep_bytes_offloaded"] / 1024**3, st["image_store_bytes"] / max(st["sleep_bytes_offloaded"], 1))
         gc.collect()
         torch.cuda.empty_cache()
 
