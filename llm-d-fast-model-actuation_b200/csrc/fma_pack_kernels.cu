@@ -226,7 +226,14 @@ int pack_sm_count() {
     return g_pack_sm_count;
 }
 unsigned pack_grid(uint32_t n_pages) {
-    const uint64_t cap = (uint64_t)pack_sm_count() * 8;  // 8 CTAs of 256 threads fit an SM: one wave
+    // Grid cap = SMs x CTAs per SM (grid-stride loop over pages beyond it).  8 CTAs of 256 threads fit an SM at 32 registers
+    // (K4p, K5), 5 at K4's 48.  FMA_PACK_CTAS_PER_SM overrides it for sweeps (read once).
+    static int per_sm = 0;
+    if (!per_sm) {
+        const char* v = getenv("FMA_PACK_CTAS_PER_SM");
+        per_sm = v && atoi(v) > 0 ? atoi(v) : 8;
+    }
+    const uint64_t cap = (uint64_t)pack_sm_count() * (uint64_t)per_sm;
     return (unsigned)(n_pages < cap ? n_pages : cap);
 }
 
