@@ -48,19 +48,25 @@ def test_parity_suite_against_the_host_simulated_engine(hostsim_lib, oracle):
     assert " passed" in r.stdout and "failed" not in r.stdout, tail
 
 
-@pytest.mark.parametrize("san,flags", [("tsan", ["-fsanitize=thread"]),
-                                        ("asan", ["-fsanitize=address,undefined", "-fno-omit-frame-pointer"])])
-def test_engine_scenario_under_sanitizers(tmp_path, san, flags):
+def test_engine_scenario_under_sanitizers(tmp_path):
+    """ThreadSanitizer and ASan+UBSan+LeakSan builds of the same scenario, compiled and run side by side."""
     if not _have_cuda_headers():
         pytest.skip("CUDA headers not installed")
-    exe = str(tmp_path / f"engine_{san}")
-    subprocess.check_call(["g++", "-std=c++17", "-O1", "-g", *flags, *INC, *SRCS, os.path.join(SIM, "engine_sanitizer_test.cpp"),
-                           "-o", exe, "-lpthread"])
-    env = dict(os.environ, ASAN_OPTIONS="detect_leaks=1", TSAN_OPTIONS="halt_on_error=1", HOSTSIM_DEVICES="2")
-    r = subprocess.run([exe], env=env, capture_output=True, text=True, timeout=600)
-    out = r.stdout + r.stderr
-    assert r.returncode == 0 and "engine sanitizer scenario ok" in out, out[-3000:]
-    assert "WARNING: ThreadSanitizer" not in out and "ERROR: AddressSanitizer" not in out and "runtime error:" not in out, out[-3000:]
+    from concurrent.futures import ThreadPoolExecutor
+
+    def one(san, flags):
+        exe = str(tmp_path / f"engine_{san}")
+        subprocess.check_call(["g++", "-std=c++17", "-O1", "-g", *flags, *INC, *SRCS, os.path.join(SIM, "engine_sanitizer_test.cpp"),
+                               "-o", exe, "-lpthread"])
+        env = dict(os.environ, ASAN_OPTIONS="detect_leaks=1", TSAN_OPTIONS="halt_on_error=1", HOSTSIM_DEVICES="2")
+        r = subprocess.run([exe], env=env, capture_output=True, text=True, timeout=900)
+        return san, r.returncode, r.stdout + r.stderr
+
+    with ThreadPoolExecutor(2) as pool:
+        results = list(pool.map(lambda a: one(*a), [("tsan", ["-fsanitize=thread"]), ("asan", ["-fsanitize=address,undefined", "-fno-omit-frame-pointer"])]))
+    for san, rc, out in results:
+        assert rc == 0 and "engine sanitizer scenario ok" in out, (san, out[-3000:])
+        assert "WARNING: ThreadSanitizer" not in out and "ERROR: AddressSanitizer" not in out and "runtime error:" not in out, (san, out[-3000:])
 
 
 def test_bench_packed_image_child_runs_against_the_host_simulated_engine(hostsim_lib, oracle):

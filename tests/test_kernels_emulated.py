@@ -17,35 +17,31 @@ EMU = os.path.join(ROOT, "tests", "cpp", "cuda_emu")
 CSRC = os.path.join(ROOT, "llm-d-fast-model-actuation_b200", "csrc")
 
 
-@pytest.mark.parametrize("san,flags", [("plain", ["-O2"]), ("tsan", ["-O1", "-fsanitize=thread"])])
-def test_pack_kernels_source_on_the_cpu_execution_model(tmp_path, san, flags):
-    if not os.path.exists("/usr/local/cuda/include/cuda_runtime.h"):
-        pytest.skip("CUDA headers not installed")
-    exe = str(tmp_path / f"pack_emu_{san}")
+def _build_and_run(tmp_path, src, name, san, flags, marker):
+    exe = str(tmp_path / f"{name}_{san}")
     subprocess.check_call(["g++", "-std=c++17", "-g", *flags, "-DFMA_CUDA_EMU", "-include", os.path.join(EMU, "cuda_emu.h"),
-                           "-I/usr/local/cuda/include", "-I" + CSRC, os.path.join(EMU, "pack_kernels_emu_test.cpp"),
-                           os.path.join(ROOT, "oracle", "fma_oracle.c"), "-o", exe, "-lpthread"])
+                           "-I/usr/local/cuda/include", "-I" + CSRC, os.path.join(EMU, src), os.path.join(ROOT, "oracle", "fma_oracle.c"),
+                           "-o", exe, "-lpthread"])
     env = dict(os.environ, TSAN_OPTIONS="halt_on_error=1")
     if san != "plain":
         env["FMA_EMU_FAST"] = "1"          # fewer pages under the sanitizer (every code branch is still taken)
     r = subprocess.run([exe], env=env, capture_output=True, text=True, timeout=900)
     out = r.stdout + r.stderr
-    assert r.returncode == 0 and "pack kernels (emulated) ok" in out, out[-3000:]
-    assert "WARNING: ThreadSanitizer" not in out, out[-3000:]
+    assert r.returncode == 0 and marker in out, (name, san, out[-3000:])
+    assert "WARNING: ThreadSanitizer" not in out, (name, san, out[-3000:])
+    return True
 
 
-@pytest.mark.parametrize("san,flags", [("plain", ["-O2"]), ("tsan", ["-O1", "-fsanitize=thread"])])
-def test_hot_path_kernels_source_on_the_cpu_execution_model(tmp_path, san, flags):
-    """csrc/fma_kernels.cu — K0 fill, K1/K2 page copy (TMA pipeline in five shapes + LDG variant), K3 digest — the exact source
-    that is validated on B200 hardware, here against the oracle on the CPU model (its nvcc build is byte-identical SASS with and
-    without the emulation guards: checked when they were added)."""
+def test_kernel_sources_on_the_cpu_execution_model(tmp_path):
+    """Four builds side by side: {packed-image kernels (K4p, K4, K5 + TMA-pipelined K4 / K5), hot-path kernels (K0, K1/K2 TMA in
+    five shapes + LDG, K3 — the source validated on B200 hardware; the emulation guards leave its nvcc SASS byte-identical)}
+    x {plain, ThreadSanitizer}, each against the oracle."""
     if not os.path.exists("/usr/local/cuda/include/cuda_runtime.h"):
         pytest.skip("CUDA headers not installed")
-    exe = str(tmp_path / f"kernels_emu_{san}")
-    subprocess.check_call(["g++", "-std=c++17", "-g", *flags, "-DFMA_CUDA_EMU", "-include", os.path.join(EMU, "cuda_emu.h"),
-                           "-I/usr/local/cuda/include", "-I" + CSRC, os.path.join(EMU, "kernels_emu_test.cpp"),
-                           os.path.join(ROOT, "oracle", "fma_oracle.c"), "-o", exe, "-lpthread"])
-    r = subprocess.run([exe], env=dict(os.environ, TSAN_OPTIONS="halt_on_error=1"), capture_output=True, text=True, timeout=900)
-    out = r.stdout + r.stderr
-    assert r.returncode == 0 and "kernels (emulated) ok" in out, out[-3000:]
-    assert "WARNING: ThreadSanitizer" not in out, out[-3000:]
+    from concurrent.futures import ThreadPoolExecutor
+
+    jobs = [("pack_kernels_emu_test.cpp", "pack_emu", "pack kernels (emulated) ok"), ("kernels_emu_test.cpp", "kernels_emu", "kernels (emulated) ok")]
+    variants = [("plain", ["-O2"]), ("tsan", ["-O1", "-fsanitize=thread"])]
+    with ThreadPoolExecutor(4) as pool:
+        futs = [pool.submit(_build_and_run, tmp_path, src, name, san, flags, marker) for src, name, marker in jobs for san, flags in variants]
+        assert all(f.result() for f in futs)
