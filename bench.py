@@ -19,6 +19,11 @@ config[2] (Llama-3-70B TP=8 per-rank shard, every rank concurrently, no collecti
   roofline       K2 (TMA page scatter) launches inside the timed region vs the measured HBM copy peak
   pcie           e2e per-GPU GB/s vs the 64 GB/s PCIe Gen5 x16 figure north_star names
   cpu_baseline   the reference data path (vLLM CuMemAllocator) timed in the same run on this box (N=1, rank 0)
+  packed_image   (N=1, extra evidence, own process) the same table filled with bf16 dummy weights, slept and woken with the
+                 PACKED host image (K4 / K5: 0.758 of the bytes cross PCIe); never part of `value` / `e2e`
+
+  --contents bf16   fill both arms with bf16 U(-1e-3, 1e-3) (vLLM's dummy weights) instead of incompressible bytes
+  --pack 1          this arm sleeps / wakes with the PACKED image (e2e.link_bytes_per_step = bytes that crossed the link)
 
 Synthetic data: counter-based splitmix64 bytes (seed 1234 + rank); the working set (>= 15 GiB per rank) is far
 larger than the 126 MB L2, so no L2 flush is needed between iterations.
