@@ -24,6 +24,7 @@ config[2] (Llama-3-70B TP=8 per-rank shard, every rank concurrently, no collecti
 
   --contents bf16   fill both arms with bf16 U(-1e-3, 1e-3) (vLLM's dummy weights) instead of incompressible bytes
   --pack 1          this arm sleeps / wakes with the PACKED image (e2e.link_bytes_per_step = bytes that crossed the link)
+  --incremental 1   sleeps whose weights still match the image in the host store release the device side without a copy
 
 Synthetic data: counter-based splitmix64 bytes (seed 1234 + rank); the working set (>= 15 GiB per rank) is far
 larger than the 126 MB L2, so no L2 flush is needed between iterations.
@@ -146,6 +147,8 @@ def run_ours(args) -> None:
                                 chunk_bytes=args.chunk_mib << 20, ring_slots=args.ring_slots, map_threads=args.map_threads,
                                 pack=args.pack)
     eng = fma_b200.Engine(local_rank, cfg)
+    if args.incremental:
+        eng.set_option("incremental", 1)
     workload = workload_for(args.gpus, args.workload)
     table = W.allocation_table(workload, kv_cache_bytes=int(args.kv_gib * GiB))
     for s in table:
@@ -245,13 +248,14 @@ def run_ours(args) -> None:
                        "segments_per_rank": len(table), "mode": ["auto", "direct", "staged", "kernel"][st["mode"]],
                        "kernel": args.kernel, "chunk_mib": args.chunk_mib or "default", "copy_streams": args.copy_streams or "default",
                        "contents": "splitmix64 bytes (incompressible)" if args.contents == "prng" else "bf16 U(-1e-3, 1e-3) (vLLM dummy weights)",
-                       "pack": bool(st["image_packed"]) if args.pack else False,
+                       "pack": bool(st["image_packed"]) if args.pack else False, "incremental_sleep": bool(args.incremental),
                        "l2": "working set >> 126 MB L2 (no flush needed)", "parallelism": f"{world} independent ranks"},
             "wake_latency_s": round(wake_wall_m, 5), "wake_latency_s_median": round(wake_wall_med, 5),
             "e2e_median_gbs": round(W_total / wake_wall_med / 1e9, 3),   # value/e2e use the MEAN over the K steps
             "wake_latency_s_rank0_steps": [round(r[1]["wake_seconds"], 4) for r in rows],
             "sleep_latency_s": round(sleep_wall_m, 5),
-            "sleep_d2h_gbs": round(W_total / sleep_dev_m / 1e9, 3),
+            "sleep_d2h_gbs": round(W_total / sleep_dev_m / 1e9, 3) if sleep_dev_m > 0 else None,   # None: incremental sleeps moved nothing
+            "sleep_copy_ops_last": rows[-1][0]["copy_ops"],
             "wake_map_s": round(map_s, 5), "sleep_unmap_s": round(unmap_s, 5), "host_pin_s_untimed": round(pin_s, 3),
             "bit_exact": bool(all_exact),
             "e2e": {"value": round(e2e_gbs, 3), "unit": "GB/s", "h2d_bytes_per_step": int(W_total),
@@ -604,6 +608,7 @@ def main() -> None:
     ap.add_argument("--peer-extra", type=int, default=1, help="at N>1 also measure the NVLink peer-HBM tier (reported under peer_tier)")
     ap.add_argument("--contents", choices=["prng", "bf16"], default="prng", help="synthetic weights: incompressible bytes (default) or bf16 dummy weights")
     ap.add_argument("--pack", type=int, default=0, help="1 = PACKED host image (lossless bf16 page code; pays off with --contents bf16)")
+    ap.add_argument("--incremental", type=int, default=0, help="1 = INCREMENTAL sleep: a sleep whose weights still match the image in the host store moves nothing")
     ap.add_argument("--packed-extra", type=int, default=1, help="at N=1 also measure the PACKED image on bf16 dummy weights in a child process (reported under packed_image)")
     ap.add_argument("--packed-child", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()

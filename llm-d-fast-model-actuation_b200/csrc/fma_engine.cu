@@ -366,9 +366,17 @@ void host_store_free(HostStore& h) {
     h = HostStore{};
 }
 
+void invalidate_shadows(fma_engine_t* e) {
+    for (Segment& s : e->segs) s.shadow_off = kNoOffset;
+    e->shadow_image_bytes = 0;
+    e->shadow_store_bytes = 0;
+    e->shadow_packed = false;
+}
+
 int host_store_reserve(fma_engine_t* e, size_t bytes) {
     bytes = round_up(std::max<size_t>(bytes, FMA_PAGE_BYTES), FMA_PAGE_BYTES);
     if (e->host.base && e->host.cap >= bytes) return FMA_OK;
+    invalidate_shadows(e);  // a new store starts empty
     host_store_free(e->host);
     const double t0 = now_s();
     HostStore h;
@@ -694,6 +702,7 @@ int fma_engine_create(int device, const fma_config_t* cfg, fma_engine_t** out) {
     if (!e->cfg.ring_slots) e->cfg.ring_slots = env_int("FMA_RING_SLOTS", 0);
     if (!e->cfg.map_threads) e->cfg.map_threads = env_int("FMA_MAP_THREADS", 0);
     if (!e->cfg.pack) e->cfg.pack = env_int("FMA_PACK", 0);
+    e->incremental = env_int("FMA_INCREMENTAL", 0);
     e->tma.tile_bytes = (uint32_t)env_int("FMA_TMA_TILE_KIB", (int)(e->tma.tile_bytes >> 10)) << 10;
     e->tma.stages = (uint32_t)env_int("FMA_TMA_STAGES", (int)e->tma.stages);
     e->tma.pipes = (uint32_t)env_int("FMA_TMA_PIPES", (int)e->tma.pipes);
@@ -940,6 +949,7 @@ int fma_host_release(fma_engine_t* e) {
         if (s.has_backup && s.backup_tier == FMA_TIER_HOST) return fail(FMA_ESTATE, "host store holds a sleeping image");
     DeviceGuard guard(e->device);
     cudaDeviceSynchronize();
+    invalidate_shadows(e);
     host_store_free(e->host);
     e->st.host_store_bytes = 0;
     return FMA_OK;
@@ -950,7 +960,7 @@ int fma_host_store_view(fma_engine_t* e, const void** base, uint64_t* bytes) {
     if (!base || !bytes) return fail(FMA_EINVAL, "NULL out pointer");
     if (!e->host.base || e->image_tier != FMA_TIER_HOST) return fail(FMA_ESTATE, "no host image");
     *base = e->host.base;
-    *bytes = e->image_bytes;
+    *bytes = e->image_packed ? e->image_store_bytes : e->image_bytes;  // what the image occupies in the store
     return FMA_OK;
 }
 
@@ -1227,6 +1237,9 @@ int fma_set_option(fma_engine_t* e, const char* key, int64_t value) {
     } else if (k == "pack") {
         if (value != 0 && value != 1) return fail(FMA_EINVAL, "pack must be 0 or 1");
         e->cfg.pack = (int32_t)value;
+    } else if (k == "incremental") {
+        if (value != 0 && value != 1) return fail(FMA_EINVAL, "incremental must be 0 or 1");
+        e->incremental = (int)value;
     } else if (k == "pack_kernel") {  // process-wide: 0 = LDG/STG kernels, 1 = TMA-pipelined kernels (K4 / K5)
         if (value != FMA_K_PACK_VARIANT_LDG && value != FMA_K_PACK_VARIANT_TMA) return fail(FMA_EINVAL, "pack_kernel must be 0 or 1");
         fma_k_set_pack_variant((int)value);

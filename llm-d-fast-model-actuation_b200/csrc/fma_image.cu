@@ -113,6 +113,7 @@ int fma_image_adopt(fma_engine_t* e, int fd, uint64_t tag_mask, uint32_t flags) 
     if (off != hd.image_bytes) return bail(FMA_EINVAL, "image size mismatch");
     DeviceGuard guard(e->device);
     cudaDeviceSynchronize();
+    invalidate_shadows(e);
     host_store_free(e->host);
     const double t0 = now_s();
     cudaError_t r = cudaHostRegister(p, map_bytes, cudaHostRegisterPortable | cudaHostRegisterMapped);

@@ -119,6 +119,9 @@ struct Segment {
     uint64_t packed_off = kNoOffset;
     uint64_t digest = 0;
     bool digest_valid = false;
+    // INCREMENTAL sleep: after a host-tier wake the store still holds this segment's bytes at shadow_off, and `digest` is
+    // their K3 digest; kNoOffset = no such copy (never slept, image overwritten or released, layout changed)
+    uint64_t shadow_off = kNoOffset;
 };
 
 using fma_layout::Arena;
@@ -201,6 +204,13 @@ struct fma_engine {
     std::vector<uint64_t> img_off;
     std::vector<uint32_t> img_bytes;
     uint64_t image_store_bytes = 0;  // bytes the image occupies in its store (== image_bytes unless packed)
+    // INCREMENTAL sleep (option "incremental"): weights do not change while a model serves, so after a wake the host store
+    // still holds the image.  The next sleep digests the segments on the device (K3, one HBM read) and, if every offloaded
+    // segment still has the digest and the image offset of that copy, releases the device side WITHOUT moving a byte.
+    int incremental = 0;
+    bool shadow_packed = false;       // form / size of the image the shadows belong to (img_off / img_bytes are kept for it)
+    uint64_t shadow_store_bytes = 0;
+    uint64_t shadow_image_bytes = 0;
     fma_k_pack_desc* d_pdesc = nullptr;  // per-page descriptors of K4 / K5
     fma_k_pack_desc* h_pdesc = nullptr;
     uint32_t* d_psize = nullptr;         // K4p output; d_psize[pdesc_cap] is the K4/K5 error counter
@@ -273,6 +283,7 @@ void host_store_free(HostStore& h);
 int host_store_reserve(fma_engine_t* e, size_t bytes);
 int park_release(fma_engine_t* e);
 int park_reserve(fma_engine_t* e, int park_device, size_t bytes);
+void invalidate_shadows(fma_engine_t* e);   // the host store no longer holds a usable copy of any segment
 // ---- pipelines ----
 int do_sleep(fma_engine_t* e, uint64_t offload_mask, int tier, uint32_t flags);   // fma_sleep.cu
 int do_wake(fma_engine_t* e, uint64_t tag_mask, uint32_t flags);                  // fma_wake.cu

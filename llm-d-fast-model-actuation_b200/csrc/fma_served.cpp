@@ -23,7 +23,7 @@
 // while /is_sleeping and /health never take it (the controller polls them while a sleep is in flight).
 //
 //   fma_served --port 8005 --device 0 [--device 1 ...] --seg weights:1002 --seg weights:48 ... --seg kv_cache:32768
-//              [--tier host|local] [--pack 1] [--seed 1234] [--startup-delay 0] [--host 127.0.0.1]
+//              [--tier host|local] [--pack 1] [--incremental 1] [--seed 1234] [--startup-delay 0] [--host 127.0.0.1]
 //   (sizes in MiB; port 0 picks a free port; "listening on <port>" is printed once it serves)
 #include <arpa/inet.h>
 #include <netinet/in.h>
@@ -308,7 +308,7 @@ int die(const char* what) {
 }  // namespace
 
 int main(int argc, char** argv) {
-    int port = 8005, pack = 0;
+    int port = 8005, pack = 0, incremental = 0;
     std::string host = "127.0.0.1";
     std::vector<int> devices;
     std::vector<SegSpec> segs;
@@ -322,6 +322,7 @@ int main(int argc, char** argv) {
         else if (a == "--device") devices.push_back(atoi(val()));
         else if (a == "--seed") seed = strtoull(val(), nullptr, 0);
         else if (a == "--pack") pack = atoi(val());
+        else if (a == "--incremental") incremental = atoi(val());
         else if (a == "--startup-delay") startup_delay = atof(val());
         else if (a == "--tier") {
             const std::string t = val();
@@ -348,6 +349,7 @@ int main(int argc, char** argv) {
         cfg.numa_bind = -1;
         cfg.pack = pack;
         if (fma_engine_create(rk.device, &cfg, &rk.e) != 0) return die("fma_engine_create");
+        if (incremental && fma_set_option(rk.e, "incremental", 1) != 0) return die("fma_set_option");
         rk.tag_weights = fma_tag_intern(rk.e, "weights");
         uint64_t first_word = 0;
         for (const SegSpec& s : segs) {

@@ -433,24 +433,51 @@ int do_sleep(fma_engine_t* e, uint64_t offload_mask, int tier, uint32_t flags) {
     });
     std::vector<Extent> ex;
     uint64_t W = 0, discarded = 0;
+    bool shadows_match = e->incremental && tier == FMA_TIER_HOST && !(flags & kFlagAdopt) && e->host.base != nullptr;
+    std::vector<uint64_t> shadow_digest;  // digest of the copy the store holds, per extent
     for (size_t i : by_addr) {
         Segment& s = e->segs[i];
-        s.has_backup = false;
-        s.packed_off = kNoOffset;
-        s.digest_valid = false;
         if (tag_bit_set(offload_mask, s.tag)) {
+            shadows_match = shadows_match && s.digest_valid && s.shadow_off == W;  // same bytes expected at the same image offset
+            shadow_digest.push_back(s.digest);
             ex.push_back(Extent{i, s.va, s.bytes, W});
             W += s.bytes;
         } else {
             discarded += s.bytes;
         }
+        s.has_backup = false;
+        s.packed_off = kNoOffset;
+        s.digest_valid = false;
     }
+    // INCREMENTAL sleep: does the host store still hold exactly this image?  One K3 pass over the device copy decides.
+    bool clean = false;
+    if (shadows_match && W && W == e->shadow_image_bytes && e->host.cap >= e->shadow_store_bytes) {
+        RT(cudaDeviceSynchronize());  // the caller's streams may still be writing weights
+        std::vector<size_t> idx;
+        for (const Extent& x : ex) idx.push_back(x.seg_index);
+        std::vector<uint64_t> now;
+        rc = digest_segments(e, idx, &now);
+        if (rc != FMA_OK) return rc;
+        clean = now == shadow_digest;
+        for (size_t k = 0; k < idx.size(); ++k) {  // either way these are the digests of what sleeps now
+            e->segs[idx[k]].digest = now[k];
+            e->segs[idx[k]].digest_valid = true;
+        }
+    }
+    if (clean) flags |= kFlagAdopt;            // release the device side only: not a byte moves
+    else invalidate_shadows(e);                // this sleep rewrites the store (or leaves the host tier alone: be conservative)
     int mode = resolve_mode(e, tier);
     if (W && !(flags & kFlagAdopt) && mode == FMA_MODE_STAGED && ensure_ring(e, W) != FMA_OK) mode = FMA_MODE_DIRECT;  // HBM too full for a ring
     // PACKED image (config.pack): decide per page what its stored form is BEFORE the store is sized
     bool packed = false;
     uint64_t Wp = W;
-    {
+    if (clean) {  // the image in the store, its form and its page table stay as they are
+        packed = e->shadow_packed;
+        Wp = e->shadow_store_bytes;
+        e->image_packed = packed;
+        e->image_store_bytes = Wp;
+        e->image_bytes = W;
+    } else {
         std::vector<uint64_t> pk_off;
         std::vector<uint32_t> pk_bytes;
         // host tier: through the staging ring (STAGED); parking tiers (peer / local HBM): K4 writes the store itself (KERNEL)
@@ -483,8 +510,12 @@ int do_sleep(fma_engine_t* e, uint64_t offload_mask, int tier, uint32_t flags) {
         }
     }
 
+    // The caller's own streams may still be writing weights: drain the device once, as the
+    // reference's blocking cudaMemcpy on the legacy stream implicitly does (before anything reads the segments).
+    RT(cudaDeviceSynchronize());
+
     const bool adopt = (flags & kFlagAdopt) != 0;  // the store already holds the image: release the device side only
-    if ((flags & FMA_FLAG_VERIFY) && W && !adopt) {
+    if (((flags & FMA_FLAG_VERIFY) || (e->incremental && tier == FMA_TIER_HOST)) && W && !adopt) {  // incremental: digests seed the next sleep's check
         std::vector<size_t> idx;
         for (const Extent& x : ex) idx.push_back(x.seg_index);
         std::vector<uint64_t> dg;
@@ -495,10 +526,6 @@ int do_sleep(fma_engine_t* e, uint64_t offload_mask, int tier, uint32_t flags) {
             e->segs[idx[k]].digest_valid = true;
         }
     }
-
-    // The caller's own streams may still be writing weights: drain the device once, as the
-    // reference's blocking cudaMemcpy on the legacy stream implicitly does.
-    RT(cudaDeviceSynchronize());
 
     // ---- unmapper thread (types above): cuMemUnmap runs UNDER the copy pipeline instead of after it ----
     Unmapper un;
@@ -562,6 +589,11 @@ int do_sleep(fma_engine_t* e, uint64_t offload_mask, int tier, uint32_t flags) {
     double copy_s = 0;
     if (W && adopt) {
         publish_consumed(W, e->ks);  // nothing to copy: every offloaded unit can go at once
+        e->pending_events = 0;       // no kernel ran: the per-operation kernel statistics read zero
+        e->st.kernel_seconds = 0;
+        e->st.kernel_bytes = 0;
+        e->st.kernel_launches = 0;
+        if (!e->ring_attached && env_int("FMA_RING_PERSIST", 0) == 0) release_ring(e);  // a sleeping model holds no staging ring
     } else if (W) {
         char* store = static_cast<char*>(store_copy_base(e, tier));
         rc = timer.begin();

@@ -539,11 +539,20 @@ int do_wake(fma_engine_t* e, uint64_t tag_mask, uint32_t flags) {
                                  (unsigned long long)e->segs[idx[k]].va, (unsigned long long)dg[k],
                                  (unsigned long long)e->segs[idx[k]].digest);
     }
-    if (!(flags & FMA_FLAG_KEEP_BACKUP))
+    if (!(flags & FMA_FLAG_KEEP_BACKUP)) {
         for (size_t i : with_backup) {  // data.cpu_backup_tensor = None (cumem.py:249)
-            e->segs[i].has_backup = false;
-            e->segs[i].packed_off = kNoOffset;
+            Segment& s = e->segs[i];
+            // INCREMENTAL sleep: the host store keeps these bytes; remember where, together with their digest
+            s.shadow_off = (tier == FMA_TIER_HOST && s.digest_valid && verify_rc == FMA_OK) ? s.packed_off : kNoOffset;
+            s.has_backup = false;
+            s.packed_off = kNoOffset;
         }
+        if (tier == FMA_TIER_HOST && W) {
+            e->shadow_packed = e->image_packed;
+            e->shadow_store_bytes = e->image_store_bytes;
+            e->shadow_image_bytes = e->image_bytes;
+        }
+    }
 
     e->st.wake_seconds = now_s() - t_entry;
     e->st.wake_copy_seconds = copy_s;

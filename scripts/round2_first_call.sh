@@ -30,4 +30,8 @@ timeout 400 python bench.py --steps 10 --warmup 3 --contents bf16 --pack 0 --no-
 timeout 400 python bench.py --steps 10 --warmup 3 --contents bf16 --pack 1 --no-cpu-baseline --packed-extra 0 > "$out/bench_bf16_packed.json" 2>> "$out/bench_default.err"; echo "bench packed rc=$?" | tee -a "$out/status.txt"
 timeout 400 env FMA_PACK_KERNEL=1 python bench.py --steps 10 --warmup 3 --contents bf16 --pack 1 --no-cpu-baseline --packed-extra 0 > "$out/bench_bf16_packed_tma.json" 2>> "$out/bench_default.err"; echo "bench packed (TMA kernels) rc=$?" | tee -a "$out/status.txt"
 
+# 5. INCREMENTAL sleep (gated test + bench: sleeps after the first move nothing)
+timeout 300 env FMA_TEST_NEW_ON_GPU=1 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "incremental or random_alloc" > "$out/pytest_new.log" 2>&1; echo "pytest incremental + random histories rc=$?" | tee -a "$out/status.txt"
+timeout 400 python bench.py --steps 10 --warmup 3 --incremental 1 --no-cpu-baseline --packed-extra 0 > "$out/bench_incremental.json" 2>> "$out/bench_default.err"; echo "bench incremental rc=$?" | tee -a "$out/status.txt"
+
 cat "$out/status.txt"

@@ -230,6 +230,7 @@ int main() {
             OK(fma_set_option(c, "chunk_bytes", (int64_t)(1 + rnd(3)) * 2 * P));
             OK(fma_set_option(c, "ring_slots", 2 + rnd(3)));
             OK(fma_set_option(c, "pack", rnd(2)));
+            OK(fma_set_option(c, "incremental", rnd(2)));
             uint64_t mask = 0;
             if (rnd(5)) mask |= 1ull << tw;
             if (rnd(5)) mask |= 1ull << ta;

@@ -848,7 +848,8 @@ def test_packed_random_tables_and_wake_orders(built, oracle, seed):
         eng.set_option("pack", 1)
         eng.set_option("chunk_bytes", int(rng.choice([2, 4, 6, 512])) << 20)
         eng.set_option("ring_slots", int(rng.integers(2, 5)))
-        for cycle in range(2):
+        eng.set_option("incremental", int(rng.integers(0, 2)))
+        for cycle in range(3):
             eng.sleep(offload, flags=L.FMA_FLAG_VERIFY if cycle == 0 else 0)
             st = eng.stats()
             W = sum(len(k) * PAGE for t, k, _ in segs if t in offload)
@@ -923,6 +924,7 @@ def test_random_alloc_free_sleep_wake_sequences(built, oracle, seed):
             eng.set_option("mode", mode)
             eng.set_option("chunk_bytes", int(rng.choice([2, 4, 6, 32])) << 20)
             eng.set_option("ring_slots", int(rng.integers(2, 5)))
+            eng.set_option("incremental", int(rng.integers(0, 2)))
             offload = [t for t in ("weights", "adapters") if rng.random() < 0.8]
             eng.sleep(offload, tier=tier, flags=L.FMA_FLAG_VERIFY if rng.random() < 0.5 else 0)
             st = eng.stats()
@@ -947,3 +949,64 @@ def test_random_alloc_free_sleep_wake_sequences(built, oracle, seed):
                     d = rng.integers(0, 256, eng.segment(i).bytes, dtype=np.uint8)
                     eng.write(i, d.tobytes()); live[ptr] = (tag, d)
             assert eng.current_usage() == sum(eng.segment(eng.find(p)).bytes for p in live)
+
+
+@_NEW_THIS_ROUND
+@pytest.mark.parametrize("pack", [0, 1])
+def test_incremental_sleep_moves_nothing_when_the_weights_did_not_change(engine, oracle, pack):
+    """Option "incremental": after a wake the host store still holds the image; the next sleep digests the device copy (K3)
+    and, when nothing changed, only releases the device side — no copy, no kernel besides the digest.  Any change (a written
+    segment, a new or freed segment, a released store) falls back to a full sleep; the bytes that wake are always right."""
+    L = _L()
+    table = _tiny_table()
+    ptrs, ref = _load(engine, oracle, table)
+    if pack:
+        for k, i in enumerate(sorted(ref)):
+            ref[i] = np.resize(oracle.bf16_weights(1 << 20, 300 + k).view(np.uint8), table[i].bytes)
+            engine.write(i, ref[i].tobytes())
+        engine.set_option("pack", 1)
+    engine.set_option("mode", L.FMA_MODE_STAGED)
+    engine.set_option("incremental", 1)
+    W = sum(table[i].bytes for i in ref)
+
+    def cycle(expect_clean, flags=0):
+        ops0 = engine.stats()["total_copy_ops"]
+        engine.sleep(["weights"], flags=flags)
+        st = engine.stats()
+        moved = engine.stats()["total_copy_ops"] - ops0
+        assert st["sleep_bytes_offloaded"] == W and st["image_packed"] == pack and st["hbm_mapped_bytes"] == 0
+        assert (moved == 0 and st["copy_ops"] == 0 and st["kernel_launches"] == 0) if expect_clean else moved > 0, (expect_clean, moved)
+        engine.wake(None, flags=L.FMA_FLAG_VERIFY)
+        for i in ref:
+            assert engine.read(i, table[i].bytes) == ref[i].tobytes()
+        assert [s.va for s in engine.segments()] == ptrs
+
+    cycle(False)                                   # first sleep: the store is empty
+    image = _host_image(engine).copy()
+    cycle(True); cycle(True, flags=L.FMA_FLAG_VERIFY)
+    assert np.array_equal(_host_image(engine)[:image.size], image)          # the store was not touched
+    i0 = sorted(ref)[1]                            # one segment rewritten while awake -> full sleep, then clean again
+    ref[i0] = ref[i0].copy(); ref[i0][12345] ^= 0xFF
+    engine.write(i0, ref[i0].tobytes())
+    cycle(False); cycle(True)
+    engine.wake(["kv_cache"])                      # (already awake: harmless)
+    extra = engine.alloc(2 * PAGE, "weights")      # the table grew: the image layout is different
+    ptrs.append(extra)
+    engine.write(engine.find(extra), b"\x07" * (2 * PAGE))
+    ops0 = engine.stats()["total_copy_ops"]
+    engine.sleep(["weights"]); assert engine.stats()["total_copy_ops"] > ops0
+    engine.wake(None)
+    assert engine.read(engine.find(extra), 2 * PAGE) == b"\x07" * (2 * PAGE)
+    ops0 = engine.stats()["total_copy_ops"]
+    engine.sleep(["weights"]); assert engine.stats()["total_copy_ops"] == ops0        # clean again with the new layout
+    engine.wake(None)
+    engine.free(extra); ptrs.pop()
+    ops0 = engine.stats()["total_copy_ops"]
+    engine.sleep(["weights"]); assert engine.stats()["total_copy_ops"] > ops0          # a segment left: full sleep
+    engine.wake(None)
+    engine.host_release()                          # the store is gone: the next sleep cannot be incremental
+    cycle(False); cycle(True)
+    engine.sleep(["weights"], tier=L.FMA_TIER_LOCAL); engine.wake(None)                # another tier in between: conservative
+    cycle(False); cycle(True)
+    engine.set_option("incremental", 0)
+    cycle(False)
