@@ -450,7 +450,8 @@ int do_sleep(fma_engine_t* e, uint64_t offload_mask, int tier, uint32_t flags) {
         s.digest_valid = false;
     }
     // INCREMENTAL sleep: does the host store still hold exactly this image?  One K3 pass over the device copy decides.
-    bool clean = false;
+    bool clean = false, partial = false, digests_known = false;
+    std::vector<Extent> dirty;  // segments whose device bytes differ from the copy in the store
     if (shadows_match && W && W == e->shadow_image_bytes && e->host.cap >= e->shadow_store_bytes) {
         RT(cudaDeviceSynchronize());  // the caller's streams may still be writing weights
         std::vector<size_t> idx;
@@ -458,15 +459,24 @@ int do_sleep(fma_engine_t* e, uint64_t offload_mask, int tier, uint32_t flags) {
         std::vector<uint64_t> now;
         rc = digest_segments(e, idx, &now);
         if (rc != FMA_OK) return rc;
-        clean = now == shadow_digest;
-        for (size_t k = 0; k < idx.size(); ++k) {  // either way these are the digests of what sleeps now
-            e->segs[idx[k]].digest = now[k];
+        uint64_t dirty_bytes = 0;
+        for (size_t k = 0; k < idx.size(); ++k) {
+            if (now[k] != shadow_digest[k]) {
+                dirty.push_back(ex[k]);
+                dirty_bytes += ex[k].bytes;
+            }
+            e->segs[idx[k]].digest = now[k];  // either way these are the digests of what sleeps now
             e->segs[idx[k]].digest_valid = true;
         }
+        digests_known = true;
+        clean = dirty.empty();
+        // a few changed segments (an adapter, fp8 KV scales reset after wake, one synced layer): only they cross the link, into
+        // their old place in the kept image.  Not for PACKED images: a re-coded page may change size and move its neighbours.
+        partial = !clean && !e->shadow_packed && 2 * dirty_bytes <= W;
     }
-    if (clean) flags |= kFlagAdopt;            // release the device side only: not a byte moves
-    else invalidate_shadows(e);                // this sleep rewrites the store (or leaves the host tier alone: be conservative)
-    int mode = resolve_mode(e, tier);
+    if (clean) flags |= kFlagAdopt;                  // release the device side only: not a byte moves
+    else if (!partial) invalidate_shadows(e);        // this sleep rewrites the store (or leaves the host tier alone: be conservative)
+    int mode = partial ? FMA_MODE_DIRECT : resolve_mode(e, tier);
     if (W && !(flags & kFlagAdopt) && mode == FMA_MODE_STAGED && ensure_ring(e, W) != FMA_OK) mode = FMA_MODE_DIRECT;  // HBM too full for a ring
     // PACKED image (config.pack): decide per page what its stored form is BEFORE the store is sized
     bool packed = false;
@@ -515,7 +525,7 @@ int do_sleep(fma_engine_t* e, uint64_t offload_mask, int tier, uint32_t flags) {
     RT(cudaDeviceSynchronize());
 
     const bool adopt = (flags & kFlagAdopt) != 0;  // the store already holds the image: release the device side only
-    if (((flags & FMA_FLAG_VERIFY) || (e->incremental && tier == FMA_TIER_HOST)) && W && !adopt) {  // incremental: digests seed the next sleep's check
+    if (((flags & FMA_FLAG_VERIFY) || (e->incremental && tier == FMA_TIER_HOST)) && W && !adopt && !digests_known) {  // incremental: digests seed the next sleep's check
         std::vector<size_t> idx;
         for (const Extent& x : ex) idx.push_back(x.seg_index);
         std::vector<uint64_t> dg;
@@ -598,8 +608,11 @@ int do_sleep(fma_engine_t* e, uint64_t offload_mask, int tier, uint32_t flags) {
         char* store = static_cast<char*>(store_copy_base(e, tier));
         rc = timer.begin();
         if (rc != FMA_OK) return rc;
-        SleepPipe pipe{e, ex, W, tier, store, kt, copy_ops, publish_consumed};
-        if (mode == FMA_MODE_DIRECT) rc = sleep_direct(pipe);
+        SleepPipe pipe{e, partial ? dirty : ex, W, tier, store, kt, copy_ops, publish_consumed};
+        if (partial) {  // only the changed segments move; everything below each of them is in the store already
+            rc = sleep_direct(pipe);
+            if (rc == FMA_OK) rc = publish_consumed(W, e->cs[0]);  // cs[0] has joined the other streams after the last extent
+        } else if (mode == FMA_MODE_DIRECT) rc = sleep_direct(pipe);
         else if (mode == FMA_MODE_KERNEL) rc = packed ? sleep_kernel_packed(pipe) : sleep_kernel(pipe);
         else rc = packed ? sleep_staged_packed(pipe) : sleep_staged(pipe);
         if (rc != FMA_OK) return rc;
