@@ -234,6 +234,9 @@ FMA_API int  fma_peer_release(fma_engine_t* e);
  * image is copied once into an anonymous pinned store.  A PACKED image travels with its page table (descriptor v2).
  * Status: exercised on the CUDA host simulation only (tests/test_engine_hostsim.py); not yet run on a B200. */
 FMA_API int  fma_image_export(fma_engine_t* e, int* out_fd);          /* caller owns (closes) the returned fd          */
+/* flags: FMA_FLAG_VERIFY = "sleep by adoption": the engine holds the weights itself (another replica of the model the image
+ * came from) and its device bytes must match the image's digests — then its device side is released and it shares that
+ * image (one host copy per node instead of one per replica); on a mismatch nothing is touched and FMA_EINTEGRITY comes back. */
 FMA_API int  fma_image_adopt(fma_engine_t* e, int fd, uint64_t tag_mask, uint32_t flags);  /* fd stays owned by the caller */
 
 /* ---- integrity (K3) and synthetic data (K0) --------------------------------------- */

@@ -113,6 +113,21 @@ int fma_image_adopt(fma_engine_t* e, int fd, uint64_t tag_mask, uint32_t flags) 
     if (off != hd.image_bytes) return bail(FMA_EINVAL, "image size mismatch");
     DeviceGuard guard(e->device);
     cudaDeviceSynchronize();
+    if (flags & FMA_FLAG_VERIFY) {
+        // "Sleep by adoption": this engine HAS the weights and wants to share somebody else's image of the same model (a second
+        // replica on the node: one host copy for all).  Only legal if its device bytes are what the image holds — K3 digests
+        // against the descriptor's; a mismatch leaves the engine awake and untouched.
+        std::vector<uint64_t> now;
+        int vrc = digest_segments(e, order, &now);
+        if (vrc != FMA_OK) {
+            munmap(p, map_bytes);
+            close(myfd);
+            return vrc;
+        }
+        for (size_t i = 0; i < ds.size(); ++i)
+            if (!ds[i].digest_valid || ds[i].digest != now[i])
+                return bail(FMA_EINTEGRITY, ds[i].digest_valid ? "the image holds different bytes than this engine's segments" : "the image carries no digests to compare with");
+    }
     invalidate_shadows(e);
     host_store_free(e->host);
     const double t0 = now_s();

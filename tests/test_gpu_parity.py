@@ -1026,3 +1026,36 @@ def test_incremental_sleep_moves_nothing_when_the_weights_did_not_change(engine,
     cycle(False); cycle(True)
     engine.set_option("incremental", 0)
     cycle(False)
+
+
+@_HOSTSIM_ONLY
+def test_sleep_by_adopting_a_replicas_image(engine, oracle, monkeypatch):
+    """Two replicas of one model on a node: the second one sleeps by adopting the first one's image (FMA_FLAG_VERIFY = its device
+    bytes must match the image's digests) — one host copy for both.  A replica with different bytes is refused and stays awake."""
+    import fma_b200
+    from fma_b200 import FmaError
+
+    L = _L()
+    monkeypatch.setenv("FMA_HOST_STORE_SHM", "1")
+    table = _tiny_table()
+    _, ref = _load(engine, oracle, table)
+    engine.sleep(["weights"], flags=L.FMA_FLAG_VERIFY)                 # digests travel in the descriptor
+    fd = engine.image_export()
+    try:
+        with fma_b200.Engine(0) as twin:
+            _, ref2 = _load(twin, oracle, table)                       # same seed -> same bytes
+            ops0 = twin.stats()["total_copy_ops"]
+            twin.image_adopt(fd, ["weights"], flags=L.FMA_FLAG_VERIFY)
+            assert twin.is_sleeping() and twin.stats()["total_copy_ops"] == ops0 and twin.stats()["hbm_mapped_bytes"] == 0
+            twin.wake(None, flags=L.FMA_FLAG_VERIFY)
+            for i in ref2:
+                assert twin.read(i, table[i].bytes) == ref[i].tobytes()
+        with fma_b200.Engine(0) as other:
+            _load(other, oracle, table, seed=999)                      # same shapes, different weights
+            with pytest.raises(FmaError) as ei:
+                other.image_adopt(fd, ["weights"], flags=L.FMA_FLAG_VERIFY)
+            assert ei.value.code == L.FMA_EINTEGRITY and not other.is_sleeping()
+            assert all(s.mapped for s in other.segments())
+    finally:
+        os.close(fd)
+    engine.wake(None, flags=L.FMA_FLAG_VERIFY)
