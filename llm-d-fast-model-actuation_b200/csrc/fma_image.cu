@@ -43,6 +43,7 @@ int fma_image_export(fma_engine_t* e, int* out_fd) {
     }
     int fd = dup(e->host.fd);
     if (fd < 0) return fail(FMA_ENOMEM, "dup failed: %s", strerror(errno));
+    e->host.shared = true;  // whoever receives the fd reads this image: never write it again (see HostStore::shared)
     *out_fd = fd;
     return FMA_OK;
 }
@@ -158,6 +159,7 @@ int fma_image_adopt(fma_engine_t* e, int fd, uint64_t tag_mask, uint32_t flags) 
         p = q;
     } else {
         h.base = p; h.cap = cap; h.map_bytes = map_bytes; h.fd = myfd; h.registered = true;
+        h.shared = true;  // the exporter (and other adopters) map the same pages
     }
     void* alias = nullptr;
     if (cudaHostGetDevicePointer(&alias, p, 0) == cudaSuccess) h.dev_alias = alias;

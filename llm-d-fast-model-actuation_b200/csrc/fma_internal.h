@@ -145,6 +145,8 @@ struct HostStore {
     int numa_node = -1;
     double pin_seconds = 0;
     int fd = -1;                // memfd backing (FMA_HOST_STORE_SHM=1 or an adopted image); -1 = anonymous memory
+    bool shared = false;        // somebody else may hold this image too (exported, or adopted in place): it is READ-ONLY from
+                                // now on — a sleep that has to write gets a fresh private store first (copy-on-write per store)
     size_t map_bytes = 0;       // bytes mapped at base (cap + descriptor tail for memfd stores)
 };
 

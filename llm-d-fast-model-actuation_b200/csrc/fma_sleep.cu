@@ -472,7 +472,7 @@ int do_sleep(fma_engine_t* e, uint64_t offload_mask, int tier, uint32_t flags) {
         clean = dirty.empty();
         // a few changed segments (an adapter, fp8 KV scales reset after wake, one synced layer): only they cross the link, into
         // their old place in the kept image.  Not for PACKED images: a re-coded page may change size and move its neighbours.
-        partial = !clean && !e->shadow_packed && 2 * dirty_bytes <= W;
+        partial = !clean && !e->shadow_packed && 2 * dirty_bytes <= W && !e->host.shared;  // a shared image is read-only
     }
     if (clean) flags |= kFlagAdopt;                  // release the device side only: not a byte moves
     else if (!partial) invalidate_shadows(e);        // this sleep rewrites the store (or leaves the host tier alone: be conservative)
@@ -506,6 +506,10 @@ int do_sleep(fma_engine_t* e, uint64_t offload_mask, int tier, uint32_t flags) {
         if (tier == FMA_TIER_HOST && (flags & kFlagAdopt)) {
             if (!e->host.base) return fail(FMA_ESTATE, "adopt without a store");  // the adopted store IS the image: never re-sized
         } else if (tier == FMA_TIER_HOST) {
+            if (e->host.shared) {  // this sleep writes: leave the shared image to its other holders and take a private store
+                invalidate_shadows(e);
+                host_store_free(e->host);
+            }
             rc = host_store_reserve(e, Wp);
             if (rc != FMA_OK) return rc;
             if (mode == FMA_MODE_KERNEL && !e->host.dev_alias) return fail(FMA_ECUDA, "host store has no device alias for zero-copy mode");

@@ -1059,3 +1059,42 @@ def test_sleep_by_adopting_a_replicas_image(engine, oracle, monkeypatch):
     finally:
         os.close(fd)
     engine.wake(None, flags=L.FMA_FLAG_VERIFY)
+
+
+@_HOSTSIM_ONLY
+def test_shared_images_are_read_only_for_everybody(engine, oracle, monkeypatch):
+    """An exported / adopted image is shared memory: the exporter waking, changing its weights and sleeping again must not
+    rewrite the bytes an adopter is still asleep on (it gets a fresh private store), and vice versa."""
+    import fma_b200
+
+    L = _L()
+    monkeypatch.setenv("FMA_HOST_STORE_SHM", "1")
+    table = _tiny_table()
+    _, ref = _load(engine, oracle, table)
+    engine.set_option("incremental", 1)
+    engine.sleep(["weights"], flags=L.FMA_FLAG_VERIFY)
+    fd = engine.image_export()
+    try:
+        with fma_b200.Engine(0) as adopter:
+            for s in table:
+                adopter.alloc(s.bytes, s.tag)
+            adopter.image_adopt(fd, ["weights"])                        # asleep on the shared image
+            engine.wake(None)
+            changed = {i: (ref[i] ^ 0x5A) for i in ref}                 # the exporter's weights change completely
+            for i in changed:
+                engine.write(i, changed[i].tobytes())
+            engine.sleep(["weights"])                                   # full sleep: must go to a private store
+            adopter.wake(None, flags=L.FMA_FLAG_VERIFY)                 # digests from the descriptor still hold
+            for i in ref:
+                assert adopter.read(i, table[i].bytes) == ref[i].tobytes()
+            # and the adopter, now awake with different bytes, sleeps without touching the exporter's new image either
+            for i in ref:
+                adopter.write(i, (ref[i] ^ 0xA5).tobytes())
+            adopter.sleep(["weights"]); adopter.wake(None)
+            for i in ref:
+                assert adopter.read(i, table[i].bytes) == (ref[i] ^ 0xA5).tobytes()
+        engine.wake(None, flags=L.FMA_FLAG_VERIFY)
+        for i in changed:
+            assert engine.read(i, table[i].bytes) == changed[i].tobytes()
+    finally:
+        os.close(fd)
