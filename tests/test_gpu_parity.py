@@ -942,6 +942,9 @@ def test_random_alloc_free_sleep_wake_sequences(built, oracle, seed):
             if rng.random() < 0.4 and live:                             # free a sleeping segment
                 ptr = list(live)[int(rng.integers(0, len(live)))]
                 eng.free(ptr); del live[ptr]
+            if rng.random() < 0.3:                                      # allocate while the rest sleeps: mapped at once, keeps its bytes
+                alloc()
+                assert eng.is_sleeping() or len(live) == 1
             order = list(tags); rng.shuffle(order)
             for t in order[:int(rng.integers(0, 3))]:
                 eng.wake([t]); eng.wake([t])
