@@ -255,7 +255,7 @@ def run_ours(args) -> None:
             "wake_latency_s_rank0_steps": [round(r[1]["wake_seconds"], 4) for r in rows],
             "sleep_latency_s": round(sleep_wall_m, 5),
             "sleep_d2h_gbs": round(W_total / sleep_dev_m / 1e9, 3) if sleep_dev_m > 0 else None,   # None: incremental sleeps moved nothing
-            "sleep_copy_ops_last": rows[-1][0]["copy_ops"],
+            "sleep_copy_ops_last": rows[-1][0]["copy_ops"], "sleep_bytes_copied_last": rows[-1][0]["sleep_bytes_copied"],
             "wake_map_s": round(map_s, 5), "sleep_unmap_s": round(unmap_s, 5), "host_pin_s_untimed": round(pin_s, 3),
             "bit_exact": bool(all_exact),
             "e2e": {"value": round(e2e_gbs, 3), "unit": "GB/s", "h2d_bytes_per_step": int(W_total),

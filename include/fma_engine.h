@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define FMA_ABI_VERSION 1
+#define FMA_ABI_VERSION 2   /* 2: fma_stats_t grew (sleep_bytes_copied), fma_config_t.pack, packed-image and image-file entry points */
 
 #if defined(__GNUC__)
 #define FMA_API __attribute__((visibility("default")))
@@ -147,6 +147,9 @@ typedef struct fma_stats {
     uint64_t parked_bytes;          /* parking buffer held in a peer's (or this GPU's) HBM               */
     uint64_t image_store_bytes;     /* bytes the last sleep's image takes in its store: == sleep_bytes_offloaded,
                                        or less for a PACKED image (these are the bytes that cross PCIe)    */
+    uint64_t sleep_bytes_copied;    /* bytes the last sleep actually moved into the store: image_store_bytes for a full
+                                       sleep, 0 for a clean INCREMENTAL sleep, the changed segments for a partial one */
+    uint64_t reserved[3];
 } fma_stats_t;
 
 /* ---- library ---------------------------------------------------------------------- */

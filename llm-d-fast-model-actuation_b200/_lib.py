@@ -4,7 +4,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-FMA_ABI_VERSION = 1
+FMA_ABI_VERSION = 2
 FMA_PAGE_BYTES = 2 << 20
 FMA_PACKED_PAGE_BYTES = (3 << 19) + (16 << 10)   # stored size of a page in the "FMP4" code (csrc/fma_codec.h)
 FMA_MAX_TAGS = 64
@@ -60,7 +60,7 @@ class fma_stats_t(C.Structure):
         ("host_store_numa_node", C.c_int32), ("tier", C.c_int32), ("mode", C.c_int32), ("image_packed", C.c_int32),
         ("total_kernel_launches", C.c_uint64), ("total_copy_ops", C.c_uint64),
         ("hbm_mapped_bytes", C.c_uint64), ("hbm_aux_bytes", C.c_uint64), ("parked_bytes", C.c_uint64),
-        ("image_store_bytes", C.c_uint64),
+        ("image_store_bytes", C.c_uint64), ("sleep_bytes_copied", C.c_uint64), ("reserved", C.c_uint64 * 3),
     ]
 
     def as_dict(self) -> dict:

@@ -671,6 +671,12 @@ int do_sleep(fma_engine_t* e, uint64_t offload_mask, int tier, uint32_t flags) {
     e->st.sleep_copy_seconds = copy_s;
     e->st.sleep_unmap_seconds = un.seconds;
     e->st.sleep_bytes_offloaded = W;
+    {
+        uint64_t copied = 0;  // what this sleep moved into the store
+        if (partial) for (const Extent& x : dirty) copied += x.bytes;
+        else if (!adopt) copied = Wp;
+        e->st.sleep_bytes_copied = copied;
+    }
     e->st.sleep_bytes_discarded = discarded;
     e->st.copy_ops = copy_ops;
     e->st.total_copy_ops += copy_ops;

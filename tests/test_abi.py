@@ -84,7 +84,7 @@ def test_no_cpu_fallback_without_a_driver(built):
     from fma_b200 import _lib as L
 
     lib = fma_b200.load_library()
-    assert lib.fma_abi_version() == 1
+    assert lib.fma_abi_version() == 2
     assert lib.fma_driver_available() == L.FMA_ENODRIVER
     with pytest.raises(fma_b200.FmaError) as ei:
         fma_b200.Engine(0)

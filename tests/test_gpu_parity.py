@@ -984,6 +984,7 @@ def test_incremental_sleep_moves_nothing_when_the_weights_did_not_change(engine,
         moved = engine.stats()["total_copy_ops"] - ops0
         assert st["sleep_bytes_offloaded"] == W and st["image_packed"] == pack and st["hbm_mapped_bytes"] == 0
         assert (moved == 0 and st["copy_ops"] == 0 and st["kernel_launches"] == 0) if expect_clean else moved > 0, (expect_clean, moved)
+        assert st["sleep_bytes_copied"] == (0 if expect_clean else st["image_store_bytes"])
         engine.wake(None, flags=L.FMA_FLAG_VERIFY)
         for i in ref:
             assert engine.read(i, table[i].bytes) == ref[i].tobytes()
@@ -1003,6 +1004,7 @@ def test_incremental_sleep_moves_nothing_when_the_weights_did_not_change(engine,
         ops0 = engine.stats()["total_copy_ops"]
         engine.sleep(["weights"])
         assert engine.stats()["total_copy_ops"] - ops0 == table[i0].bytes // (2 << 20) and engine.stats()["mode"] == L.FMA_MODE_DIRECT
+        assert engine.stats()["sleep_bytes_copied"] == table[i0].bytes
         assert np.array_equal(_host_image(engine), oracle.packed_image([ref[i] for i in sorted(ref)]))
         engine.wake(None, flags=L.FMA_FLAG_VERIFY)
         for i in ref:
