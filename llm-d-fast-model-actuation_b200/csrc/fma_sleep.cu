@@ -193,6 +193,7 @@ struct SleepPipe {
     KernelTimes& kt;
     uint32_t& copy_ops;
     std::function<int(uint64_t, cudaStream_t)> publish_consumed;
+    const std::vector<size_t>* subset = nullptr;  // INCREMENTAL + PACKED: only these image pages (ascending) are re-coded, in place
     int publish_gathered(size_t pages_done) { return publish_consumed((uint64_t)pages_done * FMA_PAGE_BYTES, e->ks); }
     // page table of the image (device addresses of its pages, in order) -> e->h_tab / e->d_tab
     int upload_page_table(size_t* n_pages) {
@@ -323,29 +324,40 @@ int sleep_staged_packed(SleepPipe& pipe) {
     if (rc != FMA_OK) return rc;
     rc = ensure_ring(e, W);
     if (rc != FMA_OK) return rc;
-    struct Slot { size_t p0, np; uint64_t bytes; };
+    // the image pages this sleep codes: all of them, or (incremental) the pages of the changed segments, whose stored size
+    // is known not to change, so each goes back to its old place in the kept image
+    std::vector<size_t> all;
+    if (!pipe.subset) {
+        all.resize(n_pages);
+        for (size_t p = 0; p < n_pages; ++p) all[p] = p;
+    }
+    const std::vector<size_t>& pages = pipe.subset ? *pipe.subset : all;
+    struct Slot { size_t k0, nk; uint64_t bytes; };  // pages[k0 .. k0+nk): adjacent in the store, together they fit a ring slot
     std::vector<Slot> slots;
-    for (size_t p = 0; p < n_pages;) {
-        Slot sl{p, 0, 0};
-        while (p < n_pages && sl.bytes + e->img_bytes[p] <= e->ring_slot_bytes) {
-            sl.bytes += e->img_bytes[p];
-            ++sl.np;
-            ++p;
+    for (size_t k = 0; k < pages.size();) {
+        Slot sl{k, 0, 0};
+        while (k < pages.size() && sl.bytes + e->img_bytes[pages[k]] <= e->ring_slot_bytes &&
+               (sl.nk == 0 || e->img_off[pages[k]] == e->img_off[pages[k - 1]] + e->img_bytes[pages[k - 1]])) {
+            sl.bytes += e->img_bytes[pages[k]];
+            ++sl.nk;
+            ++k;
         }
-        if (!sl.np) return fail(FMA_EINVAL, "ring slot of %zu bytes cannot hold one page", e->ring_slot_bytes);
+        if (!sl.nk) return fail(FMA_EINVAL, "ring slot of %zu bytes cannot hold one page", e->ring_slot_bytes);
         slots.push_back(sl);
     }
     for (size_t c = 0; c < slots.size(); ++c)
-        for (size_t p = slots[c].p0; p < slots[c].p0 + slots[c].np; ++p) {
-            fma_k_pack_desc& d = e->h_pdesc[p];
+        for (size_t k = slots[c].k0; k < slots[c].k0 + slots[c].nk; ++k) {
+            const size_t p = pages[k];
+            fma_k_pack_desc& d = e->h_pdesc[k];
             d.src = e->h_tab[p];
-            d.dst = (uint64_t)(uintptr_t)e->ring[c % e->n_ring] + (e->img_off[p] - e->img_off[slots[c].p0]);
+            d.dst = (uint64_t)(uintptr_t)e->ring[c % e->n_ring] + (e->img_off[p] - e->img_off[pages[slots[c].k0]]);
             d.mode = e->img_bytes[p] == FMA_PAGE_BYTES ? FMA_K_PACK_RAW : FMA_K_PACK_BF16;
             d.pad = 0;
         }
     uint32_t* d_err = e->d_psize + e->pdesc_cap;
-    RT(cudaMemcpyAsync(e->d_pdesc, e->h_pdesc, n_pages * sizeof(fma_k_pack_desc), cudaMemcpyHostToDevice, e->ks));
+    RT(cudaMemcpyAsync(e->d_pdesc, e->h_pdesc, pages.size() * sizeof(fma_k_pack_desc), cudaMemcpyHostToDevice, e->ks));
     RT(cudaMemsetAsync(d_err, 0, sizeof(uint32_t), e->ks));
+    cudaStream_t last_stream = e->cs[0];
     for (size_t c = 0; c < slots.size(); ++c) {
         const Slot& sl = slots[c];
         const int slot = (int)(c % e->n_ring);
@@ -353,18 +365,21 @@ int sleep_staged_packed(SleepPipe& pipe) {
         if (c >= (size_t)e->n_ring) RT(cudaStreamWaitEvent(e->ks, e->ev_ring_free[slot], 0));
         rc = kt.begin();
         if (rc != FMA_OK) return rc;
-        RT(fma_k_launch_pack(e->d_pdesc + sl.p0, (uint32_t)sl.np, d_err, e->ks));
-        rc = kt.end((uint64_t)sl.np * FMA_PAGE_BYTES + sl.bytes);
+        RT(fma_k_launch_pack(e->d_pdesc + sl.k0, (uint32_t)sl.nk, d_err, e->ks));
+        rc = kt.end((uint64_t)sl.nk * FMA_PAGE_BYTES + sl.bytes);
         if (rc != FMA_OK) return rc;
         RT(cudaEventRecord(e->ev_ring_full[slot], e->ks));
         RT(cudaStreamWaitEvent(cstream, e->ev_ring_full[slot], 0));
-        RT(cudaMemcpyAsync(store + e->img_off[sl.p0], e->ring[slot], sl.bytes, cudaMemcpyDefault, cstream));
+        RT(cudaMemcpyAsync(store + e->img_off[pages[sl.k0]], e->ring[slot], sl.bytes, cudaMemcpyDefault, cstream));
         if (c > 0) RT(cudaStreamWaitEvent(cstream, e->ev_ring_free[(c - 1) % e->n_ring], 0));  // same chaining as below
         RT(cudaEventRecord(e->ev_ring_free[slot], cstream));
         ++copy_ops;
-        rc = publish_consumed((uint64_t)(sl.p0 + sl.np) * FMA_PAGE_BYTES, cstream);
+        // every image byte below the last page of this slot is in the store: coded just now, or kept from the last wake
+        rc = publish_consumed((uint64_t)(pages[sl.k0 + sl.nk - 1] + 1) * FMA_PAGE_BYTES, cstream);
         if (rc != FMA_OK) return rc;
+        last_stream = cstream;
     }
+    if (pipe.subset) rc = publish_consumed(W, last_stream);  // the clean tail of the image needs no copy
     return rc;
 }
 
@@ -450,8 +465,9 @@ int do_sleep(fma_engine_t* e, uint64_t offload_mask, int tier, uint32_t flags) {
         s.digest_valid = false;
     }
     // INCREMENTAL sleep: does the host store still hold exactly this image?  One K3 pass over the device copy decides.
-    bool clean = false, partial = false, digests_known = false;
-    std::vector<Extent> dirty;  // segments whose device bytes differ from the copy in the store
+    bool clean = false, partial = false, partial_packed = false, digests_known = false;
+    std::vector<Extent> dirty;        // segments whose device bytes differ from the copy in the store
+    std::vector<size_t> dirty_pages;  // their image pages (PACKED image)
     if (shadows_match && W && W == e->shadow_image_bytes && e->host.cap >= e->shadow_store_bytes) {
         RT(cudaDeviceSynchronize());  // the caller's streams may still be writing weights
         std::vector<size_t> idx;
@@ -473,15 +489,35 @@ int do_sleep(fma_engine_t* e, uint64_t offload_mask, int tier, uint32_t flags) {
         // a few changed segments (an adapter, fp8 KV scales reset after wake, one synced layer): only they cross the link, into
         // their old place in the kept image.  Not for PACKED images: a re-coded page may change size and move its neighbours.
         partial = !clean && !e->shadow_packed && 2 * dirty_bytes <= W && !e->host.shared;  // a shared image is read-only
+        // PACKED image: a changed page can go back to its old place only if its stored size stays what it was (K4p on those pages)
+        if (!clean && e->shadow_packed && e->cfg.pack && 2 * dirty_bytes <= W && !e->host.shared && resolve_mode(e, tier) == FMA_MODE_STAGED) {
+            for (const Extent& x : dirty)
+                for (size_t o = 0; o < x.bytes; o += FMA_PAGE_BYTES) dirty_pages.push_back((size_t)((x.packed_off + o) / FMA_PAGE_BYTES));
+            rc = ensure_tables(e, dirty_pages.size());
+            if (rc != FMA_OK) return rc;
+            rc = ensure_pack_bufs(e, std::max<size_t>(dirty_pages.size(), W / FMA_PAGE_BYTES));
+            if (rc != FMA_OK) return rc;
+            size_t k = 0;
+            for (const Extent& x : dirty)
+                for (size_t o = 0; o < x.bytes; o += FMA_PAGE_BYTES) e->h_tab[k++] = (uint64_t)x.va + o;
+            RT(cudaMemcpyAsync(e->d_tab, e->h_tab, k * sizeof(uint64_t), cudaMemcpyHostToDevice, e->ks));
+            RT(fma_k_launch_pack_probe(e->d_tab, (uint32_t)k, e->d_psize, e->ks));
+            RT(cudaMemcpyAsync(e->h_psize, e->d_psize, k * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->ks));
+            RT(cudaStreamSynchronize(e->ks));
+            e->st.total_kernel_launches += 1;
+            partial_packed = dirty_pages.size() <= e->img_bytes.size();
+            for (size_t q = 0; q < k && partial_packed; ++q)
+                partial_packed = dirty_pages[q] < e->img_bytes.size() && e->h_psize[q] == e->img_bytes[dirty_pages[q]];
+        }
     }
     if (clean) flags |= kFlagAdopt;                  // release the device side only: not a byte moves
-    else if (!partial) invalidate_shadows(e);        // this sleep rewrites the store (or leaves the host tier alone: be conservative)
+    else if (!partial && !partial_packed) invalidate_shadows(e);  // this sleep rewrites the store (or leaves the host tier alone: be conservative)
     int mode = partial ? FMA_MODE_DIRECT : resolve_mode(e, tier);
     if (W && !(flags & kFlagAdopt) && mode == FMA_MODE_STAGED && ensure_ring(e, W) != FMA_OK) mode = FMA_MODE_DIRECT;  // HBM too full for a ring
     // PACKED image (config.pack): decide per page what its stored form is BEFORE the store is sized
     bool packed = false;
     uint64_t Wp = W;
-    if (clean) {  // the image in the store, its form and its page table stay as they are
+    if (clean || partial_packed) {  // the image in the store, its form and its page table stay as they are
         packed = e->shadow_packed;
         Wp = e->shadow_store_bytes;
         e->image_packed = packed;
@@ -613,7 +649,10 @@ int do_sleep(fma_engine_t* e, uint64_t offload_mask, int tier, uint32_t flags) {
         rc = timer.begin();
         if (rc != FMA_OK) return rc;
         SleepPipe pipe{e, partial ? dirty : ex, W, tier, store, kt, copy_ops, publish_consumed};
-        if (partial) {  // only the changed segments move; everything below each of them is in the store already
+        if (partial_packed) {  // only the changed segments' pages are re-coded, each into its old place
+            pipe.subset = &dirty_pages;
+            rc = sleep_staged_packed(pipe);
+        } else if (partial) {  // only the changed segments move; everything below each of them is in the store already
             rc = sleep_direct(pipe);
             if (rc == FMA_OK) rc = publish_consumed(W, e->cs[0]);  // cs[0] has joined the other streams after the last extent
         } else if (mode == FMA_MODE_DIRECT) rc = sleep_direct(pipe);
@@ -674,6 +713,7 @@ int do_sleep(fma_engine_t* e, uint64_t offload_mask, int tier, uint32_t flags) {
     {
         uint64_t copied = 0;  // what this sleep moved into the store
         if (partial) for (const Extent& x : dirty) copied += x.bytes;
+        else if (partial_packed) for (size_t p : dirty_pages) copied += e->img_bytes[p];
         else if (!adopt) copied = Wp;
         e->st.sleep_bytes_copied = copied;
     }

@@ -848,14 +848,17 @@ def test_packed_random_tables_and_wake_orders(built, oracle, seed):
         eng.set_option("pack", 1)
         eng.set_option("chunk_bytes", int(rng.choice([2, 4, 6, 512])) << 20)
         eng.set_option("ring_slots", int(rng.integers(2, 5)))
-        eng.set_option("incremental", int(rng.integers(0, 2)))
+        incremental = int(rng.integers(0, 2))
+        eng.set_option("incremental", incremental)
         for cycle in range(3):
             eng.sleep(offload, flags=L.FMA_FLAG_VERIFY if cycle == 0 else 0)
             st = eng.stats()
             W = sum(len(k) * PAGE for t, k, _ in segs if t in offload)
             packed_total = sum(stored_size[x] for t, k, _ in segs if t in offload for x in k)
             assert st["sleep_bytes_offloaded"] == W
-            if W and packed_total * 100 <= W * 95:
+            if incremental and cycle > 0:        # a partial sleep keeps the form the kept image has, whatever a fresh plan would choose
+                assert st["image_store_bytes"] == (packed_total if st["image_packed"] else W)
+            elif W and packed_total * 100 <= W * 95:
                 assert st["image_packed"] == 1 and st["image_store_bytes"] == packed_total
             else:
                 assert st["image_packed"] == 0 and st["image_store_bytes"] == W
@@ -873,6 +876,12 @@ def test_packed_random_tables_and_wake_orders(built, oracle, seed):
                     assert eng.read(i, len(kinds) * PAGE) == b"".join(pool[k].tobytes() for k in kinds), (seed, cycle, i)
                 else:                                                   # discarded: mapped again, contents undefined -> rewrite
                     eng.write(i, b"".join(pool[k].tobytes() for k in kinds))
+            if rng.random() < 0.5:                                      # a segment gets new page kinds while awake (incremental: partial / full)
+                j = int(rng.integers(0, len(segs)))
+                tag, kinds, ptr = segs[j]
+                kinds = [int(k) for k in rng.integers(0, len(pool), len(kinds))]
+                segs[j] = (tag, kinds, ptr)
+                eng.write(j, b"".join(pool[k].tobytes() for k in kinds))
 
 
 _NEW_THIS_ROUND = pytest.mark.skipif(os.environ.get("FMA_HOSTSIM") != "1" and os.environ.get("FMA_TEST_NEW_ON_GPU") != "1",
@@ -997,8 +1006,23 @@ def test_incremental_sleep_moves_nothing_when_the_weights_did_not_change(engine,
     i0 = sorted(ref)[1]                            # one segment rewritten while awake
     ref[i0] = ref[i0].copy(); ref[i0][12345] ^= 0xFF
     engine.write(i0, ref[i0].tobytes())
-    if pack:
-        cycle(False)                               # packed image: a changed page may change size -> full sleep
+    if pack:                                       # packed image: the changed segment's pages keep their stored size -> re-coded in place
+        ops0 = engine.stats()["total_copy_ops"]
+        engine.sleep(["weights"])
+        st = engine.stats()
+        n_pg = table[i0].bytes // PAGE
+        assert st["image_packed"] == 1 and st["sleep_bytes_copied"] == n_pg * L.FMA_PACKED_PAGE_BYTES and 1 <= st["total_copy_ops"] - ops0 <= n_pg
+        off, nb = engine.image_pages()
+        want_pages = [oracle.pack_page(ref[i][o:o + PAGE]) for i in sorted(ref) for o in range(0, table[i].bytes, PAGE)]
+        img = _host_image(engine)
+        assert all(_same_stored_page(img[o:o + n], w) for o, n, w in zip(off, nb, want_pages))     # the whole kept image is current
+        engine.wake(None, flags=L.FMA_FLAG_VERIFY)
+        for i in ref:
+            assert engine.read(i, table[i].bytes) == ref[i].tobytes()
+        # a page that stops coding (noise) changes its stored size: that sleep is a full one
+        noisy = ref[i0].copy(); noisy[:PAGE] = np.random.default_rng(1).integers(0, 256, PAGE, dtype=np.uint8)
+        ref[i0] = noisy; engine.write(i0, noisy.tobytes())
+        cycle(False)
     else:                                          # plain image: only the changed segment crosses the link, into its old place
         engine.set_option("chunk_bytes", 2 << 20)
         ops0 = engine.stats()["total_copy_ops"]
