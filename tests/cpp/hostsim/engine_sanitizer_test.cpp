@@ -225,6 +225,12 @@ int main() {
                 else alloc_one();
             }
             if (live.empty()) alloc_one();
+            if (rnd(3) == 0) {  // a segment is rewritten while awake (incremental: only it crosses the link next time)
+                Live& l = live[rnd((uint32_t)live.size())];
+                OK(fma_fill_segment(c, index_of(l.p), 900 + rnd(1000), rnd(1u << 20)));
+                OK(fma_digest_segment(c, index_of(l.p), &l.digest));
+                l.defined = true;
+            }
             const int modes[3] = {FMA_MODE_DIRECT, FMA_MODE_STAGED, FMA_MODE_KERNEL};
             OK(fma_set_option(c, "mode", modes[rnd(3)]));
             OK(fma_set_option(c, "chunk_bytes", (int64_t)(1 + rnd(3)) * 2 * P));
