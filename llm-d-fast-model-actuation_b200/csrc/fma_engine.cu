@@ -376,7 +376,7 @@ void invalidate_shadows(fma_engine_t* e) {
 int host_store_reserve(fma_engine_t* e, size_t bytes) {
     bytes = round_up(std::max<size_t>(bytes, FMA_PAGE_BYTES), FMA_PAGE_BYTES);
     if (e->host.base && e->host.cap >= bytes) return FMA_OK;
-    invalidate_shadows(e);  // a new store starts empty
+    if (e->shadow_tier == FMA_TIER_HOST) invalidate_shadows(e);  // a new store starts empty
     host_store_free(e->host);
     const double t0 = now_s();
     HostStore h;
@@ -455,6 +455,7 @@ int host_store_reserve(fma_engine_t* e, size_t bytes) {
 
 int park_release(fma_engine_t* e) {
     if (!e->park.va) return FMA_OK;
+    if (e->shadow_tier != FMA_TIER_HOST) invalidate_shadows(e);  // the parking buffer held the kept image
     cudaDeviceSynchronize();
     g_drv.MemUnmap(e->park.va, e->park.cap);
     g_drv.MemRelease(e->park.handle);

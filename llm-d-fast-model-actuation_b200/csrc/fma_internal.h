@@ -210,6 +210,7 @@ struct fma_engine {
     // still holds the image.  The next sleep digests the segments on the device (K3, one HBM read) and, if every offloaded
     // segment still has the digest and the image offset of that copy, releases the device side WITHOUT moving a byte.
     int incremental = 0;
+    int shadow_tier = FMA_TIER_HOST;  // the store the shadows live in (host store, or the peer / local parking buffer)
     bool shadow_packed = false;       // form / size of the image the shadows belong to (img_off / img_bytes are kept for it)
     uint64_t shadow_store_bytes = 0;
     uint64_t shadow_image_bytes = 0;

@@ -448,7 +448,10 @@ int do_sleep(fma_engine_t* e, uint64_t offload_mask, int tier, uint32_t flags) {
     });
     std::vector<Extent> ex;
     uint64_t W = 0, discarded = 0;
-    bool shadows_match = e->incremental && tier == FMA_TIER_HOST && !(flags & kFlagAdopt) && e->host.base != nullptr;
+    // the store that would hold the kept image: the host store, or the parking buffer of the same (peer / local) tier
+    const bool kept_store = tier == FMA_TIER_HOST ? e->host.base != nullptr
+                                                  : (e->park.va != 0 && (tier == FMA_TIER_LOCAL ? e->park.device == e->device : e->park.device != e->device));
+    bool shadows_match = e->incremental && tier == e->shadow_tier && !(flags & kFlagAdopt) && kept_store;
     std::vector<uint64_t> shadow_digest;  // digest of the copy the store holds, per extent
     for (size_t i : by_addr) {
         Segment& s = e->segs[i];
@@ -468,7 +471,7 @@ int do_sleep(fma_engine_t* e, uint64_t offload_mask, int tier, uint32_t flags) {
     bool clean = false, partial = false, partial_packed = false, digests_known = false;
     std::vector<Extent> dirty;        // segments whose device bytes differ from the copy in the store
     std::vector<size_t> dirty_pages;  // their image pages (PACKED image)
-    if (shadows_match && W && W == e->shadow_image_bytes && e->host.cap >= e->shadow_store_bytes) {
+    if (shadows_match && W && W == e->shadow_image_bytes && (tier == FMA_TIER_HOST ? e->host.cap : e->park.cap) >= e->shadow_store_bytes) {
         RT(cudaDeviceSynchronize());  // the caller's streams may still be writing weights
         std::vector<size_t> idx;
         for (const Extent& x : ex) idx.push_back(x.seg_index);
@@ -488,9 +491,10 @@ int do_sleep(fma_engine_t* e, uint64_t offload_mask, int tier, uint32_t flags) {
         clean = dirty.empty();
         // a few changed segments (an adapter, fp8 KV scales reset after wake, one synced layer): only they cross the link, into
         // their old place in the kept image.  Not for PACKED images: a re-coded page may change size and move its neighbours.
-        partial = !clean && !e->shadow_packed && 2 * dirty_bytes <= W && !e->host.shared;  // a shared image is read-only
+        // (partial sleeps are a host-tier refinement; in a parking tier a changed image is simply parked again)
+        partial = tier == FMA_TIER_HOST && !clean && !e->shadow_packed && 2 * dirty_bytes <= W && !e->host.shared;  // a shared image is read-only
         // PACKED image: a changed page can go back to its old place only if its stored size stays what it was (K4p on those pages)
-        if (!clean && e->shadow_packed && e->cfg.pack && 2 * dirty_bytes <= W && !e->host.shared && resolve_mode(e, tier) == FMA_MODE_STAGED) {
+        if (tier == FMA_TIER_HOST && !clean && e->shadow_packed && e->cfg.pack && 2 * dirty_bytes <= W && !e->host.shared && resolve_mode(e, tier) == FMA_MODE_STAGED) {
             for (const Extent& x : dirty)
                 for (size_t o = 0; o < x.bytes; o += FMA_PAGE_BYTES) dirty_pages.push_back((size_t)((x.packed_off + o) / FMA_PAGE_BYTES));
             rc = ensure_tables(e, dirty_pages.size());
@@ -565,7 +569,7 @@ int do_sleep(fma_engine_t* e, uint64_t offload_mask, int tier, uint32_t flags) {
     RT(cudaDeviceSynchronize());
 
     const bool adopt = (flags & kFlagAdopt) != 0;  // the store already holds the image: release the device side only
-    if (((flags & FMA_FLAG_VERIFY) || (e->incremental && tier == FMA_TIER_HOST)) && W && !adopt && !digests_known) {  // incremental: digests seed the next sleep's check
+    if (((flags & FMA_FLAG_VERIFY) || e->incremental) && W && !adopt && !digests_known) {  // incremental: digests seed the next sleep's check
         std::vector<size_t> idx;
         for (const Extent& x : ex) idx.push_back(x.seg_index);
         std::vector<uint64_t> dg;

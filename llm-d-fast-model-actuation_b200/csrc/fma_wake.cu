@@ -543,11 +543,12 @@ int do_wake(fma_engine_t* e, uint64_t tag_mask, uint32_t flags) {
         for (size_t i : with_backup) {  // data.cpu_backup_tensor = None (cumem.py:249)
             Segment& s = e->segs[i];
             // INCREMENTAL sleep: the host store keeps these bytes; remember where, together with their digest
-            s.shadow_off = (tier == FMA_TIER_HOST && s.digest_valid && verify_rc == FMA_OK) ? s.packed_off : kNoOffset;
+            s.shadow_off = (s.digest_valid && verify_rc == FMA_OK) ? s.packed_off : kNoOffset;   // host store or parking buffer: both outlive the wake
             s.has_backup = false;
             s.packed_off = kNoOffset;
         }
-        if (tier == FMA_TIER_HOST && W) {
+        if (W) {
+            e->shadow_tier = tier;
             e->shadow_packed = e->image_packed;
             e->shadow_store_bytes = e->image_store_bytes;
             e->shadow_image_bytes = e->image_bytes;

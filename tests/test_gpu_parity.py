@@ -1053,6 +1053,15 @@ def test_incremental_sleep_moves_nothing_when_the_weights_did_not_change(engine,
     cycle(False); cycle(True)
     engine.sleep(["weights"], tier=L.FMA_TIER_LOCAL); engine.wake(None)                # another tier in between: conservative
     cycle(False); cycle(True)
+    # the parking tiers keep their image across a wake too: the second sleep into the same tier moves nothing over NVLink
+    for rep in range(3):
+        ops0 = engine.stats()["total_copy_ops"]
+        engine.sleep(["weights"], tier=L.FMA_TIER_LOCAL)
+        st = engine.stats()
+        assert (st["total_copy_ops"] == ops0 and st["sleep_bytes_copied"] == 0) if rep else st["total_copy_ops"] > ops0
+        engine.wake(None, flags=L.FMA_FLAG_VERIFY)
+        for i in ref:
+            assert engine.read(i, table[i].bytes) == ref[i].tobytes()
     engine.set_option("incremental", 0)
     cycle(False)
 
