@@ -82,6 +82,8 @@ def test_bench_packed_image_child_runs_against_the_host_simulated_engine(hostsim
     out = json.loads(r.stdout.strip().splitlines()[-1])
     assert out["bit_exact"] is True and out["image_packed"] is True
     assert 0.75 < out["stored_frac"] < 0.80 and out["e2e_effective_gbs"] > out["e2e_link_gbs"] > 0
+    inc = out["incremental_sleep"]
+    assert inc["bit_exact"] is True and inc["sleep_bytes_copied"][0] > 0 and inc["sleep_bytes_copied"][1:] == [0, 0, 0]
 
 
 def test_vllm_loader_streaming_core_against_the_host_simulated_engine(hostsim_lib, tmp_path):
