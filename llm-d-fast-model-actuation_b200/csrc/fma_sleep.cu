@@ -490,8 +490,8 @@ int do_sleep(fma_engine_t* e, uint64_t offload_mask, int tier, uint32_t flags) {
         digests_known = true;
         clean = dirty.empty();
         // a few changed segments (an adapter, fp8 KV scales reset after wake, one synced layer): only they cross the link, into
-        // their old place in the kept image.  Not for PACKED images: a re-coded page may change size and move its neighbours.
-        // (partial sleeps are a host-tier refinement; in a parking tier a changed image is simply parked again)
+        // their old place in the kept image (partial sleeps are a host-tier refinement; in a parking tier a changed image is
+        // simply parked again)
         partial = tier == FMA_TIER_HOST && !clean && !e->shadow_packed && 2 * dirty_bytes <= W && !e->host.shared;  // a shared image is read-only
         // PACKED image: a changed page can go back to its old place only if its stored size stays what it was (K4p on those pages)
         if (tier == FMA_TIER_HOST && !clean && e->shadow_packed && e->cfg.pack && 2 * dirty_bytes <= W && !e->host.shared && resolve_mode(e, tier) == FMA_MODE_STAGED) {
@@ -512,6 +512,7 @@ int do_sleep(fma_engine_t* e, uint64_t offload_mask, int tier, uint32_t flags) {
             partial_packed = dirty_pages.size() <= e->img_bytes.size();
             for (size_t q = 0; q < k && partial_packed; ++q)
                 partial_packed = dirty_pages[q] < e->img_bytes.size() && e->h_psize[q] == e->img_bytes[dirty_pages[q]];
+            if (partial_packed && ensure_ring(e, W) != FMA_OK) partial_packed = false;  // no HBM for a ring: full sleep through the plain path
         }
     }
     if (clean) flags |= kFlagAdopt;                  // release the device side only: not a byte moves
