@@ -995,8 +995,9 @@ def test_incremental_sleep_moves_nothing_when_the_weights_did_not_change(engine,
         assert (moved == 0 and st["copy_ops"] == 0 and st["kernel_launches"] == 0) if expect_clean else moved > 0, (expect_clean, moved)
         assert st["sleep_bytes_copied"] == (0 if expect_clean else st["image_store_bytes"])
         engine.wake(None, flags=L.FMA_FLAG_VERIFY)
+        got = engine.digest_all(["weights"])                         # K3 == oracle digest of the expected bytes (cheaper than reading back)
         for i in ref:
-            assert engine.read(i, table[i].bytes) == ref[i].tobytes()
+            assert got[i] == oracle.digest(ref[i]), i
         assert [s.va for s in engine.segments()] == ptrs
 
     cycle(False)                                   # first sleep: the store is empty
