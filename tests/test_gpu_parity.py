@@ -1137,3 +1137,61 @@ def test_shared_images_are_read_only_for_everybody(engine, oracle, monkeypatch):
             assert engine.read(i, table[i].bytes) == changed[i].tobytes()
     finally:
         os.close(fd)
+
+
+@_NEW_THIS_ROUND
+@pytest.mark.parametrize("seed", list(range(1, int(os.environ.get("FMA_TEST_SEEDS", "7")))))
+def test_random_swaps_and_cold_loads_between_two_engines(built, oracle, tmp_path, seed):
+    """Two engines on one GPU, seeded random options (modes, ring shapes, pack, incremental) and a random sequence of hot swaps,
+    plain cycles and cold loads of random byte ranges of a file: after every step the awake model has the bytes it should have."""
+    import fma_b200
+
+    L = _L()
+    rng = np.random.default_rng(5000 + seed)
+    blob = rng.integers(0, 256, 24 * PAGE + 4096, dtype=np.uint8)
+    path = str(tmp_path / "blob.bin")
+    blob.tofile(path)
+    with fma_b200.Engine(0) as A, fma_b200.Engine(0) as B:
+        models = []
+        for eng in (A, B):
+            data = []
+            for _ in range(int(rng.integers(2, 6))):
+                n = int(rng.integers(1, 5)) * PAGE
+                eng.alloc(n, "weights")
+                d = rng.integers(0, 256, n, dtype=np.uint8)
+                eng.write(len(data), d.tobytes()); data.append(d)
+            eng.alloc(2 * PAGE, "kv_cache")
+            for key, val in (("mode", int(rng.choice([L.FMA_MODE_AUTO, L.FMA_MODE_DIRECT, L.FMA_MODE_STAGED]))), ("chunk_bytes", int(rng.choice([2, 4, 6])) << 20),
+                             ("ring_slots", int(rng.integers(2, 4))), ("pack", int(rng.integers(0, 2))), ("incremental", int(rng.integers(0, 2)))):
+                eng.set_option(key, val)
+            models.append(data)
+
+        def check(eng, data):
+            assert not eng.is_sleeping()
+            got = eng.digest_all(["weights"])
+            assert [got[i] for i in range(len(data))] == [oracle.digest(d) for d in data]
+
+        B.sleep(["weights"])
+        awake, asleep = 0, 1
+        engs = (A, B)
+        for step in range(8):
+            r = rng.random()
+            if r < 0.5:                                                   # hot swap: the awake model sleeps while the other wakes
+                engs[awake].swap_out_for(engs[asleep], offload_tags=["weights"])
+                awake, asleep = asleep, awake
+            elif r < 0.75:                                                # plain cycle of the awake model
+                engs[awake].sleep(["weights"]); engs[awake].wake(None)
+            else:                                                         # cold load of a random file range into one of its segments
+                k = int(rng.integers(0, len(models[awake])))
+                seg = engs[awake].segment(k)
+                nbytes = int(rng.integers(1, seg.bytes // 4096 + 1)) * 4096
+                foff = int(rng.integers(0, (blob.size - nbytes) // 16 + 1)) * 16
+                doff = int(rng.integers(0, (seg.bytes - nbytes) // 16 + 1)) * 16
+                engs[awake].set_option("load_chunk_bytes", int(rng.choice([1, 3])) << 20)
+                engs[awake].load_file(path, [(foff, nbytes, seg.va + doff)])
+                models[awake][k] = models[awake][k].copy()
+                models[awake][k][doff:doff + nbytes] = blob[foff:foff + nbytes]
+            check(engs[awake], models[awake])
+            assert engs[asleep].is_sleeping()
+        engs[asleep].wake(None)
+        check(engs[asleep], models[asleep])
