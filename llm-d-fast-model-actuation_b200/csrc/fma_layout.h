@@ -85,11 +85,13 @@ struct Run {
 
 // Group sleeping segments (already sorted by (arena, va)) into maximal VA-contiguous runs of one arena and one backup
 // state; order: runs with a backup first, by image offset (they gate the copy pipeline), remap-only runs after them.
-inline std::vector<Run> plan_runs(const std::vector<SegView>& sorted, bool merge) {
+// piece_bytes > 0 cuts backed-up runs into pieces of at least that size (at segment boundaries): more, smaller mappings, so
+// that a slow or stalled driver call delays only what lies behind it while the copy pipeline works on the pieces before it.
+inline std::vector<Run> plan_runs(const std::vector<SegView>& sorted, bool merge, size_t piece_bytes = 0) {
     std::vector<Run> runs;
     for (const SegView& s : sorted) {
         if (merge && !runs.empty() && runs.back().arena == s.arena && runs.back().va + runs.back().bytes == s.va &&
-            runs.back().has_backup == s.has_backup) {
+            runs.back().has_backup == s.has_backup && !(piece_bytes && s.has_backup && runs.back().bytes >= piece_bytes)) {
             runs.back().bytes += s.bytes;
             runs.back().segs.push_back(s.index);
         } else {

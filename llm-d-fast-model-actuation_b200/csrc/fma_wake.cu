@@ -324,7 +324,8 @@ int do_wake(fma_engine_t* e, uint64_t tag_mask, uint32_t flags) {
             const Segment& s = e->segs[i];
             view.push_back(fma_layout::SegView{i, s.arena, (uint64_t)s.va, s.bytes, s.has_backup, s.packed_off});
         }
-        runs = fma_layout::plan_runs(view, env_int("FMA_MERGE_RUNS", 1) != 0);
+        // FMA_MAP_PIECE_MIB (default 0 = whole runs): map backed-up runs in pieces of about that size
+        runs = fma_layout::plan_runs(view, env_int("FMA_MERGE_RUNS", 1) != 0, (size_t)std::max(env_int("FMA_MAP_PIECE_MIB", 0), 0) << 20);
     }
     const int tier = e->image_tier;
     int mode = resolve_mode(e, tier);
@@ -350,10 +351,13 @@ int do_wake(fma_engine_t* e, uint64_t tag_mask, uint32_t flags) {
             Arena& a = e->arenas[r0.arena];
             const size_t slot = ring_slot_for(e, w_bytes);
             const size_t total = slot * ring_slots_for(e);
-            const bool at_top = r0.has_backup && (r0.va + r0.bytes == a.base + a.top) && a.top + total <= a.cap;
+            // end of the VA-contiguous chain of backed-up runs that starts with the first one (one run, or its pieces)
+            uint64_t chain_end = r0.va + r0.bytes;
+            for (size_t k = 1; k < runs.size() && runs[k].has_backup && runs[k].arena == r0.arena && runs[k].va == chain_end; ++k) chain_end += runs[k].bytes;
+            const bool at_top = r0.has_backup && (chain_end == a.base + a.top) && a.top + total <= a.cap;
             if (at_top && env_int("FMA_RING_ATTACH", 1) != 0 && ensure_ring_events(e, ring_slots_for(e)) == FMA_OK) {
                 Run rr;
-                rr.va = r0.va + r0.bytes; rr.bytes = total; rr.arena = r0.arena; rr.has_backup = true; rr.first_off = 0;  // no segments
+                rr.va = chain_end; rr.bytes = total; rr.arena = r0.arena; rr.has_backup = true; rr.first_off = 0;  // no segments
                 a.top += total;  // later allocations of this tag land after the ring; the range returns at unmap
                 e->n_ring = ring_slots_for(e);
                 e->ring_slot_bytes = slot;

@@ -10,6 +10,10 @@ mkdir -p "$out"
 # 1. isolated K4p / K4 / K5 throughput, both variants
 timeout 300 python scripts/pack_sweep.py > "$out/pack_sweep.log" 2>&1; echo "pack sweep rc=$?" | tee -a "$out/status_profiles.txt"
 
+# 1b. piecewise mapping of the weights run: per-step wake latencies with and without (24 steps each)
+timeout 400 python bench.py --steps 24 --warmup 3 --no-cpu-baseline --packed-extra 0 > "$out/bench_24_whole_runs.json" 2> "$out/bench_pieces.err"
+timeout 400 env FMA_MAP_PIECE_MIB=2048 python bench.py --steps 24 --warmup 3 --no-cpu-baseline --packed-extra 0 > "$out/bench_24_pieces_2g.json" 2>> "$out/bench_pieces.err"; echo "bench pieces rc=$?" | tee -a "$out/status_profiles.txt"
+
 # 2. VMM granularity / VA alignment probe (seconds)
 timeout 120 python scripts/gran_probe.py > "$out/gran_probe.log" 2>&1
 

@@ -86,6 +86,13 @@ static void test_plan_runs() {
     auto r3 = plan_runs(x, true);
     assert(r3.size() == 3 && r3[0].segs[0] == 1 && r3[1].segs[0] == 3 && r3[2].segs[0] == 2);
     assert(plan_runs({}, true).empty());
+    // pieces: a contiguous backed-up run of 4+2+6+3 pages cut at >= 5 pages -> (4+2), (6), (3); the remap-only run stays whole
+    std::vector<SegView> y = {{1, 0, 0, 4 * P, true, 0}, {2, 0, 4 * P, 2 * P, true, 4 * P}, {3, 0, 6 * P, 6 * P, true, 6 * P},
+                              {4, 0, 12 * P, 3 * P, true, 12 * P}, {5, 1, 500 * P, 9 * P, false, 0}, {6, 1, 509 * P, 9 * P, false, 0}};
+    auto r4 = plan_runs(y, true, 5 * P);
+    assert(r4.size() == 4 && r4[0].bytes == 6 * P && r4[1].bytes == 6 * P && r4[2].bytes == 3 * P && !r4[3].has_backup && r4[3].bytes == 18 * P);
+    assert(r4[0].va + r4[0].bytes == r4[1].va && r4[1].va + r4[1].bytes == r4[2].va && r4[1].segs == std::vector<size_t>({3}));
+    assert(plan_runs(y, true, 0).size() == 2);
 }
 
 int main() {
