@@ -29,9 +29,13 @@ their PUBLISHED behaviour:
 PyYAML's emitter is a port of the same libyaml emitter yaml.v2's ``emitterc.go`` was ported from, so it is driven here
 event by event (bypassing PyYAML's own resolver and representer, whose YAML-1.1 rules differ from yaml.v2's).
 
-**Parity unpinned**: the reference has no test that fixes an expected ID or YAML text for any input
-(SURVEY.md §8f-2); only a live controller could confirm byte equality.  tests/test_isc.py pins this restatement
-against hand-derived expectations of the published rules.
+Pinning.  The MARSHALLER is pinned against the reference's own files: its three generated CRDs (config/crd/*.yaml, 8834
+lines written by controller-gen v0.19.0 through the same sigs.k8s.io/yaml stack: sorted keys, 80-column folding, quoting,
+literal blocks, indentless sequences) are parsed and re-emitted by ``go_yaml_marshal`` byte for byte
+(tests/test_isc.py::test_marshal_reproduces_the_references_generated_crds, run where /root/reference exists).  The ID
+composition around it (what is hashed, separator, base64 flavour, "I"/"i" wrapping) follows inference-server.go:801-829
+line by line but stays **unpinned**: the reference has no test or document that fixes an expected ID for any input
+(SURVEY.md §8f-2); only a live controller could confirm it.
 """
 from __future__ import annotations
 
@@ -180,7 +184,12 @@ def _scalar(text: str, style: Optional[str]) -> _ev.ScalarEvent:
 
 
 def _emit_value(out: list, v) -> None:
-    if isinstance(v, Mapping):
+    if isinstance(v, (list, tuple)):
+        out.append(_ev.SequenceStartEvent(anchor=None, tag=None, implicit=True, flow_style=not v))
+        for x in v:
+            _emit_value(out, x)
+        out.append(_ev.SequenceEndEvent())
+    elif isinstance(v, Mapping):
         out.append(_ev.MappingStartEvent(anchor=None, tag=None, implicit=True, flow_style=not v))
         for k in sorted_keys(v.keys()):
             _emit_value(out, k)
@@ -190,6 +199,8 @@ def _emit_value(out: list, v) -> None:
         out.append(_scalar("true" if v else "false", None))
     elif isinstance(v, int):
         out.append(_scalar(str(v), None))
+    elif isinstance(v, float):
+        out.append(_scalar(repr(v), None))
     elif v is None:
         out.append(_scalar("null", None))
     elif isinstance(v, str):
@@ -205,7 +216,7 @@ def _emit_value(out: list, v) -> None:
 
 
 def go_yaml_marshal(obj: Mapping) -> bytes:
-    """What ``sigs.k8s.io/yaml.Marshal`` writes for a JSON-object-shaped value (maps of strings / ints / maps)."""
+    """What ``sigs.k8s.io/yaml.Marshal`` writes for a JSON-shaped value (maps, lists, strings, ints, bools, null)."""
     evs: list = [_ev.StreamStartEvent(encoding=None), _ev.DocumentStartEvent(explicit=False)]
     _emit_value(evs, obj)
     evs += [_ev.DocumentEndEvent(explicit=False), _ev.StreamEndEvent()]
