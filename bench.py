@@ -26,6 +26,8 @@ config[2] (Llama-3-70B TP=8 per-rank shard, every rank concurrently, no collecti
   --contents bf16   fill both arms with bf16 U(-1e-3, 1e-3) (vLLM's dummy weights) instead of incompressible bytes
   --pack 1          this arm sleeps / wakes with the PACKED image (e2e.link_bytes_per_step = bytes that crossed the link)
   --incremental 1   sleeps whose weights still match the image in the host store release the device side without a copy
+  --extras packed,incremental   (any N, opt-in) after the main line, on the same engines: bf16 refill, PACKED cycles, then
+                    INCREMENTAL cycles, aggregated like the main line (reported under `extras`)
 
 Synthetic data: counter-based splitmix64 bytes (seed 1234 + rank); the working set (>= 15 GiB per rank) is far
 larger than the 126 MB L2, so no L2 flush is needed between iterations.
@@ -227,6 +229,10 @@ def run_ours(args) -> None:
     if args.peer_extra and world > 1 and tier == L.FMA_TIER_HOST:
         peer = measure_peer(eng, L, Wb, local_rank, world, barrier, max_over_ranks, before, steps=3)
 
+    extras = None
+    if args.extras and tier == L.FMA_TIER_HOST:
+        extras = measure_extras(args, eng, L, table, Wb, rank, world, barrier, max_over_ranks, sum_over_ranks, torch, group)
+
     if rank == 0:
         peak, peak_src = hbm_peak()
         achieved = (k2_b / k2_s / 1e9) if k2_s > 0 else None
@@ -282,6 +288,8 @@ def run_ours(args) -> None:
         }
         if peer:
             out["peer_tier"] = peer
+        if extras:
+            out["extras"] = extras
         if world == 1:
             eng.close()   # everything above is measured: give the HBM and the pinned store back before the baseline / extra processes run
         if world == 1 and not args.no_cpu_baseline:
@@ -413,6 +421,51 @@ def pcie_ceiling_gbs(torch, nbytes: int = 2 << 30, reps: int = 3) -> float:
         best = max(best, nbytes / e0.elapsed_time(e1) / 1e6)
     del h, d
     return best
+
+
+def measure_extras(args, eng, L, table, Wb, rank, world, barrier, max_over_ranks, sum_over_ranks, torch, group, steps=4):
+    """--extras packed,incremental (opt-in; one torchrun then measures everything — an N=8 box is charged 8x): on the SAME
+    engines, after the main measurement, every rank refills its shard with bf16 dummy weights and cycles with the PACKED image,
+    then with INCREMENTAL sleep.  Aggregates like the main line: sum of bytes over ranks / max over ranks of the mean time."""
+    out = {}
+    try:
+        from fma_b200 import ranks as R
+
+        fill_weights(eng, table, R.shard_seed(rank), "bf16", torch)
+        before = eng.digest_all(["weights"])
+        mean = lambda xs: sum(xs) / len(xs)
+        W_total = sum_over_ranks(float(Wb))
+        if "packed" in args.extras:
+            eng.set_option("pack", 1)
+            rows = []
+            for i in range(steps + 1):
+                barrier(); eng.sleep(["weights"]); s1 = eng.stats()
+                barrier(); eng.wake(None); s2 = eng.stats()
+                if i:
+                    rows.append((s1, s2))
+            wake = max_over_ranks(mean([r[1]["wake_seconds"] for r in rows]))
+            sleep = max_over_ranks(mean([r[0]["sleep_seconds"] for r in rows]))
+            stored = sum_over_ranks(float(rows[-1][0]["image_store_bytes"]))
+            out["packed"] = {"wake_latency_s": round(wake, 5), "sleep_latency_s": round(sleep, 5), "stored_frac": round(stored / W_total, 4),
+                             "e2e_effective_gbs": round(W_total / wake / 1e9, 2), "e2e_link_gbs": round(stored / wake / 1e9, 2),
+                             "image_packed": bool(rows[-1][0]["image_packed"]), "bit_exact": bool(group.all_true(eng.digest_all(["weights"]) == before))}
+        if "incremental" in args.extras:
+            eng.set_option("incremental", 1)
+            rows = []
+            for i in range(steps + 1):
+                barrier(); eng.sleep(["weights"]); s1 = eng.stats()
+                barrier(); eng.wake(None); s2 = eng.stats()
+                if i:                                  # cycle 0 seeds the digests
+                    rows.append((s1, s2))
+            out["incremental"] = {"sleep_latency_s": round(max_over_ranks(mean([r[0]["sleep_seconds"] for r in rows])), 5),
+                                  "sleep_bytes_copied": int(sum_over_ranks(float(rows[-1][0]["sleep_bytes_copied"]))),
+                                  "wake_latency_s": round(max_over_ranks(mean([r[1]["wake_seconds"] for r in rows])), 5),
+                                  "bit_exact": bool(group.all_true(eng.digest_all(["weights"]) == before))}
+            eng.set_option("incremental", 0)
+        eng.set_option("pack", args.pack)
+    except Exception as e:       # extras never fail the main line
+        out["error"] = str(e)[:200]
+    return out
 
 
 def measure_peer(eng, L, Wb, local_rank, world, barrier, max_over_ranks, before, steps=3):
@@ -627,6 +680,7 @@ def main() -> None:
     ap.add_argument("--pack", type=int, default=0, help="1 = PACKED host image (lossless bf16 page code; pays off with --contents bf16)")
     ap.add_argument("--incremental", type=int, default=0, help="1 = INCREMENTAL sleep: a sleep whose weights still match the image in the host store moves nothing")
     ap.add_argument("--packed-extra", type=int, default=1, help="at N=1 also measure the PACKED image on bf16 dummy weights in a child process (reported under packed_image)")
+    ap.add_argument("--extras", default="", help="comma list of in-process extras measured after the main line on the same engines: packed,incremental (any N)")
     ap.add_argument("--packed-child", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.packed_child:

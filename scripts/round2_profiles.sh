@@ -14,6 +14,9 @@ timeout 300 python scripts/pack_sweep.py > "$out/pack_sweep.log" 2>&1; echo "pac
 timeout 400 python bench.py --steps 24 --warmup 3 --no-cpu-baseline --packed-extra 0 > "$out/bench_24_whole_runs.json" 2> "$out/bench_pieces.err"
 timeout 400 env FMA_MAP_PIECE_MIB=2048 python bench.py --steps 24 --warmup 3 --no-cpu-baseline --packed-extra 0 > "$out/bench_24_pieces_2g.json" 2>> "$out/bench_pieces.err"; echo "bench pieces rc=$?" | tee -a "$out/status_profiles.txt"
 
+# (N>1, run separately, 8x charged:  gpurun --gpus 8 -- 'python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1
+#   --master-port 29511 bench.py --gpus 8 --steps 10 --warmup 3 --extras packed,incremental'  -> one run carries plain + packed + incremental)
+
 # 2. VMM granularity / VA alignment probe (seconds)
 timeout 120 python scripts/gran_probe.py > "$out/gran_probe.log" 2>&1
 
