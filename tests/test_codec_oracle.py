@@ -106,3 +106,32 @@ def test_format_is_pinned_by_the_golden_fixture(oracle):
         assert stored.size == w["stored_bytes"] and hashlib.sha256(stored.tobytes()).hexdigest() == w["stored_sha256"], name
         seen += 1
     assert seen == len(want) == 7
+
+
+def _numpy_pack(page: np.ndarray) -> np.ndarray:
+    """A third, vectorised restatement of the format (numpy), written from the spec in csrc/fma_codec.h — not from the C oracle."""
+    v = page.view(np.uint16).astype(np.uint32)
+    e = (v >> 7) & 0xFF
+    emax = e.reshape(-1, 256).max(axis=1)
+    d = np.repeat(emax, 256) - e
+    code = np.where(d <= 13, d, np.where(e == 0, 14, 15)).astype(np.uint8)
+    exc = np.flatnonzero(code == 15)
+    if exc.size > 2048:
+        return page.copy()
+    out = np.zeros(PACKED, np.uint8)
+    out[:N] = (((v >> 15) << 7) | (v & 0x7F)).astype(np.uint8)
+    out[N:N + N // 2] = code[0::2] | (code[1::2] << 4)
+    out[EMAX_OFF:EMAX_OFF + 4096] = emax.astype(np.uint8)
+    out[EXC_OFF:EXC_OFF + 4 * exc.size] = (exc.astype(np.uint32) | (e[exc] << 20)).astype("<u4").view(np.uint8)
+    out[HDR_OFF:HDR_OFF + 8] = np.array([0x34504D46, exc.size], "<u4").view(np.uint8)
+    return out
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13])
+def test_oracle_agrees_with_an_independent_numpy_restatement(oracle, seed):
+    rng = np.random.default_rng(seed)
+    gau = _page(rng.normal(0, 0.03, N).astype(np.float32).view(np.uint32) >> 16)
+    sparse = gau.copy().view(np.uint16); sparse[rng.random(N) < 0.2] = 0
+    heavy = _page((rng.standard_t(3, N) * 0.01).astype(np.float32).view(np.uint32) >> 16)
+    for page in (gau, sparse.view(np.uint8), heavy, oracle.bf16_weights(N, seed).view(np.uint8), rng.integers(0, 256, PAGE, dtype=np.uint8)):
+        assert np.array_equal(oracle.pack_page(page), _numpy_pack(page))
