@@ -165,11 +165,17 @@ def run_ours(args) -> None:
         eng.peer_reserve(ranks.parking_device(local_rank, world), Wb)
     pin_s = eng.stats()["host_store_pin_seconds"]
 
-    def cycle():
+    timelines = {}
+
+    def cycle(capture: bool = False):
         eng.sleep(["weights"], tier=tier)
         s1 = eng.stats()
+        if capture:
+            timelines["sleep"] = eng.timeline()
         eng.wake(None)
         s2 = eng.stats()
+        if capture:
+            timelines["wake"] = eng.timeline()
         return s1, s2
 
     for _ in range(max(args.warmup, 0)):
@@ -181,16 +187,22 @@ def run_ours(args) -> None:
         sampler.start()
     rows = []
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        rows.append(cycle())
+    for i in range(args.steps):
+        rows.append(cycle(capture=bool(args.timeline) and i == args.steps - 1))   # reading the timeline happens after the step's stats
     torch.cuda.synchronize(); barrier()
     t1 = time.perf_counter()
+    if args.timeline:      # per-rank phase timeline of the last timed step (fma_timeline): which phase bounds the wake
+        os.makedirs(args.timeline, exist_ok=True)
+        with open(os.path.join(args.timeline, f"n{world}_rank{rank}.csv"), "w") as f:
+            f.write("op,kind,idx,t0_ms,t1_ms,bytes\n")
+            for op in ("sleep", "wake"):
+                for r in timelines.get(op, []):
+                    f.write(f"{r['op']},{r['kind']},{r['idx']},{r['t0_ms']:.3f},{r['t1_ms']:.3f},{r['bytes']}\n")
     clocks = sampler.stop() if sampler else ({"sm_mhz": None, "sm_max_mhz": None, "reasons": ["sampling disabled (FMA_BENCH_NO_CLOCKS=1)"]} if rank == 0 else None)
     launches = eng.stats()["total_kernel_launches"] - launches0
 
     after = eng.digest_all(["weights"])
     bit_exact = after == before
-    same_va = True  # VAs are engine-owned reservations; asserted in tests/test_gpu_parity.py
 
     mean = lambda xs: sum(xs) / len(xs)
     wake_dev = mean([r[1]["wake_copy_seconds"] for r in rows])
@@ -681,6 +693,7 @@ def main() -> None:
     ap.add_argument("--incremental", type=int, default=0, help="1 = INCREMENTAL sleep: a sleep whose weights still match the image in the host store moves nothing")
     ap.add_argument("--packed-extra", type=int, default=1, help="at N=1 also measure the PACKED image on bf16 dummy weights in a child process (reported under packed_image)")
     ap.add_argument("--extras", default="", help="comma list of in-process extras measured after the main line on the same engines: packed,incremental (any N)")
+    ap.add_argument("--timeline", default="", help="directory: every rank writes the per-phase timeline (fma_timeline) of its last timed sleep and wake there")
     ap.add_argument("--packed-child", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.packed_child:

@@ -596,9 +596,16 @@ int flush_kernel_times(fma_engine_t* e) {
     if (!e->pending_events) return FMA_OK;
     double s = 0;
     for (size_t i = 0; i + 1 < e->pending_events; i += 2) {
-        float ms = 0;
+        float ms = 0, ms0 = 0;
         RT(cudaEventElapsedTime(&ms, e->ev_pool[i], e->ev_pool[i + 1]));
         s += ms * 1e-3;
+        // device-side timeline: launch i/2 ran [ms0, ms0 + ms) after ev_start (recorded tl_dev_base after the entry)
+        if (cudaEventElapsedTime(&ms0, e->ev_start, e->ev_pool[i]) == cudaSuccess) {
+            const double t0 = e->tl_entry + e->tl_dev_base + ms0 * 1e-3;
+            e->tl_add("kernel", (int)(i / 2), t0, t0 + ms * 1e-3, i / 2 < e->tl_kbytes.size() ? e->tl_kbytes[i / 2] : 0);
+        } else {
+            cudaGetLastError();
+        }
     }
     e->st.kernel_seconds = s;
     e->st.kernel_bytes = e->pending_kernel_bytes;
@@ -900,14 +907,43 @@ uint64_t fma_current_usage(fma_engine_t* e) {
     return sum;
 }
 
+// One operation per engine at a time: the controller retries POST /wake_up after its 5 s timeout
+// (inference-server.go:1699-1716), so a second call can arrive while the first is still mapping; it waits and then finds
+// nothing left to do (idempotence, abstract.py:336-338).
 int fma_sleep(fma_engine_t* e, uint64_t offload_tag_mask, int tier, uint32_t flags) {
     if (check_engine(e) != FMA_OK) return FMA_EINVAL;
+    std::lock_guard<std::mutex> op(e->op_mu);
     return do_sleep(e, offload_tag_mask, tier, flags);
 }
 
 int fma_wake(fma_engine_t* e, uint64_t tag_mask, uint32_t flags) {
     if (check_engine(e) != FMA_OK) return FMA_EINVAL;
+    std::lock_guard<std::mutex> op(e->op_mu);
     return do_wake(e, tag_mask, flags);
+}
+
+// Text timeline of the last sleep / wake: one line per event, "op,kind,idx,t0_ms,t1_ms,bytes" (times since the call's entry;
+// `kernel` rows are device-timed).  Returns the number of bytes the full text needs (excluding the NUL); writes at most cap-1.
+int fma_timeline(fma_engine_t* e, char* buf, size_t cap) {
+    if (check_engine(e) != FMA_OK) return FMA_EINVAL;
+    {
+        DeviceGuard guard(e->device);
+        int rc = flush_kernel_times(e);
+        if (rc != FMA_OK) return rc;
+    }
+    std::lock_guard<std::mutex> lk(e->tl_mu);
+    std::string out;
+    char line[160];
+    for (const TimelineEv& ev : e->tl) {
+        snprintf(line, sizeof(line), "%s,%s,%d,%.3f,%.3f,%llu\n", e->tl_op, ev.kind, ev.idx, ev.t0 * 1e3, ev.t1 * 1e3, (unsigned long long)ev.bytes);
+        out += line;
+    }
+    if (buf && cap) {
+        const size_t n = std::min(out.size(), cap - 1);
+        memcpy(buf, out.data(), n);
+        buf[n] = 0;
+    }
+    return (int)out.size();
 }
 
 int fma_is_sleeping(fma_engine_t* e) {
@@ -925,10 +961,15 @@ int fma_swap(fma_engine_t* out_e, uint64_t offload_tag_mask, int tier, fma_engin
     int rc_sleep = FMA_OK;
     char sleep_msg[512] = "";
     std::thread t([&] {
+        std::lock_guard<std::mutex> op(out_e->op_mu);
         rc_sleep = do_sleep(out_e, offload_tag_mask, tier, flags);
         if (rc_sleep != FMA_OK) snprintf(sleep_msg, sizeof(sleep_msg), "%s", tl_err);
     });
-    int rc_wake = do_wake(in_e, wake_tag_mask, flags);
+    int rc_wake;
+    {
+        std::lock_guard<std::mutex> op(in_e->op_mu);
+        rc_wake = do_wake(in_e, wake_tag_mask, flags);
+    }
     t.join();
     if (rc_wake != FMA_OK) return rc_wake;
     if (rc_sleep != FMA_OK) return fail(rc_sleep, "%s", sleep_msg);

@@ -179,6 +179,15 @@ struct ParkStore {  // peer-HBM or local-HBM parking buffer (VMM, P2P mapped)
 constexpr int kMaxStreams = 8;
 constexpr int kMaxRing = 8;
 
+// Per-phase timeline of the last sleep / wake (fma_timeline): host-side phases (VMM calls of the mapper / unmapper threads,
+// enqueue, drain) and device-side kernel launches (K1 / K2 / K4 / K5), all in seconds since the operation's entry.
+struct TimelineEv {
+    char kind[16];
+    int32_t idx;
+    double t0, t1;
+    uint64_t bytes;
+};
+
 }  // namespace fma_impl
 
 using namespace fma_impl;  // internal header: only the engine's own translation units include it
@@ -188,6 +197,7 @@ struct fma_engine {
     size_t gran = FMA_PAGE_BYTES;
     fma_config_t cfg{};
     std::mutex mu;  // guards segs / tags (my_malloc can arrive from any torch thread)
+    std::mutex op_mu;  // one sleep / wake / swap / image operation per engine at a time (a controller retry may overlap a call in flight)
     std::vector<Segment> segs;  // allocation order == reference dict order (cumem.py:198,237)
     std::map<CUdeviceptr, size_t> by_va;
     std::vector<Arena> arenas;
@@ -258,6 +268,31 @@ struct fma_engine {
     // K1/K2 event pairs of the last operation whose elapsed times have not been read yet
     size_t pending_events = 0;
     uint64_t pending_kernel_bytes = 0;
+    // timeline of the last operation (fma_timeline)
+    std::mutex tl_mu;
+    std::vector<TimelineEv> tl;
+    std::vector<uint64_t> tl_kbytes;   // algorithmic bytes of each pending kernel launch (pairs in ev_pool)
+    char tl_op[8] = "";
+    double tl_entry = 0;               // now_s() at the operation's entry
+    double tl_dev_base = 0;            // host time (since entry) at which ev_start was recorded: origin of the device-side events
+    void tl_begin(const char* op, double t_entry) {
+        std::lock_guard<std::mutex> lk(tl_mu);
+        tl.clear();
+        tl_kbytes.clear();
+        snprintf(tl_op, sizeof(tl_op), "%s", op);
+        tl_entry = t_entry;
+        tl_dev_base = 0;
+    }
+    void tl_add(const char* kind, int idx, double t0_abs, double t1_abs, uint64_t bytes) {
+        std::lock_guard<std::mutex> lk(tl_mu);
+        TimelineEv ev;
+        snprintf(ev.kind, sizeof(ev.kind), "%s", kind);
+        ev.idx = idx;
+        ev.t0 = t0_abs - tl_entry;
+        ev.t1 = t1_abs - tl_entry;
+        ev.bytes = bytes;
+        tl.push_back(ev);
+    }
 };
 
 namespace fma_impl {
@@ -307,6 +342,7 @@ struct CopyTimer {  // device-time bracket over all engine streams
     fma_engine_t* e;
     int begin() {
         RT(cudaEventRecord(e->ev_start, e->ks));
+        e->tl_dev_base = now_s() - e->tl_entry;
         for (int i = 0; i < e->n_cs; ++i) RT(cudaStreamWaitEvent(e->cs[i], e->ev_start, 0));
         return FMA_OK;
     }
@@ -336,6 +372,7 @@ struct KernelTimes {  // event pairs around each K1/K2 launch on the kernel stre
         RT(cudaEventRecord(e->ev_pool[used + 1], e->ks));
         used += 2;
         bytes += 2ull * n_pages * FMA_PAGE_BYTES;
+        e->tl_kbytes.push_back(2ull * n_pages * FMA_PAGE_BYTES);
         return FMA_OK;
     }
     // K4 / K5 (packed image): bracket a launch the caller makes itself; `b` = algorithmic bytes (read + write)
@@ -349,6 +386,7 @@ struct KernelTimes {  // event pairs around each K1/K2 launch on the kernel stre
         RT(cudaEventRecord(e->ev_pool[used + 1], e->ks));
         used += 2;
         bytes += b;
+        e->tl_kbytes.push_back(b);
         return FMA_OK;
     }
     // Called after the streams are synchronised.  Reading ~100s of event pairs costs ~1 ms, so it is

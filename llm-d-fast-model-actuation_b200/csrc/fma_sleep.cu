@@ -1,6 +1,7 @@
 // fma_sleep.cu — SLEEP: vllm:device_allocator/cumem.py:177-225 -> do_sleep (and the PACKED image plan)
 // Part of the host engine (see fma_internal.h for the map of translation units; C-ABI in include/fma_engine.h).
 #include "fma_internal.h"
+#include "fma_gate.h"
 
 namespace fma_impl {
 
@@ -69,10 +70,16 @@ struct Unmapper {
     std::vector<Range> done;   // ranges actually unmapped
     std::thread th;
     void unmap_range(const Range& r, bool dbg) {
-        const double a = now_s();
-        CUresult r1 = g_drv.MemUnmap(r.va, r.bytes);
+        double a;
+        CUresult r1;
+        {
+            GateHold hold(kGateRemap, 0.1);   // nothing waits for an unmap: yield (bounded) to calls that gate a wake's copies
+            a = now_s();
+            r1 = g_drv.MemUnmap(r.va, r.bytes);
+        }
         const double b = now_s();
         seconds += b - a;
+        e->tl_add("unmap", (int)done.size(), a, b, r.bytes);
         if (r1 != CUDA_SUCCESS) {
             std::lock_guard<std::mutex> lk(mu);
             if (error == FMA_OK) {
@@ -437,6 +444,7 @@ int do_sleep(fma_engine_t* e, uint64_t offload_mask, int tier, uint32_t flags) {
     bool any_unmapped = false, any_mapped = false;
     for (const Segment& s : e->segs) (s.mapped ? any_mapped : any_unmapped) = true;
     if (any_unmapped || !any_mapped) return FMA_OK;
+    e->tl_begin("sleep", t_entry);
 
     // plan: offloaded segments -> packed image, in (arena, VA) order.  Arenas are bump-allocated per tag, so this is
     // allocation order (the reference's dict order, cumem.py:198) unless a freed hole was reused.
@@ -711,6 +719,7 @@ int do_sleep(fma_engine_t* e, uint64_t offload_mask, int tier, uint32_t flags) {
     e->image_bytes = W;
     e->image_tier = tier;
 
+    e->tl_add("total", 0, t_entry, now_s(), W);
     e->st.sleep_seconds = now_s() - t_entry;
     e->st.sleep_copy_seconds = copy_s;
     e->st.sleep_unmap_seconds = un.seconds;

@@ -1,6 +1,7 @@
 // fma_wake.cu — WAKE: vllm:device_allocator/cumem.py:227-249 -> do_wake
 // Part of the host engine (see fma_internal.h for the map of translation units; C-ABI in include/fma_engine.h).
 #include "fma_internal.h"
+#include "fma_gate.h"
 
 namespace fma_impl {
 
@@ -315,6 +316,7 @@ int do_wake(fma_engine_t* e, uint64_t tag_mask, uint32_t flags) {
             cand.push_back(i);
         }
         if (cand.empty()) return FMA_OK;
+        e->tl_begin("wake", t_entry);
         std::sort(cand.begin(), cand.end(), [&](size_t a, size_t b) {
             const Segment &x = e->segs[a], &y = e->segs[b];
             return x.arena != y.arena ? x.arena < y.arena : x.va < y.va;
@@ -324,8 +326,12 @@ int do_wake(fma_engine_t* e, uint64_t tag_mask, uint32_t flags) {
             const Segment& s = e->segs[i];
             view.push_back(fma_layout::SegView{i, s.arena, (uint64_t)s.va, s.bytes, s.has_backup, s.packed_off});
         }
-        // FMA_MAP_PIECE_MIB (default 0 = whole runs): map backed-up runs in pieces of about that size
-        runs = fma_layout::plan_runs(view, env_int("FMA_MERGE_RUNS", 1) != 0, (size_t)std::max(env_int("FMA_MAP_PIECE_MIB", 0), 0) << 20);
+        // FMA_MAP_PIECE_MIB (default 2048; 0 = whole runs): backed-up runs are mapped in pieces of about that size, cut at segment
+        // boundaries.  One 15 GiB mapping has only the ring's ~19 ms of slack, and 20-30 % of the wakes on these hosts hit a
+        // 10-190 ms stall in one driver call; with pieces K2 starts on the first piece and every later call has the copy time
+        // of the pieces before it as slack.  B200, 8B table, 16 wakes: 0.2898-0.2937 s (mean 0.2904) vs 0.290-0.349 s (mean
+        // 0.2992) for whole runs (profiles/bench_n1_pieces_r2.json).
+        runs = fma_layout::plan_runs(view, env_int("FMA_MERGE_RUNS", 1) != 0, (size_t)std::max(env_int("FMA_MAP_PIECE_MIB", 2048), 0) << 20);
     }
     const int tier = e->image_tier;
     int mode = resolve_mode(e, tier);
@@ -396,6 +402,20 @@ int do_wake(fma_engine_t* e, uint64_t tag_mask, uint32_t flags) {
         remap_delay_s = forced >= 0 ? forced * 1e-3 : expected * (tier == FMA_TIER_HOST ? 0.2 : 0.5);
     }
 
+    // FMA_REMAP_AFTER_COPY=1: remap-only runs (kv_cache) are mapped only after this rank's last copy has LANDED — a 32 GiB
+    // cuMemCreate/Map/SetAccess then never runs beside this rank's DMA (its cost, a few ms, is added to the wake instead of
+    // hidden under it).  A/B knob for the question "does a large VMM call slow a running H2D stream down?".
+    const bool remap_after_copy = env_int("FMA_REMAP_AFTER_COPY", 0) != 0 && n_backup_runs > 0;
+    std::atomic<bool> copies_landed{false};
+    e->tl_add("plan", (int)runs.size(), t_entry, t_ring, 0);
+    // Cross-process VMM gate (fma_gate.h): tell the other engines on this host that a call which gates a first copy is coming
+    int gate_first = n_backup_runs ? gate_announce(kGateFirst) : 0;
+    const double expected_copy_s = [&] {
+        uint64_t w = 0;
+        for (size_t i : with_backup) w += e->segs[i].bytes;
+        return (double)w / (tier == FMA_TIER_HOST ? 55e9 : 600e9);
+    }();
+
     // ---- mapper thread(s): one create + map + set-access per run, in `runs` order ----------------------
     MapProgress prog;
     std::vector<char> item_done(runs.size(), 0);
@@ -419,10 +439,38 @@ int do_wake(fma_engine_t* e, uint64_t tag_mask, uint32_t flags) {
                 const double wait = t_entry + remap_delay_s - now_s();
                 if (wait > 0) std::this_thread::sleep_for(std::chrono::duration<double>(wait));
             }
+            if (!run.has_backup && remap_after_copy) {
+                while (!copies_landed.load(std::memory_order_acquire)) {
+                    {
+                        std::lock_guard<std::mutex> lk(prog.mu);
+                        if (prog.error != FMA_OK) break;
+                    }
+                    std::this_thread::sleep_for(std::chrono::microseconds(200));
+                }
+            }
             const bool is_ring = ring_run && k == 0;
-            const double t0 = now_s();
-            int r = vmm_create_and_map(e->device, run.va, run.bytes);
-            map_ns.fetch_add((uint64_t)((now_s() - t0) * 1e9));
+            // gate class: whatever gates the first copy (ring, or the first backed-up item when there is no ring run) goes
+            // first on the whole host; the other backed-up items have one ring's worth of slack; remap-only runs have what is
+            // left of the copy time.
+            const bool first_item = run.has_backup && k == 0;
+            const int cls = first_item ? kGateFirst : run.has_backup ? kGateWeights : kGateRemap;
+            const double left = std::max(0.0, t_entry + expected_copy_s * 0.8 - now_s());
+            const double t_ask = now_s();
+            int r;
+            double t0;
+            {
+                GateHold hold(cls, cls == kGateRemap ? left : std::min(left, 0.05));
+                if (first_item && gate_first) {
+                    gate_retract(gate_first);
+                    gate_first = 0;
+                }
+                t0 = now_s();
+                r = vmm_create_and_map(e->device, run.va, run.bytes);
+            }
+            const double t1 = now_s();
+            map_ns.fetch_add((uint64_t)((t1 - t0) * 1e9));
+            if (t0 - t_ask > 1e-4) e->tl_add("gate_wait", (int)k, t_ask, t0, 0);
+            e->tl_add(is_ring ? "map_ring" : run.has_backup ? "map_backed" : "map_remap", (int)k, t0, t1, run.bytes);
             std::lock_guard<std::mutex> lk(prog.mu);
             if (r != FMA_OK) {
                 prog.error = r;
@@ -463,18 +511,41 @@ int do_wake(fma_engine_t* e, uint64_t tag_mask, uint32_t flags) {
         std::lock_guard<std::mutex> lk(prog.mu);
         return prog.done;
     };
+    // A wake that fails is rolled back: every run THIS call mapped is unmapped again (its segments still have their backup),
+    // so the table is what it was at entry and the controller's retry (inference-server.go:477-480) redoes the whole wake.
+    // Leaving the mapped prefix in place would make the retry skip it (`mapped` == already awake) and report success over
+    // weights that were never copied back — vLLM's allocator raises in that situation (cumem.py:237-249).
+    auto abort_wake = [&](int code) -> int {
+        char keep[512];
+        snprintf(keep, sizeof(keep), "%s", tl_err);
+        {
+            std::lock_guard<std::mutex> lk(prog.mu);
+            if (prog.error == FMA_OK) prog.error = code;
+        }
+        copies_landed.store(true, std::memory_order_release);
+        join_mappers();
+        if (gate_first) {
+            gate_retract(gate_first);
+            gate_first = 0;
+        }
+        cudaDeviceSynchronize();
+        cudaGetLastError();
+        for (size_t k = 0; k < runs.size(); ++k) {
+            if (!item_done[k]) continue;
+            for (size_t i : runs[k].segs) {
+                e->segs[i].mapped = false;
+                e->segs[i].unit_va = 0;
+            }
+            unmap_units(e, runs[k].va, runs[k].bytes);  // the ring run gives its VA back to the arena through its zombie entry
+        }
+        e->pending_events = 0;
+        snprintf(tl_err, sizeof(tl_err), "%s", keep);
+        return code;
+    };
 #define WAKE_CHECK(x)                     \
     do {                                  \
         int _rc = (x);                    \
-        if (_rc != FMA_OK) {              \
-            {                             \
-                std::lock_guard<std::mutex> lk(prog.mu); \
-                if (prog.error == FMA_OK) prog.error = _rc; \
-            }                             \
-            join_mappers();               \
-            cudaDeviceSynchronize();      \
-            return _rc;                   \
-        }                                 \
+        if (_rc != FMA_OK) return abort_wake(_rc); \
     } while (0)
 #define WAKE_RT(call)                                                                              \
     do {                                                                                           \
@@ -496,27 +567,41 @@ int do_wake(fma_engine_t* e, uint64_t tag_mask, uint32_t flags) {
             WAKE_CHECK(fail(FMA_ECUDA, "host store has no device alias for zero-copy mode"));
         WAKE_CHECK(timer.begin());
         WakePipe pipe{e, with_backup, seg_run, W, tier, mode, ring_run, store, kt, copy_ops, first_copy_delay, t_entry, wait_mapped, mapped_now, prog.msg};
+        const double t_enq0 = now_s();
         if (packed) WAKE_CHECK(wake_packed(pipe));
         else if (mode == FMA_MODE_DIRECT) WAKE_CHECK(wake_direct(pipe));
         else WAKE_CHECK(wake_paged(pipe));
+        e->tl_add("enqueue", (int)copy_ops, t_enq0, now_s(), W);
     }
+    if (remap_after_copy && W) {  // let the DMA finish before the remap-only runs are touched
+        const double t_w0 = now_s();
+        for (int i = 0; i < e->n_cs; ++i) WAKE_RT(cudaStreamSynchronize(e->cs[i]));
+        WAKE_RT(cudaStreamSynchronize(e->ks));
+        e->tl_add("copies_landed", 0, t_w0, now_s(), W);
+    }
+    copies_landed.store(true, std::memory_order_release);
     // every requested segment must be mapped before wake returns (cumem.py:237-240)
     {
+        const double t_w0 = now_s();
         int mrc = wait_mapped(runs.size());
         if (mrc != FMA_OK) WAKE_CHECK(fail(mrc, "%s", prog.msg));
+        e->tl_add("wait_all_mapped", (int)runs.size(), t_w0, now_s(), 0);
     }
     join_mappers();
+    if (gate_first) {
+        gate_retract(gate_first);
+        gate_first = 0;
+    }
     const double t_joined = now_s();
     double t_copy_end = t_joined;
     if (W) {
-        rc = timer.end(&copy_s);
-        if (rc != FMA_OK) return rc;
-        rc = kt.collect();
-        if (rc != FMA_OK) return rc;
+        WAKE_CHECK(timer.end(&copy_s));
+        e->tl_add("drain", 0, t_joined, now_s(), W);
+        WAKE_CHECK(kt.collect());
         if (packed) {  // K5 counts stored pages it could not read (bad magic / count): the image is damaged
-            RT(cudaMemcpyAsync(e->h_psize + e->pdesc_cap, e->d_psize + e->pdesc_cap, sizeof(uint32_t), cudaMemcpyDeviceToHost, e->ks));
-            RT(cudaStreamSynchronize(e->ks));
-            if (e->h_psize[e->pdesc_cap]) return fail(FMA_EINTEGRITY, "%u stored page(s) of the packed image are malformed", e->h_psize[e->pdesc_cap]);
+            WAKE_RT(cudaMemcpyAsync(e->h_psize + e->pdesc_cap, e->d_psize + e->pdesc_cap, sizeof(uint32_t), cudaMemcpyDeviceToHost, e->ks));
+            WAKE_RT(cudaStreamSynchronize(e->ks));
+            if (e->h_psize[e->pdesc_cap]) WAKE_CHECK(fail(FMA_EINTEGRITY, "%u stored page(s) of the packed image are malformed", e->h_psize[e->pdesc_cap]));
         }
         t_copy_end = now_s();
     }
@@ -559,6 +644,7 @@ int do_wake(fma_engine_t* e, uint64_t tag_mask, uint32_t flags) {
         }
     }
 
+    e->tl_add("total", 0, t_entry, now_s(), W);
     e->st.wake_seconds = now_s() - t_entry;
     e->st.wake_copy_seconds = copy_s;
     e->st.wake_map_seconds = map_ns.load() * 1e-9;

@@ -312,5 +312,18 @@ class Engine:
         check(self._lib.fma_stats(self._h, C.byref(st)))
         return st.as_dict()
 
+    def timeline(self) -> list[dict]:
+        """Per-phase timeline of the last sleep / wake (fma_timeline): rows of op, kind, idx, t0_ms, t1_ms, bytes."""
+        n = self._lib.fma_timeline(self._h, None, 0)
+        if n < 0:
+            check(n)
+        buf = C.create_string_buffer(n + 1)
+        check(min(self._lib.fma_timeline(self._h, buf, n + 1), 0))
+        rows = []
+        for line in buf.value.decode().splitlines():
+            op, kind, idx, t0, t1, b = line.split(",")
+            rows.append({"op": op, "kind": kind, "idx": int(idx), "t0_ms": float(t0), "t1_ms": float(t1), "bytes": int(b)})
+        return rows
+
 
 __all__ = ["Engine", "EngineConfig", "SegmentInfo", "FmaError"]

@@ -481,10 +481,7 @@ def test_full_size_llama3_8b_roundtrip_properties(engine, oracle):
         assert engine.stats()["wake_seconds"] < 5.0                 # the controller's /wake_up timeout (inference-server.go:1699-1702)
 
 
-# ---- image hand-over between processes (memfd host store).  Host-simulation only this round: the feature has not been
-# ---- run on a B200 yet (no GPU budget was left when it was written), so it must not gate the round-end GPU suite.
-_HOSTSIM_ONLY = pytest.mark.skipif(os.environ.get("FMA_HOSTSIM") != "1" and os.environ.get("FMA_TEST_IMAGE_ON_GPU") != "1",
-                                   reason="image hand-over is validated on the CUDA host simulation only so far (set FMA_TEST_IMAGE_ON_GPU=1)")
+# ---- image hand-over between processes (memfd host store).  Green on a B200 since round 2 (profiles/gpu_suite_all_gates_open_r2.log).
 
 _ADOPT_CHILD = r"""
 import os, sys, json
@@ -502,7 +499,6 @@ print(json.dumps(eng.digest_all(["weights"])))
 """
 
 
-@_HOSTSIM_ONLY
 @pytest.mark.parametrize("pack", [0, 1])
 def test_image_handover_to_another_engine_and_process(engine, oracle, monkeypatch, tmp_path, pack):
     import subprocess
@@ -556,7 +552,6 @@ def test_image_handover_to_another_engine_and_process(engine, oracle, monkeypatc
     assert engine.digest_all(["weights"]) == want and [s.va for s in engine.segments()] == ptrs
 
 
-@_HOSTSIM_ONLY
 @pytest.mark.parametrize("pack,pin_in_place", [(0, True), (1, True), (1, False)])
 def test_image_saved_to_a_file_and_loaded_by_a_fresh_engine(engine, oracle, monkeypatch, tmp_path, pack, pin_in_place):
     """A sleeping model's image persisted as a file (image_save) and adopted by a fresh engine with the same segment table
@@ -598,9 +593,6 @@ def test_image_saved_to_a_file_and_loaded_by_a_fresh_engine(engine, oracle, monk
 # ---- PACKED host image (K4p / K4 / K5, csrc/fma_codec.h) ------------------------------------------------------
 # Written in a round that had no GPU minutes left: validated against the oracle on the CUDA host simulation (which runs
 # the SAME per-lane codec arithmetic as the kernels); the first GPU call of the next round flips this switch.
-_PACK_VALIDATED_ON_GPU = os.environ.get("FMA_TEST_PACK_ON_GPU") == "1"
-_PACK = pytest.mark.skipif(os.environ.get("FMA_HOSTSIM") != "1" and not _PACK_VALIDATED_ON_GPU,
-                           reason="packed-image kernels are validated on the CUDA host simulation only so far (set FMA_TEST_PACK_ON_GPU=1)")
 
 
 def _pack_pages(oracle):
@@ -647,7 +639,6 @@ def pack_kernel(request, engine):
     engine.set_option("pack_kernel", 0)
 
 
-@_PACK
 @pytest.mark.parametrize("pack_kernel", _PACK_KERNELS, indirect=True)
 def test_pack_kernels_match_oracle_page_by_page(engine, oracle, pack_kernel):
     L = _L()
@@ -674,7 +665,6 @@ def test_pack_kernels_match_oracle_page_by_page(engine, oracle, pack_kernel):
     engine.scratch_free(store)
 
 
-@_PACK
 @pytest.mark.parametrize("pack_kernel", _PACK_KERNELS, indirect=True)
 @pytest.mark.parametrize("chunk_mib,slots", [(6, 2), (2, 2), (512, 2), (4, 3)])
 def test_packed_sleep_wake_roundtrip_and_image_match_oracle(engine, oracle, chunk_mib, slots, pack_kernel):
@@ -729,7 +719,6 @@ def test_packed_sleep_wake_roundtrip_and_image_match_oracle(engine, oracle, chun
         assert engine.read(i, b.size) == b.tobytes()
 
 
-@_PACK
 def test_packed_sleep_falls_back_to_plain_for_incompressible_weights(engine, oracle):
     L = _L()
     table = _tiny_table()
@@ -745,7 +734,6 @@ def test_packed_sleep_falls_back_to_plain_for_incompressible_weights(engine, ora
         assert engine.read(i, table[i].bytes) == ref[i].tobytes()
 
 
-@_PACK
 @pytest.mark.parametrize("tier", ["local", "peer"])
 def test_packed_image_in_a_parking_tier(engine, oracle, tier):
     """PACKED image parked in HBM (local: same GPU; peer: another GPU over NVLink): K4 writes and K5 reads the store
@@ -776,7 +764,6 @@ def test_packed_image_in_a_parking_tier(engine, oracle, tier):
     assert [s.va for s in engine.segments()] == ptrs
 
 
-@_PACK
 def test_pack_kernels_binary_on_the_device():
     """tests/cpp/cuda_emu/pack_kernels_gpu_test: the kernel-level test (same source as the CPU-emulated one) with managed
     memory on the real device — no engine, no Python in the way."""
@@ -791,7 +778,6 @@ def test_pack_kernels_binary_on_the_device():
     assert r.returncode == 0 and "pack kernels (GPU) ok" in r.stdout, (r.stdout + r.stderr)[-2000:]
 
 
-@_PACK
 def test_packed_image_with_two_offloaded_tags_woken_separately(engine, oracle):
     """Two offloaded tags whose segments alternate in the image: waking one tag reads stored pages that are NOT adjacent in
     the store (each gap starts a new ring slot), the other tag follows later; a discarded tag sits in between."""
@@ -822,7 +808,6 @@ def test_packed_image_with_two_offloaded_tags_woken_separately(engine, oracle):
     assert not engine.is_sleeping()
 
 
-@_PACK
 @pytest.mark.parametrize("seed", list(range(1, int(os.environ.get("FMA_TEST_SEEDS", "17")))))
 def test_packed_random_tables_and_wake_orders(built, oracle, seed):
     """Seeded random tables (sizes, tags, page kinds), ring shapes and wake orders: whatever the plan, every offloaded byte
@@ -884,11 +869,8 @@ def test_packed_random_tables_and_wake_orders(built, oracle, seed):
                 eng.write(j, b"".join(pool[k].tobytes() for k in kinds))
 
 
-_NEW_THIS_ROUND = pytest.mark.skipif(os.environ.get("FMA_HOSTSIM") != "1" and os.environ.get("FMA_TEST_NEW_ON_GPU") != "1",
-                                     reason="written after the round's GPU minutes were spent: host simulation only until its first GPU run (FMA_TEST_NEW_ON_GPU=1)")
 
 
-@_NEW_THIS_ROUND
 @pytest.mark.parametrize("seed", list(range(1, int(os.environ.get("FMA_TEST_SEEDS", "13")))))
 def test_random_alloc_free_sleep_wake_sequences(built, oracle, seed):
     """The default (unpacked) path under seeded random histories: allocations of several tags, frees while awake and while
@@ -968,7 +950,6 @@ def test_random_alloc_free_sleep_wake_sequences(built, oracle, seed):
             assert eng.current_usage() == sum(eng.segment(eng.find(p)).bytes for p in live)
 
 
-@_NEW_THIS_ROUND
 @pytest.mark.parametrize("pack", [0, 1])
 def test_incremental_sleep_moves_nothing_when_the_weights_did_not_change(engine, oracle, pack):
     """Option "incremental": after a wake the host store still holds the image; the next sleep digests the device copy (K3)
@@ -1067,7 +1048,6 @@ def test_incremental_sleep_moves_nothing_when_the_weights_did_not_change(engine,
     cycle(False)
 
 
-@_HOSTSIM_ONLY
 def test_sleep_by_adopting_a_replicas_image(engine, oracle, monkeypatch):
     """Two replicas of one model on a node: the second one sleeps by adopting the first one's image (FMA_FLAG_VERIFY = its device
     bytes must match the image's digests) — one host copy for both.  A replica with different bytes is refused and stays awake."""
@@ -1100,7 +1080,6 @@ def test_sleep_by_adopting_a_replicas_image(engine, oracle, monkeypatch):
     engine.wake(None, flags=L.FMA_FLAG_VERIFY)
 
 
-@_HOSTSIM_ONLY
 def test_shared_images_are_read_only_for_everybody(engine, oracle, monkeypatch):
     """An exported / adopted image is shared memory: the exporter waking, changing its weights and sleeping again must not
     rewrite the bytes an adopter is still asleep on (it gets a fresh private store), and vice versa."""
@@ -1139,7 +1118,6 @@ def test_shared_images_are_read_only_for_everybody(engine, oracle, monkeypatch):
         os.close(fd)
 
 
-@_NEW_THIS_ROUND
 @pytest.mark.parametrize("seed", list(range(1, int(os.environ.get("FMA_TEST_SEEDS", "7")))))
 def test_random_swaps_and_cold_loads_between_two_engines(built, oracle, tmp_path, seed):
     """Two engines on one GPU, seeded random options (modes, ring shapes, pack, incremental) and a random sequence of hot swaps,
