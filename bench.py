@@ -166,12 +166,17 @@ def run_ours(args) -> None:
     pin_s = eng.stats()["host_store_pin_seconds"]
 
     timelines = {}
+    phase_barrier = group.phase_barrier
 
     def cycle(capture: bool = False):
+        # Executor semantics (vllm:v1/executor/abstract.py:327,347): sleep / wake_up are fanned out to every rank and return
+        # when ALL ranks are done -> no rank starts waking while another still sleeps.  Host-side hand-shake, no GPU work.
+        phase_barrier()
         eng.sleep(["weights"], tier=tier)
         s1 = eng.stats()
         if capture:
             timelines["sleep"] = eng.timeline()
+        phase_barrier()
         eng.wake(None)
         s2 = eng.stats()
         if capture:
@@ -205,19 +210,21 @@ def run_ours(args) -> None:
     bit_exact = after == before
 
     mean = lambda xs: sum(xs) / len(xs)
-    wake_dev = mean([r[1]["wake_copy_seconds"] for r in rows])
-    wake_wall = mean([r[1]["wake_seconds"] for r in rows])
-    sleep_dev = mean([r[0]["sleep_copy_seconds"] for r in rows])
-    sleep_wall = mean([r[0]["sleep_seconds"] for r in rows])
     k2_s = sum(r[1]["kernel_seconds"] for r in rows); k2_b = sum(r[1]["kernel_bytes"] for r in rows)
     k2_n = sum(r[1]["kernel_launches"] for r in rows)
     k1_s = sum(r[0]["kernel_seconds"] for r in rows); k1_b = sum(r[0]["kernel_bytes"] for r in rows)
     k1_n = sum(r[0]["kernel_launches"] for r in rows)
 
-    wake_wall_med = max_over_ranks(statistics.median([r[1]["wake_seconds"] for r in rows]))
+    # job-level latency of step k = the slowest rank of step k (the executor returns when every rank is done)
+    wake_dev_steps = group.max_vec([r[1]["wake_copy_seconds"] for r in rows])
+    wake_wall_steps = group.max_vec([r[1]["wake_seconds"] for r in rows])
+    sleep_dev_steps = group.max_vec([r[0]["sleep_copy_seconds"] for r in rows])
+    sleep_wall_steps = group.max_vec([r[0]["sleep_seconds"] for r in rows])
+    wake_dev_med, wake_wall_med = statistics.median(wake_dev_steps), statistics.median(wake_wall_steps)
+    wake_dev_m, wake_wall_m = mean(wake_dev_steps), mean(wake_wall_steps)
+    sleep_dev_m, sleep_wall_m = mean(sleep_dev_steps), mean(sleep_wall_steps)
+    sleep_wall_med = statistics.median(sleep_wall_steps)
     total_s = max_over_ranks(t1 - t0)
-    wake_dev_m, wake_wall_m = max_over_ranks(wake_dev), max_over_ranks(wake_wall)
-    sleep_dev_m, sleep_wall_m = max_over_ranks(sleep_dev), max_over_ranks(sleep_wall)
     W_total = sum_over_ranks(float(Wb))
     launches_total = int(sum_over_ranks(float(launches)))
     all_exact = group.all_true(bit_exact)
@@ -242,55 +249,64 @@ def run_ours(args) -> None:
         peer = measure_peer(eng, L, Wb, local_rank, world, barrier, max_over_ranks, before, steps=3)
 
     extras = None
-    if args.extras and tier == L.FMA_TIER_HOST:
+    if ("packed" in args.extras or "incremental" in args.extras) and tier == L.FMA_TIER_HOST:
         extras = measure_extras(args, eng, L, table, Wb, rank, world, barrier, max_over_ranks, sum_over_ranks, torch, group)
+
+    roundrobin = None
+    if "roundrobin" in args.extras and world >= 2 and tier == L.FMA_TIER_HOST:
+        roundrobin = measure_roundrobin(args, L, W, local_rank, rank, world, group, torch)
 
     if rank == 0:
         peak, peak_src = hbm_peak()
         achieved = (k2_b / k2_s / 1e9) if k2_s > 0 else None
-        traffic = None
+        bytes_per_launch = int(k2_b / k2_n) if k2_n else 0
+        traffic, traffic_src = None, None
         tp = os.path.join(ROOT, "profiles", "k2_traffic.json")
-        if os.path.exists(tp):
+        if os.path.exists(tp):      # NOT measured in this run: the ncu --set full capture of the same kernel, kept under profiles/
             try:
-                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+                tj = json.load(open(tp))
+                if abs(tj.get("algorithmic_bytes_per_launch", 0) - bytes_per_launch) <= 0.02 * max(bytes_per_launch, 1):
+                    traffic = tj.get("dram_bytes_per_launch")
+                    traffic_src = "profiles/k2_traffic.json: dram__bytes_read+write of one launch of this size under ncu --set full (round-1 capture; a constant, not measured in this run)"
+                else:
+                    traffic_src = "no ncu capture for this launch size (profiles/k2_traffic.json is for 512 MiB slots)"
             except Exception:
                 traffic = None
-        e2e_gbs = W_total / wake_wall_m / 1e9
+        e2e_gbs = W_total / wake_wall_med / 1e9
+        e2e_mean_gbs = W_total / wake_wall_m / 1e9
         link_peak = PCIE_GEN5_X16_GBS if tier == L.FMA_TIER_HOST else NVLINK5_GBS
         out = {
-            "metric": "wake_h2d_gbs", "value": round(W_total / wake_dev_m / 1e9, 3), "unit": "GB/s",
+            "metric": "wake_h2d_gbs", "value": round(W_total / wake_dev_med / 1e9, 3), "unit": "GB/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(total_s / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": f"{workload} level-1 sleep->wake, {args.tier} tier, per-rank shard, no collective",
-                       "weights_gib_per_rank": round(Wb / GiB, 3), "kv_cache_gib_per_rank": args.kv_gib,
-                       "segments_per_rank": len(table), "mode": ["auto", "direct", "staged", "kernel"][st["mode"]],
-                       "kernel": args.kernel, "chunk_mib": args.chunk_mib or "default", "copy_streams": args.copy_streams or "default",
-                       "contents": "splitmix64 bytes (incompressible)" if args.contents == "prng" else "bf16 U(-1e-3, 1e-3) (vLLM dummy weights)",
-                       "pack": bool(st["image_packed"]) if args.pack else False, "incremental_sleep": bool(args.incremental),
-                       "l2": "working set >> 126 MB L2 (no flush needed)", "parallelism": f"{world} independent ranks"},
-            "wake_latency_s": round(wake_wall_m, 5), "wake_latency_s_median": round(wake_wall_med, 5),
-            "e2e_median_gbs": round(W_total / wake_wall_med / 1e9, 3),   # value/e2e use the MEAN over the K steps
-            "wake_latency_s_rank0_steps": [round(r[1]["wake_seconds"], 4) for r in rows],
-            "sleep_latency_s": round(sleep_wall_m, 5),
+            "config": bench_config(args, workload, Wb, len(table), world, ["auto", "direct", "staged", "kernel"][st["mode"]],
+                                   bool(st["image_packed"]) if args.pack else False),
+            "aggregation": "value / e2e = whole-job bytes / MEDIAN over the K timed steps of the per-step job latency (max over ranks of that "
+                           "step); the mean-based figures are value_mean / e2e.mean_gbs / wake_latency_s_mean",
+            "value_mean": round(W_total / wake_dev_m / 1e9, 3),
+            "wake_latency_s": round(wake_wall_med, 5), "wake_latency_s_mean": round(wake_wall_m, 5),
+            "wake_latency_s_min_max": [round(min(wake_wall_steps), 5), round(max(wake_wall_steps), 5)],
+            "wake_latency_s_steps": [round(x, 4) for x in wake_wall_steps],
+            "sleep_latency_s": round(sleep_wall_med, 5), "sleep_latency_s_mean": round(sleep_wall_m, 5),
             "sleep_d2h_gbs": round(W_total / sleep_dev_m / 1e9, 3) if sleep_dev_m > 0 else None,   # None: incremental sleeps moved nothing
             "sleep_copy_ops_last": rows[-1][0]["copy_ops"], "sleep_bytes_copied_last": rows[-1][0]["sleep_bytes_copied"],
             "wake_map_s": round(map_s, 5), "sleep_unmap_s": round(unmap_s, 5), "host_pin_s_untimed": round(pin_s, 3),
             "bit_exact": bool(all_exact),
             "e2e": {"value": round(e2e_gbs, 3), "unit": "GB/s", "h2d_bytes_per_step": int(W_total),
-                    "d2h_bytes_per_step": int(W_total),
+                    "d2h_bytes_per_step": int(W_total), "mean_gbs": round(e2e_mean_gbs, 3),
                     "link_bytes_per_step": int(sum_store),
                     "api": "fma_wake() through the C-ABI: VMM remap of weights+kv_cache, H2D from the pinned host store, K2, sync"},
             "gpu_launches": launches_total,
             "roofline": {"bound": "hbm", "kernel": "fma_k_page_copy_tma (K2 scatter, wake)" if args.kernel == "tma" else "fma_k_page_copy_ldg (K2)",
                          "achieved": round(achieved, 1) if achieved else None, "peak": peak, "unit": "GB/s",
-                         "frac": round(achieved / peak, 4) if achieved else None, "traffic": traffic,
-                         "launches": k2_n, "bytes_per_launch": int(k2_b / k2_n) if k2_n else 0,
+                         "frac": round(achieved / peak, 4) if achieved else None, "traffic": traffic, "traffic_source": traffic_src,
+                         "launches": k2_n, "bytes_per_launch": bytes_per_launch,
                          "avg_launch_us": round(k2_s / k2_n * 1e6, 2) if k2_n else None, "peak_source": peak_src,
                          "k1_gather_achieved": round(k1_b / k1_s / 1e9, 1) if k1_s > 0 else None, "k1_launches": k1_n},
             "pcie" if tier == L.FMA_TIER_HOST else "nvlink": {
                 "bound": "pcie_gen5_x16" if tier == L.FMA_TIER_HOST else "nvlink5",
-                "achieved_per_gpu": round(e2e_gbs / world, 3), "device_timed_per_gpu": round(W_total / wake_dev_m / 1e9 / world, 3),
+                "achieved_per_gpu": round(e2e_gbs / world, 3), "device_timed_per_gpu": round(W_total / wake_dev_med / 1e9 / world, 3),
                 "peak": link_peak, "unit": "GB/s", "frac": round(e2e_gbs / world / link_peak, 4),
                 "naive_pinned_h2d_per_gpu": round(ceiling, 3) if ceiling else None,
                 "vs_naive_pinned_h2d": round(e2e_gbs / world / ceiling, 4) if ceiling else None,
@@ -302,8 +318,14 @@ def run_ours(args) -> None:
             out["peer_tier"] = peer
         if extras:
             out["extras"] = extras
+        if roundrobin:
+            out["roundrobin_config5"] = roundrobin
         if world == 1:
             eng.close()   # everything above is measured: give the HBM and the pinned store back before the baseline / extra processes run
+        if world == 1 and "swap" in args.extras and tier == L.FMA_TIER_HOST:
+            out["swap_config4"] = measure_swap(args, L, W)
+        if world == 1 and "scaling_base" in args.extras and tier == L.FMA_TIER_HOST and workload != args.scaling_workload:
+            out["n1_on_scaling_workload"] = measure_scaling_base(args, L, W, cfg)
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = reference_sample(args, workload)
         if world == 1 and args.packed_extra and not args.pack and tier == L.FMA_TIER_HOST:
@@ -311,6 +333,154 @@ def run_ours(args) -> None:
         print(json.dumps(out), flush=True)
     eng.close()
     group.close()
+
+
+def bench_config(args, workload: str, weight_bytes: int, n_segments: int, world: int, mode: str, packed: bool) -> dict:
+    """The `config` object of BOTH arms' JSON lines (the reference arm runs on this arm's config: same table, same kv_cache
+    region, same contents; the engine-only knobs describe what this arm would use)."""
+    return {"workload": f"{workload} level-1 sleep->wake, {args.tier} tier, per-rank shard, no collective",
+            "weights_gib_per_rank": round(weight_bytes / GiB, 3), "kv_cache_gib_per_rank": args.kv_gib,
+            "segments_per_rank": n_segments, "mode": mode,
+            "kernel": args.kernel, "chunk_mib": args.chunk_mib or "default", "copy_streams": args.copy_streams or "default",
+            "contents": "splitmix64 bytes (incompressible)" if args.contents == "prng" else "bf16 U(-1e-3, 1e-3) (vLLM dummy weights)",
+            "pack": packed, "incremental_sleep": bool(args.incremental),
+            "phases": "executor semantics: every rank finishes sleeping before any rank wakes (host-side barrier between the phases)",
+            "l2": "working set >> 126 MB L2 (no flush needed)", "parallelism": f"{world} independent ranks"}
+
+
+def load_model(eng, W, model: str, kv_gib: float, seed: int):
+    table = W.allocation_table(model, kv_cache_bytes=int(kv_gib * GiB))
+    for s in table:
+        eng.alloc(s.bytes, s.tag)
+    first = 0
+    for i, s in enumerate(table):
+        if s.tag == "weights":
+            eng.fill(i, seed, first)
+            first += s.bytes // 8
+    return table, W.weight_bytes(table)
+
+
+def measure_swap(args, L, W, cycles: int = 10) -> dict:
+    """BASELINE config 4: Llama-3-8B <-> Mistral-7B under one owner on one B200.  `fma_swap` = sleep(out) || wake(in): the D2H of
+    the outgoing model and the H2D of the incoming one use the two PCIe directions at once.  Beside it, the serial form (sleep,
+    then wake: what two independent reconciles of the reference controller produce).  Medians over `cycles`."""
+    import fma_b200
+
+    try:
+        A, B = fma_b200.Engine(0), fma_b200.Engine(0)
+        ma, mb = args.swap_models.split(",")
+        _, wa = load_model(A, W, ma, args.extras_kv_gib, 1)
+        _, wb = load_model(B, W, mb, args.extras_kv_gib, 2)
+        A.host_reserve(wa); B.host_reserve(wb)
+        da, db = A.digest_all(["weights"]), B.digest_all(["weights"])
+        B.sleep(["weights"])
+        serial, swap, d2h, h2d = [], [], [], []
+        for i in range(cycles + 2):
+            t0 = time.perf_counter(); A.sleep(["weights"]); B.wake(None); t_ab = time.perf_counter() - t0
+            t0 = time.perf_counter(); B.sleep(["weights"]); A.wake(None); t_ba = time.perf_counter() - t0
+            t0 = time.perf_counter(); A.swap_out_for(B, ["weights"]); s_ab = time.perf_counter() - t0
+            sa, sb = A.stats(), B.stats()
+            t0 = time.perf_counter(); B.swap_out_for(A, ["weights"]); s_ba = time.perf_counter() - t0
+            if i >= 2:
+                serial += [t_ab, t_ba]; swap += [s_ab, s_ba]
+                d2h.append(wa / sa["sleep_copy_seconds"] / 1e9); h2d.append(wb / sb["wake_copy_seconds"] / 1e9)
+        ok = A.digest_all(["weights"]) == da
+        A.swap_out_for(B, ["weights"]); ok = ok and B.digest_all(["weights"]) == db
+        A.close(); B.close()
+        med = statistics.median
+        return {"models": f"{ma} ({wa / GiB:.2f} GiB) <-> {mb} ({wb / GiB:.2f} GiB), {args.extras_kv_gib:g} GiB kv_cache each, 1xB200, host tier",
+                "swap_s_median": round(med(swap), 4), "swap_s_min_max": [round(min(swap), 4), round(max(swap), 4)],
+                "serial_sleep_then_wake_s_median": round(med(serial), 4), "serial_s_min_max": [round(min(serial), 4), round(max(serial), 4)],
+                "speedup_vs_serial": round(med(serial) / med(swap), 3),
+                "d2h_gbs_during_swap_median": round(med(d2h), 2), "h2d_gbs_during_swap_median": round(med(h2d), 2),
+                "both_directions_gbs": round(med(d2h) + med(h2d), 2), "cycles": len(swap), "bit_exact": bool(ok)}
+    except Exception as e:
+        return {"error": str(e)[:300]}
+
+
+def measure_scaling_base(args, L, W, cfg, cycles: int = 6) -> dict:
+    """N=1 on the workload the N>1 lines use (one Llama-3-70B TP=8 shard), so the 1 -> 2 -> 4 -> 8 curve has a same-table base
+    (the main N=1 line is BASELINE config[1], the 8B table, whose W differs by 10 %)."""
+    import fma_b200
+
+    try:
+        eng = fma_b200.Engine(0, cfg)
+        _, wb = load_model(eng, W, args.scaling_workload, args.kv_gib, 1234)
+        eng.host_reserve(wb)
+        before = eng.digest_all(["weights"])
+        wakes, devs = [], []
+        for i in range(cycles + 2):
+            eng.sleep(["weights"]); eng.wake(None); st = eng.stats()
+            if i >= 2:
+                wakes.append(st["wake_seconds"]); devs.append(st["wake_copy_seconds"])
+        ok = eng.digest_all(["weights"]) == before
+        eng.close()
+        med = statistics.median
+        return {"workload": f"{args.scaling_workload} shard (the N>1 table) on 1 GPU", "weights_gib": round(wb / GiB, 3),
+                "value": round(wb / med(devs) / 1e9, 3), "e2e": round(wb / med(wakes) / 1e9, 3), "unit": "GB/s",
+                "wake_latency_s": round(med(wakes), 5), "wake_latency_s_min_max": [round(min(wakes), 5), round(max(wakes), 5)],
+                "cycles": len(wakes), "bit_exact": bool(ok)}
+    except Exception as e:
+        return {"error": str(e)[:300]}
+
+
+def measure_roundrobin(args, L, W, local_rank, rank, world, group, torch, rounds: int = 3) -> dict | None:
+    """BASELINE config 5: N/2 sleeping Llama-3-8B models parked in the idle GPUs' HBM over NVSwitch (rank r < N/2 parks on GPU
+    r + N/2), woken round-robin (one at a time, the other GPUs idle) and then all at once.  Ranks >= N/2 only lend their HBM."""
+    import fma_b200
+
+    half = world // 2
+    out = None
+    try:
+        eng = None
+        if rank < half:
+            eng = fma_b200.Engine(local_rank)
+            _, wb = load_model(eng, W, args.swap_models.split(",")[0], args.extras_kv_gib, 4321 + rank)
+            before = eng.digest_all(["weights"])
+            eng.peer_reserve(local_rank + half, wb)
+            eng.sleep(["weights"], tier=L.FMA_TIER_PEER)
+        single, single_dev, together = [], [], []
+        for rnd in range(rounds + 1):
+            for turn in range(half):
+                group.phase_barrier()
+                t = d = 0.0
+                if rank == turn:
+                    eng.wake(None); st = eng.stats(); t, d = st["wake_seconds"], st["wake_copy_seconds"]
+                    eng.sleep(["weights"], tier=L.FMA_TIER_PEER)
+                t, d = group.max(t), group.max(d)
+                if rnd:
+                    single.append(t); single_dev.append(d)
+        for rnd in range(rounds + 1):
+            group.phase_barrier()
+            t = 0.0
+            if rank < half:
+                eng.wake(None); t = eng.stats()["wake_seconds"]
+            t = group.max(t)
+            group.phase_barrier()
+            if rank < half:
+                eng.sleep(["weights"], tier=L.FMA_TIER_PEER)
+            if rnd:
+                together.append(t)
+        ok = True
+        if rank < half:
+            eng.wake(None)
+            ok = eng.digest_all(["weights"]) == before
+            wbytes = float(wb)
+            eng.peer_release(); eng.close()
+        else:
+            wbytes = 0.0
+        ok = group.all_true(ok)
+        w8 = group.max(wbytes)
+        med = statistics.median
+        out = {"models": half, "model": f"{args.swap_models.split(',')[0]} ({w8 / GiB:.2f} GiB)", "placement": f"rank r < {half} parks on GPU r + {half}",
+               "roundrobin_wake_s_median": round(med(single), 5), "roundrobin_wake_s_min_max": [round(min(single), 5), round(max(single), 5)],
+               "roundrobin_gbs_e2e": round(w8 / med(single) / 1e9, 1), "roundrobin_gbs_device": round(w8 / med(single_dev) / 1e9, 1),
+               "frac_of_nvlink_900": round(w8 / med(single) / 1e9 / NVLINK5_GBS, 4), "wakes": len(single),
+               "all_at_once_wake_s_median": round(med(together), 5), "all_at_once_aggregate_gbs": round(half * w8 / med(together) / 1e9, 1),
+               "bit_exact": bool(ok)}
+    except Exception as e:
+        out = {"error": str(e)[:300]}
+    return out
 
 
 def fill_weights(eng, table, seed: int, contents: str, torch) -> None:
@@ -576,30 +746,38 @@ def run_reference_workers(n_gpus: int, workload: str, kv_gib: float, steps: int,
 
 
 def summarise_reference(results, steps):
+    """Same aggregation as this repo's arm: per-step job latency = slowest rank of that step; median (and mean) over the steps."""
     errs = [r["error"] for r in results if "error" in r]
     if errs:
         return None, errs[0]
     n = len(results)
     W_total = sum(r["W"] for r in results)
-    wake = max(sum(x[1] for x in r["rows"]) / len(r["rows"]) for r in results)
-    sleep = max(sum(x[0] for x in r["rows"]) / len(r["rows"]) for r in results)
-    return {"W_total": W_total, "wake_s": wake, "sleep_s": sleep, "ok": all(r["ok"] for r in results), "n": n,
+    k = min(len(r["rows"]) for r in results)
+    wake_steps = [max(r["rows"][i][1] for r in results) for i in range(k)]
+    sleep_steps = [max(r["rows"][i][0] for r in results) for i in range(k)]
+    return {"W_total": W_total, "wake_s": statistics.median(wake_steps), "sleep_s": statistics.median(sleep_steps),
+            "wake_s_mean": sum(wake_steps) / k, "sleep_s_mean": sum(sleep_steps) / k,
+            "wake_steps": wake_steps, "ok": all(r["ok"] for r in results), "n": n,
             "segments": results[0]["segments"]}, None
 
 
-def reference_sample(args, workload) -> dict:
-    """cpu_baseline: the reference data path timed on this box in the same run (bounded: 1 warm-up + 2 cycles)."""
+def reference_sample(args, workload, cycles: int = 5) -> dict:
+    """cpu_baseline: the reference data path timed on this box in the same run (bounded: 1 warm-up + 5 timed cycles; median)."""
     cores = os.cpu_count()
     try:
-        res = run_reference_workers(1, workload, args.kv_gib, steps=2, warmup=1, contents=args.contents)
-        summ, err = summarise_reference(res, 2)
+        res = run_reference_workers(1, workload, args.kv_gib, steps=cycles, warmup=1, contents=args.contents)
+        summ, err = summarise_reference(res, cycles)
         if err:
             raise RuntimeError(err)
+        ws = summ["wake_steps"]
         return {"value": round(summ["W_total"] / summ["wake_s"] / 1e9, 3), "unit": "GB/s", "cores": 1, "kind": "reference",
-                "wake_latency_s": round(summ["wake_s"], 4), "sleep_latency_s": round(summ["sleep_s"], 4), "bit_exact": summ["ok"],
+                "value_min_max": [round(summ["W_total"] / max(ws) / 1e9, 3), round(summ["W_total"] / min(ws) / 1e9, 3)],
+                "wake_latency_s": round(summ["wake_s"], 4), "wake_latency_s_min_max": [round(min(ws), 4), round(max(ws), 4)],
+                "sleep_latency_s": round(summ["sleep_s"], 4), "bit_exact": summ["ok"],
                 "host_cores_available": cores,
                 "sample": f"vLLM {vllm_version()} CuMemAllocator.sleep(('weights',)) -> wake_up() over the full {workload} table "
-                          f"({summ['segments']} segments incl. kv_cache), 1 warm-up + 2 timed cycles, one Python thread per rank"}
+                          f"({summ['segments']} segments incl. kv_cache), 1 warm-up + {cycles} timed cycles (median; min-max beside it), "
+                          f"one Python thread per rank"}
     except Exception as e:
         return port_sample(workload, note=f"vLLM allocator unavailable ({str(e)[:120]})")
 
@@ -650,6 +828,7 @@ def run_reference(args) -> None:
         kind, cores = "reference", args.gpus
         value = summ["W_total"] / summ["wake_s"] / 1e9
         wake_s, sleep_s, ok = summ["wake_s"], summ["sleep_s"], summ["ok"]
+        wake_mean, sleep_mean = summ["wake_s_mean"], summ["sleep_s_mean"]
         W_total = summ["W_total"]
         sample = (f"vLLM {vllm_version()} CuMemAllocator (unmodified, the data path POST /sleep and /wake_up reach through the "
                   f"reference launcher): sleep(('weights',)) -> wake_up() of the full {workload} table per GPU, "
@@ -657,14 +836,22 @@ def run_reference(args) -> None:
     except Exception as e:
         p = port_sample(workload, note=f"vLLM allocator unavailable ({str(e)[:120]})")
         kind, cores, value, wake_s, sleep_s, ok, sample = "port", 1, p["value"], p["wake_latency_s"], p["sleep_latency_s"], True, p["sample"]
+        wake_mean, sleep_mean = wake_s, sleep_s
         W_total = 0
     total = time.perf_counter() - t0
+    import fma_b200  # noqa: F401  (table shapes only: workloads.py holds no engine code)
+    from fma_b200 import workloads as W
+
+    table = W.allocation_table(workload, kv_cache_bytes=int(args.kv_gib * GiB))
+    mode = args.mode if args.mode != "auto" else ("staged" if args.tier == "host" else "kernel")
     out = {"impl": "reference", "metric": "wake_h2d_gbs", "value": round(value, 3), "unit": "GB/s", "n_gpus": args.gpus,
-           "steps": args.steps, "warmup": args.warmup, "ms_per_step": round((wake_s + sleep_s) * 1e3, 3),
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": round((wake_mean + sleep_mean) * 1e3, 3),
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-           "config": {"workload": f"{workload} level-1 sleep->wake, host tier, per-rank shard, no collective",
-                      "kv_cache_gib_per_rank": args.kv_gib, "parallelism": f"{args.gpus} independent ranks"},
-           "wake_latency_s": round(wake_s, 5), "sleep_latency_s": round(sleep_s, 5), "bit_exact": bool(ok),
+           "config": bench_config(args, workload, W.weight_bytes(table), len(table), args.gpus, mode, False),
+           "aggregation": "same as the repo's arm: whole-job bytes / MEDIAN over the K timed steps of the per-step job latency (max over ranks)",
+           "value_mean": round(W_total / wake_mean / 1e9, 3) if W_total else None,
+           "wake_latency_s": round(wake_s, 5), "wake_latency_s_mean": round(wake_mean, 5),
+           "sleep_latency_s": round(sleep_s, 5), "bit_exact": bool(ok),
            "cpu_baseline": {"value": round(value, 3), "unit": "GB/s", "cores": cores, "kind": kind, "sample": sample},
            "e2e": {"value": round(value, 3), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0, "wall_s_total": round(total, 1)}
@@ -692,7 +879,13 @@ def main() -> None:
     ap.add_argument("--pack", type=int, default=0, help="1 = PACKED host image (lossless bf16 page code; pays off with --contents bf16)")
     ap.add_argument("--incremental", type=int, default=0, help="1 = INCREMENTAL sleep: a sleep whose weights still match the image in the host store moves nothing")
     ap.add_argument("--packed-extra", type=int, default=1, help="at N=1 also measure the PACKED image on bf16 dummy weights in a child process (reported under packed_image)")
-    ap.add_argument("--extras", default="", help="comma list of in-process extras measured after the main line on the same engines: packed,incremental (any N)")
+    ap.add_argument("--extras", default="swap,scaling_base,roundrobin",
+                    help="comma list of extras measured after the main line: swap (N=1: BASELINE config 4, Llama-3-8B <-> Mistral-7B), scaling_base "
+                         "(N=1: the N>1 table on one GPU), roundrobin (N>=2: BASELINE config 5, N/2 parked 8B sleepers woken round-robin), "
+                         "packed,incremental (any N, on the same engines; opt-in)")
+    ap.add_argument("--swap-models", default="llama-3-8b,mistral-7b", help="the two models of the swap extra (the first is also the round-robin sleeper)")
+    ap.add_argument("--scaling-workload", default="llama-3-70b-tp8", help="table of the scaling_base extra (= the N>1 workload)")
+    ap.add_argument("--extras-kv-gib", type=float, default=16.0, help="kv_cache bytes per model in the swap / roundrobin extras")
     ap.add_argument("--timeline", default="", help="directory: every rank writes the per-phase timeline (fma_timeline) of its last timed sleep and wake there")
     ap.add_argument("--packed-child", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()

@@ -367,6 +367,7 @@ void host_store_free(HostStore& h) {
 }
 
 void invalidate_shadows(fma_engine_t* e) {
+    std::lock_guard<std::mutex> lk(e->mu);
     for (Segment& s : e->segs) s.shadow_off = kNoOffset;
     e->shadow_image_bytes = 0;
     e->shadow_store_bytes = 0;
@@ -976,19 +977,30 @@ int fma_swap(fma_engine_t* out_e, uint64_t offload_tag_mask, int tier, fma_engin
     return FMA_OK;
 }
 
+// Store management takes the engine's operation lock: the Python shim pre-pins from a background thread right after the weights
+// pool closes (cumem.py), and a /sleep arriving meanwhile must wait for that pin instead of racing it.  The segment table is
+// only ever walked under e->mu (torch may be allocating the kv_cache pool on another thread at that moment).
 int fma_host_reserve(fma_engine_t* e, size_t bytes) {
     if (check_engine(e) != FMA_OK) return FMA_EINVAL;
-    for (const Segment& s : e->segs)
-        if (s.has_backup && s.backup_tier == FMA_TIER_HOST && e->host.cap < bytes)
-            return fail(FMA_ESTATE, "cannot regrow the host store while it holds a sleeping image");
+    std::lock_guard<std::mutex> op(e->op_mu);
+    {
+        std::lock_guard<std::mutex> lk(e->mu);
+        for (const Segment& s : e->segs)
+            if (s.has_backup && s.backup_tier == FMA_TIER_HOST && e->host.cap < bytes)
+                return fail(FMA_ESTATE, "cannot regrow the host store while it holds a sleeping image");
+    }
     DeviceGuard guard(e->device);
     return host_store_reserve(e, bytes);
 }
 
 int fma_host_release(fma_engine_t* e) {
     if (check_engine(e) != FMA_OK) return FMA_EINVAL;
-    for (const Segment& s : e->segs)
-        if (s.has_backup && s.backup_tier == FMA_TIER_HOST) return fail(FMA_ESTATE, "host store holds a sleeping image");
+    std::lock_guard<std::mutex> op(e->op_mu);
+    {
+        std::lock_guard<std::mutex> lk(e->mu);
+        for (const Segment& s : e->segs)
+            if (s.has_backup && s.backup_tier == FMA_TIER_HOST) return fail(FMA_ESTATE, "host store holds a sleeping image");
+    }
     DeviceGuard guard(e->device);
     cudaDeviceSynchronize();
     invalidate_shadows(e);
@@ -1008,16 +1020,24 @@ int fma_host_store_view(fma_engine_t* e, const void** base, uint64_t* bytes) {
 
 int fma_peer_reserve(fma_engine_t* e, int peer_device, size_t bytes) {
     if (check_engine(e) != FMA_OK) return FMA_EINVAL;
-    for (const Segment& s : e->segs)
-        if (s.has_backup && s.backup_tier != FMA_TIER_HOST) return fail(FMA_ESTATE, "parking buffer holds a sleeping image");
+    std::lock_guard<std::mutex> op(e->op_mu);
+    {
+        std::lock_guard<std::mutex> lk(e->mu);
+        for (const Segment& s : e->segs)
+            if (s.has_backup && s.backup_tier != FMA_TIER_HOST) return fail(FMA_ESTATE, "parking buffer holds a sleeping image");
+    }
     DeviceGuard guard(e->device);
     return park_reserve(e, peer_device, bytes);
 }
 
 int fma_peer_release(fma_engine_t* e) {
     if (check_engine(e) != FMA_OK) return FMA_EINVAL;
-    for (const Segment& s : e->segs)
-        if (s.has_backup && s.backup_tier != FMA_TIER_HOST) return fail(FMA_ESTATE, "parking buffer holds a sleeping image");
+    std::lock_guard<std::mutex> op(e->op_mu);
+    {
+        std::lock_guard<std::mutex> lk(e->mu);
+        for (const Segment& s : e->segs)
+            if (s.has_backup && s.backup_tier != FMA_TIER_HOST) return fail(FMA_ESTATE, "parking buffer holds a sleeping image");
+    }
     DeviceGuard guard(e->device);
     return park_release(e);
 }

@@ -135,16 +135,16 @@ void open_gate() {
     });
 }
 
-// does any OTHER live process want a class above (numerically below) `cls`?
+// does anybody — another live process, or another thread of this one (two engines in one process: a hot swap) — want a class
+// above (numerically below) `cls`?  The caller itself only ever counts in want[cls], so its own slot can be scanned as well.
 bool higher_waiting(int cls, bool check_alive) {
     Shm* s = g.shm;
     for (int i = 0; i < kSlots; ++i) {
-        if (i == g.slot) continue;
         const int32_t pid = s->slots[i].pid.load(std::memory_order_relaxed);
         if (!pid) continue;
         for (int c = 0; c < cls; ++c) {
             if (s->slots[i].want[c].load(std::memory_order_relaxed) > 0) {
-                if (check_alive && !pid_alive(pid)) {  // reclaim a dead process's slot
+                if (check_alive && i != g.slot && !pid_alive(pid)) {  // reclaim a dead process's slot
                     for (int k = 0; k < kGateClasses; ++k) s->slots[i].want[k].store(0);
                     int32_t expect = pid;
                     s->slots[i].pid.compare_exchange_strong(expect, 0);

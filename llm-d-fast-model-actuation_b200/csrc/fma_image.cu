@@ -8,6 +8,7 @@ extern "C" {
 
 int fma_image_export(fma_engine_t* e, int* out_fd) {
     if (check_engine(e) != FMA_OK) return FMA_EINVAL;
+    std::lock_guard<std::mutex> op(e->op_mu);
     if (!out_fd) return fail(FMA_EINVAL, "out_fd is NULL");
     if (e->host.fd < 0 || !e->host.base) return fail(FMA_ESTATE, "the host store is not shareable (set FMA_HOST_STORE_SHM=1 before the first sleep)");
     if (e->image_tier != FMA_TIER_HOST) return fail(FMA_ESTATE, "no host-tier image");
@@ -50,6 +51,7 @@ int fma_image_export(fma_engine_t* e, int* out_fd) {
 
 int fma_image_adopt(fma_engine_t* e, int fd, uint64_t tag_mask, uint32_t flags) {
     if (check_engine(e) != FMA_OK) return FMA_EINVAL;
+    std::lock_guard<std::mutex> op(e->op_mu);
     if (!tag_mask) return fail(FMA_EINVAL, "adopt needs the tag mask the image was slept with");
     for (const Segment& s : e->segs)
         if (!s.mapped) return fail(FMA_ESTATE, "adopt needs a fully awake engine");
@@ -107,6 +109,8 @@ int fma_image_adopt(fma_engine_t* e, int fd, uint64_t tag_mask, uint32_t flags) 
     for (size_t i = 0; i < ds.size(); ++i) {
         memcpy(&ds[i], tail + sizeof(hd) + i * sizeof(ImageSegDesc), sizeof(ImageSegDesc));
         const Segment& s = e->segs[order[i]];
+        // the descriptor comes from a file or another process: bound what it claims before using it as a length
+        if (ds[i].tag_len >= sizeof(ds[i].tag) || ds[i].digest_valid > 1) return bail(FMA_EINVAL, "image descriptor is malformed (tag length / digest flag)");
         if (ds[i].bytes != s.bytes || ds[i].packed_off != off || std::string(ds[i].tag, ds[i].tag_len) != e->tags[s.tag])
             return bail(FMA_EINVAL, "image and engine disagree on a segment's size, offset or tag");
         off += s.bytes;

@@ -19,6 +19,7 @@ class RankGroup:
         self.rank, self.world, self.local_rank = rank_env()
         self.backend = backend
         self._dist = None
+        self._cpu_group = None
         self._device = "cpu"
         if self.world > 1:
             import torch
@@ -34,10 +35,29 @@ class RankGroup:
             if not dist.is_initialized():
                 dist.init_process_group(backend, **kw)
             self._dist = dist
+            # CPU-side group for the executor's "every rank has finished" hand-shake between the phases of a step
+            # (vLLM waits for all workers over a shm message queue, multiproc_executor.py:339-379): no GPU work, no NCCL kernel
+            self._cpu_group = dist.new_group(backend="gloo") if backend == "nccl" else None
 
     def barrier(self) -> None:
         if self._dist is not None:
             self._dist.barrier()
+
+    def phase_barrier(self) -> None:
+        """Executor semantics (abstract.py:327,347): ``sleep`` / ``wake_up`` are fanned out to every rank and return when ALL
+        ranks are done, so no rank starts waking while another still sleeps.  Host-side only (gloo)."""
+        if self._dist is not None:
+            self._dist.barrier(group=self._cpu_group) if self._cpu_group is not None else self._dist.barrier()
+
+    def max_vec(self, xs: list[float]) -> list[float]:
+        """Element-wise max over ranks (per-step job latency = the slowest rank of that step)."""
+        if self._dist is None:
+            return [float(x) for x in xs]
+        import torch
+
+        t = torch.tensor([float(x) for x in xs], dtype=torch.float64, device=self._device)
+        self._dist.all_reduce(t, op=self._dist.ReduceOp.MAX)
+        return [float(v) for v in t.tolist()]
 
     def _reduce(self, x: float, op_name: str) -> float:
         if self._dist is None:

@@ -20,6 +20,7 @@ plumbing, not a data-path fallback: it owns no weights).
 from __future__ import annotations
 
 import logging
+import threading
 import time
 from typing import Iterable, Protocol
 
@@ -73,8 +74,20 @@ class SleepState:
         self.sleeping_tags: set[str] = set()
         self.last_sleep_seconds = 0.0
         self.last_wake_seconds = 0.0
+        # The routes are sync endpoints (thread pool): a controller retry after its 5 s /wake_up timeout
+        # (inference-server.go:1699-1716) can overlap the call still in flight.  vLLM serialises these through the engine
+        # core's RPC queue, go/fma/server.go and fma_served.cpp with a mutex; so does this.
+        self._lock = threading.Lock()
 
     def sleep(self, level: int = 1) -> None:
+        with self._lock:
+            self._sleep(level)
+
+    def wake_up(self, tags: list[str] | None = None) -> None:
+        with self._lock:
+            self._wake_up(tags)
+
+    def _sleep(self, level: int = 1) -> None:
         if self.is_sleeping:
             logger.warning("Executor is already sleeping.")
             return
@@ -85,7 +98,7 @@ class SleepState:
         self.is_sleeping = True
         logger.info("It took %.6f seconds to fall asleep.", self.last_sleep_seconds)
 
-    def wake_up(self, tags: list[str] | None = None) -> None:
+    def _wake_up(self, tags: list[str] | None = None) -> None:
         if not self.is_sleeping:
             logger.warning("Executor is not sleeping.")
             return

@@ -20,6 +20,8 @@ when ``FMA_B200=1``.  Not yet run on a GPU: the window / aliasing logic is teste
 """
 from __future__ import annotations
 
+import os
+
 from typing import Callable, Iterable, Iterator
 
 from . import loader as _fmt
@@ -92,13 +94,21 @@ class _CudaArray:
         self._owner = owner
 
 
-def torch_view(torch, owner):
-    """view(device_address, offset, entry) -> torch tensor of the entry's dtype and shape aliasing the staging buffer
-    (a private copy when the file left the tensor misaligned for its dtype)."""
+def torch_view(torch, owner, alias: bool | None = None):
+    """view(device_address, offset, entry) -> torch tensor of the entry's dtype and shape.
+
+    Default: a private device copy of the staging bytes (one HBM-speed D2D copy per tensor).  The staging segment is
+    overwritten by the next window and freed at the end, and vLLM weight loaders may keep ``loaded_weight`` past their
+    iteration (fused / MoE expert stacking, deferred quantisation, copies on another stream), so handing out aliases is only
+    safe for loaders known to consume each tensor at once: ``FMA_LOADER_ALIAS=1`` (or ``alias=True``) turns the zero-copy
+    aliasing on (a misaligned tensor is cloned either way)."""
+    if alias is None:
+        alias = os.environ.get("FMA_LOADER_ALIAS") == "1"
+
     def view(ptr: int, off: int, t: _fmt.TensorEntry):
         raw = torch.as_tensor(_CudaArray(ptr + off, t.nbytes, owner), device="cuda")
         dtype = getattr(torch, TORCH_DTYPES[t.dtype])
-        if (ptr + off) % max(_fmt.DTYPE_BYTES[t.dtype], 1):
+        if not alias or (ptr + off) % max(_fmt.DTYPE_BYTES[t.dtype], 1):
             raw = raw.clone()
         return raw.view(dtype).reshape(t.shape)
     return view

@@ -91,6 +91,28 @@ int main() {
     hostsim_fail_create_after(-1);
     OK(fma_wake(a, 0, FMA_FLAG_VERIFY));                        // the controller's retry
     assert(fma_is_sleeping(a) == 0);
+    // The failure arrives at the LAST run (the kv_cache remap) while the weights runs are already mapped and (partly) restored:
+    // the failed call must roll its own mappings back — otherwise the retry finds the weights "awake", skips them and reports
+    // success over bytes that were never copied (fma_wake.cu) — and the retry restores every weight bit-exact.
+    for (int fail_at = 1; fail_at <= 3; ++fail_at) {
+        auto before = digests(a);
+        OK(fma_sleep(a, 1ull << w, FMA_TIER_HOST, 0));
+        hostsim_fail_create_after(fail_at);
+        rc = fma_wake(a, 0, 0);
+        hostsim_fail_create_after(-1);
+        if (rc == 0) continue;   // fewer runs than fail_at: nothing was injected
+        const int n = fma_segment_count(a);
+        for (int i = 0; i < n; ++i) {
+            fma_segment_info_t si;
+            OK(fma_segment_info(a, i, &si));
+            assert(si.mapped == 0);                               // everything this call mapped is unmapped again ...
+            if (si.tag == w) assert(si.has_backup == 1);          // ... and the image is still there
+        }
+        OK(fma_wake(a, 0, 0));
+        assert(fma_is_sleeping(a) == 0);
+        auto after = digests(a);
+        for (size_t i = 0; i + 1 < before.size(); ++i) assert(after[i] == before[i]);
+    }
 
     // failed SLEEP (a D2H refuses to enqueue after a few slots): whatever was already released has its bytes in the
     // store, the rest is still mapped -> a wake brings everything back bit-exact, in every mode

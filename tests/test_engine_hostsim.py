@@ -126,7 +126,7 @@ print("ok")
     assert r.returncode == 0 and "ok" in r.stdout, (r.stdout + r.stderr)[-3000:]
 
 
-def test_bench_main_flow_runs_against_the_host_simulated_engine(hostsim_lib, oracle):
+def test_bench_main_flow_runs_against_the_host_simulated_engine(hostsim_lib, oracle, tmp_path):
     """The whole of bench.py's own arm at N=1 — table, fill, digests, timed cycles, JSON line with every contract key,
     cpu_baseline fallback (the oracle port: vLLM's allocator cannot load here) and the packed_image child — with torch
     replaced by tests/stubs/torch.  Numbers are meaningless here; the flow and the keys are what is checked."""
@@ -135,9 +135,16 @@ def test_bench_main_flow_runs_against_the_host_simulated_engine(hostsim_lib, ora
     env = dict(os.environ, FMA_B200_LIB=hostsim_lib, FMA_HOSTSIM="1", HOSTSIM_DEVICES="1",
                PYTHONPATH=os.path.join(ROOT, "tests", "stubs") + os.pathsep + os.environ.get("PYTHONPATH", ""))
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", "tiny-llama-test", "--kv-gib", "0.03125",
-                        "--steps", "2", "--warmup", "3"], env=env, cwd=ROOT, capture_output=True, text=True, timeout=900)
+                        "--steps", "2", "--warmup", "3", "--swap-models", "tiny-llama-test,tiny-llama-test", "--scaling-workload", "opt-125m",
+                        "--extras-kv-gib", "0.03125", "--timeline", str(tmp_path / "tl")], env=env, cwd=ROOT, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
     out = json.loads(r.stdout.strip().splitlines()[-1])
+    assert out["swap_config4"].get("bit_exact") is True and out["swap_config4"]["cycles"] == 20, out["swap_config4"]
+    assert out["n1_on_scaling_workload"].get("bit_exact") is True, out["n1_on_scaling_workload"]
+    assert out["config"]["segments_per_rank"] > 0 and "phases" in out["config"]
+    assert out["wake_latency_s_min_max"][0] <= out["wake_latency_s"] <= out["wake_latency_s_min_max"][1]
+    tl = open(tmp_path / "tl" / "n1_rank0.csv").read()
+    assert "wake,map_backed" in tl and "wake,total" in tl and "sleep,unmap" in tl and "wake,kernel" in tl, tl[:600]
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
                 "data", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks", "packed_image"):
         assert key in out, key

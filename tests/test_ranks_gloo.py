@@ -27,6 +27,8 @@ def _worker(rank, world, port, q):
     out = dict(rank=g.rank, world=g.world, max=g.max(t_wake), sum=g.sum(float(Wb)), all_ok=g.all_true(True),
                one_bad=g.all_true(rank != 1), seed=ranks.shard_seed(rank), park=ranks.parking_device(rank, world), W=Wb)
     out["gbs"] = ranks.aggregate_wake(out["sum"], out["max"])
+    g.phase_barrier()
+    out["max_vec"] = g.max_vec([0.1 * (rank + 1), 0.5 - 0.2 * rank])      # per-step max over ranks
     g.barrier()
     g.close()
     q.put(out)
@@ -50,6 +52,7 @@ def test_two_rank_gloo_aggregation():
     assert [r["seed"] for r in res] == [1234, 1235]
     assert sorted(r["park"] for r in res) == [0, 1] and all(r["park"] != r["rank"] for r in res)
     assert all(abs(r["gbs"] - 2 * res[0]["W"] / 0.35 / 1e9) < 1e-6 for r in res)
+    assert all(r["max_vec"] == pytest.approx([0.2, 0.5]) for r in res)
 
 
 def test_parking_is_a_fixed_point_free_permutation():

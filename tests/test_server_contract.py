@@ -88,3 +88,42 @@ def test_cpu_worker_semantics_move_nothing():
     c = TestClient(server.create_app(server.CpuWorkerSemantics()))
     assert c.post("/sleep").status_code == 200 and c.get("/is_sleeping").json()["is_sleeping"] is True
     assert c.post("/wake_up").status_code == 200 and c.get("/is_sleeping").json()["is_sleeping"] is False
+
+
+def test_a_retried_wake_up_never_overlaps_the_one_in_flight():
+    """The controller retries POST /wake_up after its 5 s timeout (inference-server.go:1699-1716): the retry must wait for the
+    call in flight (then find nothing to do), never enter the engine beside it — vLLM's engine-core RPC queue, go/fma/server.go
+    and fma_served.cpp serialise the same way."""
+    import threading
+    import time
+
+    from fma_b200.server import SleepState
+
+    class SlowBackend:
+        def __init__(self):
+            self.inside = 0
+            self.max_inside = 0
+            self.wakes = 0
+            self.lock = threading.Lock()
+
+        def sleep(self, level):
+            pass
+
+        def wake_up(self, tags):
+            with self.lock:
+                self.inside += 1
+                self.max_inside = max(self.max_inside, self.inside)
+                self.wakes += 1
+            time.sleep(0.2)
+            with self.lock:
+                self.inside -= 1
+
+    b = SlowBackend()
+    st = SleepState(b)
+    st.sleep(1)
+    ts = [threading.Thread(target=st.wake_up) for _ in range(4)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert b.max_inside == 1 and b.wakes == 1 and not st.is_sleeping
