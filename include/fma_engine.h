@@ -235,12 +235,33 @@ FMA_API int  fma_peer_release(fma_engine_t* e);
  * restores the weights at PCIe speed instead of re-reading a checkpoint.  The fd may also be a regular FILE holding
  * the same bytes (Engine.image_save / image_load in the Python binding): if its mapping cannot be pinned in place the
  * image is copied once into an anonymous pinned store.  A PACKED image travels with its page table (descriptor v2).
- * Status: exercised on the CUDA host simulation only (tests/test_engine_hostsim.py); not yet run on a B200. */
+ * Status: green on a B200 (in-process and cross-process, plain and PACKED: tests/test_gpu_parity.py, profiles/gpu_suite_all_gates_open_r2.log). */
 FMA_API int  fma_image_export(fma_engine_t* e, int* out_fd);          /* caller owns (closes) the returned fd          */
 /* flags: FMA_FLAG_VERIFY = "sleep by adoption": the engine holds the weights itself (another replica of the model the image
  * came from) and its device bytes must match the image's digests — then its device side is released and it shares that
  * image (one host copy per node instead of one per replica); on a mismatch nothing is touched and FMA_EINTEGRITY comes back. */
 FMA_API int  fma_image_adopt(fma_engine_t* e, int fd, uint64_t tag_mask, uint32_t flags);  /* fd stays owned by the caller */
+
+/* ---- node-level parking buffers (exportable) ------------------- */
+/* The reference launcher restricts every instance to its own GPUs (inference_server/launcher/launcher.py:171-187), and
+ * whatever an instance allocates dies with it — which is when the controller cold-starts
+ * (pkg/controller/dual-pods/inference-server.go:416-448).  A node-level owner (the node agent) therefore creates the
+ * parking buffer: a VMM allocation in `device`'s HBM with a POSIX-fd shareable handle.  *out_fd can be sent to any process
+ * on the node (SCM_RIGHTS, inheritance); the buffer lives until fma_parking_destroy AND the last importer has let go. */
+FMA_API int  fma_parking_create(int device, size_t bytes, uint64_t* out_handle, int* out_fd);
+FMA_API int  fma_parking_export(uint64_t handle, int* out_fd, uint64_t* out_bytes);   /* another fd for another instance   */
+FMA_API int  fma_parking_destroy(uint64_t handle);
+/* Instance side: use the owner's buffer (`bytes` = the size it was created with, a multiple of 2 MiB) as this engine's
+ * peer-tier store.  Imports the handle, maps it and grants access to the ENGINE's GPU only; the buffer's GPU need not be
+ * visible to this process.  Replaces fma_peer_reserve for instances that cannot see their parking GPU. */
+FMA_API int  fma_peer_attach(fma_engine_t* e, int fd, size_t bytes);
+/* Hand-over of an image parked in such a buffer.  fma_image_describe(tier) returns the descriptor of the image sleeping in
+ * `tier` (segment sizes, tags, K3 digests, page table of a PACKED image; at most 2 MiB; call with buf=NULL to size it) —
+ * the owner keeps it next to the fd.  A fresh engine with the same segment sequence (another process, after the first one
+ * died) calls fma_peer_attach and then fma_image_adopt_parked: it releases its device side and wakes from the parked image.
+ * With FMA_FLAG_VERIFY the engine's current device bytes must equal the image's (sleep by adoption). */
+FMA_API int  fma_image_describe(fma_engine_t* e, int tier, void* buf, size_t cap);
+FMA_API int  fma_image_adopt_parked(fma_engine_t* e, const void* desc, size_t desc_bytes, uint64_t tag_mask, uint32_t flags);
 
 /* ---- integrity (K3) and synthetic data (K0) --------------------------------------- */
 /* 64-bit position-sensitive digest of a mapped segment, computed on the device.

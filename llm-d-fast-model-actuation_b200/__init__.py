@@ -23,11 +23,12 @@ from ._lib import (  # noqa: F401
     lib_path,
     load_library,
 )
-from .engine import Engine, EngineConfig  # noqa: F401
+from .engine import Engine, EngineConfig, ParkingBuffer  # noqa: F401
 
 __all__ = [
     "Engine",
     "EngineConfig",
+    "ParkingBuffer",
     "FmaError",
     "lib_path",
     "load_library",

@@ -138,6 +138,12 @@ _PROTOTYPES = {
     "fma_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
     "fma_stats": (C.c_int, [C.c_void_p, C.POINTER(fma_stats_t)]),
     "fma_timeline": (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t]),
+    "fma_parking_create": (C.c_int, [C.c_int, C.c_size_t, C.POINTER(C.c_uint64), C.POINTER(C.c_int)]),
+    "fma_parking_export": (C.c_int, [C.c_uint64, C.POINTER(C.c_int), C.POINTER(C.c_uint64)]),
+    "fma_parking_destroy": (C.c_int, [C.c_uint64]),
+    "fma_peer_attach": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t]),
+    "fma_image_describe": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
+    "fma_image_adopt_parked": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint32]),
 }
 
 _lib = None

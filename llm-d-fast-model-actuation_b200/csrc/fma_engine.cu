@@ -78,7 +78,9 @@ static void load_driver() {
               resolve("cuMemAddressFree", g_drv.MemAddressFree) && resolve("cuMemCreate", g_drv.MemCreate) &&
               resolve("cuMemRelease", g_drv.MemRelease) && resolve("cuMemMap", g_drv.MemMap) &&
               resolve("cuMemUnmap", g_drv.MemUnmap) && resolve("cuMemSetAccess", g_drv.MemSetAccess) &&
-              resolve("cuMemGetAllocationGranularity", g_drv.MemGetAllocationGranularity);
+              resolve("cuMemGetAllocationGranularity", g_drv.MemGetAllocationGranularity) &&
+              resolve("cuMemExportToShareableHandle", g_drv.MemExportToShareableHandle) &&
+              resolve("cuMemImportFromShareableHandle", g_drv.MemImportFromShareableHandle);
     g_drv.ok = ok;
 }
 
@@ -1040,6 +1042,118 @@ int fma_peer_release(fma_engine_t* e) {
     }
     DeviceGuard guard(e->device);
     return park_release(e);
+}
+
+// ---- node-level parking buffers: exportable VMM allocations ------------------------------------------
+// The reference launcher pins every instance to its own GPUs (inference_server/launcher/launcher.py:171-187 overwrites
+// CUDA_VISIBLE_DEVICES), so an instance cannot cuMemCreate on an idle peer itself, and whatever it allocates dies with it —
+// exactly when the controller would otherwise cold-start (pkg/controller/dual-pods/inference-server.go:416-448).  A node-level
+// owner (the node agent, which sees every GPU) therefore creates the parking buffer with a POSIX-fd shareable handle, keeps
+// it alive, and hands the fd to instances (SCM_RIGHTS / inheritance); an instance imports it, maps it and grants access to
+// ITS GPU only — reads and writes then go over NVLink / NVSwitch although the buffer's GPU is not visible to the instance.
+namespace {
+struct Parking {
+    CUmemGenericAllocationHandle handle;
+    size_t bytes;
+    int device;
+};
+std::mutex g_parking_mu;
+std::map<uint64_t, Parking> g_parkings;
+uint64_t g_next_parking = 1;
+}  // namespace
+
+int fma_parking_create(int device, size_t bytes, uint64_t* out_handle, int* out_fd) {
+    if (!out_handle || !out_fd) return fail(FMA_EINVAL, "out pointers are NULL");
+    if (!driver_ready()) return fail(FMA_ENODRIVER, "%s", g_drv_err);
+    int ndev = 0;
+    RT(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(FMA_EINVAL, "device %d not visible (have %d)", device, ndev);
+    DeviceGuard guard(device);
+    RT(cudaFree(nullptr));  // the device's primary context must exist
+    CUmemAllocationProp prop = device_prop(device);
+    prop.requestedHandleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+    size_t gran = FMA_PAGE_BYTES;
+    DRV(g_drv.MemGetAllocationGranularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_MINIMUM));
+    bytes = round_up(std::max<size_t>(bytes, FMA_PAGE_BYTES), std::max<size_t>(gran, FMA_PAGE_BYTES));
+    Parking p;
+    p.bytes = bytes;
+    p.device = device;
+    DRV(g_drv.MemCreate(&p.handle, bytes, &prop, 0));
+    int fd = -1;
+    CUresult r = g_drv.MemExportToShareableHandle(&fd, p.handle, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0);
+    if (r != CUDA_SUCCESS) {
+        g_drv.MemRelease(p.handle);
+        return fail(FMA_ECUDA, "cuMemExportToShareableHandle failed: %s", cu_err(r));
+    }
+    std::lock_guard<std::mutex> lk(g_parking_mu);
+    *out_handle = g_next_parking++;
+    g_parkings[*out_handle] = p;
+    *out_fd = fd;
+    return FMA_OK;
+}
+
+int fma_parking_export(uint64_t handle, int* out_fd, uint64_t* out_bytes) {
+    if (!out_fd) return fail(FMA_EINVAL, "out_fd is NULL");
+    std::lock_guard<std::mutex> lk(g_parking_mu);
+    auto it = g_parkings.find(handle);
+    if (it == g_parkings.end()) return fail(FMA_ENOTFOUND, "unknown parking handle %llu", (unsigned long long)handle);
+    int fd = -1;
+    DRV(g_drv.MemExportToShareableHandle(&fd, it->second.handle, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0));
+    *out_fd = fd;
+    if (out_bytes) *out_bytes = it->second.bytes;
+    return FMA_OK;
+}
+
+int fma_parking_destroy(uint64_t handle) {
+    std::lock_guard<std::mutex> lk(g_parking_mu);
+    auto it = g_parkings.find(handle);
+    if (it == g_parkings.end()) return fail(FMA_ENOTFOUND, "unknown parking handle %llu", (unsigned long long)handle);
+    g_drv.MemRelease(it->second.handle);  // the memory goes once the last importer has unmapped it
+    g_parkings.erase(it);
+    return FMA_OK;
+}
+
+int fma_peer_attach(fma_engine_t* e, int fd, size_t bytes) {
+    if (check_engine(e) != FMA_OK) return FMA_EINVAL;
+    if (fd < 0 || bytes == 0 || bytes % FMA_PAGE_BYTES) return fail(FMA_EINVAL, "attach needs the owner's fd and the buffer's size (a multiple of 2 MiB)");
+    std::lock_guard<std::mutex> op(e->op_mu);
+    {
+        std::lock_guard<std::mutex> lk(e->mu);
+        for (const Segment& s : e->segs)
+            if (s.has_backup && s.backup_tier != FMA_TIER_HOST) return fail(FMA_ESTATE, "parking buffer holds a sleeping image");
+    }
+    DeviceGuard guard(e->device);
+    int rc = park_release(e);
+    if (rc != FMA_OK) return rc;
+    ParkStore p;
+    p.device = kForeignDevice;
+    p.cap = bytes;
+    DRV(g_drv.MemImportFromShareableHandle(&p.handle, reinterpret_cast<void*>(static_cast<uintptr_t>(fd)), CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR));
+    CUresult r = g_drv.MemAddressReserve(&p.va, bytes, FMA_PAGE_BYTES, 0, 0);
+    if (r != CUDA_SUCCESS) {
+        g_drv.MemRelease(p.handle);
+        return fail(FMA_ECUDA, "cuMemAddressReserve(attach) failed: %s", cu_err(r));
+    }
+    r = g_drv.MemMap(p.va, bytes, 0, p.handle, 0);
+    if (r != CUDA_SUCCESS) {
+        g_drv.MemAddressFree(p.va, bytes);
+        g_drv.MemRelease(p.handle);
+        return fail(FMA_ECUDA, "cuMemMap(attach, %zu bytes) failed: %s (is `bytes` the size the owner created?)", bytes, cu_err(r));
+    }
+    CUmemAccessDesc acc;
+    memset(&acc, 0, sizeof(acc));
+    acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    acc.location.id = e->device;
+    acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+    r = g_drv.MemSetAccess(p.va, bytes, &acc, 1);
+    if (r != CUDA_SUCCESS) {
+        g_drv.MemUnmap(p.va, bytes);
+        g_drv.MemAddressFree(p.va, bytes);
+        g_drv.MemRelease(p.handle);
+        return fail(FMA_ECUDA, "cuMemSetAccess(attach) failed: %s (no P2P path from device %d to the buffer's GPU?)", cu_err(r), e->device);
+    }
+    e->park = p;
+    return FMA_OK;
 }
 
 int fma_digest_segment(fma_engine_t* e, int index, uint64_t* out) {

@@ -4,24 +4,24 @@
 
 using namespace fma_impl;
 
-extern "C" {
+namespace fma_impl {
 
-int fma_image_export(fma_engine_t* e, int* out_fd) {
-    if (check_engine(e) != FMA_OK) return FMA_EINVAL;
-    std::lock_guard<std::mutex> op(e->op_mu);
-    if (!out_fd) return fail(FMA_EINVAL, "out_fd is NULL");
-    if (e->host.fd < 0 || !e->host.base) return fail(FMA_ESTATE, "the host store is not shareable (set FMA_HOST_STORE_SHM=1 before the first sleep)");
-    if (e->image_tier != FMA_TIER_HOST) return fail(FMA_ESTATE, "no host-tier image");
+// Descriptor of the image sleeping in `tier`'s store: header, one ImageSegDesc per offloaded segment in image order and, for a
+// PACKED image (version 2), the per-page stored sizes (offsets are their prefix sums).  At most kImageTail bytes.
+int image_descriptor_build(fma_engine_t* e, int tier, std::vector<char>* out) {
     std::vector<const Segment*> segs;
-    for (const Segment& s : e->segs)
-        if (s.has_backup && s.backup_tier == FMA_TIER_HOST && !s.mapped) segs.push_back(&s);
-    if (segs.empty()) return fail(FMA_ESTATE, "nothing is asleep in the host store");
+    {
+        std::lock_guard<std::mutex> lk(e->mu);
+        for (const Segment& s : e->segs)
+            if (s.has_backup && (tier == FMA_TIER_HOST ? s.backup_tier == FMA_TIER_HOST : s.backup_tier != FMA_TIER_HOST) && !s.mapped) segs.push_back(&s);
+    }
+    if (segs.empty()) return fail(FMA_ESTATE, "nothing is asleep in that store");
     std::sort(segs.begin(), segs.end(), [](const Segment* a, const Segment* b) { return a->packed_off < b->packed_off; });
-    // version 2 = PACKED image: the per-page stored sizes follow the segment descriptors (offsets are their prefix sums)
     const size_t n_img_pages = e->image_packed ? e->img_bytes.size() : 0;
-    if (sizeof(ImageHeader) + segs.size() * sizeof(ImageSegDesc) + sizeof(uint32_t) * (1 + n_img_pages) > kImageTail)
-        return fail(FMA_ENOMEM, "too many segments / pages for the descriptor");
-    char* tail = static_cast<char*>(e->host.base) + e->host.cap;
+    const size_t total = sizeof(ImageHeader) + segs.size() * sizeof(ImageSegDesc) + sizeof(uint32_t) * (1 + n_img_pages);
+    if (total > kImageTail) return fail(FMA_ENOMEM, "too many segments / pages for the descriptor");
+    out->assign(total, 0);
+    char* tail = out->data();
     ImageHeader hd{kImageMagic, e->image_packed ? 2u : 1u, (uint32_t)segs.size(), e->image_bytes};
     memcpy(tail, &hd, sizeof(hd));
     for (size_t i = 0; i < segs.size(); ++i) {
@@ -36,12 +36,102 @@ int fma_image_export(fma_engine_t* e, int* out_fd) {
         memcpy(d.tag, t.data(), d.tag_len);
         memcpy(tail + sizeof(hd) + i * sizeof(d), &d, sizeof(d));
     }
-    if (e->image_packed) {
-        char* pt = tail + sizeof(hd) + segs.size() * sizeof(ImageSegDesc);
-        const uint32_t np = (uint32_t)n_img_pages;
-        memcpy(pt, &np, sizeof(np));
-        memcpy(pt + sizeof(np), e->img_bytes.data(), n_img_pages * sizeof(uint32_t));
+    char* pt = tail + sizeof(hd) + segs.size() * sizeof(ImageSegDesc);
+    const uint32_t np = (uint32_t)n_img_pages;
+    memcpy(pt, &np, sizeof(np));
+    if (np) memcpy(pt + sizeof(np), e->img_bytes.data(), n_img_pages * sizeof(uint32_t));
+    return FMA_OK;
+}
+
+namespace {
+
+// Parsed + validated descriptor, matched against the engine's segments for `tag_mask` (same order rule as fma_sleep).
+struct ParsedImage {
+    ImageHeader hd;
+    std::vector<ImageSegDesc> ds;
+    std::vector<size_t> order;          // engine segment index of descriptor entry i
+    std::vector<uint64_t> page_off;     // version 2: the PACKED image's page table
+    std::vector<uint32_t> page_bytes;
+};
+
+int image_descriptor_parse(fma_engine_t* e, const char* tail, size_t tail_bytes, size_t store_cap, uint64_t tag_mask, ParsedImage* out) {
+    ParsedImage& pi = *out;
+    if (tail_bytes < sizeof(ImageHeader)) return fail(FMA_EINVAL, "image descriptor missing or corrupt");
+    memcpy(&pi.hd, tail, sizeof(pi.hd));
+    const ImageHeader& hd = pi.hd;
+    if (hd.magic != kImageMagic || (hd.version != 1 && hd.version != 2) || (hd.version == 1 && hd.image_bytes > store_cap) ||
+        sizeof(ImageHeader) + (size_t)hd.n_segments * sizeof(ImageSegDesc) + sizeof(uint32_t) > tail_bytes)
+        return fail(FMA_EINVAL, "image descriptor missing or corrupt");
+    if (hd.version == 2) {
+        const char* pt = tail + sizeof(hd) + (size_t)hd.n_segments * sizeof(ImageSegDesc);
+        uint32_t np = 0;
+        memcpy(&np, pt, sizeof(np));
+        if ((uint64_t)np * FMA_PAGE_BYTES != hd.image_bytes || sizeof(ImageHeader) + (size_t)hd.n_segments * sizeof(ImageSegDesc) + sizeof(uint32_t) * (1 + (size_t)np) > tail_bytes)
+            return fail(FMA_EINVAL, "packed image: page table does not match the image size");
+        pi.page_bytes.resize(np);
+        pi.page_off.resize(np);
+        memcpy(pi.page_bytes.data(), pt + sizeof(np), (size_t)np * sizeof(uint32_t));
+        uint64_t total = 0;
+        for (uint32_t q = 0; q < np; ++q) {
+            if (pi.page_bytes[q] != FMA_K_PACKED_PAGE_BYTES && pi.page_bytes[q] != FMA_PAGE_BYTES) return fail(FMA_EINVAL, "packed image: bad stored page size");
+            pi.page_off[q] = total;
+            total += pi.page_bytes[q];
+        }
+        if (total > store_cap) return fail(FMA_EINVAL, "packed image: stored pages exceed the store");
     }
+    std::lock_guard<std::mutex> lk(e->mu);
+    for (size_t i = 0; i < e->segs.size(); ++i)
+        if (tag_bit_set(tag_mask, e->segs[i].tag)) pi.order.push_back(i);
+    std::sort(pi.order.begin(), pi.order.end(), [&](size_t a, size_t b) {
+        const Segment &x = e->segs[a], &y = e->segs[b];
+        return x.arena != y.arena ? x.arena < y.arena : x.va < y.va;
+    });
+    if (pi.order.size() != hd.n_segments) return fail(FMA_EINVAL, "image and engine disagree on the number of segments");
+    pi.ds.resize(hd.n_segments);
+    uint64_t off = 0;
+    for (size_t i = 0; i < pi.ds.size(); ++i) {
+        memcpy(&pi.ds[i], tail + sizeof(hd) + i * sizeof(ImageSegDesc), sizeof(ImageSegDesc));
+        const Segment& s = e->segs[pi.order[i]];
+        // the descriptor comes from a file or another process: bound what it claims before using it as a length
+        if (pi.ds[i].tag_len >= sizeof(pi.ds[i].tag) || pi.ds[i].digest_valid > 1) return fail(FMA_EINVAL, "image descriptor is malformed (tag length / digest flag)");
+        if (pi.ds[i].bytes != s.bytes || pi.ds[i].packed_off != off || std::string(pi.ds[i].tag, pi.ds[i].tag_len) != e->tags[s.tag])
+            return fail(FMA_EINVAL, "image and engine disagree on a segment's size, offset or tag");
+        off += s.bytes;
+    }
+    if (off != hd.image_bytes) return fail(FMA_EINVAL, "image size mismatch");
+    return FMA_OK;
+}
+
+// after do_sleep(kFlagAdopt): take over the exporter's page table and integrity data
+void image_apply(fma_engine_t* e, ParsedImage& pi) {
+    if (pi.hd.version == 2) {  // wake through K5 with the exporter's page table
+        e->image_packed = true;
+        e->image_store_bytes = pi.page_off.empty() ? 0 : pi.page_off.back() + pi.page_bytes.back();
+        e->img_off = std::move(pi.page_off);
+        e->img_bytes = std::move(pi.page_bytes);
+    }
+    for (size_t i = 0; i < pi.ds.size(); ++i) {  // integrity data travels with the image: FMA_FLAG_VERIFY on wake checks it
+        Segment& s = e->segs[pi.order[i]];
+        s.digest = pi.ds[i].digest;
+        s.digest_valid = pi.ds[i].digest_valid != 0;
+    }
+}
+
+}  // namespace
+}  // namespace fma_impl
+
+extern "C" {
+
+int fma_image_export(fma_engine_t* e, int* out_fd) {
+    if (check_engine(e) != FMA_OK) return FMA_EINVAL;
+    std::lock_guard<std::mutex> op(e->op_mu);
+    if (!out_fd) return fail(FMA_EINVAL, "out_fd is NULL");
+    if (e->host.fd < 0 || !e->host.base) return fail(FMA_ESTATE, "the host store is not shareable (set FMA_HOST_STORE_SHM=1 before the first sleep)");
+    if (e->image_tier != FMA_TIER_HOST) return fail(FMA_ESTATE, "no host-tier image");
+    std::vector<char> desc;
+    int drc = image_descriptor_build(e, FMA_TIER_HOST, &desc);
+    if (drc != FMA_OK) return drc;
+    memcpy(static_cast<char*>(e->host.base) + e->host.cap, desc.data(), desc.size());
     int fd = dup(e->host.fd);
     if (fd < 0) return fail(FMA_ENOMEM, "dup failed: %s", strerror(errno));
     e->host.shared = true;  // whoever receives the fd reads this image: never write it again (see HostStore::shared)
@@ -71,51 +161,18 @@ int fma_image_adopt(fma_engine_t* e, int fd, uint64_t tag_mask, uint32_t flags) 
         return fail(code, "%s", why);
     };
     const char* tail = static_cast<const char*>(p) + cap;
-    ImageHeader hd;
-    memcpy(&hd, tail, sizeof(hd));
-    if (hd.magic != kImageMagic || (hd.version != 1 && hd.version != 2) || (hd.version == 1 && hd.image_bytes > cap) ||
-        sizeof(ImageHeader) + (size_t)hd.n_segments * sizeof(ImageSegDesc) + sizeof(uint32_t) > kImageTail)
-        return bail(FMA_EINVAL, "image descriptor missing or corrupt");
-    std::vector<uint64_t> adopt_off;   // version 2: the PACKED image's page table
-    std::vector<uint32_t> adopt_bytes;
-    if (hd.version == 2) {
-        const char* pt = tail + sizeof(hd) + (size_t)hd.n_segments * sizeof(ImageSegDesc);
-        uint32_t np = 0;
-        memcpy(&np, pt, sizeof(np));
-        if ((uint64_t)np * FMA_PAGE_BYTES != hd.image_bytes || sizeof(ImageHeader) + (size_t)hd.n_segments * sizeof(ImageSegDesc) + sizeof(uint32_t) * (1 + (size_t)np) > kImageTail)
-            return bail(FMA_EINVAL, "packed image: page table does not match the image size");
-        adopt_bytes.resize(np);
-        adopt_off.resize(np);
-        memcpy(adopt_bytes.data(), pt + sizeof(np), (size_t)np * sizeof(uint32_t));
-        uint64_t total = 0;
-        for (uint32_t q = 0; q < np; ++q) {
-            if (adopt_bytes[q] != FMA_K_PACKED_PAGE_BYTES && adopt_bytes[q] != FMA_PAGE_BYTES) return bail(FMA_EINVAL, "packed image: bad stored page size");
-            adopt_off[q] = total;
-            total += adopt_bytes[q];
+    ParsedImage pi;
+    {
+        int prc = image_descriptor_parse(e, tail, kImageTail, cap, tag_mask, &pi);
+        if (prc != FMA_OK) {
+            char why[512];
+            snprintf(why, sizeof(why), "%s", tl_err);
+            return bail(prc, why);
         }
-        if (total > cap) return bail(FMA_EINVAL, "packed image: stored pages exceed the store");
     }
-    // the segments this engine would offload for tag_mask, in image order (same rule as fma_sleep)
-    std::vector<size_t> order;
-    for (size_t i = 0; i < e->segs.size(); ++i)
-        if (tag_bit_set(tag_mask, e->segs[i].tag)) order.push_back(i);
-    std::sort(order.begin(), order.end(), [&](size_t a, size_t b) {
-        const Segment &x = e->segs[a], &y = e->segs[b];
-        return x.arena != y.arena ? x.arena < y.arena : x.va < y.va;
-    });
-    if (order.size() != hd.n_segments) return bail(FMA_EINVAL, "image and engine disagree on the number of segments");
-    std::vector<ImageSegDesc> ds(hd.n_segments);
-    uint64_t off = 0;
-    for (size_t i = 0; i < ds.size(); ++i) {
-        memcpy(&ds[i], tail + sizeof(hd) + i * sizeof(ImageSegDesc), sizeof(ImageSegDesc));
-        const Segment& s = e->segs[order[i]];
-        // the descriptor comes from a file or another process: bound what it claims before using it as a length
-        if (ds[i].tag_len >= sizeof(ds[i].tag) || ds[i].digest_valid > 1) return bail(FMA_EINVAL, "image descriptor is malformed (tag length / digest flag)");
-        if (ds[i].bytes != s.bytes || ds[i].packed_off != off || std::string(ds[i].tag, ds[i].tag_len) != e->tags[s.tag])
-            return bail(FMA_EINVAL, "image and engine disagree on a segment's size, offset or tag");
-        off += s.bytes;
-    }
-    if (off != hd.image_bytes) return bail(FMA_EINVAL, "image size mismatch");
+    const ImageHeader& hd = pi.hd;
+    std::vector<ImageSegDesc>& ds = pi.ds;
+    const std::vector<size_t>& order = pi.order;
     DeviceGuard guard(e->device);
     cudaDeviceSynchronize();
     if (flags & FMA_FLAG_VERIFY) {
@@ -175,17 +232,52 @@ int fma_image_adopt(fma_engine_t* e, int fd, uint64_t tag_mask, uint32_t flags) 
     // release the device side exactly as a sleep would, without copying anything out
     int rc = do_sleep(e, tag_mask, FMA_TIER_HOST, (flags & ~FMA_FLAG_VERIFY) | kFlagAdopt);
     if (rc != FMA_OK) return rc;
-    if (hd.version == 2) {  // wake through K5 with the exporter's page table
-        e->image_packed = true;
-        e->image_store_bytes = adopt_off.empty() ? 0 : adopt_off.back() + adopt_bytes.back();
-        e->img_off = std::move(adopt_off);
-        e->img_bytes = std::move(adopt_bytes);
+    (void)hd;
+    image_apply(e, pi);
+    return FMA_OK;
+}
+
+// ---- the same hand-over for an image PARKED in peer HBM (fma_peer_attach'ed buffer of a node-level owner) ----------------
+// The buffer itself is the owner's; what has to travel is the descriptor: the owner keeps it next to the fd.
+
+int fma_image_describe(fma_engine_t* e, int tier, void* buf, size_t cap) {
+    if (check_engine(e) != FMA_OK) return FMA_EINVAL;
+    std::lock_guard<std::mutex> op(e->op_mu);
+    if (tier != e->image_tier) return fail(FMA_ESTATE, "no image sleeps in tier %d", tier);
+    std::vector<char> desc;
+    int rc = image_descriptor_build(e, tier, &desc);
+    if (rc != FMA_OK) return rc;
+    if (buf && cap >= desc.size()) memcpy(buf, desc.data(), desc.size());
+    return (int)desc.size();
+}
+
+int fma_image_adopt_parked(fma_engine_t* e, const void* desc, size_t desc_bytes, uint64_t tag_mask, uint32_t flags) {
+    if (check_engine(e) != FMA_OK) return FMA_EINVAL;
+    std::lock_guard<std::mutex> op(e->op_mu);
+    if (!desc || !tag_mask) return fail(FMA_EINVAL, "adopt needs the descriptor and the tag mask the image was slept with");
+    if (!e->park.va || e->park.device == e->device) return fail(FMA_ESTATE, "adopt_parked needs an attached / reserved peer parking buffer first");
+    {
+        std::lock_guard<std::mutex> lk(e->mu);
+        for (const Segment& s : e->segs)
+            if (!s.mapped) return fail(FMA_ESTATE, "adopt needs a fully awake engine");
     }
-    for (size_t i = 0; i < ds.size(); ++i) {  // integrity data travels with the image: FMA_FLAG_VERIFY on wake checks it
-        Segment& s = e->segs[order[i]];
-        s.digest = ds[i].digest;
-        s.digest_valid = ds[i].digest_valid != 0;
+    ParsedImage pi;
+    int rc = image_descriptor_parse(e, static_cast<const char*>(desc), desc_bytes, e->park.cap, tag_mask, &pi);
+    if (rc != FMA_OK) return rc;
+    DeviceGuard guard(e->device);
+    cudaDeviceSynchronize();
+    if (flags & FMA_FLAG_VERIFY) {  // "sleep by adoption" (see fma_image_adopt): only if this engine's bytes ARE the image's
+        std::vector<uint64_t> now;
+        rc = digest_segments(e, pi.order, &now);
+        if (rc != FMA_OK) return rc;
+        for (size_t i = 0; i < pi.ds.size(); ++i)
+            if (!pi.ds[i].digest_valid || pi.ds[i].digest != now[i])
+                return fail(FMA_EINTEGRITY, pi.ds[i].digest_valid ? "the image holds different bytes than this engine's segments" : "the image carries no digests to compare with");
     }
+    if (e->shadow_tier != FMA_TIER_HOST) invalidate_shadows(e);
+    rc = do_sleep(e, tag_mask, FMA_TIER_PEER, (flags & ~FMA_FLAG_VERIFY) | kFlagAdopt);
+    if (rc != FMA_OK) return rc;
+    image_apply(e, pi);
     return FMA_OK;
 }
 

@@ -71,6 +71,8 @@ struct Driver {
     CUresult (*MemUnmap)(CUdeviceptr, size_t) = nullptr;
     CUresult (*MemSetAccess)(CUdeviceptr, size_t, const CUmemAccessDesc*, size_t) = nullptr;
     CUresult (*MemGetAllocationGranularity)(size_t*, const CUmemAllocationProp*, CUmemAllocationGranularity_flags) = nullptr;
+    CUresult (*MemExportToShareableHandle)(void*, CUmemGenericAllocationHandle, CUmemAllocationHandleType, unsigned long long) = nullptr;
+    CUresult (*MemImportFromShareableHandle)(CUmemGenericAllocationHandle*, void*, CUmemAllocationHandleType) = nullptr;
 };
 extern Driver g_drv;
 extern char g_drv_err[256];
@@ -169,11 +171,13 @@ struct ImageHeader {
 };
 constexpr uint32_t kFlagAdopt = 1u << 31;  // internal: "sleep" onto an adopted image without copying
 
+constexpr int kForeignDevice = -2;  // ParkStore::device of an attached buffer: it lives on a GPU this process may not even see
+
 struct ParkStore {  // peer-HBM or local-HBM parking buffer (VMM, P2P mapped)
     CUdeviceptr va = 0;
     size_t cap = 0;
     CUmemGenericAllocationHandle handle = 0;
-    int device = -1;
+    int device = -1;            // kForeignDevice: imported from a node-level owner's fd (fma_peer_attach)
 };
 
 constexpr int kMaxStreams = 8;
@@ -321,6 +325,9 @@ void host_store_free(HostStore& h);
 int host_store_reserve(fma_engine_t* e, size_t bytes);
 int park_release(fma_engine_t* e);
 int park_reserve(fma_engine_t* e, int park_device, size_t bytes);
+CUmemAllocationProp device_prop(int device);
+// ---- image descriptor (fma_image.cu): what a sleeping image is made of, so another engine / process can adopt it ----
+int image_descriptor_build(fma_engine_t* e, int tier, std::vector<char>* out);
 void invalidate_shadows(fma_engine_t* e);   // the host store no longer holds a usable copy of any segment
 // ---- pipelines ----
 int do_sleep(fma_engine_t* e, uint64_t offload_mask, int tier, uint32_t flags);   // fma_sleep.cu

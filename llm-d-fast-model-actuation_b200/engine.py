@@ -171,6 +171,22 @@ class Engine:
     def peer_release(self) -> None:
         check(self._lib.fma_peer_release(self._h))
 
+    def peer_attach(self, fd: int, nbytes: int) -> None:
+        """Use a node-level owner's parking buffer (``ParkingBuffer``; fd received over SCM_RIGHTS / inherited) as this engine's
+        peer-tier store.  The buffer's GPU need not be visible to this process (launcher.py:171-187 hides it)."""
+        check(self._lib.fma_peer_attach(self._h, fd, nbytes))
+
+    def image_describe(self, tier: int = L.FMA_TIER_PEER) -> bytes:
+        """Descriptor of the image sleeping in ``tier`` (the node-level owner keeps it next to the buffer's fd)."""
+        n = check(self._lib.fma_image_describe(self._h, tier, None, 0))
+        buf = C.create_string_buffer(n)
+        check(self._lib.fma_image_describe(self._h, tier, buf, n))
+        return buf.raw
+
+    def image_adopt_parked(self, descriptor: bytes, tags: Sequence[str], flags: int = 0) -> None:
+        """After ``peer_attach``: become 'asleep with the image parked in that buffer' (same segment sequence for ``tags``)."""
+        check(self._lib.fma_image_adopt_parked(self._h, descriptor, len(descriptor), self.tag_mask(tags), flags))
+
     # -- integrity / synthetic data -------------------------------------------------------
     def digest(self, index: int) -> int:
         out = C.c_uint64()
@@ -326,4 +342,37 @@ class Engine:
         return rows
 
 
-__all__ = ["Engine", "EngineConfig", "SegmentInfo", "FmaError"]
+class ParkingBuffer:
+    """Node-level owner's side of the peer tier: an exportable VMM allocation in ``device``'s HBM (fma_parking_create).  The
+    owner process must see ``device``; instances need not.  ``fd`` / ``export_fd()`` go to instances (``Engine.peer_attach``)."""
+
+    def __init__(self, device: int, nbytes: int):
+        self._lib = L.load_library()
+        h, fd, nb = C.c_uint64(), C.c_int(-1), C.c_uint64()
+        check(self._lib.fma_parking_create(device, nbytes, C.byref(h), C.byref(fd)))
+        self.handle, self.fd, self.device = int(h.value), int(fd.value), device
+        fd2 = C.c_int(-1)
+        check(self._lib.fma_parking_export(self.handle, C.byref(fd2), C.byref(nb)))
+        import os
+
+        os.close(fd2.value)
+        self.nbytes = int(nb.value)
+
+    def export_fd(self) -> int:
+        fd = C.c_int(-1)
+        check(self._lib.fma_parking_export(self.handle, C.byref(fd), None))
+        return int(fd.value)
+
+    def close(self) -> None:
+        if self.handle:
+            import os
+
+            self._lib.fma_parking_destroy(self.handle)
+            self.handle = 0
+            try:
+                os.close(self.fd)
+            except OSError:
+                pass
+
+
+__all__ = ["Engine", "EngineConfig", "SegmentInfo", "FmaError", "ParkingBuffer"]

@@ -16,6 +16,9 @@
 #include <cuda_runtime.h>
 
 #include <sys/mman.h>
+#include <sys/stat.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 
 #include <atomic>
 #include <chrono>
@@ -32,6 +35,7 @@ struct Mapping { size_t bytes; unsigned long long handle; };
 std::map<unsigned long long, size_t> g_reservations;          // va -> size
 std::map<unsigned long long, Mapping> g_mappings;             // va -> mapping
 std::map<unsigned long long, size_t> g_handles;               // handle -> size (alive until released AND unmapped)
+std::map<unsigned long long, int> g_handle_fd;                // exportable handles (CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR): memfd behind them
 std::set<unsigned long long> g_released;
 std::atomic<unsigned long long> g_next_handle{1};
 thread_local int tl_device = 0;
@@ -89,7 +93,37 @@ CUresult simMemCreate(CUmemGenericAllocationHandle* h, size_t size, const CUmemA
     std::lock_guard<std::mutex> lk(g_mu);
     *h = g_next_handle++;
     g_handles[*h] = size;
+    if (prop->requestedHandleTypes == CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR) {   // shareable: the "physical memory" is a memfd
+        int fd = (int)syscall(SYS_memfd_create, "hostsim-vmm", 1u);
+        if (fd < 0 || ftruncate(fd, (off_t)size) != 0) return CUDA_ERROR_OUT_OF_MEMORY;
+        g_handle_fd[*h] = fd;
+    }
     return CUDA_SUCCESS;
+}
+CUresult simMemExportToShareableHandle(void* out, CUmemGenericAllocationHandle h, CUmemAllocationHandleType t, unsigned long long) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (t != CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR || !g_handle_fd.count(h)) return CUDA_ERROR_INVALID_VALUE;
+    const int fd = dup(g_handle_fd[h]);
+    if (fd < 0) return CUDA_ERROR_OUT_OF_MEMORY;
+    *static_cast<int*>(out) = fd;
+    return CUDA_SUCCESS;
+}
+CUresult simMemImportFromShareableHandle(CUmemGenericAllocationHandle* h, void* os_handle, CUmemAllocationHandleType t) {
+    if (t != CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR) return CUDA_ERROR_INVALID_VALUE;
+    const int fd = dup((int)(uintptr_t)os_handle);
+    struct stat sb;
+    if (fd < 0 || fstat(fd, &sb) != 0 || sb.st_size <= 0) return CUDA_ERROR_INVALID_VALUE;
+    std::lock_guard<std::mutex> lk(g_mu);
+    *h = g_next_handle++;
+    g_handles[*h] = (size_t)sb.st_size;
+    g_handle_fd[*h] = fd;
+    return CUDA_SUCCESS;
+}
+static void drop_handle_locked(unsigned long long h) {
+    g_handles.erase(h);
+    g_released.erase(h);
+    auto it = g_handle_fd.find(h);
+    if (it != g_handle_fd.end()) { close(it->second); g_handle_fd.erase(it); }
 }
 CUresult simMemRelease(CUmemGenericAllocationHandle h) {
     std::lock_guard<std::mutex> lk(g_mu);
@@ -97,7 +131,7 @@ CUresult simMemRelease(CUmemGenericAllocationHandle h) {
     g_released.insert(h);
     bool mapped = false;
     for (auto& m : g_mappings) mapped |= m.second.handle == h;
-    if (!mapped) { g_handles.erase(h); g_released.erase(h); }
+    if (!mapped) drop_handle_locked(h);
     return CUDA_SUCCESS;
 }
 CUresult simMemMap(CUdeviceptr ptr, size_t size, size_t offset, CUmemGenericAllocationHandle h, unsigned long long) {
@@ -108,7 +142,8 @@ CUresult simMemMap(CUdeviceptr ptr, size_t size, size_t offset, CUmemGenericAllo
     if (!inside) return CUDA_ERROR_INVALID_VALUE;
     for (auto& m : g_mappings)
         if (ptr < m.first + m.second.bytes && m.first < ptr + size) return CUDA_ERROR_INVALID_VALUE;  // overlaps a live mapping
-    void* p = mmap((void*)ptr, size, PROT_NONE, MAP_FIXED | MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+    void* p = g_handle_fd.count(h) ? mmap((void*)ptr, size, PROT_NONE, MAP_FIXED | MAP_SHARED, g_handle_fd[h], 0)   // shared with importers
+                                   : mmap((void*)ptr, size, PROT_NONE, MAP_FIXED | MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
     if (p == MAP_FAILED) return CUDA_ERROR_OUT_OF_MEMORY;
     g_mappings[ptr] = Mapping{size, h};
     return CUDA_SUCCESS;
@@ -135,7 +170,7 @@ CUresult simMemUnmap(CUdeviceptr ptr, size_t size) {
     while (it != g_mappings.end() && it->first < ptr + size) {
         const unsigned long long h = it->second.handle;
         it = g_mappings.erase(it);
-        if (g_released.count(h)) { g_handles.erase(h); g_released.erase(h); }   // released handle + last mapping gone: memory freed
+        if (g_released.count(h)) drop_handle_locked(h);   // released handle + last mapping gone: memory freed
     }
     mmap((void*)ptr, size, PROT_NONE, MAP_FIXED | MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);  // contents are gone
     return CUDA_SUCCESS;
@@ -203,7 +238,8 @@ cudaError_t cudaGetDriverEntryPoint(const char* name, void** fn, unsigned long l
         {"cuGetErrorString", (void*)simGetErrorString}, {"cuMemAddressReserve", (void*)simMemAddressReserve},
         {"cuMemAddressFree", (void*)simMemAddressFree}, {"cuMemCreate", (void*)simMemCreate}, {"cuMemRelease", (void*)simMemRelease},
         {"cuMemMap", (void*)simMemMap}, {"cuMemUnmap", (void*)simMemUnmap}, {"cuMemSetAccess", (void*)simMemSetAccess},
-        {"cuMemGetAllocationGranularity", (void*)simMemGetAllocationGranularity}};
+        {"cuMemGetAllocationGranularity", (void*)simMemGetAllocationGranularity},
+        {"cuMemExportToShareableHandle", (void*)simMemExportToShareableHandle}, {"cuMemImportFromShareableHandle", (void*)simMemImportFromShareableHandle}};
     for (auto& t : tab)
         if (!strcmp(t.n, name)) { *fn = t.f; if (st) *st = cudaDriverEntryPointSuccess; return cudaSuccess; }
     if (st) *st = cudaDriverEntryPointSymbolNotFound;
