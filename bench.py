@@ -324,6 +324,8 @@ def run_ours(args) -> None:
             eng.close()   # everything above is measured: give the HBM and the pinned store back before the baseline / extra processes run
         if world == 1 and "swap" in args.extras and tier == L.FMA_TIER_HOST:
             out["swap_config4"] = measure_swap(args, L, W)
+        if world == 1 and "multipath" in args.extras and tier == L.FMA_TIER_HOST and torch.cuda.device_count() > 1:
+            out["multipath_wake"] = measure_multipath(args, L, W, cfg, workload, torch.cuda.device_count())
         if world == 1 and "scaling_base" in args.extras and tier == L.FMA_TIER_HOST and workload != args.scaling_workload:
             out["n1_on_scaling_workload"] = measure_scaling_base(args, L, W, cfg)
         if world == 1 and not args.no_cpu_baseline:
@@ -394,6 +396,43 @@ def measure_swap(args, L, W, cycles: int = 10) -> dict:
                 "speedup_vs_serial": round(med(serial) / med(swap), 3),
                 "d2h_gbs_during_swap_median": round(med(d2h), 2), "h2d_gbs_during_swap_median": round(med(h2d), 2),
                 "both_directions_gbs": round(med(d2h) + med(h2d), 2), "cycles": len(swap), "bit_exact": bool(ok)}
+    except Exception as e:
+        return {"error": str(e)[:300]}
+
+
+def measure_multipath(args, L, W, cfg, workload: str, n_visible: int, cycles: int = 6) -> dict:
+    """MULTI-PATH wake (fma_paths_set) at N=1 with idle peers on the box: the same table, host tier; helpers = GPUs 1..k lend their
+    PCIe links, K2 on GPU 0 gathers their staging slots over NVLink.  The single-link ceiling (55.6 GB/s measured) stops applying."""
+    import fma_b200
+
+    try:
+        eng = fma_b200.Engine(0, cfg)
+        _, wb = load_model(eng, W, workload, args.kv_gib, 1234)
+        eng.host_reserve(wb)
+        before = eng.digest_all(["weights"])
+        rows = []
+        ks = [k for k in (1, 3, 7) if k < n_visible]
+        plans = [(k, 128, 3) for k in ks] + ([(ks[-1], 32, 4), (ks[-1], 512, 2)] if ks else [])
+        for k, slot_mib, slots in plans:
+            eng.set_paths(list(range(1, k + 1)), slot_bytes=slot_mib << 20, slots=slots)
+            wakes, devs = [], []
+            for i in range(cycles + 1):
+                eng.sleep(["weights"]); eng.wake(None); st = eng.stats()
+                if i:
+                    wakes.append(st["wake_seconds"]); devs.append(st["wake_copy_seconds"])
+            chunks = {r["idx"]: r["bytes"] for r in eng.timeline() if r["kind"] == "path_chunks"}
+            med = statistics.median
+            rows.append({"helpers": k, "paths": k + 1, "slot_mib": slot_mib, "slots": slots, "wake_latency_s": round(med(wakes), 5),
+                         "wake_latency_s_min_max": [round(min(wakes), 5), round(max(wakes), 5)], "e2e_gbs": round(wb / med(wakes) / 1e9, 1),
+                         "device_gbs": round(wb / med(devs) / 1e9, 1), "x_single_link_64": round(wb / med(wakes) / 1e9 / PCIE_GEN5_X16_GBS, 2),
+                         "gib_per_path_device": {str(d): round(b / GiB, 2) for d, b in sorted(chunks.items())}})
+        eng.set_paths([])
+        ok = eng.digest_all(["weights"]) == before
+        eng.close()
+        best = min(rows, key=lambda r: r["wake_latency_s"]) if rows else None
+        return {"workload": workload, "weights_gib": round(wb / GiB, 3), "visible_gpus": n_visible, "rows": rows,
+                "best": {k: best[k] for k in ("helpers", "slot_mib", "wake_latency_s", "e2e_gbs")} if best else None, "bit_exact": bool(ok),
+                "note": "helpers are idle GPUs of the same box (BASELINE config 5's parking GPUs, or any N=1 deployment on an 8-GPU node)"}
     except Exception as e:
         return {"error": str(e)[:300]}
 
@@ -879,9 +918,9 @@ def main() -> None:
     ap.add_argument("--pack", type=int, default=0, help="1 = PACKED host image (lossless bf16 page code; pays off with --contents bf16)")
     ap.add_argument("--incremental", type=int, default=0, help="1 = INCREMENTAL sleep: a sleep whose weights still match the image in the host store moves nothing")
     ap.add_argument("--packed-extra", type=int, default=1, help="at N=1 also measure the PACKED image on bf16 dummy weights in a child process (reported under packed_image)")
-    ap.add_argument("--extras", default="swap,scaling_base,roundrobin",
+    ap.add_argument("--extras", default="swap,scaling_base,roundrobin,multipath",
                     help="comma list of extras measured after the main line: swap (N=1: BASELINE config 4, Llama-3-8B <-> Mistral-7B), scaling_base "
-                         "(N=1: the N>1 table on one GPU), roundrobin (N>=2: BASELINE config 5, N/2 parked 8B sleepers woken round-robin), "
+                         "(N=1: the N>1 table on one GPU), multipath (N=1 with more GPUs visible: MULTI-PATH wake over idle peers' links), roundrobin (N>=2: BASELINE config 5, N/2 parked 8B sleepers woken round-robin), "
                          "packed,incremental (any N, on the same engines; opt-in)")
     ap.add_argument("--swap-models", default="llama-3-8b,mistral-7b", help="the two models of the swap extra (the first is also the round-robin sleeper)")
     ap.add_argument("--scaling-workload", default="llama-3-70b-tp8", help="table of the scaling_base extra (= the N>1 workload)")

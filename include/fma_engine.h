@@ -242,6 +242,16 @@ FMA_API int  fma_image_export(fma_engine_t* e, int* out_fd);          /* caller 
  * image (one host copy per node instead of one per replica); on a mismatch nothing is touched and FMA_EINTEGRITY comes back. */
 FMA_API int  fma_image_adopt(fma_engine_t* e, int fd, uint64_t tag_mask, uint32_t flags);  /* fd stays owned by the caller */
 
+/* ---- MULTI-PATH wake: borrow idle peers' PCIe links ---------------------------------------------------------------------
+ * A host-tier wake is bounded by ONE x16 Gen5 link (55.6 GB/s measured of 64): 0.29 s for Llama-3-8B however good the engine
+ * is.  When other GPUs of the box are idle (BASELINE config 5: the GPUs that only park sleepers; any N=1 deployment on an
+ * 8-GPU node) their links are idle too.  fma_paths_set names such helper GPUs; a following fma_wake of a plain host image
+ * then cuts the image into chunks, lets every path — own link included — pull chunks through ITS copy engine into a small
+ * staging buffer in ITS HBM, and K2 on the waking GPU gathers each chunk over NVLink / NVSwitch into the destination pages.
+ * n = 0 turns it off.  slot_bytes / slots: staging per path (0 = 128 MiB x 3).  The reference has one blocking cudaMemcpy
+ * per segment on one link (cumem.py:237-249). */
+FMA_API int  fma_paths_set(fma_engine_t* e, const int* helper_devices, int n, size_t slot_bytes, int slots);
+
 /* ---- node-level parking buffers (exportable) ------------------- */
 /* The reference launcher restricts every instance to its own GPUs (inference_server/launcher/launcher.py:171-187), and
  * whatever an instance allocates dies with it — which is when the controller cold-starts

@@ -138,6 +138,7 @@ _PROTOTYPES = {
     "fma_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
     "fma_stats": (C.c_int, [C.c_void_p, C.POINTER(fma_stats_t)]),
     "fma_timeline": (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t]),
+    "fma_paths_set": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.c_int, C.c_size_t, C.c_int]),
     "fma_parking_create": (C.c_int, [C.c_int, C.c_size_t, C.POINTER(C.c_uint64), C.POINTER(C.c_int)]),
     "fma_parking_export": (C.c_int, [C.c_uint64, C.POINTER(C.c_int), C.POINTER(C.c_uint64)]),
     "fma_parking_destroy": (C.c_int, [C.c_uint64]),

@@ -456,6 +456,32 @@ int host_store_reserve(fma_engine_t* e, size_t bytes) {
     return FMA_OK;
 }
 
+void paths_release(fma_engine_t* e) {
+    for (WakePath& p : e->paths) {
+        {
+            DeviceGuard g(p.device);
+            if (p.copy) cudaStreamSynchronize(p.copy);
+            if (p.copy) cudaStreamDestroy(p.copy);
+            for (int i = 0; i < kMaxRing; ++i)
+                if (p.ev_full[i]) cudaEventDestroy(p.ev_full[i]);
+        }
+        DeviceGuard g(e->device);
+        if (p.kern) cudaStreamSynchronize(p.kern);
+        if (p.kern) cudaStreamDestroy(p.kern);
+        for (int i = 0; i < kMaxRing; ++i)
+            if (p.ev_free[i]) cudaEventDestroy(p.ev_free[i]);
+        if (p.ev_done) cudaEventDestroy(p.ev_done);
+        if (p.va) {
+            g_drv.MemUnmap(p.va, p.bytes);
+            g_drv.MemAddressFree(p.va, p.bytes);
+        }
+    }
+    e->paths.clear();
+    e->path_slot_bytes = 0;
+    e->path_slots = 0;
+    cudaGetLastError();
+}
+
 int park_release(fma_engine_t* e) {
     if (!e->park.va) return FMA_OK;
     if (e->shadow_tier != FMA_TIER_HOST) invalidate_shadows(e);  // the parking buffer held the kept image
@@ -755,6 +781,7 @@ int fma_engine_destroy(fma_engine_t* e) {
     e->segs.clear();
     host_store_free(e->host);
     park_release(e);
+    paths_release(e);
     release_ring(e);
     for (int i = 0; i < kMaxRing; ++i) {
         if (e->ev_ring_full[i]) cudaEventDestroy(e->ev_ring_full[i]);
@@ -1153,6 +1180,77 @@ int fma_peer_attach(fma_engine_t* e, int fd, size_t bytes) {
         return fail(FMA_ECUDA, "cuMemSetAccess(attach) failed: %s (no P2P path from device %d to the buffer's GPU?)", cu_err(r), e->device);
     }
     e->park = p;
+    return FMA_OK;
+}
+
+// MULTI-PATH wake: declare the idle peer GPUs whose PCIe links a host-tier wake of this engine may borrow (n = 0: none).
+// slot_bytes / slots: size and depth of the staging buffer each path (own link included) gets; 0 = defaults (128 MiB x 3).
+int fma_paths_set(fma_engine_t* e, const int* helper_devices, int n, size_t slot_bytes, int slots) {
+    if (check_engine(e) != FMA_OK) return FMA_EINVAL;
+    if (n < 0 || n > kMaxPaths - 1 || (n && !helper_devices)) return fail(FMA_EINVAL, "0..%d helper devices", kMaxPaths - 1);
+    std::lock_guard<std::mutex> op(e->op_mu);
+    DeviceGuard guard(e->device);
+    cudaDeviceSynchronize();
+    paths_release(e);
+    if (n == 0) return FMA_OK;
+    slot_bytes = round_up(slot_bytes ? slot_bytes : ((size_t)128 << 20), FMA_PAGE_BYTES);
+    slots = slots > 0 ? std::min(slots, kMaxRing) : 3;
+    int ndev = 0;
+    RT(cudaGetDeviceCount(&ndev));
+    std::vector<int> devs{e->device};
+    for (int i = 0; i < n; ++i) {
+        const int d = helper_devices[i];
+        if (d < 0 || d >= ndev || std::find(devs.begin(), devs.end(), d) != devs.end())
+            return fail(FMA_EINVAL, "helper device %d is not visible, is the engine's own GPU, or is listed twice", d);
+        int can = 0;
+        RT(cudaDeviceCanAccessPeer(&can, e->device, d));
+        if (!can) return fail(FMA_ECUDA, "device %d cannot access helper %d (no NVLink/P2P path)", e->device, d);
+        devs.push_back(d);
+    }
+    e->path_slot_bytes = slot_bytes;
+    e->path_slots = slots;
+    for (int d : devs) {
+        WakePath p;
+        p.device = d;
+        p.bytes = slot_bytes * (size_t)slots;
+        int rc = FMA_OK;
+        {
+            DeviceGuard g(d);
+            if (cudaFree(nullptr) != cudaSuccess) rc = fail(FMA_ECUDA, "cannot initialise helper device %d", d);
+            CUmemAllocationProp prop = device_prop(d);
+            CUmemGenericAllocationHandle h = 0;
+            CUresult r = rc == FMA_OK ? g_drv.MemCreate(&h, p.bytes, &prop, 0) : CUDA_ERROR_UNKNOWN;
+            if (rc == FMA_OK && r != CUDA_SUCCESS) rc = fail(r == CUDA_ERROR_OUT_OF_MEMORY ? FMA_ENOMEM : FMA_ECUDA, "cuMemCreate(path staging on device %d) failed: %s", d, cu_err(r));
+            if (rc == FMA_OK) {
+                r = g_drv.MemAddressReserve(&p.va, p.bytes, FMA_PAGE_BYTES, 0, 0);
+                if (r == CUDA_SUCCESS) r = g_drv.MemMap(p.va, p.bytes, 0, h, 0);
+                CUmemAccessDesc acc[2];
+                memset(acc, 0, sizeof(acc));
+                acc[0].location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+                acc[0].location.id = d;
+                acc[0].flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+                acc[1] = acc[0];
+                acc[1].location.id = e->device;
+                if (r == CUDA_SUCCESS) r = g_drv.MemSetAccess(p.va, p.bytes, acc, d != e->device ? 2 : 1);
+                g_drv.MemRelease(h);   // the mapping keeps the memory alive
+                if (r != CUDA_SUCCESS) rc = fail(FMA_ECUDA, "mapping the path staging buffer of device %d failed: %s", d, cu_err(r));
+            }
+            if (rc == FMA_OK && cudaStreamCreateWithFlags(&p.copy, cudaStreamNonBlocking) != cudaSuccess) rc = fail(FMA_ECUDA, "stream on helper %d", d);
+            for (int i = 0; i < slots && rc == FMA_OK; ++i)
+                if (cudaEventCreateWithFlags(&p.ev_full[i], cudaEventDisableTiming) != cudaSuccess) rc = fail(FMA_ECUDA, "event on helper %d", d);
+        }
+        if (rc == FMA_OK && cudaStreamCreateWithFlags(&p.kern, cudaStreamNonBlocking) != cudaSuccess) rc = fail(FMA_ECUDA, "kernel stream for path %d", d);
+        for (int i = 0; i < slots && rc == FMA_OK; ++i)
+            if (cudaEventCreateWithFlags(&p.ev_free[i], cudaEventDisableTiming) != cudaSuccess) rc = fail(FMA_ECUDA, "event for path %d", d);
+        if (rc == FMA_OK && cudaEventCreateWithFlags(&p.ev_done, cudaEventDisableTiming) != cudaSuccess) rc = fail(FMA_ECUDA, "event for path %d", d);
+        e->paths.push_back(p);   // also on failure: paths_release below frees what exists
+        if (rc != FMA_OK) {
+            char keep[512];
+            snprintf(keep, sizeof(keep), "%s", tl_err);
+            paths_release(e);
+            return fail(rc, "%s", keep);
+        }
+    }
     return FMA_OK;
 }
 

@@ -182,6 +182,22 @@ struct ParkStore {  // peer-HBM or local-HBM parking buffer (VMM, P2P mapped)
 
 constexpr int kMaxStreams = 8;
 constexpr int kMaxRing = 8;
+constexpr int kMaxPaths = 8;
+
+// MULTI-PATH wake (fma_paths_set): one PCIe path into the waking GPU per entry.  Path 0 is the engine's own link; every other
+// path is an idle peer GPU whose copy engine pulls chunks of the host image over ITS x16 link into a small staging buffer in
+// ITS HBM, from where K2 on the waking GPU gathers them over NVLink / NVSwitch (900 GB/s >> k x 55 GB/s) straight into the
+// destination pages.  A lone wake is then bounded by k links instead of one.
+struct WakePath {
+    int device = -1;
+    CUdeviceptr va = 0;                      // n_slots x slot_bytes in `device`'s HBM; access for `device` and the engine's GPU
+    size_t bytes = 0;
+    cudaStream_t copy = nullptr;             // on `device`: H2D host store -> slot
+    cudaStream_t kern = nullptr;             // on the engine's GPU: K2 slot -> destination pages
+    cudaEvent_t ev_full[kMaxRing] = {};      // on `device`
+    cudaEvent_t ev_free[kMaxRing] = {};      // on the engine's GPU
+    cudaEvent_t ev_done = nullptr;           // on the engine's GPU
+};
 
 // Per-phase timeline of the last sleep / wake (fma_timeline): host-side phases (VMM calls of the mapper / unmapper threads,
 // enqueue, drain) and device-side kernel launches (K1 / K2 / K4 / K5), all in seconds since the operation's entry.
@@ -267,6 +283,11 @@ struct fma_engine {
     size_t load_chunk = (size_t)16 << 20;  // 12 -> 48.7, 16 -> 46.9 GB/s from the page cache (pread is the limiter)
     int load_slots = 24;
 
+    // MULTI-PATH wake
+    std::vector<WakePath> paths;
+    size_t path_slot_bytes = 0;
+    int path_slots = 0;
+
     fma_k_tma_cfg tma = fma_k_default_tma_cfg();
     fma_stats_t st{};
     // K1/K2 event pairs of the last operation whose elapsed times have not been read yet
@@ -323,6 +344,7 @@ int ensure_event_pool(fma_engine_t* e, size_t n);
 // ---- stores (fma_engine.cu) ----
 void host_store_free(HostStore& h);
 int host_store_reserve(fma_engine_t* e, size_t bytes);
+void paths_release(fma_engine_t* e);
 int park_release(fma_engine_t* e);
 int park_reserve(fma_engine_t* e, int park_device, size_t bytes);
 CUmemAllocationProp device_prop(int device);
@@ -372,11 +394,15 @@ struct KernelTimes {  // event pairs around each K1/K2 launch on the kernel stre
     size_t used = 0;
     uint64_t bytes = 0;
     int launch(const uint64_t* src_tab, uint64_t src_base, const uint64_t* dst_tab, uint64_t dst_base, uint32_t n_pages) {
+        return launch_on(e->ks, src_tab, src_base, dst_tab, dst_base, n_pages);
+    }
+    // same on another stream of the engine's GPU (multi-path wake: one kernel stream per path; the caller serialises the calls)
+    int launch_on(cudaStream_t stream, const uint64_t* src_tab, uint64_t src_base, const uint64_t* dst_tab, uint64_t dst_base, uint32_t n_pages) {
         int rc = ensure_event_pool(e, used + 2);
         if (rc != FMA_OK) return rc;
-        RT(cudaEventRecord(e->ev_pool[used], e->ks));
-        RT(fma_k_launch_page_copy(src_tab, src_base, dst_tab, dst_base, n_pages, e->cfg.kernel, &e->tma, e->ks));
-        RT(cudaEventRecord(e->ev_pool[used + 1], e->ks));
+        RT(cudaEventRecord(e->ev_pool[used], stream));
+        RT(fma_k_launch_page_copy(src_tab, src_base, dst_tab, dst_base, n_pages, e->cfg.kernel, &e->tma, stream));
+        RT(cudaEventRecord(e->ev_pool[used + 1], stream));
         used += 2;
         bytes += 2ull * n_pages * FMA_PAGE_BYTES;
         e->tl_kbytes.push_back(2ull * n_pages * FMA_PAGE_BYTES);

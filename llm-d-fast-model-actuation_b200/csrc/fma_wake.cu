@@ -279,6 +279,116 @@ int wake_paged(WakePipe& pipe) {
     return FMA_OK;
 }
 
+// MULTI-PATH (fma_paths_set): the host image is cut into chunks; every path — the engine's own PCIe link and one per idle peer
+// GPU — pulls the next chunk whenever one of its staging slots is free (H2D by THAT GPU's copy engine over THAT GPU's x16
+// link), and K2 on the waking GPU gathers the chunk from the path's staging slot (own HBM, or the peer's HBM over NVLink) into
+// the destination pages.  Self-balancing: a slower path (other NUMA node, busy link) simply takes fewer chunks.
+int wake_multipath(WakePipe& pipe) {
+    fma_engine_t* e = pipe.e;
+    const std::vector<size_t>& with_backup = pipe.with_backup;
+    const std::vector<size_t>& seg_run = pipe.seg_run;
+    KernelTimes& kt = pipe.kt;
+    const char* store = pipe.store;
+    const uint64_t W = pipe.W;
+    struct Dst { uint64_t packed_off; size_t w; };
+    std::vector<Dst> d;
+    for (size_t w = 0; w < with_backup.size(); ++w) d.push_back(Dst{e->segs[with_backup[w]].packed_off, w});
+    std::sort(d.begin(), d.end(), [](const Dst& a, const Dst& b) { return a.packed_off < b.packed_off; });
+    const size_t n_pages = W / FMA_PAGE_BYTES;
+    PIPE_CHECK(ensure_tables(e, n_pages));
+    uint64_t* dst_tab = e->h_tab;
+    std::vector<uint64_t> src_off(n_pages);
+    std::vector<size_t> need_item(n_pages);
+    size_t p = 0;
+    for (const Dst& x : d) {
+        const Segment& s = e->segs[with_backup[x.w]];
+        for (size_t o = 0; o < s.bytes; o += FMA_PAGE_BYTES, ++p) {
+            dst_tab[p] = (uint64_t)s.va + o;
+            src_off[p] = s.packed_off + o;
+            need_item[p] = seg_run[with_backup[x.w]] + 1;
+        }
+    }
+    RT(cudaMemcpyAsync(e->d_tab, dst_tab, n_pages * sizeof(uint64_t), cudaMemcpyHostToDevice, e->ks));
+    cudaEvent_t ev_tab = nullptr;   // the page table must be on the device before any path's K2 reads it
+    PIPE_CHECK(ensure_ring_events(e, 1));
+    ev_tab = e->ev_ring_full[0];
+    RT(cudaEventRecord(ev_tab, e->ks));
+    struct Chunk { size_t p0, np, need; };
+    std::vector<Chunk> chunks;
+    const size_t chunk_pages = std::max<size_t>(e->path_slot_bytes / FMA_PAGE_BYTES, 1);
+    for (size_t q = 0; q < n_pages;) {
+        Chunk c{q, 1, need_item[q]};
+        while (c.np < chunk_pages && q + c.np < n_pages && src_off[q + c.np] == src_off[q + c.np - 1] + FMA_PAGE_BYTES) {
+            c.need = std::max(c.need, need_item[q + c.np]);
+            ++c.np;
+        }
+        chunks.push_back(c);
+        q += c.np;
+    }
+    std::atomic<size_t> next_chunk{0};
+    std::atomic<int> error{FMA_OK};
+    std::atomic<bool> first_copy_seen{false};
+    std::mutex kt_mu;
+    char err_msg[512] = "";
+    std::vector<uint32_t> per_path(e->paths.size(), 0);
+    auto worker = [&](size_t pi) {
+        WakePath& path = e->paths[pi];
+        cudaSetDevice(e->device);
+        auto failw = [&](int code, const char* what, cudaError_t ce) {
+            int expect = FMA_OK;
+            if (error.compare_exchange_strong(expect, code)) snprintf(err_msg, sizeof(err_msg), "%s failed on path %zu (device %d): %s", what, pi, path.device, ce == cudaSuccess ? pipe.map_msg : cudaGetErrorString(ce));
+        };
+        cudaError_t ce = cudaStreamWaitEvent(path.kern, ev_tab, 0);
+        if (ce != cudaSuccess) return failw(FMA_ECUDA, "cudaStreamWaitEvent(table)", ce);
+        uint32_t mine = 0;
+        for (;;) {
+            if (error.load() != FMA_OK) return;
+            const size_t c = next_chunk.fetch_add(1);
+            if (c >= chunks.size()) break;
+            const Chunk& ch = chunks[c];
+            const int slot = (int)(mine % (uint32_t)e->path_slots);
+            if (mine >= (uint32_t)e->path_slots) {   // K2 has read the chunk that used this slot before
+                ce = cudaEventSynchronize(path.ev_free[slot]);
+                if (ce != cudaSuccess) return failw(FMA_ECUDA, "cudaEventSynchronize(slot free)", ce);
+            }
+            char* slot_ptr = reinterpret_cast<char*>(path.va) + (size_t)slot * e->path_slot_bytes;
+            ce = cudaMemcpyAsync(slot_ptr, store + src_off[ch.p0], ch.np * FMA_PAGE_BYTES, cudaMemcpyDefault, path.copy);
+            if (ce != cudaSuccess) return failw(FMA_ECUDA, "cudaMemcpyAsync(H2D)", ce);
+            if (!first_copy_seen.exchange(true)) pipe.first_copy_delay = now_s() - pipe.t_entry;
+            ce = cudaEventRecord(path.ev_full[slot], path.copy);
+            if (ce != cudaSuccess) return failw(FMA_ECUDA, "cudaEventRecord(slot full)", ce);
+            const int mrc = pipe.wait_mapped(ch.need);
+            if (mrc != FMA_OK) return failw(mrc, "mapping", cudaSuccess);
+            ce = cudaStreamWaitEvent(path.kern, path.ev_full[slot], 0);
+            if (ce != cudaSuccess) return failw(FMA_ECUDA, "cudaStreamWaitEvent(slot full)", ce);
+            {
+                std::lock_guard<std::mutex> lk(kt_mu);
+                const int krc = kt.launch_on(path.kern, nullptr, (uint64_t)(uintptr_t)slot_ptr, e->d_tab + ch.p0, 0, (uint32_t)ch.np);
+                if (krc != FMA_OK) return failw(krc, "K2 launch", cudaGetLastError());
+            }
+            ce = cudaEventRecord(path.ev_free[slot], path.kern);
+            if (ce != cudaSuccess) return failw(FMA_ECUDA, "cudaEventRecord(slot free)", ce);
+            ++mine;
+        }
+        per_path[pi] = mine;
+        ce = cudaEventRecord(path.ev_done, path.kern);
+        if (ce != cudaSuccess) return failw(FMA_ECUDA, "cudaEventRecord(done)", ce);
+    };
+    std::vector<std::thread> th;
+    for (size_t pi = 0; pi < e->paths.size(); ++pi) th.emplace_back(worker, pi);
+    for (auto& t : th) t.join();
+    if (error.load() != FMA_OK) {
+        for (WakePath& path : e->paths) cudaStreamSynchronize(path.copy);   // nothing may still be writing the staging slots
+        return fail(error.load(), "%s", err_msg);
+    }
+    for (size_t pi = 0; pi < e->paths.size(); ++pi) {
+        RT(cudaStreamWaitEvent(e->ks, e->paths[pi].ev_done, 0));   // the wake's device-time bracket and the final sync cover every path
+        pipe.copy_ops += per_path[pi];
+        e->tl_add("path_chunks", e->paths[pi].device, pipe.t_entry, now_s(), (uint64_t)per_path[pi] * e->path_slot_bytes);
+    }
+    return FMA_OK;
+}
+
 #undef PIPE_CHECK
 
 }  // namespace
@@ -348,11 +458,15 @@ int do_wake(fma_engine_t* e, uint64_t tag_mask, uint32_t flags) {
     // Needs the run to end at its arena's bump pointer; otherwise (or FMA_RING_ATTACH=0) one cudaMalloc provides it.
     // Either way the ring must exist BEFORE the other runs start taking HBM.
     bool ring_run = false;
+    // MULTI-PATH: idle peers' PCIe links are borrowed for a host-tier wake of a plain image (fma_paths_set)
+    const bool multipath = !e->paths.empty() && tier == FMA_TIER_HOST && mode == FMA_MODE_STAGED && !packed;
     {
         uint64_t w_bytes = 0;
         for (const Run& r : runs)
             if (r.has_backup) w_bytes += r.bytes;
-        if (w_bytes && mode == FMA_MODE_STAGED && !e->n_ring) {
+        if (w_bytes && mode == FMA_MODE_STAGED && multipath) {
+            // every path brings its own staging slots: no ring
+        } else if (w_bytes && mode == FMA_MODE_STAGED && !e->n_ring) {
             const Run& r0 = runs[0];
             Arena& a = e->arenas[r0.arena];
             const size_t slot = ring_slot_for(e, w_bytes);
@@ -569,6 +683,7 @@ int do_wake(fma_engine_t* e, uint64_t tag_mask, uint32_t flags) {
         WakePipe pipe{e, with_backup, seg_run, W, tier, mode, ring_run, store, kt, copy_ops, first_copy_delay, t_entry, wait_mapped, mapped_now, prog.msg};
         const double t_enq0 = now_s();
         if (packed) WAKE_CHECK(wake_packed(pipe));
+        else if (multipath) WAKE_CHECK(wake_multipath(pipe));
         else if (mode == FMA_MODE_DIRECT) WAKE_CHECK(wake_direct(pipe));
         else WAKE_CHECK(wake_paged(pipe));
         e->tl_add("enqueue", (int)copy_ops, t_enq0, now_s(), W);

@@ -171,6 +171,11 @@ class Engine:
     def peer_release(self) -> None:
         check(self._lib.fma_peer_release(self._h))
 
+    def set_paths(self, helper_devices: Sequence[int], slot_bytes: int = 0, slots: int = 0) -> None:
+        """MULTI-PATH wake: idle peer GPUs whose PCIe links a host-tier wake may borrow ([] = off).  See fma_paths_set."""
+        arr = (C.c_int * max(len(helper_devices), 1))(*helper_devices)
+        check(self._lib.fma_paths_set(self._h, arr, len(helper_devices), slot_bytes, slots))
+
     def peer_attach(self, fd: int, nbytes: int) -> None:
         """Use a node-level owner's parking buffer (``ParkingBuffer``; fd received over SCM_RIGHTS / inherited) as this engine's
         peer-tier store.  The buffer's GPU need not be visible to this process (launcher.py:171-187 hides it)."""

@@ -277,6 +277,30 @@ int main() {
         OK(fma_engine_destroy(c));
     }
 
+    // MULTI-PATH wake (fma_paths_set): own link + one helper GPU, 2 MiB chunks -> many chunks, three threads (two paths + the
+    // mapper); a failing H2D in the middle rolls the wake back and the retry restores every byte
+    {
+        const int helper = 1;
+        OK(fma_set_option(a, "mode", FMA_MODE_AUTO));
+        OK(fma_paths_set(a, &helper, 1, 2 * P, 2));
+        auto before = digests(a);
+        for (int rep = 0; rep < 3; ++rep) {
+            OK(fma_sleep(a, 1ull << w, FMA_TIER_HOST, FMA_FLAG_VERIFY));
+            if (rep == 1) {
+                hostsim_fail_memcpy_after(5);
+                int rc2 = fma_wake(a, 0, 0);
+                hostsim_fail_memcpy_after(-1);
+                assert(rc2 != 0 && fma_is_sleeping(a) == 1);
+            }
+            OK(fma_wake(a, 0, FMA_FLAG_VERIFY));
+            auto after = digests(a);
+            for (size_t i = 0; i + 1 < before.size(); ++i) assert(after[i] == before[i]);
+        }
+        OK(fma_paths_set(a, nullptr, 0, 0, 0));
+        OK(fma_sleep(a, 1ull << w, FMA_TIER_HOST, FMA_FLAG_VERIFY));
+        OK(fma_wake(a, 0, FMA_FLAG_VERIFY));
+    }
+
     OK(fma_engine_destroy(a));
     OK(fma_engine_destroy(b));
     assert(hostsim_live_mapped_bytes() == 0 && hostsim_live_handles() == 0);   // nothing leaked: no mapping, no handle

@@ -46,3 +46,9 @@ class cuda:
     @staticmethod
     def synchronize():
         pass
+
+    @staticmethod
+    def device_count():
+        import os
+
+        return int(os.environ.get("HOSTSIM_DEVICES", "1"))

@@ -132,7 +132,7 @@ def test_bench_main_flow_runs_against_the_host_simulated_engine(hostsim_lib, ora
     replaced by tests/stubs/torch.  Numbers are meaningless here; the flow and the keys are what is checked."""
     import json
 
-    env = dict(os.environ, FMA_B200_LIB=hostsim_lib, FMA_HOSTSIM="1", HOSTSIM_DEVICES="1",
+    env = dict(os.environ, FMA_B200_LIB=hostsim_lib, FMA_HOSTSIM="1", HOSTSIM_DEVICES="2",
                PYTHONPATH=os.path.join(ROOT, "tests", "stubs") + os.pathsep + os.environ.get("PYTHONPATH", ""))
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", "tiny-llama-test", "--kv-gib", "0.03125",
                         "--steps", "2", "--warmup", "3", "--swap-models", "tiny-llama-test,tiny-llama-test", "--scaling-workload", "opt-125m",
@@ -141,6 +141,7 @@ def test_bench_main_flow_runs_against_the_host_simulated_engine(hostsim_lib, ora
     out = json.loads(r.stdout.strip().splitlines()[-1])
     assert out["swap_config4"].get("bit_exact") is True and out["swap_config4"]["cycles"] == 20, out["swap_config4"]
     assert out["n1_on_scaling_workload"].get("bit_exact") is True, out["n1_on_scaling_workload"]
+    assert out["multipath_wake"].get("bit_exact") is True and out["multipath_wake"]["rows"][0]["paths"] == 2, out["multipath_wake"]
     assert out["config"]["segments_per_rank"] > 0 and "phases" in out["config"]
     assert out["wake_latency_s_min_max"][0] <= out["wake_latency_s"] <= out["wake_latency_s_min_max"][1]
     tl = open(tmp_path / "tl" / "n1_rank0.csv").read()

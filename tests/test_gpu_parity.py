@@ -449,6 +449,61 @@ def test_peer_tier_roundtrip(engine, oracle, kernel):
     engine.peer_release()
 
 
+# ---- MULTI-PATH wake: idle peers' PCIe links + NVLink forward (needs >= 2 GPUs) --------------------------------------------
+@pytest.mark.parametrize("slot_mib,slots", [(2, 2), (6, 3), (128, 3)])
+def test_multipath_wake_matches_oracle(engine, oracle, slot_mib, slots):
+    """Host-tier wake with the image striped over the engine's own link and the helper GPUs' links (fma_paths_set): every
+    weight byte == oracle, addresses unchanged, kv_cache remapped; chunks really went over more than one path; tag-selective
+    wake, a table with a reused hole, and switching the paths off again."""
+    n = _n_gpus()
+    if n < 2:
+        pytest.skip("multi-path wake needs a second GPU")
+    L = _L()
+    table = _tiny_table()
+    ptrs, ref = _load(engine, oracle, table)
+    helpers = list(range(1, min(n, 4)))
+    engine.set_paths(helpers, slot_bytes=slot_mib << 20, slots=slots)
+    for rep in range(2):
+        engine.sleep(["weights"], flags=L.FMA_FLAG_VERIFY)
+        assert engine.is_sleeping()
+        engine.wake(None, flags=L.FMA_FLAG_VERIFY)
+        assert [s.va for s in engine.segments()] == ptrs and not engine.is_sleeping()
+        for i in ref:
+            assert engine.read(i, table[i].bytes) == ref[i].tobytes()
+        rows = [r for r in engine.timeline() if r["kind"] == "path_chunks"]
+        assert len(rows) == 1 + len(helpers) and sum(r["bytes"] for r in rows) >= sum(table[i].bytes for i in ref)
+        if (slot_mib << 20) * 4 <= sum(table[i].bytes for i in ref):
+            assert sum(1 for r in rows if r["bytes"]) >= 2, rows            # more than one path moved chunks
+    # a freed + re-used hole (image order != VA order), then weights first and kv_cache later
+    hole = sorted(ref)[1]
+    engine.free(ptrs[hole])
+    p_new = engine.alloc(table[hole].bytes, "weights")
+    idx = engine.find(p_new)
+    engine.fill(idx, 99, 7)
+    ref2 = {engine.find(ptrs[i]): ref[i] for i in ref if i != hole}
+    ref2[idx] = oracle.fill(table[hole].bytes, 99, 7)
+    engine.sleep(["weights"], flags=L.FMA_FLAG_VERIFY)
+    engine.wake(["weights"], flags=L.FMA_FLAG_VERIFY)
+    assert engine.is_sleeping()                                             # kv_cache still asleep
+    engine.wake(["kv_cache"])
+    assert not engine.is_sleeping()
+    segs = engine.segments()
+    for i, want in ref2.items():
+        assert engine.read(i, segs[i].bytes) == want.tobytes()
+    engine.set_paths([])                                                    # off again: the single-link pipeline
+    engine.sleep(["weights"], flags=L.FMA_FLAG_VERIFY)
+    engine.wake(None, flags=L.FMA_FLAG_VERIFY)
+    assert not [r for r in engine.timeline() if r["kind"] == "path_chunks"]
+    for i, want in ref2.items():
+        assert engine.read(i, segs[i].bytes) == want.tobytes()
+    from fma_b200 import FmaError
+
+    with pytest.raises(FmaError):
+        engine.set_paths([0])                                               # the engine's own GPU is not a helper
+    with pytest.raises(FmaError):
+        engine.set_paths([99])
+
+
 # ---- the peer tier under the real launcher: the parking buffer belongs to a node-level owner, the instance sees only its own GPU
 _PARKED_INSTANCE = r"""
 import os, sys, json, hashlib
