@@ -351,8 +351,7 @@ FMA_API int  fma_load_file(fma_engine_t* e, const char* path, const fma_load_spa
 
 /* ---- tuning ----------------------------------------------------------------------- */
 /* Change one knob of a live engine (between operations).  Keys: "mode", "kernel",
- * "copy_streams", "chunk_bytes", "ring_slots", "map_threads", "pack", "pack_kernel" (process-wide: 0 = LDG/STG, 1 =
- * TMA-pipelined K4 / K5), "incremental" (1 = a host-tier sleep whose offloaded segments still have the K3 digests and image
+ * "copy_streams", "chunk_bytes", "ring_slots", "map_threads", "pack", "incremental" (1 = a host-tier sleep whose offloaded segments still have the K3 digests and image
  * offsets of the copy the host store kept from the last wake releases the device side without moving a byte; anything else
  * is a full sleep), "tma_tile_bytes",
  * "tma_stages", "tma_pipes", "tma_ctas_per_sm", "load_threads", "load_chunk_bytes", "load_slots". */

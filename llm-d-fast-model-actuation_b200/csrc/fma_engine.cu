@@ -1435,7 +1435,7 @@ static int run_pack_op(fma_engine_t* e, bool unpack, const uint64_t* dev_pages, 
         d.src = unpack ? store_base + off : dev;
         d.dst = unpack ? dev : store_base + off;
         d.mode = stored_bytes[p] == FMA_PAGE_BYTES ? FMA_K_PACK_RAW : FMA_K_PACK_BF16;
-        d.pad = 0;
+        d.state = 0;
         off += stored_bytes[p];
     }
     uint32_t* d_err = e->d_psize + e->pdesc_cap;
@@ -1514,9 +1514,6 @@ int fma_set_option(fma_engine_t* e, const char* key, int64_t value) {
     } else if (k == "incremental") {
         if (value != 0 && value != 1) return fail(FMA_EINVAL, "incremental must be 0 or 1");
         e->incremental = (int)value;
-    } else if (k == "pack_kernel") {  // process-wide: 0 = LDG/STG kernels, 1 = TMA-pipelined kernels (K4 / K5)
-        if (value != FMA_K_PACK_VARIANT_LDG && value != FMA_K_PACK_VARIANT_TMA) return fail(FMA_EINVAL, "pack_kernel must be 0 or 1");
-        fma_k_set_pack_variant((int)value);
     } else if (k == "tma_tile_bytes") {
         if (value < 1024 || (FMA_PAGE_BYTES % (size_t)value) != 0 || value % 16) return fail(FMA_EINVAL, "bad tma tile %lld", (long long)value);
         e->tma.tile_bytes = (uint32_t)value;

@@ -40,19 +40,11 @@ struct fma_k_pack_desc {
     uint64_t src;   // K4: device address of the 2 MiB page          K5: address of the stored page (ring slot / store alias)
     uint64_t dst;   // K4: where the stored page goes (ring slot)    K5: device address of the 2 MiB page
     uint32_t mode;  // FMA_K_PACK_*
-    uint32_t pad;
+    uint32_t state; // K4 scratch, MUST be 0 at launch: exceptions taken so far (low 24 bits) | finished parts of the page << 24
 };
 
 // K4p: out_bytes[p] = stored size of page p (FMA_K_PACKED_PAGE_BYTES, or FMA_K_PAGE_BYTES when it has to stay raw)
 cudaError_t fma_k_launch_pack_probe(const uint64_t* src_tab, uint32_t n_pages, uint32_t* out_bytes, cudaStream_t stream);
 // K4 / K5: *err_count (device, zeroed by the caller) counts pages that could not be coded / decoded
-cudaError_t fma_k_launch_pack(const fma_k_pack_desc* descs, uint32_t n_pages, uint32_t* err_count, cudaStream_t stream);
+cudaError_t fma_k_launch_pack(fma_k_pack_desc* descs, uint32_t n_pages, uint32_t* err_count, cudaStream_t stream);   // writes descs[].state
 cudaError_t fma_k_launch_unpack(const fma_k_pack_desc* descs, uint32_t n_pages, uint32_t* err_count, cudaStream_t stream);
-// TMA-pipelined variants of K4 / K5 (fma_pack_tma_kernels.cu); fma_k_launch_pack / _unpack dispatch to them when the
-// process-wide variant is 1 (fma_k_set_pack_variant; default from FMA_PACK_KERNEL)
-#define FMA_K_PACK_VARIANT_LDG 0
-#define FMA_K_PACK_VARIANT_TMA 1
-void fma_k_set_pack_variant(int variant);
-int fma_k_pack_variant();
-cudaError_t fma_k_launch_pack_tma(const fma_k_pack_desc* descs, uint32_t n_pages, uint32_t* err_count, cudaStream_t stream);
-cudaError_t fma_k_launch_unpack_tma(const fma_k_pack_desc* descs, uint32_t n_pages, uint32_t* err_count, cudaStream_t stream);

@@ -8,11 +8,16 @@
 // copy engines then move 0.758 x the bytes over PCIe Gen5, which is what bounds a wake.  The reference
 // has no such stage (vllm:device_allocator/cumem.py:198-213 copies verbatim).
 //
-// Work decomposition: one CTA per page (grid-stride), 8 warps; a warp owns a 256-value tile (one 16-byte load per
-// lane, 512 B per warp and instruction), four tiles in flight per warp.  Tile maximum by redux.sync; exception slots
-// from one shared-memory counter per page; the 4 KiB emax plane is staged in shared memory and written with 16-byte
-// stores.  HBM-bound: reads 2 MiB, writes 1.52 MiB per page, all accesses whole 32-byte sectors except the (rare)
-// exception patches.  All arithmetic is in fma_codec.h, shared with the CPU stand-in that the host-simulated engine
+// Work decomposition: a page is cut into kParts = 8 parts of 512 tiles; one CTA (8 warps) per (page, part), grid-stride over
+// the work items; a warp owns a 256-value tile (one 16-byte load per lane, 512 B per warp and instruction), four tiles in
+// flight per warp.  Tile maximum by redux.sync.  K4: exception slots of a page come from ONE counter in global memory (the
+// low 24 bits of the page descriptor's `state` word; the high 8 bits count finished parts and the part that finishes last
+// writes the page header); each part stages its 512 B slice of the emax plane in shared memory.  K5: each part decodes its
+// tiles and then patches the exceptions that fall into its value range.
+// Why parts (round 2, B200): with one CTA per page a ring slot's worth of pages (256-337) is 1.7-2.3 waves of 148 SMs at
+// 28 % of the warps an SM can hold — K5 ran at 2.7-3.3 TB/s per slot-sized launch against 5.6 TB/s for 1024 pages
+// (profiles/pack_sweep_r2.json, profiles/k5_full_r2.md); 8 x as many, 8 x smaller work items fill the machine at every size.
+// HBM-bound: reads 2 MiB, writes 1.52 MiB per page, all accesses whole 32-byte sectors except the (rare) exception patches.  All arithmetic is in fma_codec.h, shared with the CPU stand-in that the host-simulated engine
 // tests run, and restated in oracle/fma_oracle.c.
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -68,10 +73,16 @@ inline void st_stream4(void* p, uint32_t a) { memcpy(p, &a, 4); }
 
 // tile handled by (iteration, warp, u): consecutive warps take consecutive groups of kU tiles
 __device__ __forceinline__ uint32_t tile_of(uint32_t it, uint32_t warp, uint32_t u) { return (it * kWarps + warp) * kU + u; }
-constexpr uint32_t kIters = kTiles / (kWarps * kU);  // 128
+constexpr uint32_t kIters = kTiles / (kWarps * kU);  // 128 iterations cover a page
+constexpr uint32_t kParts = 8;                       // work items per page
+constexpr uint32_t kItersPart = kIters / kParts;     // 16
+constexpr uint32_t kTilesPart = kTiles / kParts;     // 512
+constexpr uint32_t kValuesPart = kValues / kParts;   // 131072
+constexpr uint32_t kCountMask = 0x00FFFFFFu;         // fma_k_pack_desc::state: exceptions so far | finished parts << 24
 
-__device__ __forceinline__ void copy_page_raw(const unsigned char* src, unsigned char* dst) {
-    for (uint32_t o = threadIdx.x * 16u; o < kPageBytes; o += kThreads * 16u * 4u) {
+__device__ __forceinline__ void copy_part_raw(const unsigned char* src, unsigned char* dst, uint32_t part) {
+    const uint32_t lo = part * (kPageBytes / kParts), hi = lo + kPageBytes / kParts;
+    for (uint32_t o = lo + threadIdx.x * 16u; o < hi; o += kThreads * 16u * 4u) {
         uint4 v[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) v[u] = ld_stream16(src + o + u * kThreads * 16u);
@@ -117,22 +128,21 @@ fma_k_pack_probe(const uint64_t* __restrict__ src_tab, uint32_t n_pages, uint32_
 // K4: gather + encode
 // ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
-fma_k_pack(const fma_k_pack_desc* __restrict__ descs, uint32_t n_pages, uint32_t* __restrict__ err) {
-    __shared__ uint32_t s_nexc;
-    __shared__ __align__(16) unsigned char s_emax[kTiles];
+fma_k_pack(fma_k_pack_desc* __restrict__ descs, uint32_t n_pages, uint32_t* __restrict__ err) {
+    __shared__ __align__(16) unsigned char s_emax[kTilesPart];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (uint32_t p = blockIdx.x; p < n_pages; p += gridDim.x) {
-        const fma_k_pack_desc d = descs[p];
-        const unsigned char* src = reinterpret_cast<const unsigned char*>(d.src);
-        unsigned char* dst = reinterpret_cast<unsigned char*>(d.dst);
-        if (d.mode == FMA_K_PACK_RAW) {
-            copy_page_raw(src, dst);
+    const uint32_t n_items = n_pages * kParts;
+    for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const uint32_t p = item / kParts, part = item % kParts;
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(descs[p].src);
+        unsigned char* dst = reinterpret_cast<unsigned char*>(descs[p].dst);
+        if (descs[p].mode == FMA_K_PACK_RAW) {
+            copy_part_raw(src, dst, part);
             continue;
         }
-        if (threadIdx.x == 0) s_nexc = 0;
-        __syncthreads();
+        uint32_t* state = &descs[p].state;   // zeroed by the host with the descriptor upload
         uint32_t* exc = reinterpret_cast<uint32_t*>(dst + kExcOff);
-        for (uint32_t it = 0; it < kIters; ++it) {
+        for (uint32_t it = part * kItersPart; it < (part + 1) * kItersPart; ++it) {
             uint4 v[kU];
 #pragma unroll
             for (int u = 0; u < kU; ++u) v[u] = ld_stream16(src + tile_of(it, warp, u) * 512u + lane * 16u);
@@ -145,24 +155,30 @@ fma_k_pack(const fma_k_pack_desc* __restrict__ descs, uint32_t n_pages, uint32_t
                 lane_encode(w, emax, lo, hi, nib, xm);
                 st_stream8(dst + kSmOff + tile * kTileValues + lane * 8u, lo, hi);
                 st_stream4(dst + kNibOff + tile * (kTileValues / 2) + lane * 4u, nib);
-                if (lane == 0) s_emax[tile] = (unsigned char)emax;
+                if (lane == 0) s_emax[tile - part * kTilesPart] = (unsigned char)emax;
                 while (xm) {  // rare: a value more than 13 binades below its tile's maximum
                     const uint32_t k = __ffs(xm) - 1;
                     xm &= xm - 1;
-                    const uint32_t slot = atomicAdd(&s_nexc, 1u);
+                    const uint32_t slot = atomicAdd(state, 1u) & kCountMask;
                     const uint32_t word = k < 2 ? v[u].x : k < 4 ? v[u].y : k < 6 ? v[u].z : v[u].w;  // no dynamic index
                     const uint32_t val = (word >> (16 * (k & 1))) & 0xFFFFu;
                     if (slot < kExcCap) exc[slot] = exc_entry(tile * kTileValues + lane * kLaneValues + k, exp_of(val));
                 }
             }
         }
-        __syncthreads();
-        st_stream16(dst + kEmaxOff + threadIdx.x * 16u, *reinterpret_cast<const uint4*>(s_emax + threadIdx.x * 16u));
+        __syncthreads();   // the part's emax slice is complete; every exception slot this CTA takes has been taken
+        if (threadIdx.x < kTilesPart / 16)
+            st_stream16(dst + kEmaxOff + part * kTilesPart + threadIdx.x * 16u, *reinterpret_cast<const uint4*>(s_emax + threadIdx.x * 16u));
         if (threadIdx.x == 0) {
-            uint32_t* hdr = reinterpret_cast<uint32_t*>(dst + kHdrOff);
-            hdr[0] = kMagic;
-            hdr[1] = s_nexc;
-            if (s_nexc > kExcCap) atomicAdd(err, 1u);  // the page changed after the probe: the caller fails the sleep
+            __threadfence();
+            const uint32_t old = atomicAdd(state, 1u << 24);
+            if ((old >> 24) == kParts - 1) {   // the last part of the page to finish writes the header
+                const uint32_t n_exc = old & kCountMask;
+                uint32_t* hdr = reinterpret_cast<uint32_t*>(dst + kHdrOff);
+                hdr[0] = kMagic;
+                hdr[1] = n_exc;
+                if (n_exc > kExcCap) atomicAdd(err, 1u);  // the page changed after the probe: the caller fails the sleep
+            }
         }
         __syncthreads();
     }
@@ -174,20 +190,21 @@ fma_k_pack(const fma_k_pack_desc* __restrict__ descs, uint32_t n_pages, uint32_t
 __global__ void __launch_bounds__(kThreads)
 fma_k_unpack(const fma_k_pack_desc* __restrict__ descs, uint32_t n_pages, uint32_t* __restrict__ err) {
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (uint32_t p = blockIdx.x; p < n_pages; p += gridDim.x) {
-        const fma_k_pack_desc d = descs[p];
-        const unsigned char* src = reinterpret_cast<const unsigned char*>(d.src);
-        unsigned char* dst = reinterpret_cast<unsigned char*>(d.dst);
-        if (d.mode == FMA_K_PACK_RAW) {
-            copy_page_raw(src, dst);
+    const uint32_t n_items = n_pages * kParts;
+    for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const uint32_t p = item / kParts, part = item % kParts;
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(descs[p].src);
+        unsigned char* dst = reinterpret_cast<unsigned char*>(descs[p].dst);
+        if (descs[p].mode == FMA_K_PACK_RAW) {
+            copy_part_raw(src, dst, part);
             continue;
         }
         const uint32_t magic = ld_stream4(src + kHdrOff), n_exc = ld_stream4(src + kHdrOff + 4);
-        if (magic != kMagic || n_exc > kExcCap) {  // uniform per CTA
-            if (threadIdx.x == 0) atomicAdd(err, 1u);
+        if (magic != kMagic || n_exc > kExcCap) {  // uniform per CTA; counted once per page
+            if (threadIdx.x == 0 && part == 0) atomicAdd(err, 1u);
             continue;
         }
-        for (uint32_t it = 0; it < kIters; ++it) {
+        for (uint32_t it = part * kItersPart; it < (part + 1) * kItersPart; ++it) {
             uint2 sm[kU];
             uint32_t nib[kU], emax[kU];
 #pragma unroll
@@ -204,11 +221,13 @@ fma_k_unpack(const fma_k_pack_desc* __restrict__ descs, uint32_t n_pages, uint32
                 st_stream16(dst + tile_of(it, warp, u) * 512u + lane * 16u, make_uint4(w[0], w[1], w[2], w[3]));
             }
         }
-        __syncthreads();  // the page's values are written (block-visible) before the exceptions patch them
+        __syncthreads();  // the part's values are written (block-visible) before the exceptions patch them
         const uint32_t* exc = reinterpret_cast<const uint32_t*>(src + kExcOff);
-        for (uint32_t i = threadIdx.x; i < n_exc; i += kThreads) {
+        for (uint32_t i = threadIdx.x; i < n_exc; i += kThreads) {   // every part scans the page's list (<= 8 KiB) for its own range
             const uint32_t entry = ld_stream4(exc + i);
-            unsigned short* pv = reinterpret_cast<unsigned short*>(dst) + exc_index(entry);
+            const uint32_t index = exc_index(entry);
+            if (index / kValuesPart != part) continue;
+            unsigned short* pv = reinterpret_cast<unsigned short*>(dst) + index;
             *pv = (unsigned short)apply_exception(__ldcg(pv), entry);
         }
         __syncthreads();
@@ -225,7 +244,7 @@ int pack_sm_count() {
     }
     return g_pack_sm_count;
 }
-unsigned pack_grid(uint32_t n_pages) {
+unsigned pack_grid(uint32_t n_items) {
     // Grid cap = SMs x CTAs per SM (grid-stride loop over pages beyond it).  8 CTAs of 256 threads fit an SM at 32 registers
     // (K4p, K5), 5 at K4's 48.  FMA_PACK_CTAS_PER_SM overrides it for sweeps (read once).
     static int per_sm = 0;
@@ -234,21 +253,10 @@ unsigned pack_grid(uint32_t n_pages) {
         per_sm = v && atoi(v) > 0 ? atoi(v) : 8;
     }
     const uint64_t cap = (uint64_t)pack_sm_count() * (uint64_t)per_sm;
-    return (unsigned)(n_pages < cap ? n_pages : cap);
+    return (unsigned)(n_items < cap ? n_items : cap);
 }
 
 }  // namespace
-
-// process-wide choice between the LDG/STG kernels of this file and the TMA-pipelined ones (fma_pack_tma_kernels.cu)
-static int g_pack_variant = -1;
-void fma_k_set_pack_variant(int variant) { g_pack_variant = variant == FMA_K_PACK_VARIANT_TMA ? FMA_K_PACK_VARIANT_TMA : FMA_K_PACK_VARIANT_LDG; }
-int fma_k_pack_variant() {
-    if (g_pack_variant < 0) {
-        const char* v = getenv("FMA_PACK_KERNEL");
-        g_pack_variant = (v && atoi(v) == 1) ? FMA_K_PACK_VARIANT_TMA : FMA_K_PACK_VARIANT_LDG;
-    }
-    return g_pack_variant;
-}
 
 cudaError_t fma_k_launch_pack_probe(const uint64_t* src_tab, uint32_t n_pages, uint32_t* out_bytes, cudaStream_t stream) {
     if (n_pages == 0) return cudaSuccess;
@@ -256,16 +264,14 @@ cudaError_t fma_k_launch_pack_probe(const uint64_t* src_tab, uint32_t n_pages, u
     return cudaGetLastError();
 }
 
-cudaError_t fma_k_launch_pack(const fma_k_pack_desc* descs, uint32_t n_pages, uint32_t* err_count, cudaStream_t stream) {
+cudaError_t fma_k_launch_pack(fma_k_pack_desc* descs, uint32_t n_pages, uint32_t* err_count, cudaStream_t stream) {
     if (n_pages == 0) return cudaSuccess;
-    if (fma_k_pack_variant() == FMA_K_PACK_VARIANT_TMA) return fma_k_launch_pack_tma(descs, n_pages, err_count, stream);
-    FMA_LAUNCH(fma_k_pack, pack_grid(n_pages), kThreads, 0, stream, descs, n_pages, err_count);
+    FMA_LAUNCH(fma_k_pack, pack_grid(n_pages * kParts), kThreads, 0, stream, descs, n_pages, err_count);
     return cudaGetLastError();
 }
 
 cudaError_t fma_k_launch_unpack(const fma_k_pack_desc* descs, uint32_t n_pages, uint32_t* err_count, cudaStream_t stream) {
     if (n_pages == 0) return cudaSuccess;
-    if (fma_k_pack_variant() == FMA_K_PACK_VARIANT_TMA) return fma_k_launch_unpack_tma(descs, n_pages, err_count, stream);
-    FMA_LAUNCH(fma_k_unpack, pack_grid(n_pages), kThreads, 0, stream, descs, n_pages, err_count);
+    FMA_LAUNCH(fma_k_unpack, pack_grid(n_pages * kParts), kThreads, 0, stream, descs, n_pages, err_count);
     return cudaGetLastError();
 }

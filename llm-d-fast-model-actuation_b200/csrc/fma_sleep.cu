@@ -269,7 +269,7 @@ int sleep_kernel_packed(SleepPipe& pipe) {
         d.src = e->h_tab[p];
         d.dst = dbase + e->img_off[p];
         d.mode = e->img_bytes[p] == FMA_PAGE_BYTES ? FMA_K_PACK_RAW : FMA_K_PACK_BF16;
-        d.pad = 0;
+        d.state = 0;
     }
     uint32_t* d_err = e->d_psize + e->pdesc_cap;
     RT(cudaMemcpyAsync(e->d_pdesc, e->h_pdesc, n_pages * sizeof(fma_k_pack_desc), cudaMemcpyHostToDevice, e->ks));
@@ -359,7 +359,7 @@ int sleep_staged_packed(SleepPipe& pipe) {
             d.src = e->h_tab[p];
             d.dst = (uint64_t)(uintptr_t)e->ring[c % e->n_ring] + (e->img_off[p] - e->img_off[pages[slots[c].k0]]);
             d.mode = e->img_bytes[p] == FMA_PAGE_BYTES ? FMA_K_PACK_RAW : FMA_K_PACK_BF16;
-            d.pad = 0;
+            d.state = 0;
         }
     uint32_t* d_err = e->d_psize + e->pdesc_cap;
     RT(cudaMemcpyAsync(e->d_pdesc, e->h_pdesc, pages.size() * sizeof(fma_k_pack_desc), cudaMemcpyHostToDevice, e->ks));

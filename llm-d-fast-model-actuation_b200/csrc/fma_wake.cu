@@ -102,7 +102,7 @@ int wake_packed(WakePipe& pipe) {
                 pd.src = (uint64_t)(uintptr_t)e->ring[c % e->n_ring] + (soff[q] - soff[slots[c].p0]);
                 pd.dst = dsts[q];
                 pd.mode = sbytes[q] == FMA_PAGE_BYTES ? FMA_K_PACK_RAW : FMA_K_PACK_BF16;
-                pd.pad = 0;
+                pd.state = 0;
             }
         RT(cudaMemcpyAsync(e->d_pdesc, e->h_pdesc, n_pages * sizeof(fma_k_pack_desc), cudaMemcpyHostToDevice, e->ks));
         for (size_t c = 0; c < slots.size(); ++c) {
@@ -131,7 +131,7 @@ int wake_packed(WakePipe& pipe) {
             pd.src = sbase + soff[q];
             pd.dst = dsts[q];
             pd.mode = sbytes[q] == FMA_PAGE_BYTES ? FMA_K_PACK_RAW : FMA_K_PACK_BF16;
-            pd.pad = 0;
+            pd.state = 0;
         }
         RT(cudaMemcpyAsync(e->d_pdesc, e->h_pdesc, n_pages * sizeof(fma_k_pack_desc), cudaMemcpyHostToDevice, e->ks));
         const size_t batch_pages = std::max<size_t>(staged_slot(e) / FMA_PAGE_BYTES, 1);

@@ -29,8 +29,7 @@ for n in (37, 148, 256, 337, 592, 1024):
     sizes, ms_probe = eng.op_pack_probe(n, pages=src)
     assert all(b == PACKED for b in sizes), "dummy weights must code"
     rows.append(dict(kernel="K4p", n_pages=n, us=ms_probe * 1e3, gbs=n * PAGE / ms_probe / 1e6))
-    for variant in (0, 1):
-        eng.set_option("pack_kernel", variant)
+    for variant in (0,):
         t4 = sorted(eng.op_pack(sizes, store, src_pages=src) for _ in range(7))[1]
         t5 = sorted(eng.op_unpack(sizes, store, dst_base=back) for _ in range(7))[1]
         ok = eng.op_page_digest(n, base=back, first_word=[0] * n)[0] == eng.op_page_digest(n, pages=src, first_word=[0] * n)[0]
@@ -38,7 +37,6 @@ for n in (37, 148, 256, 337, 592, 1024):
         rows.append(dict(kernel="K4", variant="tma" if variant else "ldg", n_pages=n, us=t4 * 1e3, gbs=alg / t4 / 1e6, bit_exact=ok))
         rows.append(dict(kernel="K5", variant="tma" if variant else "ldg", n_pages=n, us=t5 * 1e3, gbs=alg / t5 / 1e6, bit_exact=ok))
         print(n, "pages", "tma" if variant else "ldg", f"K4 {t4 * 1e3:.1f} us {alg / t4 / 1e6:.0f} GB/s | K5 {t5 * 1e3:.1f} us {alg / t5 / 1e6:.0f} GB/s | exact {ok}", flush=True)
-eng.set_option("pack_kernel", 0)
 os.makedirs("gpurun_out/sweep", exist_ok=True)
 json.dump(rows, open("gpurun_out/sweep/pack_sweep.json", "w"), indent=1)
 eng.close()

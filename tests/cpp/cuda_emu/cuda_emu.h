@@ -218,6 +218,7 @@ inline unsigned long long __shfl_down_sync(unsigned, unsigned long long v, unsig
 }
 inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 inline uint32_t atomicAdd(uint32_t* p, uint32_t v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 template <class T> inline T __ldg(const T* p) { return *p; }
 template <class T> inline T __ldcg(const T* p) { return *p; }
 inline int __popc(uint32_t v) { return __builtin_popcount(v); }

@@ -1,5 +1,4 @@
-// Runs the ACTUAL kernel sources csrc/fma_pack_kernels.cu (K4p / K4 / K5) and csrc/fma_pack_tma_kernels.cu (their
-// TMA-pipelined variants) on the CPU execution model of cuda_emu.h and
+// Runs the ACTUAL kernel source csrc/fma_pack_kernels.cu (K4p / K4 / K5) on the CPU execution model of cuda_emu.h and
 // checks it against the oracle (oracle/fma_oracle.c) page by page: probe decisions, stored bytes (exceptions compared
 // as sets), decode, gather/scatter through descriptor tables, the error counter.  Built by tests/test_kernels_emulated.py
 // with g++ -DFMA_CUDA_EMU -include cuda_emu.h, plain and under ThreadSanitizer (missing barriers = data races).
@@ -39,7 +38,6 @@ template <class T> using DevAlloc = std::allocator<T>;
 #endif
 
 #include "../../../llm-d-fast-model-actuation_b200/csrc/fma_pack_kernels.cu"
-#include "../../../llm-d-fast-model-actuation_b200/csrc/fma_pack_tma_kernels.cu"   // the TMA-pipelined K4 / K5 (variant 1)
 
 extern "C" {
 uint32_t fma_oracle_pack_page(const void* page, void* stored);
@@ -71,8 +69,7 @@ static bool same_stored(const unsigned char* a, const unsigned char* b, uint32_t
     return ea == eb;
 }
 
-static int run_variant(int variant) {
-    fma_k_set_pack_variant(variant);
+static int run_all() {
     std::vector<Page> pages;
     pages.push_back(weights(110, 12));                                  // well inside 13 binades
     pages.push_back(weights(100, 27));                                  // wide: many exceptions -> probably raw
@@ -156,15 +153,12 @@ static int run_variant(int variant) {
     assert(fma_k_launch_unpack(bad.data(), 1, &err, nullptr) == cudaSuccess);
     DEVICE_SYNC();
     assert(err == 1);
-    printf("variant %d (%s) ok\n", variant, variant ? "TMA-pipelined" : "LDG/STG");
     return 0;
 }
 
 int main() {
-    for (int variant = 0; variant < 2; ++variant) {
-        const int rc = run_variant(variant);
-        if (rc) return rc;
-    }
+    const int rc = run_all();
+    if (rc) return rc;
 #if defined(FMA_GPU_TEST)
     puts("pack kernels (GPU) ok");
 #else

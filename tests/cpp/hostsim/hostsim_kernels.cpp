@@ -52,10 +52,6 @@ cudaError_t fma_k_launch_fill(const fma_k_page_desc* pages, uint32_t n_pages, ui
 #include "fma_codec.h"
 namespace fc = fma_codec;
 
-static int g_variant = 0;  // the stand-ins below serve both kernel variants: same bytes by contract
-void fma_k_set_pack_variant(int v) { g_variant = v; }
-int fma_k_pack_variant() { return g_variant; }
-
 static void load_lane(const unsigned char* src, uint32_t tile, uint32_t lane, uint32_t w[4]) { memcpy(w, src + tile * 512u + lane * 16u, 16); }
 
 static uint32_t tile_emax(const unsigned char* src, uint32_t tile) {
@@ -87,7 +83,7 @@ cudaError_t fma_k_launch_pack_probe(const uint64_t* src_tab, uint32_t n_pages, u
     return cudaSuccess;
 }
 
-cudaError_t fma_k_launch_pack(const fma_k_pack_desc* descs, uint32_t n_pages, uint32_t* err_count, cudaStream_t) {
+cudaError_t fma_k_launch_pack(fma_k_pack_desc* descs, uint32_t n_pages, uint32_t* err_count, cudaStream_t) {
     for (uint32_t p = 0; p < n_pages; ++p) {
         const unsigned char* src = reinterpret_cast<const unsigned char*>(descs[p].src);
         unsigned char* dst = reinterpret_cast<unsigned char*>(descs[p].dst);

@@ -40,7 +40,7 @@ def hostsim_lib(tmp_path_factory):
 
 def test_parity_suite_against_the_host_simulated_engine(hostsim_lib, oracle):
     env = dict(os.environ, FMA_B200_LIB=hostsim_lib, FMA_HOSTSIM="1", HOSTSIM_DEVICES="2")
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-x", "-q", "-m", "gpu",
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), os.path.join(ROOT, "tests", "test_gpu_http.py"), "-x", "-q", "-m", "gpu",
                         "-k", "not shim and not torch_pool and not full_size", "-p", "no:cacheprovider"],
                        env=env, cwd=ROOT, capture_output=True, text=True, timeout=900)
     tail = (r.stdout + r.stderr)[-3000:]

@@ -782,19 +782,7 @@ def _same_stored_page(a: np.ndarray, b: np.ndarray) -> bool:
                 and np.array_equal(a[hdr:hdr + 4], b[hdr:hdr + 4]))
 
 
-_PACK_KERNELS = [int(v) for v in os.environ.get("FMA_TEST_PACK_KERNELS", "0,1").split(",")]   # first GPU contact: run "0" alone first
-
-
-@pytest.fixture()
-def pack_kernel(request, engine):
-    """K4 / K5 variant for a test: 0 = LDG/STG kernels, 1 = TMA-pipelined kernels (process-wide switch, reset afterwards)."""
-    engine.set_option("pack_kernel", request.param)
-    yield request.param
-    engine.set_option("pack_kernel", 0)
-
-
-@pytest.mark.parametrize("pack_kernel", _PACK_KERNELS, indirect=True)
-def test_pack_kernels_match_oracle_page_by_page(engine, oracle, pack_kernel):
+def test_pack_kernels_match_oracle_page_by_page(engine, oracle):
     L = _L()
     pages = _pack_pages(oracle)
     n = len(pages)
@@ -819,9 +807,8 @@ def test_pack_kernels_match_oracle_page_by_page(engine, oracle, pack_kernel):
     engine.scratch_free(store)
 
 
-@pytest.mark.parametrize("pack_kernel", _PACK_KERNELS, indirect=True)
 @pytest.mark.parametrize("chunk_mib,slots", [(6, 2), (2, 2), (512, 2), (4, 3)])
-def test_packed_sleep_wake_roundtrip_and_image_match_oracle(engine, oracle, chunk_mib, slots, pack_kernel):
+def test_packed_sleep_wake_roundtrip_and_image_match_oracle(engine, oracle, chunk_mib, slots):
     L = _L()
     pages = _pack_pages(oracle)
     rng = np.random.default_rng(5)

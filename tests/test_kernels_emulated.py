@@ -1,6 +1,6 @@
-"""The ACTUAL kernel sources of the packed-image path (csrc/fma_pack_kernels.cu: K4p, K4, K5; csrc/fma_pack_tma_kernels.cu:
-their TMA-pipelined variants, whose mbarrier / cp.async.bulk traffic runs on a LAZY model of the async proxy — a copy happens
-when somebody legitimately waits for it, so a missing wait yields wrong bytes) executed on a CPU model of
+"""The ACTUAL kernel sources of the packed-image path (csrc/fma_pack_kernels.cu: K4p, K4, K5) and of the hot path (csrc/fma_kernels.cu,
+whose mbarrier / cp.async.bulk traffic runs on a LAZY model of the async proxy — a copy happens when somebody legitimately waits
+for it, so a missing wait yields wrong bytes) executed on a CPU model of
 the CUDA execution hierarchy (tests/cpp/cuda_emu/cuda_emu.h: a CTA = blockDim OS threads, __syncthreads = barrier, warp
 collectives = warp barrier + scratch line, __shared__ = static) and compared with the oracle page by page.  Under
 ThreadSanitizer a missing __syncthreads() shows up as a data race (checked by mutation when this was written).
@@ -33,7 +33,7 @@ def _build_and_run(tmp_path, src, name, san, flags, marker):
 
 
 def test_kernel_sources_on_the_cpu_execution_model(tmp_path):
-    """Four builds side by side: {packed-image kernels (K4p, K4, K5 + TMA-pipelined K4 / K5), hot-path kernels (K0, K1/K2 TMA in
+    """Four builds side by side: {packed-image kernels (K4p, K4, K5: sub-page work items, a global exception counter per page, last-part header), hot-path kernels (K0, K1/K2 TMA in
     five shapes + LDG, K3 — the source validated on B200 hardware; the emulation guards leave its nvcc SASS byte-identical)}
     x {plain, ThreadSanitizer}, each against the oracle."""
     if not os.path.exists("/usr/local/cuda/include/cuda_runtime.h"):
