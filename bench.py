@@ -408,11 +408,10 @@ def measure_multipath(args, L, W, cfg, workload: str, n_visible: int, cycles: in
     try:
         eng = fma_b200.Engine(0, cfg)
         _, wb = load_model(eng, W, workload, args.kv_gib, 1234)
-        eng.host_reserve(wb)
         before = eng.digest_all(["weights"])
         rows = []
         ks = [k for k in (1, 3, 7) if k < n_visible]
-        plans = [(k, 128, 3) for k in ks] + ([(ks[-1], 32, 4), (ks[-1], 512, 2)] if ks else [])
+        plans = [(k, 128, 3) for k in ks] + ([(ks[-1], 64, 4)] if ks else [])
         for k, slot_mib, slots in plans:
             eng.set_paths(list(range(1, k + 1)), slot_bytes=slot_mib << 20, slots=slots)
             wakes, devs = [], []
@@ -420,12 +419,15 @@ def measure_multipath(args, L, W, cfg, workload: str, n_visible: int, cycles: in
                 eng.sleep(["weights"]); eng.wake(None); st = eng.stats()
                 if i:
                     wakes.append(st["wake_seconds"]); devs.append(st["wake_copy_seconds"])
-            chunks = {r["idx"]: r["bytes"] for r in eng.timeline() if r["kind"] == "path_chunks"}
+            tl = eng.timeline()
+            chunks = {r["idx"]: r["bytes"] for r in tl if r["kind"] == "path_chunks"}
+            local = {r["idx"]: r["bytes"] for r in tl if r["kind"] == "path_local"}
             med = statistics.median
             rows.append({"helpers": k, "paths": k + 1, "slot_mib": slot_mib, "slots": slots, "wake_latency_s": round(med(wakes), 5),
                          "wake_latency_s_min_max": [round(min(wakes), 5), round(max(wakes), 5)], "e2e_gbs": round(wb / med(wakes) / 1e9, 1),
                          "device_gbs": round(wb / med(devs) / 1e9, 1), "x_single_link_64": round(wb / med(wakes) / 1e9 / PCIE_GEN5_X16_GBS, 2),
-                         "gib_per_path_device": {str(d): round(b / GiB, 2) for d, b in sorted(chunks.items())}})
+                         "gib_per_path_device": {str(d): round(b / GiB, 2) for d, b in sorted(chunks.items())},
+                         "gib_numa_local_per_path_device": {str(d): round(b / GiB, 2) for d, b in sorted(local.items())}})
         eng.set_paths([])
         ok = eng.digest_all(["weights"]) == before
         eng.close()

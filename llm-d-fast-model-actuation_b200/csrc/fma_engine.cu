@@ -339,6 +339,14 @@ int ensure_event_pool(fma_engine_t* e, size_t n) {
 // cumem.py:204-209).  mmap + mbind + parallel first-touch + cudaHostRegister, fallback cudaHostAlloc.
 // ------------------------------------------------------------------------------------
 int gpu_numa_node(int device) {
+    if (const char* fake = getenv("FMA_TEST_NUMA_MAP")) {   // tests: "0,1,1" = device -> node (boxes with one node / the host simulation)
+        int d = 0;
+        for (const char* q = fake; *q; ++q) {
+            if (*q == ',') { ++d; continue; }
+            if (d == device) return atoi(q);
+        }
+        return -1;
+    }
     char bus[64] = "";
     if (cudaDeviceGetPCIBusId(bus, sizeof(bus), device) != cudaSuccess) {
         cudaGetLastError();
@@ -406,11 +414,40 @@ int host_store_reserve(fma_engine_t* e, size_t bytes) {
         if (p == MAP_FAILED) p = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
         if (p != MAP_FAILED) {
             madvise(p, bytes, MADV_HUGEPAGE);
-            if (node >= 0 && node < 64) {
+            // MULTI-PATH wake configured (fma_paths_set): stripe the store over the NUMA nodes of the paths' GPUs in proportion
+            // to the number of paths on each node, so that every path can pull chunks that are LOCAL to its GPU's socket.
+            // Measured on a B200 box whose helpers sat on the other socket: 3 helpers dragging a node-0 store across the
+            // interconnect got 26 GB/s each (78 GB/s together) instead of 55 (profiles/multipath_r2.md).
+            std::map<int, int> per_node;
+            if (want_bind)
+                for (const WakePath& wp : e->paths)
+                    if (wp.numa_node >= 0 && wp.numa_node < 64) ++per_node[wp.numa_node];
+            if (per_node.size() > 1 && per_node.size() * FMA_PAGE_BYTES <= bytes) {
+                size_t total_paths = 0, done_paths = 0, begin = 0;
+                for (auto& kv : per_node) total_paths += (size_t)kv.second;
+                if (node >= 0 && per_node.count(node)) {  // the engine's own node first: a single-path wake then starts local
+                    std::vector<std::pair<int, int>> order{{node, per_node[node]}};
+                    for (auto& kv : per_node)
+                        if (kv.first != node) order.push_back(kv);
+                    for (size_t i = 0; i < order.size(); ++i) {
+                        done_paths += (size_t)order[i].second;
+                        size_t end = i + 1 == order.size() ? bytes : round_up(bytes / total_paths * done_paths, FMA_PAGE_BYTES);
+                        end = std::min(end, bytes);
+                        if (end <= begin) continue;
+                        unsigned long mask = 1ul << order[i].first;
+                        syscall(SYS_mbind, (char*)p + begin, end - begin, 1, &mask, sizeof(mask) * 8, 0);   // best effort (MPOL_PREFERRED)
+                        h.ranges.push_back(HostStore::NumaRange{begin, end, order[i].first});
+                        begin = end;
+                    }
+                    h.numa_node = node;
+                }
+            }
+            if (h.ranges.empty() && node >= 0 && node < 64) {
                 unsigned long mask = 1ul << node;
                 // MPOL_PREFERRED = 1: fall back to the other node rather than fail under pressure
                 if (syscall(SYS_mbind, p, bytes, 1, &mask, sizeof(mask) * 8, 0) == 0) h.numa_node = node;
             }
+            if (h.ranges.empty()) h.ranges.push_back(HostStore::NumaRange{0, bytes, h.numa_node});
             // parallel first touch so the pages exist before the (serial) pin
             int nt = std::max(1, std::min(env_int("FMA_TOUCH_THREADS", 8), 32));
             std::vector<std::thread> th;
@@ -1212,6 +1249,7 @@ int fma_paths_set(fma_engine_t* e, const int* helper_devices, int n, size_t slot
     for (int d : devs) {
         WakePath p;
         p.device = d;
+        p.numa_node = gpu_numa_node(d);
         p.bytes = slot_bytes * (size_t)slots;
         int rc = FMA_OK;
         {
@@ -1250,6 +1288,22 @@ int fma_paths_set(fma_engine_t* e, const int* helper_devices, int n, size_t slot
             paths_release(e);
             return fail(rc, "%s", keep);
         }
+    }
+    // A private, empty host store that was placed before the paths were known is placed again (striped over the paths' NUMA
+    // nodes): now, not inside the next sleep.  A store that holds an image, is shared or was adopted stays as it is.
+    bool image_in_store = false;
+    {
+        std::lock_guard<std::mutex> lk(e->mu);
+        for (const Segment& s : e->segs) image_in_store = image_in_store || (s.has_backup && s.backup_tier == FMA_TIER_HOST);
+    }
+    std::map<int, int> nodes;
+    for (const WakePath& wp : e->paths) ++nodes[wp.numa_node];
+    if (e->host.base && !image_in_store && !e->host.shared && e->host.fd < 0 && e->host.registered && nodes.size() > 1 && e->host.ranges.size() < nodes.size()) {
+        const size_t cap = e->host.cap;
+        if (e->shadow_tier == FMA_TIER_HOST) invalidate_shadows(e);
+        host_store_free(e->host);
+        int rc = host_store_reserve(e, cap);
+        if (rc != FMA_OK) return rc;
     }
     return FMA_OK;
 }

@@ -150,6 +150,10 @@ struct HostStore {
     bool shared = false;        // somebody else may hold this image too (exported, or adopted in place): it is READ-ONLY from
                                 // now on — a sleep that has to write gets a fresh private store first (copy-on-write per store)
     size_t map_bytes = 0;       // bytes mapped at base (cap + descriptor tail for memfd stores)
+    // NUMA placement by byte range (MULTI-PATH wake: each path pulls the part of the image that lives on ITS GPU's node, so no
+    // path drags its share across the socket interconnect); one range covering everything otherwise
+    struct NumaRange { size_t begin, end; int node; };
+    std::vector<NumaRange> ranges;
 };
 
 // Descriptor of a packed image, stored in the last 2 MiB of a memfd-backed store (fma_image_export / fma_image_adopt).
@@ -190,6 +194,7 @@ constexpr int kMaxPaths = 8;
 // destination pages.  A lone wake is then bounded by k links instead of one.
 struct WakePath {
     int device = -1;
+    int numa_node = -1;                      // of `device` (sysfs); -1 unknown
     CUdeviceptr va = 0;                      // n_slots x slot_bytes in `device`'s HBM; access for `device` and the engine's GPU
     size_t bytes = 0;
     cudaStream_t copy = nullptr;             // on `device`: H2D host store -> slot
@@ -343,6 +348,7 @@ int ensure_ring(fma_engine_t* e, size_t image_bytes);
 int ensure_event_pool(fma_engine_t* e, size_t n);
 // ---- stores (fma_engine.cu) ----
 void host_store_free(HostStore& h);
+int gpu_numa_node(int device);
 int host_store_reserve(fma_engine_t* e, size_t bytes);
 void paths_release(fma_engine_t* e);
 int park_release(fma_engine_t* e);

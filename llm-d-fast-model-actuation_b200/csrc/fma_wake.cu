@@ -325,12 +325,42 @@ int wake_multipath(WakePipe& pipe) {
         chunks.push_back(c);
         q += c.np;
     }
-    std::atomic<size_t> next_chunk{0};
+    // chunk queues by NUMA node of the store range the chunk lives in (HostStore::ranges): a path drains the queue of ITS GPU's
+    // node first and then helps with the others, so bytes cross the socket interconnect only to balance the tail
+    std::vector<int> q_node;                       // queue -> node
+    std::vector<std::vector<size_t>> q_chunks;     // queue -> chunk indices, image order
+    for (size_t c = 0; c < chunks.size(); ++c) {
+        const uint64_t off = src_off[chunks[c].p0];
+        int node = -1;
+        for (const HostStore::NumaRange& r : e->host.ranges)
+            if (off >= r.begin && off < r.end) node = r.node;
+        size_t qi = 0;
+        while (qi < q_node.size() && q_node[qi] != node) ++qi;
+        if (qi == q_node.size()) {
+            q_node.push_back(node);
+            q_chunks.emplace_back();
+        }
+        q_chunks[qi].push_back(c);
+    }
+    std::vector<std::atomic<size_t>> q_next(q_node.size());
+    for (auto& a : q_next) a.store(0);
+    auto take_chunk = [&](int my_node, size_t* out) -> bool {
+        for (int pass = 0; pass < 2; ++pass)
+            for (size_t qi = 0; qi < q_node.size(); ++qi) {
+                if ((pass == 0) != (q_node[qi] == my_node)) continue;   // own node's queue first
+                const size_t k = q_next[qi].fetch_add(1);
+                if (k < q_chunks[qi].size()) {
+                    *out = q_chunks[qi][k];
+                    return true;
+                }
+            }
+        return false;
+    };
     std::atomic<int> error{FMA_OK};
     std::atomic<bool> first_copy_seen{false};
     std::mutex kt_mu;
     char err_msg[512] = "";
-    std::vector<uint32_t> per_path(e->paths.size(), 0);
+    std::vector<uint32_t> per_path(e->paths.size(), 0), per_path_local(e->paths.size(), 0);
     auto worker = [&](size_t pi) {
         WakePath& path = e->paths[pi];
         cudaSetDevice(e->device);
@@ -343,9 +373,14 @@ int wake_multipath(WakePipe& pipe) {
         uint32_t mine = 0;
         for (;;) {
             if (error.load() != FMA_OK) return;
-            const size_t c = next_chunk.fetch_add(1);
-            if (c >= chunks.size()) break;
+            size_t c = 0;
+            if (!take_chunk(path.numa_node, &c)) break;
             const Chunk& ch = chunks[c];
+            {
+                const uint64_t off = src_off[ch.p0];
+                for (const HostStore::NumaRange& r : e->host.ranges)
+                    if (off >= r.begin && off < r.end && r.node == path.numa_node) ++per_path_local[pi];
+            }
             const int slot = (int)(mine % (uint32_t)e->path_slots);
             if (mine >= (uint32_t)e->path_slots) {   // K2 has read the chunk that used this slot before
                 ce = cudaEventSynchronize(path.ev_free[slot]);
@@ -385,6 +420,7 @@ int wake_multipath(WakePipe& pipe) {
         RT(cudaStreamWaitEvent(e->ks, e->paths[pi].ev_done, 0));   // the wake's device-time bracket and the final sync cover every path
         pipe.copy_ops += per_path[pi];
         e->tl_add("path_chunks", e->paths[pi].device, pipe.t_entry, now_s(), (uint64_t)per_path[pi] * e->path_slot_bytes);
+        e->tl_add("path_local", e->paths[pi].device, pipe.t_entry, now_s(), (uint64_t)per_path_local[pi] * e->path_slot_bytes);
     }
     return FMA_OK;
 }

@@ -450,18 +450,29 @@ def test_peer_tier_roundtrip(engine, oracle, kernel):
 
 
 # ---- MULTI-PATH wake: idle peers' PCIe links + NVLink forward (needs >= 2 GPUs) --------------------------------------------
+@pytest.mark.parametrize("numa_map", [None, "0,1,1,0"])
 @pytest.mark.parametrize("slot_mib,slots", [(2, 2), (6, 3), (128, 3)])
-def test_multipath_wake_matches_oracle(engine, oracle, slot_mib, slots):
+def test_multipath_wake_matches_oracle(built, oracle, slot_mib, slots, numa_map, monkeypatch):
     """Host-tier wake with the image striped over the engine's own link and the helper GPUs' links (fma_paths_set): every
     weight byte == oracle, addresses unchanged, kv_cache remapped; chunks really went over more than one path; tag-selective
     wake, a table with a reused hole, and switching the paths off again."""
     n = _n_gpus()
     if n < 2:
         pytest.skip("multi-path wake needs a second GPU")
+    import fma_b200
+
+    if numa_map:   # pretend the helpers sit on another socket: the store is striped by node and each path drains its own node first
+        monkeypatch.setenv("FMA_TEST_NUMA_MAP", numa_map)
+    with fma_b200.Engine(0) as engine:
+        _multipath_body(engine, oracle, n, slot_mib, slots, numa_map)
+
+
+def _multipath_body(engine, oracle, n, slot_mib, slots, numa_map):
     L = _L()
     table = _tiny_table()
     ptrs, ref = _load(engine, oracle, table)
     helpers = list(range(1, min(n, 4)))
+    engine.host_reserve(sum(table[i].bytes for i in ref))                   # placed before the paths are known: placed again by set_paths
     engine.set_paths(helpers, slot_bytes=slot_mib << 20, slots=slots)
     for rep in range(2):
         engine.sleep(["weights"], flags=L.FMA_FLAG_VERIFY)
@@ -474,6 +485,9 @@ def test_multipath_wake_matches_oracle(engine, oracle, slot_mib, slots):
         assert len(rows) == 1 + len(helpers) and sum(r["bytes"] for r in rows) >= sum(table[i].bytes for i in ref)
         if (slot_mib << 20) * 4 <= sum(table[i].bytes for i in ref):
             assert sum(1 for r in rows if r["bytes"]) >= 2, rows            # more than one path moved chunks
+        local = [r for r in engine.timeline() if r["kind"] == "path_local"]
+        if numa_map and slot_mib == 2:                                      # striped store: most chunks were pulled by a path of their own node
+            assert sum(r["bytes"] for r in local) >= 0.5 * sum(r["bytes"] for r in rows), (local, rows)
     # a freed + re-used hole (image order != VA order), then weights first and kv_cache later
     hole = sorted(ref)[1]
     engine.free(ptrs[hole])
