@@ -108,14 +108,26 @@ class CuMemAllocator:
         import torch
 
         tier = _tier_from_env()
+        owner = None
         if tier == L.FMA_TIER_PEER:
-            # parking GPU for the NVLink tier: FMA_PEER_DEVICE (index among the devices this process sees)
-            peer = int(os.environ.get("FMA_PEER_DEVICE", "-1"))
-            if peer < 0:
-                raise L.FmaError(L.FMA_EINVAL, "FMA_TIER=peer needs FMA_PEER_DEVICE=<visible device index of the parking GPU>")
             nbytes = sum(s.bytes for s in self.engine.segments() if s.tag in offload_tags)
-            self.engine.peer_reserve(peer, nbytes)
+            if os.environ.get("FMA_NODE_AGENT_SOCK"):
+                # Under the launcher an instance sees only its own GPUs (launcher.py:171-187): the node agent owns the parking
+                # buffer (parking.py), this rank attaches to it and deposits the image descriptor afterwards, so the parked
+                # weights outlive this process.
+                from .parking import ParkingClient
+
+                owner = ParkingClient()
+                owner.park(self.engine, _instance_id(), _rank(), nbytes, avoid=_own_gpu_indices())
+            else:
+                # parking GPU for the NVLink tier: FMA_PEER_DEVICE (index among the devices this process sees)
+                peer = int(os.environ.get("FMA_PEER_DEVICE", "-1"))
+                if peer < 0:
+                    raise L.FmaError(L.FMA_EINVAL, "FMA_TIER=peer needs FMA_NODE_AGENT_SOCK (node-level owner) or FMA_PEER_DEVICE=<visible device index of the parking GPU>")
+                self.engine.peer_reserve(peer, nbytes)
         self.engine.sleep(offload_tags, tier=tier)
+        if owner is not None and self.engine.stats()["sleep_bytes_offloaded"]:
+            owner.deposit(self.engine, _instance_id(), _rank(), tier)
         st = self.engine.stats()
         total = st["sleep_bytes_offloaded"] + st["sleep_bytes_discarded"]
         # same INFO line the reference emits (cumem.py:215-222; parsed by llm-d-benchmark), plus GB/s
@@ -198,6 +210,23 @@ class CuMemAllocator:
         if self._reserve_thread is not None:
             self._reserve_thread.join()
             self._reserve_thread = None
+
+
+def _instance_id() -> str:
+    """The controller's instance ID (``"I" + base64url(sha256(...)) + "i"``, inference-server.go:801-829): the node agent passes it to
+    its children as FMA_INSTANCE_ID; a bare process falls back to its pid."""
+    return os.environ.get("FMA_INSTANCE_ID") or f"pid{os.getpid()}"
+
+
+def _rank() -> int:
+    return int(os.environ.get("RANK", os.environ.get("LOCAL_RANK", "0")) or 0)
+
+
+def _own_gpu_indices() -> list[int]:
+    """Node-level GPU indices this instance runs on (never park a model on its own GPU): FMA_NODE_GPU_INDICES, set by the node
+    agent next to CUDA_VISIBLE_DEVICES."""
+    v = os.environ.get("FMA_NODE_GPU_INDICES", "")
+    return [int(x) for x in v.split(",") if x.strip().isdigit()]
 
 
 def install_into_vllm() -> None:

@@ -269,3 +269,71 @@ def instance_id(isc_spec: Mapping, gpu_uuids: Optional[List[str]] = None) -> str
     msc = isc_spec["modelServerConfig"]
     return config_inference_server("", msc["port"], msc.get("options", ""), msc.get("env_vars"), msc.get("labels"),
                                    msc.get("annotations"), gpu_uuids)[1]
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# "same ID => wake": what the controller decides from a launcher's instance list
+# ------------------------------------------------------------------------------------------------------------------
+INFERENCE_PORT_ANNOTATION = "inference-port"      # launcherclient.go:49
+
+
+def instance_port(inst: Mapping) -> int:
+    """``getVLLMInstancePort`` (inference-server.go:968-977): the port comes from the instance's annotation, nowhere else."""
+    ann = inst.get("annotations") or {}
+    if INFERENCE_PORT_ANNOTATION not in ann:
+        raise ValueError(f"missing annotations[{INFERENCE_PORT_ANNOTATION}]")
+    v = str(ann[INFERENCE_PORT_ANNOTATION])
+    if not re.fullmatch(r"[+-]?[0-9]+", v) or not -(1 << 31) <= int(v) < (1 << 31):     # strconv.ParseInt(value, 10, 32)
+        raise ValueError(f"parse annotations[{INFERENCE_PORT_ANNOTATION}] value {v!r}")
+    return int(v)
+
+
+def select_launcher(launchers, isc_hash: str, desired_port: int, max_others: int):
+    """Restatement of ``selectBestLauncherPod`` (inference-server.go:680-785) over launcher states as the launcher REST returns
+    them (``GET /v2/vllm/instances``: ``{total_instances, running_instances, instances: [{instance_id, status, annotations}]}``).
+
+    ``launchers``: iterable of ``(name, state_or_None)`` — ``None`` = the launcher is not ready / could not be synced.
+    Returns ``(name | None, has_sleeping_instance, some_not_ready)``:
+      priority 1  a launcher that already holds an instance with THIS id (status != "stopped") -> wake it (the fast path);
+      priority 2  the first launcher with room for one more instance (total_instances <= max_others) -> create there;
+      a launcher where another instance already uses the desired port, or an instance has no usable port, is skipped."""
+    candidate = None
+    some_not_ready = False
+    for name, state in launchers:
+        if state is None:
+            some_not_ready = True
+            continue
+        has_sleeping = False
+        port_conflict = False
+        for inst in state.get("instances", []):
+            try:
+                port = instance_port(inst)
+            except ValueError:
+                port_conflict = True
+                break
+            if port == desired_port and inst.get("instance_id") != isc_hash:
+                port_conflict = True
+                break
+            if inst.get("instance_id") == isc_hash and inst.get("status") != "stopped":
+                has_sleeping = True
+        if port_conflict:
+            continue
+        if has_sleeping:
+            return name, True, False
+        if state.get("total_instances", 0) <= max_others and candidate is None:
+            candidate = name
+    if candidate is not None:
+        return candidate, False, False
+    if some_not_ready:
+        return None, False, True
+    return None, False, False
+
+
+def plan_actuation(launchers, isc_spec: Mapping, gpu_uuids=None, max_others: int = 1) -> dict:
+    """ISC + GPUs -> instance ID (``instance_id``) -> what to do on which launcher: ``wake`` the instance with that ID where it
+    sleeps, ``create`` it on a launcher with room, ``retry`` while launchers are not ready, or ``new_launcher``."""
+    iid = instance_id(isc_spec, gpu_uuids)
+    port = int(isc_spec["modelServerConfig"]["port"])
+    name, sleeping, not_ready = select_launcher(launchers, iid, port, max_others)
+    action = "wake" if sleeping else "create" if name is not None else "retry" if not_ready else "new_launcher"
+    return {"action": action, "launcher": name, "instance_id": iid, "port": port}

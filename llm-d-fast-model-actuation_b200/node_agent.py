@@ -74,12 +74,14 @@ class SwapRequest(BaseModel):
 # ------------------------------------------------------------------------------------------------------------------
 # child process
 # ------------------------------------------------------------------------------------------------------------------
-def _child_main(config: dict, log_path: str) -> None:
+def _child_main(config: dict, log_path: str, extra_env: Optional[Dict[str, str]] = None) -> None:
     """What runs in the forked child — same steps as the reference's ``vllm_kickoff`` (launcher.py:799-837)."""
     os.setpgrp()                                          # own process group: SIGKILL can take EngineCore along
     fd = os.open(log_path, os.O_WRONLY | os.O_CREAT | os.O_APPEND, 0o644)
     os.dup2(fd, 1); os.dup2(fd, 2); os.close(fd)
     sys.stdout = os.fdopen(1, "w", buffering=1); sys.stderr = os.fdopen(2, "w", buffering=1)
+    for k, v in (extra_env or {}).items():
+        os.environ.setdefault(k, v)
     for k, v in (config.get("env_vars") or {}).items():
         os.environ[k] = v
     from vllm.entrypoints.openai.api_server import run_server
@@ -153,9 +155,10 @@ class _Instance:
 
 class NodeAgent:
     def __init__(self, mock_gpus: bool = False, log_dir: str = "/tmp", start_method: str = "forkserver",
-                 preload: tuple[str, ...] = ("vllm.entrypoints.openai.api_server",)):
+                 preload: tuple[str, ...] = ("vllm.entrypoints.openai.api_server",), parking=None):
         self.mock_gpus = mock_gpus
         self.log_dir = log_dir
+        self.parking = parking                     # parking.ParkingService (node-level owner of peer-HBM images), or None
         self._lock = threading.Condition()
         self._instances: Dict[str, _Instance] = {}
         self._revision = 0
@@ -200,13 +203,18 @@ class NodeAgent:
             if instance_id in self._instances:
                 raise ValueError(f"Instance with ID {instance_id} already exists")
             cfg = config.model_copy(deep=True)
+            extra_env: Dict[str, str] = {}    # for the child only: never part of the reported state (the wire contract is the launcher's)
             if cfg.gpu_uuids:
                 idx = _translate_gpu_uuids(cfg.gpu_uuids, self.mock_gpus)
                 cfg.env_vars = dict(cfg.env_vars or {})
                 cfg.env_vars["CUDA_VISIBLE_DEVICES"] = ",".join(idx)
+                extra_env["FMA_NODE_GPU_INDICES"] = ",".join(idx)      # node-level indices: where NOT to park this model
+            if self.parking is not None:   # the instance's allocator shim parks on buffers THIS process owns (parking.py)
+                extra_env["FMA_NODE_AGENT_SOCK"] = self.parking.sock_path
+                extra_env["FMA_INSTANCE_ID"] = instance_id
             inst = _Instance(instance_id, cfg, self.log_dir)
             open(inst.log_path, "wb").close()
-            inst.proc = self._ctx.Process(target=_child_main, args=(cfg.model_dump(exclude_none=True), inst.log_path), daemon=False)
+            inst.proc = self._ctx.Process(target=_child_main, args=(cfg.model_dump(exclude_none=True), inst.log_path, extra_env), daemon=False)
             inst.proc.start()
             self._instances[instance_id] = inst
             self._revision += 1
@@ -343,7 +351,12 @@ class NodeAgent:
                             "cuda_visible_devices": (inst.config.env_vars or {}).get("CUDA_VISIBLE_DEVICES")})
             except Exception as e:  # an instance that is still starting has no port yet
                 out.append({"instance_id": iid, "is_sleeping": None, "error": str(e)[:120]})
-        return {"sleepers": out, "sleeping_count": sum(1 for s in out if s.get("is_sleeping"))}
+        res = {"sleepers": out, "sleeping_count": sum(1 for s in out if s.get("is_sleeping"))}
+        if self.parking is not None:
+            # what a sleeper costs in HBM, per GPU index, in MiB — the unit accelMemoryIsLowEnough compares against
+            # (inference-server.go:1609-1636; budget = count x 4096 MiB, cmd/dual-pods-controller/main.go:72-74)
+            res.update(self.parking.stats())
+        return res
 
 
 class LogRangeNotAvailable(Exception):

@@ -227,3 +227,68 @@ def test_native_server_speaks_the_controller_contract_over_the_host_simulated_en
             p.kill()
     err = p.stderr.read()
     assert p.returncode == 0 and "WARNING: ThreadSanitizer" not in err, err[-3000:]
+
+
+_PARKING_INSTANCE = r"""
+import os, sys, json
+sys.path.insert(0, {root!r})
+import fma_b200
+from fma_b200 import workloads as W, _lib as L
+from fma_b200.parking import ParkingClient
+phase, iid = sys.argv[1], sys.argv[2]
+eng = fma_b200.Engine(0)
+table = W.allocation_table("tiny-llama-test", kv_cache_bytes=32 << 20, kv_tensors=2)
+for s in table: eng.alloc(s.bytes, s.tag)
+cli = ParkingClient()                                  # FMA_NODE_AGENT_SOCK
+Wb = sum(s.bytes for s in table if s.tag == "weights")
+if phase == "park":
+    first = 0
+    for i, s in enumerate(table):
+        if s.tag == "weights":
+            eng.fill(i, 77, first); first += s.bytes // 8
+    print(json.dumps(eng.digest_all(["weights"])), flush=True)
+    rep = cli.park(eng, iid, 0, Wb, avoid=[0])
+    assert rep["device"] != 0
+    eng.sleep(["weights"], tier=L.FMA_TIER_PEER, flags=L.FMA_FLAG_VERIFY)
+    cli.deposit(eng, iid, 0)
+    os._exit(0)                                        # dies asleep
+else:
+    assert cli.adopt(eng, iid, 0) is True and eng.is_sleeping()
+    eng.wake(None, flags=L.FMA_FLAG_VERIFY)
+    print(json.dumps(eng.digest_all(["weights"])), flush=True)
+    assert cli.adopt(fma_b200.Engine(0), "nobody", 0) is False
+"""
+
+
+def test_node_level_parking_service_keeps_a_dead_instances_image(hostsim_lib, tmp_path):
+    """fma_b200.parking: the node agent's ParkingService owns exportable parking buffers and serves fds over a unix socket; an
+    instance parks its weights there, deposits the descriptor and DIES; a fresh instance with the same ID finds the image, attaches,
+    adopts and wakes with identical K3 digests; the owner's accounting (MiB per GPU — what a sleeper budget needs,
+    inference-server.go:1609-1636) follows.  Host-simulated engine; the C-ABI underneath is GPU-tested in tests/test_gpu_parity.py."""
+    import json
+
+    env = dict(os.environ, FMA_B200_LIB=hostsim_lib, FMA_HOSTSIM="1", HOSTSIM_DEVICES="3", FMA_NODE_AGENT_SOCK=str(tmp_path / "park.sock"))
+    owner = r"""
+import os, sys, json, subprocess
+sys.path.insert(0, %r)
+import fma_b200
+from fma_b200.parking import ParkingService, ParkingClient
+svc = ParkingService(os.environ["FMA_NODE_AGENT_SOCK"], n_devices=3)
+svc.start()
+script = sys.argv[1]
+a = subprocess.run([sys.executable, script, "park", "Iabci"], capture_output=True, text=True, timeout=300)
+assert a.returncode == 0, a.stdout + a.stderr
+st = svc.stats()
+assert st["images"] == [{"instance": "Iabci", "rank": 0, "device": 1, "mib": st["images"][0]["mib"], "has_image": True}] and st["parked_mib_per_device"]["1"] > 0, st
+b = subprocess.run([sys.executable, script, "adopt", "Iabci"], capture_output=True, text=True, timeout=300)
+assert b.returncode == 0, b.stdout + b.stderr
+assert json.loads(a.stdout.strip().splitlines()[0]) == json.loads(b.stdout.strip().splitlines()[-1])
+assert ParkingClient().stats()["ok"] and ParkingClient().release("Iabci") == 1
+assert svc.stats()["images"] == [] and svc.stats()["parked_mib_per_device"]["1"] == 0
+svc.close()
+print("parking service ok")
+""" % ROOT
+    script = tmp_path / "instance.py"
+    script.write_text(_PARKING_INSTANCE.format(root=ROOT))
+    r = subprocess.run([sys.executable, "-c", owner, str(script)], env=env, cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "parking service ok" in r.stdout, (r.stdout + r.stderr)[-3000:]

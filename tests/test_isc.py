@@ -100,3 +100,53 @@ def test_marshal_reproduces_the_references_generated_crds():
         assert "---\n" + isc.go_yaml_marshal(yaml.safe_load(text)).decode() == text, os.path.basename(f)
         lines += text.count("\n")
     assert len(files) == 3 and lines > 8000
+
+
+# ---- "same ID => wake" (selectBestLauncherPod, inference-server.go:680-785) over the launcher REST's JSON ----------------------
+def _inst(iid, port, status="running"):
+    return {"instance_id": iid, "status": status, "revision": 1, "options": f"--model m --port {port}", "annotations": {"isc-name": "x", "inference-port": str(port)}}
+
+
+def _launcher(*insts):
+    return {"revision": len(insts), "total_instances": len(insts), "running_instances": sum(1 for i in insts if i["status"] == "running"), "instances": list(insts)}
+
+
+def test_select_launcher_priorities_and_port_conflicts():
+    from fma_b200 import isc
+
+    me, other = "Iminei", "Iotheri"
+    # priority 1: the launcher that already holds MY instance wins over one that merely has room
+    assert isc.select_launcher([("l-room", _launcher()), ("l-mine", _launcher(_inst(me, 8005), _inst(other, 8006)))], me, 8005, 1) == ("l-mine", True, False)
+    # a stopped instance with my id is not a sleeper; the launcher still has room for one more (2 instances > max_others=1 -> no room)
+    assert isc.select_launcher([("l", _launcher(_inst(me, 8005, "stopped")))], me, 8005, 1) == ("l", False, False)
+    assert isc.select_launcher([("l", _launcher(_inst(me, 8005, "stopped"), _inst(other, 8006)))], me, 8005, 1) == (None, False, False)
+    # another instance already listens on my port: skip that launcher
+    assert isc.select_launcher([("l-conflict", _launcher(_inst(other, 8005))), ("l-free", _launcher())], me, 8005, 1) == ("l-free", False, False)
+    # an instance without a usable port annotation poisons its launcher
+    bad = _inst(other, 8006); bad["annotations"] = {"isc-name": "x"}
+    assert isc.select_launcher([("l-bad", _launcher(bad))], me, 8005, 1) == (None, False, False)
+    bad["annotations"]["inference-port"] = "80_05"
+    assert isc.select_launcher([("l-bad", _launcher(bad))], me, 8005, 1) == (None, False, False)
+    # not-ready launchers: retry instead of creating a new launcher, unless somebody else qualifies
+    assert isc.select_launcher([("l-nr", None)], me, 8005, 1) == (None, False, True)
+    assert isc.select_launcher([("l-nr", None), ("l-free", _launcher())], me, 8005, 1) == ("l-free", False, False)
+
+
+def test_plan_actuation_from_isc_to_wake_or_create():
+    from fma_b200 import isc
+
+    spec = {"modelServerConfig": {"port": 8005, "options": "--model meta-llama/Llama-3-8B --enable-sleep-mode", "env_vars": {"VLLM_SERVER_DEV_MODE": "1"}},
+            "launcherConfigName": "lc"}
+    gpus = ["GPU-0a", "GPU-0b"]
+    iid = isc.instance_id(spec, gpus)
+    assert iid.startswith("I") and iid.endswith("i") and len(iid) == 45
+    cfg, iid2 = isc.config_inference_server("my-isc", 8005, spec["modelServerConfig"]["options"], spec["modelServerConfig"]["env_vars"], gpu_uuids=gpus)
+    assert iid2 == iid and cfg["annotations"] == {"isc-name": "my-isc", "inference-port": "8005"}
+    # nothing there yet -> create on the launcher with room; the created instance (the launcher echoes id + annotations) then sleeps -> wake
+    plan = isc.plan_actuation([("launcher-0", _launcher())], spec, gpus)
+    assert plan == {"action": "create", "launcher": "launcher-0", "instance_id": iid, "port": 8005}
+    mine = {"instance_id": iid, "status": "running", "revision": 1, **cfg}
+    assert isc.plan_actuation([("launcher-0", _launcher(mine))], spec, gpus)["action"] == "wake"
+    # different GPUs -> different ID -> my port is taken by "another" instance on that launcher -> elsewhere / new launcher
+    assert isc.plan_actuation([("launcher-0", _launcher(mine))], spec, ["GPU-0c"]) == {"action": "new_launcher", "launcher": None, "instance_id": isc.instance_id(spec, ["GPU-0c"]), "port": 8005}
+    assert isc.plan_actuation([("launcher-0", None)], spec, gpus)["action"] == "retry"
