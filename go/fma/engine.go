@@ -15,6 +15,7 @@ import "C"
 
 import (
 	"fmt"
+	"syscall"
 	"unsafe"
 )
 
@@ -150,4 +151,98 @@ func (e *Engine) Stats() (C.fma_stats_t, error) {
 		return st, lastErr(rc)
 	}
 	return st, nil
+}
+
+// ---- round 2: node-level parking buffers, multi-path wake, phase timeline ------------------------------------------
+
+// Parking is a node-level owner's exportable parking buffer in one GPU's HBM (fma_parking_create): the launcher pins an
+// instance to its own GPUs (inference_server/launcher/launcher.py:171-187), so the OWNER allocates and instances attach by fd.
+type Parking struct {
+	Handle uint64
+	Fd     int
+	Bytes  uint64
+}
+
+func ParkingCreate(device int, bytes uint64) (*Parking, error) {
+	var h C.uint64_t
+	var fd C.int
+	if rc := C.fma_parking_create(C.int(device), C.size_t(bytes), &h, &fd); rc != 0 {
+		return nil, lastErr(rc)
+	}
+	var nb C.uint64_t
+	var fd2 C.int
+	if rc := C.fma_parking_export(h, &fd2, &nb); rc != 0 {
+		return nil, lastErr(rc)
+	}
+	syscall.Close(int(fd2))
+	return &Parking{Handle: uint64(h), Fd: int(fd), Bytes: uint64(nb)}, nil
+}
+
+// ExportFd returns a fresh descriptor to pass to an instance over a unix socket (SCM_RIGHTS).
+func (p *Parking) ExportFd() (int, error) {
+	var fd C.int
+	if rc := C.fma_parking_export(C.uint64_t(p.Handle), &fd, nil); rc != 0 {
+		return -1, lastErr(rc)
+	}
+	return int(fd), nil
+}
+
+func (p *Parking) Destroy() { C.fma_parking_destroy(C.uint64_t(p.Handle)); syscall.Close(p.Fd) }
+
+// PeerAttach makes the owner's buffer this engine's peer-tier store; the buffer's GPU need not be visible to this process.
+func (e *Engine) PeerAttach(fd int, bytes uint64) error {
+	if rc := C.fma_peer_attach(e.h, C.int(fd), C.size_t(bytes)); rc != 0 {
+		return lastErr(rc)
+	}
+	return nil
+}
+
+// ImageDescribe returns the descriptor of the image sleeping in `tier`; the owner keeps it next to the buffer's fd.
+func (e *Engine) ImageDescribe(tier int) ([]byte, error) {
+	n := C.fma_image_describe(e.h, C.int(tier), nil, 0)
+	if n < 0 {
+		return nil, lastErr(n)
+	}
+	buf := make([]byte, int(n))
+	if rc := C.fma_image_describe(e.h, C.int(tier), unsafe.Pointer(&buf[0]), C.size_t(n)); rc < 0 {
+		return nil, lastErr(rc)
+	}
+	return buf, nil
+}
+
+// ImageAdoptParked: after PeerAttach, a fresh engine with the same segment sequence becomes "asleep with the parked image".
+func (e *Engine) ImageAdoptParked(desc []byte, tagMask uint64) error {
+	if rc := C.fma_image_adopt_parked(e.h, unsafe.Pointer(&desc[0]), C.size_t(len(desc)), C.uint64_t(tagMask), 0); rc != 0 {
+		return lastErr(rc)
+	}
+	return nil
+}
+
+// PathsSet names idle peer GPUs whose PCIe links a host-tier wake may borrow (MULTI-PATH wake); nil turns it off.
+func (e *Engine) PathsSet(helpers []int, slotBytes uint64, slots int) error {
+	var p *C.int
+	c := make([]C.int, len(helpers))
+	for i, d := range helpers {
+		c[i] = C.int(d)
+	}
+	if len(c) > 0 {
+		p = &c[0]
+	}
+	if rc := C.fma_paths_set(e.h, p, C.int(len(c)), C.size_t(slotBytes), C.int(slots)); rc != 0 {
+		return lastErr(rc)
+	}
+	return nil
+}
+
+// Timeline returns the per-phase timeline of the last sleep / wake ("op,kind,idx,t0_ms,t1_ms,bytes" lines).
+func (e *Engine) Timeline() (string, error) {
+	n := C.fma_timeline(e.h, nil, 0)
+	if n < 0 {
+		return "", lastErr(n)
+	}
+	buf := make([]byte, int(n)+1)
+	if rc := C.fma_timeline(e.h, (*C.char)(unsafe.Pointer(&buf[0])), C.size_t(len(buf))); rc < 0 {
+		return "", lastErr(rc)
+	}
+	return string(buf[:n]), nil
 }

@@ -384,6 +384,17 @@ void invalidate_shadows(fma_engine_t* e) {
     e->shadow_packed = false;
 }
 
+// per-node path counts of the MULTI-PATH configuration ("" = off or all on one node): what a store's striping depends on
+static std::string paths_signature(const fma_engine_t* e) {
+    std::map<int, int> per_node;
+    for (const WakePath& wp : e->paths)
+        if (wp.numa_node >= 0 && wp.numa_node < 64) ++per_node[wp.numa_node];
+    if (per_node.size() < 2 || e->cfg.numa_bind == 0) return "";
+    std::string s;
+    for (auto& kv : per_node) s += std::to_string(kv.first) + ":" + std::to_string(kv.second) + ",";
+    return s;
+}
+
 int host_store_reserve(fma_engine_t* e, size_t bytes) {
     bytes = round_up(std::max<size_t>(bytes, FMA_PAGE_BYTES), FMA_PAGE_BYTES);
     if (e->host.base && e->host.cap >= bytes) return FMA_OK;
@@ -422,6 +433,7 @@ int host_store_reserve(fma_engine_t* e, size_t bytes) {
             if (want_bind)
                 for (const WakePath& wp : e->paths)
                     if (wp.numa_node >= 0 && wp.numa_node < 64) ++per_node[wp.numa_node];
+            h.placed_for = paths_signature(e);
             if (per_node.size() > 1 && per_node.size() * FMA_PAGE_BYTES <= bytes) {
                 size_t total_paths = 0, done_paths = 0, begin = 0;
                 for (auto& kv : per_node) total_paths += (size_t)kv.second;
@@ -1296,9 +1308,7 @@ int fma_paths_set(fma_engine_t* e, const int* helper_devices, int n, size_t slot
         std::lock_guard<std::mutex> lk(e->mu);
         for (const Segment& s : e->segs) image_in_store = image_in_store || (s.has_backup && s.backup_tier == FMA_TIER_HOST);
     }
-    std::map<int, int> nodes;
-    for (const WakePath& wp : e->paths) ++nodes[wp.numa_node];
-    if (e->host.base && !image_in_store && !e->host.shared && e->host.fd < 0 && e->host.registered && nodes.size() > 1 && e->host.ranges.size() < nodes.size()) {
+    if (e->host.base && !image_in_store && !e->host.shared && e->host.fd < 0 && e->host.registered && e->host.placed_for != paths_signature(e)) {
         const size_t cap = e->host.cap;
         if (e->shadow_tier == FMA_TIER_HOST) invalidate_shadows(e);
         host_store_free(e->host);

@@ -154,6 +154,7 @@ struct HostStore {
     // path drags its share across the socket interconnect); one range covering everything otherwise
     struct NumaRange { size_t begin, end; int node; };
     std::vector<NumaRange> ranges;
+    std::string placed_for;     // "node:paths,node:paths" the striping was computed for ("" = one node)
 };
 
 // Descriptor of a packed image, stored in the last 2 MiB of a memfd-backed store (fma_image_export / fma_image_adopt).

@@ -187,7 +187,7 @@ fma_k_pack(fma_k_pack_desc* __restrict__ descs, uint32_t n_pages, uint32_t* __re
 // ------------------------------------------------------------------------------------
 // K5: decode + scatter
 // ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 8)   // 32 registers: 8 CTAs (64 warps) per SM — K5 is latency-bound, occupancy is what it needs
 fma_k_unpack(const fma_k_pack_desc* __restrict__ descs, uint32_t n_pages, uint32_t* __restrict__ err) {
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t n_items = n_pages * kParts;

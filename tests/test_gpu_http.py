@@ -111,7 +111,7 @@ def test_compiled_server_over_http_matches_oracle_digests(built, oracle):
         pytest.skip("the product binary links the CUDA library (the host-simulated build is tests/test_engine_hostsim.py)")
     if not os.path.exists(exe):
         pytest.skip("fma_served not built")
-    pages = [6, 2, 4]
+    mib = [6, 2, 4]            # --seg <tag>:<MiB>
     p = subprocess.Popen([exe, "--port", "0", "--device", "0", "--seg", "weights:6", "--seg", "weights:2", "--seg", "kv_cache:8", "--seg", "weights:4",
                           "--seed", "1234"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     try:
@@ -119,15 +119,15 @@ def test_compiled_server_over_http_matches_oracle_digests(built, oracle):
         assert line.startswith("listening on "), line + p.stderr.read()
         base = f"http://127.0.0.1:{int(line.split()[-1])}"
         want, first = [], 0
-        for n in pages:
-            want.append(oracle.digest(oracle.fill(n << 21, 1234, first)))
-            first += (n << 21) // 8
+        for n in mib:
+            want.append(oracle.digest(oracle.fill(n << 20, 1234, first)))
+            first += (n << 20) // 8
         st, body = _call(base, "GET", "/digests")
         assert st == 200 and [int(x, 16) for x in json.loads(body)[0]] == want, body
         assert _call(base, "POST", "/sleep") == (200, b"")
         assert json.loads(_call(base, "GET", "/is_sleeping")[1]) == {"is_sleeping": True}
         stats = json.loads(_call(base, "GET", "/stats")[1])
-        assert stats["ranks"][0]["sleep_bytes_offloaded"] == sum(pages) << 21 and stats["ranks"][0]["hbm_mapped_bytes"] == 0
+        assert stats["ranks"][0]["sleep_bytes_offloaded"] == sum(mib) << 20 and stats["ranks"][0]["hbm_mapped_bytes"] == 0
         assert _call(base, "POST", "/wake_up", timeout=5) == (200, b"") and _call(base, "POST", "/wake_up", timeout=5) == (200, b"")
         assert json.loads(_call(base, "GET", "/is_sleeping")[1]) == {"is_sleeping": False}
         st, body = _call(base, "GET", "/digests")
