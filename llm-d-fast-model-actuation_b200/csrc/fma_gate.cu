@@ -23,7 +23,7 @@ namespace fma_impl {
 namespace {
 
 constexpr uint32_t kMagic = 0x464d4147u;  // "FMAG"
-constexpr uint32_t kVersion = 2;
+constexpr uint32_t kVersion = 3;
 constexpr int kSlots = 128;
 
 struct Slot {

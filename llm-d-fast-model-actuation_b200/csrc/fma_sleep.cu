@@ -73,7 +73,7 @@ struct Unmapper {
         double a;
         CUresult r1;
         {
-            GateHold hold(kGateRemap, 0.1);   // nothing waits for an unmap: yield (bounded) to calls that gate a wake's copies
+            GateHold hold(kGateUnmap, 0.1);   // nothing waits for an unmap: yield (bounded) to calls that gate a wake's copies
             a = now_s();
             r1 = g_drv.MemUnmap(r.va, r.bytes);
         }

@@ -547,7 +547,8 @@ int do_wake(fma_engine_t* e, uint64_t tag_mask, uint32_t flags) {
         uint64_t w_bytes = 0;
         for (size_t i : with_backup) w_bytes += e->segs[i].bytes;
         // a fifth of the expected host-tier copy time (55 GB/s), half of the NVLink one (600 GB/s): far below the slack
-        const double expected = (double)w_bytes / (tier == FMA_TIER_HOST ? 55e9 : 600e9);
+        // (a multi-path wake has as many links as paths: its copy time, and with it the head start, shrinks accordingly)
+        const double expected = (double)w_bytes / (tier == FMA_TIER_HOST ? 55e9 * (multipath ? (double)e->paths.size() : 1.0) : 600e9);
         const int forced = env_int("FMA_REMAP_DELAY_MS", -1);
         remap_delay_s = forced >= 0 ? forced * 1e-3 : expected * (tier == FMA_TIER_HOST ? 0.2 : 0.5);
     }
@@ -563,7 +564,7 @@ int do_wake(fma_engine_t* e, uint64_t tag_mask, uint32_t flags) {
     const double expected_copy_s = [&] {
         uint64_t w = 0;
         for (size_t i : with_backup) w += e->segs[i].bytes;
-        return (double)w / (tier == FMA_TIER_HOST ? 55e9 : 600e9);
+        return (double)w / (tier == FMA_TIER_HOST ? 55e9 * (multipath ? (double)e->paths.size() : 1.0) : 600e9);
     }();
 
     // ---- mapper thread(s): one create + map + set-access per run, in `runs` order ----------------------
@@ -603,13 +604,13 @@ int do_wake(fma_engine_t* e, uint64_t tag_mask, uint32_t flags) {
             // first on the whole host; the other backed-up items have one ring's worth of slack; remap-only runs have what is
             // left of the copy time.
             const bool first_item = run.has_backup && k == 0;
-            const int cls = first_item ? kGateFirst : run.has_backup ? kGateWeights : kGateRemap;
+            const int cls = first_item ? kGateFirst : run.has_backup ? std::min(kGateWeights + (int)k - (ring_run ? 1 : 0), kGateWeightsLast) : kGateRemap;
             const double left = std::max(0.0, t_entry + expected_copy_s * 0.8 - now_s());
             const double t_ask = now_s();
             int r;
             double t0;
             {
-                GateHold hold(cls, cls == kGateRemap ? left : std::min(left, 0.05));
+                GateHold hold(cls, cls >= kGateRemap ? left : std::min(left, 0.05));
                 if (first_item && gate_first) {
                     gate_retract(gate_first);
                     gate_first = 0;

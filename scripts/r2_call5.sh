@@ -1,0 +1,34 @@
+#!/bin/bash
+# Round 2, GPU call 5 (8 GPUs): the N=8 line (Llama-3-70B TP=8 shards, host tier; peer tier; config-5 round robin), the same with
+# the cross-process VMM gate, and multi-path wake at N=1 with 1 / 3 / 7 helpers.   gpurun --gpus 8 --timeout 900 -- 'bash scripts/r2_call5.sh'
+set -u
+out=gpurun_out/r2c5
+mkdir -p "$out"
+nvidia-smi topo -m > "$out/topo.txt" 2>&1
+run8() {
+  label=$1; shift
+  envs=(); while [ "$1" != "--" ]; do envs+=("$1"); shift; done; shift
+  timeout 300 env "${envs[@]}" python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29588 \
+      bench.py --gpus 8 --steps 10 --warmup 3 --timeline "$out/tl_$label" "$@" > "$out/bench_$label.json" 2> "$out/bench_$label.err"
+  echo "bench $label rc=$? $(python - "$out/bench_$label.json" <<'PY'
+import json,sys
+try:
+    d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+    print('value',d['value'],'e2e',d['e2e']['value'],'mean',d['e2e']['mean_gbs'],'wake',d['wake_latency_s'],d['wake_latency_s_min_max'],'sleep',d['sleep_latency_s'],'naive',d['pcie']['naive_pinned_h2d_per_gpu'],'vs_naive',d['pcie']['vs_naive_pinned_h2d'],'peer',json.dumps(d.get('peer_tier')),'rr',json.dumps(d.get('roundrobin_config5')))
+except Exception as e: print('parse error',e)
+PY
+)" | tee -a "$out/status.txt"
+}
+: > "$out/status.txt"
+run8 n8_default FMA_X=0 --
+run8 n8_gate FMA_VMM_GATE=1 -- --peer-extra 1 --extras none
+timeout 400 python bench.py --steps 6 --warmup 3 --no-cpu-baseline --packed-extra 0 --extras multipath,scaling_base > "$out/bench_n1_on8.json" 2> "$out/bench_n1_on8.err"; echo "bench n1 rc=$?" | tee -a "$out/status.txt"
+python - "$out/bench_n1_on8.json" <<'PY' | tee -a "$out/status.txt"
+import json,sys
+d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+print('n1 e2e',d['e2e']['value'],'wake',d['wake_latency_s'],d['wake_latency_s_min_max'])
+for r in (d.get('multipath_wake') or {}).get('rows',[]): print(json.dumps(r))
+print('mp', (d.get('multipath_wake') or {}).get('bit_exact'), (d.get('multipath_wake') or {}).get('error'))
+print('scaling_base', json.dumps(d.get('n1_on_scaling_workload')))
+PY
+cat "$out/status.txt"

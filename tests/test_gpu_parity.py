@@ -649,6 +649,55 @@ def test_full_size_llama3_8b_roundtrip_properties(engine, oracle):
         assert engine.stats()["wake_seconds"] < 5.0                 # the controller's /wake_up timeout (inference-server.go:1699-1702)
 
 
+def test_full_size_llama3_70b_tp8_shard_roundtrip_properties(engine, oracle):
+    """Config[2] at full size: one rank's Llama-3-70B TP=8 shard (404 segments incl. kv_cache, 16.43 GiB of weights, the table of
+    every N>1 bench line), through the plain, the PACKED (K4p / K4 / K5 on bf16-looking contents in a third of the segments) and the
+    INCREMENTAL paths: every K3 digest, the checksum of checksums and every device address unchanged; spot-checked segments equal
+    the oracle's bytes; the packed image's host bytes of a spot-checked segment equal the oracle's stored pages."""
+    from fma_b200 import workloads as W
+
+    L = _L()
+    table = W.allocation_table("llama-3-70b-tp8", kv_cache_bytes=32 << 30)     # exactly the bench's per-rank table
+    Wb = W.weight_bytes(table)
+    assert len(table) == 404 and abs(Wb / 2**30 - 16.43) < 0.01
+    ptrs = [engine.alloc(s.bytes, s.tag) for s in table]
+    first, firsts = 0, {}
+    weights = [i for i, s in enumerate(table) if s.tag == "weights"]
+    for i in weights:
+        engine.fill(i, 4321, first); firsts[i] = first; first += table[i].bytes // 8
+    # a third of the segments get bf16-looking contents (they code; the splitmix ones stay raw): one 2 MiB pattern page, repeated
+    page = oracle.bf16_weights(1 << 20, 7).view(np.uint8)
+    coded = weights[::3]
+    for i in coded:
+        engine.write(i, np.resize(page, table[i].bytes).tobytes())
+    before = engine.digest_all(["weights"])
+    spot = [i for i in weights if i not in coded and table[i].bytes <= (32 << 20)][:3]
+    for i in spot:
+        assert before[i] == oracle.digest(oracle.fill(table[i].bytes, 4321, firsts[i]))
+    total = sum(before) % (1 << 64)
+    engine.host_reserve(Wb)
+    for pack, incremental in ((0, 0), (1, 0), (1, 1), (0, 1)):
+        engine.set_option("pack", pack)
+        engine.set_option("incremental", incremental)
+        for rep in range(2 if incremental else 1):
+            engine.sleep(["weights"], flags=L.FMA_FLAG_VERIFY)
+            st = engine.stats()
+            assert st["sleep_bytes_offloaded"] == Wb and st["hbm_mapped_bytes"] == 0 and bool(st["image_packed"]) == bool(pack)
+            if pack:
+                assert st["image_store_bytes"] < 0.93 * Wb                   # a third of the pages coded at 0.758
+            if incremental and rep:
+                assert st["sleep_bytes_copied"] == 0                        # nothing changed since the last wake: nothing moves
+            engine.wake(None, flags=L.FMA_FLAG_VERIFY)
+            after = engine.digest_all(["weights"])
+            assert after == before and sum(after) % (1 << 64) == total
+            assert [s.va for s in engine.segments()] == ptrs
+            if os.environ.get("FMA_HOSTSIM") != "1":
+                assert engine.stats()["wake_seconds"] < 3.0                 # north_star: host-tier wake of a 70B TP=8 shard <= 3.0 s
+    for i in spot:
+        assert engine.read(i, table[i].bytes) == oracle.fill(table[i].bytes, 4321, firsts[i]).tobytes()
+    assert engine.read(coded[0], 4 << 20) == np.resize(page, 4 << 20).tobytes()
+
+
 # ---- image hand-over between processes (memfd host store).  Green on a B200 since round 2 (profiles/gpu_suite_all_gates_open_r2.log).
 
 _ADOPT_CHILD = r"""
