@@ -310,8 +310,8 @@ def run_ours(args) -> None:
                 "peak": link_peak, "unit": "GB/s", "frac": round(e2e_gbs / world / link_peak, 4),
                 "naive_pinned_h2d_per_gpu": round(ceiling, 3) if ceiling else None,
                 "vs_naive_pinned_h2d": round(e2e_gbs / world / ceiling, 4) if ceiling else None,
-                "naive_note": "min over ranks of a plain 2 GiB cudaMemcpyAsync from a torch pin_memory buffer, all ranks at once "
-                              "(no NUMA placement): at N=1 this is the box's copy-engine ceiling"},
+                "naive_note": "min over ranks of a plain 8 GiB cudaMemcpyAsync from a torch pin_memory buffer, all ranks at once "
+                              "(no NUMA placement, best of 3): the box's sustained copy-engine rate on the slowest rank's link"},
             "clocks": clocks,
         }
         if peer:
@@ -633,9 +633,14 @@ def run_packed_child(args) -> None:
     eng.close()
 
 
-def pcie_ceiling_gbs(torch, nbytes: int = 2 << 30, reps: int = 3) -> float:
-    """Best-of-N plain H2D of one large pinned buffer on this rank's GPU (all ranks run it at the same time)."""
-    h = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+def pcie_ceiling_gbs(torch, nbytes: int = 8 << 30, reps: int = 2) -> float:
+    """Plain H2D of one large pinned buffer on this rank's GPU, all ranks at the same time: 8 GiB per copy (about 0.15 s — long enough
+    to be the link's SUSTAINED rate; round 1 used 2 GiB bursts, which flatter a link whose long-run rate is lower), best of `reps`."""
+    try:
+        h = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    except Exception:
+        nbytes = 2 << 30
+        h = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
     d = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
     best = 0.0
     for _ in range(reps + 1):

@@ -186,8 +186,34 @@ class CuMemAllocator:
             self.engine.set_current_tag(old_tag)
             if expandable_was_enabled:
                 torch.cuda.memory._set_allocator_settings("expandable_segments:True")
+        if tag == "weights" and os.environ.get("FMA_ADOPT_PARKED") == "1" and os.environ.get("FMA_NODE_AGENT_SOCK"):
+            self._adopt_parked_image()
         if tag == "weights" and os.environ.get("FMA_PREPIN", "1") != "0" and _tier_from_env() == L.FMA_TIER_HOST:
             self._start_reserve()
+
+    def _adopt_parked_image(self) -> None:
+        """Warm start: an earlier instance with this instance ID parked its weights with the node agent and died
+        (or was deleted) asleep — the controller would cold-start here (inference-server.go:416-448).  The weights pool has just
+        been filled by the loader (``--load-format dummy`` is enough: contents are about to be replaced); if the owner holds an image
+        for (instance, rank) whose segment sequence matches, adopt it and wake: the weights come back over NVLink, digests
+        verified.  Anything else (no image, another model) leaves the loaded weights as they are."""
+        import time
+
+        from .parking import ParkingClient
+
+        t0 = time.perf_counter()
+        try:
+            if not ParkingClient().adopt(self.engine, _instance_id(), _rank(), tags=("weights",)):
+                logger.info("fma_b200: no parked image for instance %s rank %d: keeping the loaded weights", _instance_id(), _rank())
+                return
+            self.engine.wake(["weights"], flags=L.FMA_FLAG_VERIFY)
+            st = self.engine.stats()
+            logger.info("fma_b200: adopted the parked image of instance %s rank %d: %.2f GiB restored from peer HBM in %.3f s (digests verified)",
+                        _instance_id(), _rank(), st["wake_bytes_restored"] / 1024**3, time.perf_counter() - t0)
+        except L.FmaError as e:
+            if self.engine.is_sleeping():
+                raise                                   # half way: do not serve from unmapped weights
+            logger.warning("fma_b200: parked image not adopted (%s): keeping the loaded weights", e)
 
     # ---- pre-pinning off the critical path -----------------------------------------------
     def _start_reserve(self) -> None:

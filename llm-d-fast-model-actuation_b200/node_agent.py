@@ -536,9 +536,24 @@ def main() -> None:
     ap.add_argument("--port", type=int, default=8001)          # pkg/controller/common/interface.go:38
     ap.add_argument("--log-level", default="info", choices=["critical", "error", "warning", "info", "debug"])
     ap.add_argument("--log-dir", default="/tmp")
+    ap.add_argument("--parking", action="store_true", help="own the node's peer-HBM parking buffers (parking.py): instances started by this agent "
+                                                           "park sleeping weights on idle GPUs through it and the images outlive them")
     a = ap.parse_args()
     logging.basicConfig(level=getattr(logging, a.log_level.upper()), format="%(asctime)s - %(name)s - %(levelname)s - %(message)s")
-    agent = NodeAgent(mock_gpus=a.mock_gpus, log_dir=a.log_dir)
+    parking = None
+    if a.parking:
+        from .parking import ParkingService
+
+        if a.mock_gpus:
+            n_dev = a.mock_gpu_count
+        else:
+            import pynvml
+
+            pynvml.nvmlInit()
+            n_dev = pynvml.nvmlDeviceGetCount()
+        parking = ParkingService(os.path.join(a.log_dir, f"fma_node_agent.{os.getpid()}.sock"), n_devices=n_dev)
+        parking.start()
+    agent = NodeAgent(mock_gpus=a.mock_gpus, log_dir=a.log_dir, parking=parking)
     uvicorn.run(create_app(agent), host=a.host, port=a.port, log_level=a.log_level)
 
 

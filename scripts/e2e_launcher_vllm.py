@@ -24,8 +24,13 @@ LPORT, VPORT = 8001, 8005
 #   ckpt_default / ckpt_fma   a synthetic safetensors checkpoint of the same shape, loaded by vLLM's own loader vs
 #                             --load-format fma (the engine's file -> HBM stream); both must generate the same tokens
 ARMS = os.environ.get("E2E_ARMS", "reference,fma_b200").split(",")
+#   fma_b200_peer_parked   (E2E_LAUNCHER=node_agent, >= 2 GPUs) the instance sees only GPU 0 (gpu_uuids -> CUDA_VISIBLE_DEVICES), sleeps to the
+#                          peer tier through the node agent's parking service, is DELETED asleep, and a new instance with the same ID adopts the
+#                          parked image at start-up (FMA_ADOPT_PARKED=1) and must generate the same tokens
 ARM_ENV = {"reference": {}, "fma_b200": {"FMA_B200": "1"}, "fma_b200_packed": {"FMA_B200": "1", "FMA_PACK": "1"},
-           "ckpt_default": {"FMA_B200": "1"}, "ckpt_fma": {"FMA_B200": "1"}}
+           "ckpt_default": {"FMA_B200": "1"}, "ckpt_fma": {"FMA_B200": "1"},
+           "fma_b200_peer_parked": {"FMA_B200": "1", "FMA_TIER": "peer"}}
+USE_AGENT = os.environ.get("E2E_LAUNCHER", "reference") == "node_agent"
 ARM_LOAD = {"ckpt_default": "auto", "ckpt_fma": "fma"}
 
 
@@ -73,8 +78,12 @@ def http(method, url, body=None, timeout=600):
 
 env = dict(os.environ)
 env["PYTHONPATH"] = os.pathsep.join([os.path.join(ROOT, "plugin"), ROOT, os.path.join(ROOT, "scripts", "k8s_stub"), env.get("PYTHONPATH", "")])
-launcher = subprocess.Popen([sys.executable, os.path.join(ROOT, "baseline", "_ref", "launcher", "launcher.py"), "--port", str(LPORT), "--host", "127.0.0.1"],
-                            env=env, cwd=os.path.join(ROOT, "baseline", "_ref", "launcher"), stdout=open(f"{OUT}/launcher.log", "w"), stderr=subprocess.STDOUT)
+if USE_AGENT:   # this repo's launcher-compatible node agent, owning the parking buffers
+    launcher = subprocess.Popen([sys.executable, os.path.join(ROOT, "scripts", "run_node_agent.py"), "--port", str(LPORT), "--host", "127.0.0.1", "--parking",
+                                 "--log-dir", OUT], env=env, cwd=ROOT, stdout=open(f"{OUT}/launcher.log", "w"), stderr=subprocess.STDOUT)
+else:
+    launcher = subprocess.Popen([sys.executable, os.path.join(ROOT, "baseline", "_ref", "launcher", "launcher.py"), "--port", str(LPORT), "--host", "127.0.0.1"],
+                                env=env, cwd=os.path.join(ROOT, "baseline", "_ref", "launcher"), stdout=open(f"{OUT}/launcher.log", "w"), stderr=subprocess.STDOUT)
 results = {}
 try:
     for _ in range(240):
@@ -92,6 +101,11 @@ try:
         iid = f"e2e-{arm}"
         arm_options = options.replace("--load-format dummy", f"--load-format {ARM_LOAD[arm]}") if arm in ARM_LOAD else options
         body = {"options": arm_options, "env_vars": {"VLLM_SERVER_DEV_MODE": "1", **extra_env}, "annotations": {"isc-name": "e2e", "inference-port": str(VPORT)}}
+        if arm == "fma_b200_peer_parked":
+            import pynvml
+            pynvml.nvmlInit()
+            u = pynvml.nvmlDeviceGetUUID(pynvml.nvmlDeviceGetHandleByIndex(0))
+            body["gpu_uuids"] = [u.decode() if isinstance(u, bytes) else u]       # -> CUDA_VISIBLE_DEVICES=0: the parking GPU is invisible to the instance
         st, txt, _ = http("PUT", f"http://127.0.0.1:{LPORT}/v2/vllm/instances/{iid}", body)
         assert st == 201, (st, txt)
         t0 = time.time(); up = False
@@ -127,6 +141,28 @@ try:
         results[arm] = dict(load_s=load_s, rows=rows, tokens_before=before, tokens_after=after, same_tokens=before == after,
                             uses_fma=any("fma_b200" in l for l in lines), vllm_log_lines=lines[-12:])
         print(arm, json.dumps(results[arm])[:1800], flush=True)
+        if arm == "fma_b200_peer_parked":
+            # park, delete the instance ASLEEP, start a new one with the same ID: it adopts the image the node agent kept
+            s_st, _, s_t = http("POST", f"http://127.0.0.1:{VPORT}/sleep")
+            sleepers = json.loads(http("GET", f"http://127.0.0.1:{LPORT}/v2/node/sleepers")[1])
+            http("DELETE", f"http://127.0.0.1:{LPORT}/v2/vllm/instances/{iid}")
+            time.sleep(8)
+            body["env_vars"]["FMA_ADOPT_PARKED"] = "1"
+            st, txt, _ = http("PUT", f"http://127.0.0.1:{LPORT}/v2/vllm/instances/{iid}", body)
+            t0 = time.time(); up = False
+            while st == 201 and time.time() - t0 < 600:
+                try:
+                    if http("GET", f"http://127.0.0.1:{VPORT}/health", timeout=2)[0] == 200: up = True; break
+                except Exception:
+                    pass
+                time.sleep(2)
+            log2 = http("GET", f"http://127.0.0.1:{LPORT}/v2/vllm/instances/{iid}/log")[1]
+            open(f"{OUT}/{arm}_second_instance_vllm.log", "w").write(log2)
+            tokens2 = gen() if up else None
+            results[arm + "_restart"] = dict(put_status=st, up=up, start_s=time.time() - t0, sleepers_while_parked=sleepers, tokens=tokens2,
+                                             same_tokens_as_first_instance=tokens2 == before,
+                                             adopt_log_lines=[l for l in log2.splitlines() if "adopted the parked image" in l or "parked image" in l][-4:])
+            print(arm + "_restart", json.dumps(results[arm + "_restart"])[:1500], flush=True)
         st, _, _ = http("DELETE", f"http://127.0.0.1:{LPORT}/v2/vllm/instances/{iid}")
         time.sleep(8)
 finally:
