@@ -59,7 +59,9 @@ bool pid_alive(int32_t pid) {
 
 void open_gate() {
     const char* on = getenv("FMA_VMM_GATE");
-    if (!on || !*on || atoi(on) == 0) return;   // opt-in until the A/B on hardware says otherwise
+    // On unless FMA_VMM_GATE=0.  A/B at N=8 on one lease (profiles/bench_n8_gate_v2_r2.json vs bench_n8_nogate_r2.json): host tier
+    // 433.3 vs 430.4 GB/s (every rank 323-326 ms under the gate), peer tier with all ranks waking at once 0.087 vs 0.120 s.
+    if (on && *on && atoi(on) == 0) return;
     char name[128];
     const char* forced = getenv("FMA_VMM_GATE_NAME");
     if (forced && *forced) snprintf(name, sizeof(name), "%s%s", forced[0] == '/' ? "" : "/", forced);

@@ -13,7 +13,7 @@
 // Failure model: everything is bounded.  A waiter gives up waiting for higher classes after `max_wait_s` and a lock that
 // cannot be had within 2 s is skipped (the driver's own lock still serialises), so a dead or wedged peer can delay a
 // call, never hang it.  The mutex is robust (a holder that died is recovered by the next locker).  Per-process slots
-// carry the pid; slots of dead pids are reclaimed.  FMA_VMM_GATE=0 disables it; FMA_VMM_GATE_NAME picks the segment
+// carry the pid; slots of dead pids are reclaimed.  On by default; FMA_VMM_GATE=0 disables it; FMA_VMM_GATE_NAME picks the segment
 // (default "/fma_b200_gate.<uid>": the engines of one pod / one launcher share /dev/shm and therefore one gate).
 #pragma once
 #include <cstddef>

@@ -676,7 +676,7 @@ def test_full_size_llama3_70b_tp8_shard_roundtrip_properties(engine, oracle):
         assert before[i] == oracle.digest(oracle.fill(table[i].bytes, 4321, firsts[i]))
     total = sum(before) % (1 << 64)
     engine.host_reserve(Wb)
-    for pack, incremental in ((0, 0), (1, 0), (1, 1), (0, 1)):
+    for pack, incremental in ((0, 0), (0, 1), (1, 0), (1, 1)):     # an INCREMENTAL sleep keeps the kept image's form, so each form is seeded by a full sleep first
         engine.set_option("pack", pack)
         engine.set_option("incremental", incremental)
         for rep in range(2 if incremental else 1):
