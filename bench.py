@@ -414,11 +414,11 @@ def measure_multipath(args, L, W, cfg, workload: str, n_visible: int, cycles: in
         plans = [(k, 128, 3) for k in ks] + ([(ks[-1], 64, 4)] if ks else [])
         for k, slot_mib, slots in plans:
             eng.set_paths(list(range(1, k + 1)), slot_bytes=slot_mib << 20, slots=slots)
-            wakes, devs = [], []
+            wakes, devs, sleeps = [], [], []
             for i in range(cycles + 1):
-                eng.sleep(["weights"]); eng.wake(None); st = eng.stats()
+                eng.sleep(["weights"]); ss = eng.stats(); eng.wake(None); st = eng.stats()
                 if i:
-                    wakes.append(st["wake_seconds"]); devs.append(st["wake_copy_seconds"])
+                    wakes.append(st["wake_seconds"]); devs.append(st["wake_copy_seconds"]); sleeps.append(ss["sleep_seconds"])
             tl = eng.timeline()
             chunks = {r["idx"]: r["bytes"] for r in tl if r["kind"] == "path_chunks"}
             local = {r["idx"]: r["bytes"] for r in tl if r["kind"] == "path_local"}
@@ -426,6 +426,7 @@ def measure_multipath(args, L, W, cfg, workload: str, n_visible: int, cycles: in
             rows.append({"helpers": k, "paths": k + 1, "slot_mib": slot_mib, "slots": slots, "wake_latency_s": round(med(wakes), 5),
                          "wake_latency_s_min_max": [round(min(wakes), 5), round(max(wakes), 5)], "e2e_gbs": round(wb / med(wakes) / 1e9, 1),
                          "device_gbs": round(wb / med(devs) / 1e9, 1), "x_single_link_64": round(wb / med(wakes) / 1e9 / PCIE_GEN5_X16_GBS, 2),
+                         "sleep_latency_s": round(med(sleeps), 5), "sleep_e2e_gbs": round(wb / med(sleeps) / 1e9, 1),
                          "gib_per_path_device": {str(d): round(b / GiB, 2) for d, b in sorted(chunks.items())},
                          "gib_numa_local_per_path_device": {str(d): round(b / GiB, 2) for d, b in sorted(local.items())}})
         eng.set_paths([])

@@ -427,6 +427,115 @@ int sleep_staged(SleepPipe& pipe) {
     return rc;
 }
 
+// MULTI-PATH sleep (fma_paths_set): the mirror image of wake_multipath.  K1 on the sleeping GPU gathers a chunk of the image
+// into a staging slot of a PATH — its own HBM, or a helper GPU's HBM over NVLink — and THAT GPU's copy engine moves the slot into
+// the host store over THAT GPU's x16 link; chunk queues per NUMA node of the (striped) store, self-balancing.  Nothing is unmapped
+// before every byte has reached the store (one publish at the end), so a failure half way leaves the engine awake and intact.
+int sleep_multipath(SleepPipe& pipe) {
+    fma_engine_t* e = pipe.e;
+    KernelTimes& kt = pipe.kt;
+    char* store = pipe.store;
+    int rc = FMA_OK;
+    size_t n_pages = 0;
+    rc = pipe.upload_page_table(&n_pages);
+    if (rc != FMA_OK) return rc;
+    rc = ensure_ring_events(e, 1);
+    if (rc != FMA_OK) return rc;
+    cudaEvent_t ev_tab = e->ev_ring_full[0];
+    RT(cudaEventRecord(ev_tab, e->ks));
+    struct Chunk { size_t p0, np; };
+    std::vector<Chunk> chunks;
+    const size_t chunk_pages = std::max<size_t>(e->path_slot_bytes / FMA_PAGE_BYTES, 1);
+    for (size_t q = 0; q < n_pages; q += chunk_pages) chunks.push_back(Chunk{q, std::min(chunk_pages, n_pages - q)});
+    std::vector<int> q_node;
+    std::vector<std::vector<size_t>> q_chunks;
+    for (size_t c = 0; c < chunks.size(); ++c) {
+        const uint64_t off = (uint64_t)chunks[c].p0 * FMA_PAGE_BYTES;
+        int node = -1;
+        for (const HostStore::NumaRange& r : e->host.ranges)
+            if (off >= r.begin && off < r.end) node = r.node;
+        size_t qi = 0;
+        while (qi < q_node.size() && q_node[qi] != node) ++qi;
+        if (qi == q_node.size()) {
+            q_node.push_back(node);
+            q_chunks.emplace_back();
+        }
+        q_chunks[qi].push_back(c);
+    }
+    std::vector<std::atomic<size_t>> q_next(q_node.size());
+    for (auto& a : q_next) a.store(0);
+    auto take_chunk = [&](int my_node, size_t* out) -> bool {
+        for (int pass = 0; pass < 2; ++pass)
+            for (size_t qi = 0; qi < q_node.size(); ++qi) {
+                if ((pass == 0) != (q_node[qi] == my_node)) continue;
+                const size_t k = q_next[qi].fetch_add(1);
+                if (k < q_chunks[qi].size()) {
+                    *out = q_chunks[qi][k];
+                    return true;
+                }
+            }
+        return false;
+    };
+    std::atomic<int> error{FMA_OK};
+    std::mutex kt_mu;
+    char err_msg[512] = "";
+    std::vector<uint32_t> per_path(e->paths.size(), 0);
+    auto worker = [&](size_t pi) {
+        WakePath& path = e->paths[pi];
+        cudaSetDevice(e->device);
+        auto failw = [&](int code, const char* what, cudaError_t ce) {
+            int expect = FMA_OK;
+            if (error.compare_exchange_strong(expect, code)) snprintf(err_msg, sizeof(err_msg), "%s failed on path %zu (device %d): %s", what, pi, path.device, cudaGetErrorString(ce));
+        };
+        cudaError_t ce = cudaStreamWaitEvent(path.kern, ev_tab, 0);
+        if (ce != cudaSuccess) return failw(FMA_ECUDA, "cudaStreamWaitEvent(table)", ce);
+        uint32_t mine = 0;
+        for (;;) {
+            if (error.load() != FMA_OK) return;
+            size_t c = 0;
+            if (!take_chunk(path.numa_node, &c)) break;
+            const Chunk& ch = chunks[c];
+            const int slot = (int)(mine % (uint32_t)e->path_slots);
+            if (mine >= (uint32_t)e->path_slots) {   // the D2H that used this slot before has drained it (event on the path's GPU)
+                ce = cudaEventSynchronize(path.ev_full[slot]);
+                if (ce != cudaSuccess) return failw(FMA_ECUDA, "cudaEventSynchronize(slot drained)", ce);
+            }
+            char* slot_ptr = reinterpret_cast<char*>(path.va) + (size_t)slot * e->path_slot_bytes;
+            {
+                std::lock_guard<std::mutex> lk(kt_mu);
+                const int krc = kt.launch_on(path.kern, e->d_tab + ch.p0, 0, nullptr, (uint64_t)(uintptr_t)slot_ptr, (uint32_t)ch.np);   // K1: gather -> slot
+                if (krc != FMA_OK) return failw(krc, "K1 launch", cudaGetLastError());
+            }
+            ce = cudaEventRecord(path.ev_free[slot], path.kern);           // (event on the engine's GPU) the slot is full
+            if (ce != cudaSuccess) return failw(FMA_ECUDA, "cudaEventRecord(slot full)", ce);
+            ce = cudaStreamWaitEvent(path.copy, path.ev_free[slot], 0);
+            if (ce != cudaSuccess) return failw(FMA_ECUDA, "cudaStreamWaitEvent(slot full)", ce);
+            ce = cudaMemcpyAsync(store + (uint64_t)ch.p0 * FMA_PAGE_BYTES, slot_ptr, ch.np * FMA_PAGE_BYTES, cudaMemcpyDefault, path.copy);
+            if (ce != cudaSuccess) return failw(FMA_ECUDA, "cudaMemcpyAsync(D2H)", ce);
+            ce = cudaEventRecord(path.ev_full[slot], path.copy);           // (event on the path's GPU) the slot is drained
+            if (ce != cudaSuccess) return failw(FMA_ECUDA, "cudaEventRecord(slot drained)", ce);
+            ++mine;
+        }
+        per_path[pi] = mine;
+    };
+    std::vector<std::thread> th;
+    for (size_t pi = 0; pi < e->paths.size(); ++pi) th.emplace_back(worker, pi);
+    for (auto& t : th) t.join();
+    for (WakePath& path : e->paths) {   // every D2H has landed before anything is released (and before an error is reported)
+        cudaError_t ce = cudaStreamSynchronize(path.copy);
+        if (ce != cudaSuccess && error.load() == FMA_OK) {
+            error.store(FMA_ECUDA);
+            snprintf(err_msg, sizeof(err_msg), "D2H on path device %d failed: %s", path.device, cudaGetErrorString(ce));
+        }
+    }
+    if (error.load() != FMA_OK) return fail(error.load(), "%s", err_msg);
+    for (size_t pi = 0; pi < e->paths.size(); ++pi) {
+        pipe.copy_ops += per_path[pi];
+        e->tl_add("path_chunks", e->paths[pi].device, e->tl_entry, now_s(), (uint64_t)per_path[pi] * e->path_slot_bytes);
+    }
+    return pipe.publish_consumed(pipe.W, e->ks);   // all bytes are in the store: every offloaded unit may go
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------
@@ -526,7 +635,10 @@ int do_sleep(fma_engine_t* e, uint64_t offload_mask, int tier, uint32_t flags) {
     if (clean) flags |= kFlagAdopt;                  // release the device side only: not a byte moves
     else if (!partial && !partial_packed) invalidate_shadows(e);  // this sleep rewrites the store (or leaves the host tier alone: be conservative)
     int mode = partial ? FMA_MODE_DIRECT : resolve_mode(e, tier);
-    if (W && !(flags & kFlagAdopt) && mode == FMA_MODE_STAGED && ensure_ring(e, W) != FMA_OK) mode = FMA_MODE_DIRECT;  // HBM too full for a ring
+    // MULTI-PATH (fma_paths_set): a full, plain host-tier sleep is striped over the paths' links; every path has its own staging slots
+    const bool multipath = !e->paths.empty() && tier == FMA_TIER_HOST && mode == FMA_MODE_STAGED && !partial && !partial_packed && !clean &&
+                           !(flags & kFlagAdopt) && !e->cfg.pack && env_int("FMA_MULTIPATH_SLEEP", 1) != 0;
+    if (W && !(flags & kFlagAdopt) && mode == FMA_MODE_STAGED && !multipath && ensure_ring(e, W) != FMA_OK) mode = FMA_MODE_DIRECT;  // HBM too full for a ring
     // PACKED image (config.pack): decide per page what its stored form is BEFORE the store is sized
     bool packed = false;
     uint64_t Wp = W;
@@ -670,6 +782,7 @@ int do_sleep(fma_engine_t* e, uint64_t offload_mask, int tier, uint32_t flags) {
             if (rc == FMA_OK) rc = publish_consumed(W, e->cs[0]);  // cs[0] has joined the other streams after the last extent
         } else if (mode == FMA_MODE_DIRECT) rc = sleep_direct(pipe);
         else if (mode == FMA_MODE_KERNEL) rc = packed ? sleep_kernel_packed(pipe) : sleep_kernel(pipe);
+        else if (multipath && !packed) rc = sleep_multipath(pipe);
         else rc = packed ? sleep_staged_packed(pipe) : sleep_staged(pipe);
         if (rc != FMA_OK) return rc;
         {

@@ -285,6 +285,20 @@ int main() {
         OK(fma_paths_set(a, &helper, 1, 2 * P, 2));
         auto before = digests(a);
         for (int rep = 0; rep < 3; ++rep) {
+            if (rep == 2) {   // a D2H fails inside a multi-path SLEEP: no weight was released (only the discarded kv_cache went), a wake makes it whole
+                hostsim_fail_memcpy_after(4);
+                int rc3 = fma_sleep(a, 1ull << w, FMA_TIER_HOST, 0);
+                hostsim_fail_memcpy_after(-1);
+                assert(rc3 != 0);
+                for (int i = 0; i < fma_segment_count(a); ++i) {
+                    fma_segment_info_t si;
+                    OK(fma_segment_info(a, i, &si));
+                    if (si.tag == w) assert(si.mapped == 1);
+                }
+                OK(fma_wake(a, 0, 0));
+                auto still = digests(a);
+                for (size_t i = 0; i + 1 < before.size(); ++i) assert(still[i] == before[i]);
+            }
             OK(fma_sleep(a, 1ull << w, FMA_TIER_HOST, FMA_FLAG_VERIFY));
             if (rep == 1) {
                 hostsim_fail_memcpy_after(5);
