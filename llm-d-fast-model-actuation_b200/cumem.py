@@ -26,6 +26,7 @@ from __future__ import annotations
 
 import dataclasses
 import gc
+import json
 import logging
 import os
 import threading
@@ -186,6 +187,15 @@ class CuMemAllocator:
             self.engine.set_current_tag(old_tag)
             if expandable_was_enabled:
                 torch.cuda.memory._set_allocator_settings("expandable_segments:True")
+        if tag == "weights":
+            # one line for tooling (scripts/e2e_launcher_vllm.py validates the synthetic tables of workloads.py against it)
+            segs = [s for s in self.engine.segments() if s.tag == "weights"]
+            hist: dict[int, int] = {}
+            for sg in segs:
+                hist[sg.bytes >> 20] = hist.get(sg.bytes >> 20, 0) + 1
+            logger.info("fma_b200: weights pool closed: %s", json.dumps({"segments": len(segs), "bytes": sum(sg.bytes for sg in segs),
+                                                                          "first_mib": [sg.bytes >> 20 for sg in segs[:6]],
+                                                                          "mib_histogram": {str(k): v for k, v in sorted(hist.items())}}))
         if tag == "weights" and os.environ.get("FMA_ADOPT_PARKED") == "1" and os.environ.get("FMA_NODE_AGENT_SOCK"):
             self._adopt_parked_image()
         if tag == "weights" and os.environ.get("FMA_PREPIN", "1") != "0" and _tier_from_env() == L.FMA_TIER_HOST:

@@ -140,6 +140,26 @@ try:
         lines = [l for l in log.splitlines() if "It took" in l or "sleep freed" in l or "fma_b200" in l or "Loading weights took" in l]
         results[arm] = dict(load_s=load_s, rows=rows, tokens_before=before, tokens_after=after, same_tokens=before == after,
                             uses_fma=any("fma_b200" in l for l in lines), vllm_log_lines=lines[-12:])
+        pool = [l for l in log.splitlines() if "weights pool closed:" in l]
+        if pool and TP == 1:
+            # the synthetic allocation tables (workloads.py, derived from model shapes + torch's segment rules) against what a
+            # LIVE vLLM + torch really allocated under the "weights" tag: segment count, total bytes, size histogram, leading order
+            try:
+                sys.path.insert(0, ROOT)
+                import fma_b200  # noqa: F401
+                from fma_b200 import workloads as Wl
+                live = json.loads(pool[-1].split("weights pool closed:", 1)[1].strip())
+                syn = [x for x in Wl.allocation_table(MODEL) if x.tag == "weights"]
+                hist = {}
+                for x in syn:
+                    hist[str(x.bytes >> 20)] = hist.get(str(x.bytes >> 20), 0) + 1
+                synth = {"segments": len(syn), "bytes": sum(x.bytes for x in syn), "first_mib": [x.bytes >> 20 for x in syn[:6]],
+                         "mib_histogram": dict(sorted(hist.items(), key=lambda kv: int(kv[0])))}
+                results[arm]["table_validation"] = {"live": live, "synthetic": synth, "same_segment_count": live["segments"] == synth["segments"],
+                                                    "same_bytes": live["bytes"] == synth["bytes"], "same_histogram": live["mib_histogram"] == synth["mib_histogram"],
+                                                    "same_leading_order": live["first_mib"] == synth["first_mib"]}
+            except Exception as e:
+                results[arm]["table_validation"] = {"error": str(e)[:200]}
         print(arm, json.dumps(results[arm])[:1800], flush=True)
         if arm == "fma_b200_peer_parked":
             # park, delete the instance ASLEEP, start a new one with the same ID: it adopts the image the node agent kept
