@@ -39,7 +39,9 @@ struct Shm {
 };
 
 struct Local {
-    std::once_flag once;
+    std::mutex open_mu;
+    int opened_pid = 0;      // the gate was opened by this pid: a forked child must claim a slot of its own
+    bool atexit_set = false;
     Shm* shm = nullptr;
     int slot = -1;
     bool enabled = false;
@@ -129,12 +131,15 @@ void open_gate() {
     g.shm = s;
     g.slot = slot;
     g.enabled = true;
-    atexit([] {
-        if (g.shm && g.slot >= 0) {
-            for (int c = 0; c < kGateClasses; ++c) g.shm->slots[g.slot].want[c].store(0);
-            g.shm->slots[g.slot].pid.store(0);
-        }
-    });
+    if (!g.atexit_set) {
+        g.atexit_set = true;
+        atexit([] {
+            if (g.shm && g.slot >= 0 && g.opened_pid == (int)getpid()) {
+                for (int c = 0; c < kGateClasses; ++c) g.shm->slots[g.slot].want[c].store(0);
+                g.shm->slots[g.slot].pid.store(0);
+            }
+        });
+    }
 }
 
 // does anybody — another live process, or another thread of this one (two engines in one process: a hot swap) — want a class
@@ -176,7 +181,16 @@ bool lock_bounded(double seconds) {
 }  // namespace
 
 bool gate_enabled() {
-    std::call_once(g.once, open_gate);
+    const int me = (int)getpid();
+    if (g.opened_pid == me) return g.enabled;           // fast path (opened_pid is written once per process, under open_mu)
+    std::lock_guard<std::mutex> lk(g.open_mu);
+    if (g.opened_pid != me) {                            // first use in this process — also in a child forked after the parent's first use
+        g.enabled = false;
+        g.shm = nullptr;
+        g.slot = -1;
+        open_gate();
+        g.opened_pid = me;
+    }
     return g.enabled;
 }
 
