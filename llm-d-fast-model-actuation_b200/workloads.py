@@ -70,8 +70,13 @@ def simulate_segments(tensors: list[tuple[str, int]], tag: str) -> list[SegmentS
 
 
 def _llama_tensors(*, hidden: int, inter: int, heads: int, kv_heads: int, head_dim: int, vocab: int, layers: int,
-                   tp: int, dtype_bytes: int = 2, tie_embeddings: bool = False) -> list[tuple[str, int]]:
-    """Fused vLLM layouts per TP rank: qkv_proj, o_proj, gate_up_proj, down_proj, two RMSNorm weights."""
+                   tp: int, dtype_bytes: int = 2, tie_embeddings: bool = False, max_pos: int | None = None) -> list[tuple[str, int]]:
+    """Fused vLLM layouts per TP rank: qkv_proj, o_proj, gate_up_proj, down_proj, two RMSNorm weights — plus, with ``max_pos``, the
+    non-parameter buffers a live vLLM allocates under the ``weights`` tag: the rotary embedding built right after
+    layer 0's o_proj (``inv_freq``: the first small-pool allocation; ``cos_sin_cache`` = max_pos x head_dim x dtype: 1-10 MiB, so a
+    20 MiB large-pool segment), shared by all layers.  Validated against a live vLLM 0.22 + torch 2.11 weights pool on a B200
+    (Llama-3-8B shapes, ``profiles/e2e_table_validation_llama3_8b_r2.json``): 132 segments, 16 083 058 688 bytes, order
+    [1002, 48, 32, 2, 20, 224, 112, ...] MiB."""
     b = dtype_bytes
     q_rows = heads * head_dim // tp
     kv_rows = max(kv_heads // tp, 1) * head_dim
@@ -80,6 +85,9 @@ def _llama_tensors(*, hidden: int, inter: int, heads: int, kv_heads: int, head_d
     for i in range(layers):
         t.append((f"L{i}.qkv_proj", (q_rows + 2 * kv_rows) * hidden * b))
         t.append((f"L{i}.o_proj", hidden * q_rows * b))
+        if i == 0 and max_pos:
+            t.append(("rotary_emb.inv_freq", head_dim // 2 * 4))
+            t.append(("rotary_emb.cos_sin_cache", max_pos * head_dim * b))
         t.append((f"L{i}.gate_up_proj", 2 * (inter // tp) * hidden * b))
         t.append((f"L{i}.down_proj", hidden * (inter // tp) * b))
         t.append((f"L{i}.input_layernorm", hidden * b))
@@ -107,11 +115,11 @@ def _opt_tensors(*, hidden: int, ffn: int, vocab: int, max_pos: int, layers: int
 MODELS = {
     # name: (tensor generator kwargs, layers for the kv split)
     "llama-3-8b": dict(kind="llama", hidden=4096, inter=14336, heads=32, kv_heads=8, head_dim=128, vocab=128256,
-                       layers=32, tp=1),
+                       layers=32, tp=1, max_pos=8192),
     "llama-3-70b-tp8": dict(kind="llama", hidden=8192, inter=28672, heads=64, kv_heads=8, head_dim=128, vocab=128256,
-                            layers=80, tp=8),
+                            layers=80, tp=8, max_pos=8192),
     "mistral-7b": dict(kind="llama", hidden=4096, inter=14336, heads=32, kv_heads=8, head_dim=128, vocab=32768,
-                       layers=32, tp=1),
+                       layers=32, tp=1, max_pos=32768),
     "opt-125m": dict(kind="opt", hidden=768, ffn=3072, vocab=50272, max_pos=2048, layers=12),
     # small shapes for tests / smoke (same structure, seconds on the oracle)
     "tiny-llama-test": dict(kind="llama", hidden=1024, inter=6144, heads=16, kv_heads=4, head_dim=64, vocab=16384,
