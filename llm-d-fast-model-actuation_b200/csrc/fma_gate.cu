@@ -40,11 +40,11 @@ struct Shm {
 
 struct Local {
     std::mutex open_mu;
-    int opened_pid = 0;      // the gate was opened by this pid: a forked child must claim a slot of its own
+    std::atomic<int> opened_pid{0};   // the gate was opened by this pid (a forked child must claim a slot of its own); written last, release
     bool atexit_set = false;
     Shm* shm = nullptr;
     int slot = -1;
-    bool enabled = false;
+    std::atomic<bool> enabled{false};
     std::mutex st_mu;
     GateStats st;
 };
@@ -134,7 +134,7 @@ void open_gate() {
     if (!g.atexit_set) {
         g.atexit_set = true;
         atexit([] {
-            if (g.shm && g.slot >= 0 && g.opened_pid == (int)getpid()) {
+            if (g.shm && g.slot >= 0 && g.opened_pid.load() == (int)getpid()) {
                 for (int c = 0; c < kGateClasses; ++c) g.shm->slots[g.slot].want[c].store(0);
                 g.shm->slots[g.slot].pid.store(0);
             }
@@ -182,16 +182,16 @@ bool lock_bounded(double seconds) {
 
 bool gate_enabled() {
     const int me = (int)getpid();
-    if (g.opened_pid == me) return g.enabled;           // fast path (opened_pid is written once per process, under open_mu)
+    if (g.opened_pid.load(std::memory_order_acquire) == me) return g.enabled.load(std::memory_order_relaxed);   // fast path
     std::lock_guard<std::mutex> lk(g.open_mu);
-    if (g.opened_pid != me) {                            // first use in this process — also in a child forked after the parent's first use
-        g.enabled = false;
+    if (g.opened_pid.load(std::memory_order_relaxed) != me) {   // first use in this process — also in a child forked after the parent's first use
+        g.enabled.store(false);
         g.shm = nullptr;
         g.slot = -1;
         open_gate();
-        g.opened_pid = me;
+        g.opened_pid.store(me, std::memory_order_release);
     }
-    return g.enabled;
+    return g.enabled.load();
 }
 
 int gate_announce(int cls) {
