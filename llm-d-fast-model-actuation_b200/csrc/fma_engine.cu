@@ -339,7 +339,7 @@ int ensure_event_pool(fma_engine_t* e, size_t n) {
 // cumem.py:204-209).  mmap + mbind + parallel first-touch + cudaHostRegister, fallback cudaHostAlloc.
 // ------------------------------------------------------------------------------------
 int gpu_numa_node(int device) {
-    if (const char* fake = getenv("FMA_TEST_NUMA_MAP")) {   // tests: "0,1,1" = device -> node (boxes with one node / the host simulation)
+    if (const char* fake = getenv("FMA_NUMA_MAP")) {   // "0,1,1" = visible device index -> NUMA node: overrides sysfs (wrong / missing numa_node files; tests)
         int d = 0;
         for (const char* q = fake; *q; ++q) {
             if (*q == ',') { ++d; continue; }

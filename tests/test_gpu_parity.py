@@ -549,7 +549,7 @@ def test_multipath_wake_matches_oracle(built, oracle, slot_mib, slots, numa_map,
     import fma_b200
 
     if numa_map:   # pretend the helpers sit on another socket: the store is striped by node and each path drains its own node first
-        monkeypatch.setenv("FMA_TEST_NUMA_MAP", numa_map)
+        monkeypatch.setenv("FMA_NUMA_MAP", numa_map)
     with fma_b200.Engine(0) as engine:
         _multipath_body(engine, oracle, n, slot_mib, slots, numa_map)
 
