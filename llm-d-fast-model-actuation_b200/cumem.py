@@ -129,6 +129,14 @@ class CuMemAllocator:
         self.engine.sleep(offload_tags, tier=tier)
         if owner is not None and self.engine.stats()["sleep_bytes_offloaded"]:
             owner.deposit(self.engine, _instance_id(), _rank(), tier)
+        elif (tier == L.FMA_TIER_HOST and os.environ.get("FMA_DEPOSIT_HOST_IMAGE") == "1" and os.environ.get("FMA_NODE_AGENT_SOCK")
+              and os.environ.get("FMA_HOST_STORE_SHM") == "1" and self.engine.stats()["sleep_bytes_offloaded"]):
+            # HOST tier, opt-in: hand the memfd behind the store to the node agent so the image outlives this process.  The exported
+            # store is read-only from then on: this engine's NEXT sleep takes (and pins) a fresh private store — right for an instance
+            # that is about to be deleted, wrong for one that sleeps and wakes all day, hence not the default.
+            from .parking import ParkingClient
+
+            ParkingClient().deposit_host(self.engine, _instance_id(), _rank())
         st = self.engine.stats()
         total = st["sleep_bytes_offloaded"] + st["sleep_bytes_discarded"]
         # same INFO line the reference emits (cumem.py:215-222; parsed by llm-d-benchmark), plus GB/s
@@ -213,13 +221,16 @@ class CuMemAllocator:
 
         t0 = time.perf_counter()
         try:
-            if not ParkingClient().adopt(self.engine, _instance_id(), _rank(), tags=("weights",)):
+            cli = ParkingClient()
+            if not cli.adopt(self.engine, _instance_id(), _rank(), tags=("weights",)) and \
+                    not cli.adopt_host(self.engine, _instance_id(), _rank(), tags=("weights",)):
                 logger.info("fma_b200: no parked image for instance %s rank %d: keeping the loaded weights", _instance_id(), _rank())
                 return
             self.engine.wake(["weights"], flags=L.FMA_FLAG_VERIFY)
             st = self.engine.stats()
-            logger.info("fma_b200: adopted the parked image of instance %s rank %d: %.2f GiB restored from peer HBM in %.3f s (digests verified)",
-                        _instance_id(), _rank(), st["wake_bytes_restored"] / 1024**3, time.perf_counter() - t0)
+            logger.info("fma_b200: adopted the parked image of instance %s rank %d: %.2f GiB restored from %s in %.3f s (digests verified)",
+                        _instance_id(), _rank(), st["wake_bytes_restored"] / 1024**3, "the host store" if st["tier"] == L.FMA_TIER_HOST else "peer HBM",
+                        time.perf_counter() - t0)
         except L.FmaError as e:
             if self.engine.is_sleeping():
                 raise                                   # half way: do not serve from unmapped weights

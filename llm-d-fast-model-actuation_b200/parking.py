@@ -14,6 +14,8 @@ Wire format (one request per connection, JSON line + optional fd in the ancillar
     {"op": "deposit", "instance": id, "rank": r, "descriptor": hex}          -> {"ok": true}
     {"op": "lookup",  "instance": id, "rank": r}                             -> {"ok": true, "bytes": N, "device": d, "descriptor": hex} + fd
                                                                                 | {"ok": false, "error": "..."}
+    {"op": "deposit_host", "instance": id, "rank": r} + fd (memfd host store) -> {"ok": true}     the HOST-tier image (store + descriptor in its tail,
+    {"op": "lookup_host",  "instance": id, "rank": r}                        -> {"ok": true} + fd | {"ok": false}   fma_image_export) outlives the instance too
     {"op": "release", "instance": id[, "rank": r]}                           -> {"ok": true, "released": k}
     {"op": "stats"}                                                          -> {"ok": true, "parked_mib_per_device": {d: MiB}, "images": [...]}
 
@@ -45,6 +47,7 @@ class ParkingService:
         self._make = make_buffer
         self._lock = threading.Lock()
         self._images: Dict[Tuple[str, int], dict] = {}   # (instance, rank) -> {"buf", "descriptor"}
+        self._host_images: Dict[Tuple[str, int], int] = {}   # (instance, rank) -> fd of the memfd host store (image + descriptor)
         self._srv: Optional[socket.socket] = None
         self._thread: Optional[threading.Thread] = None
         self._stop = False
@@ -62,7 +65,8 @@ class ParkingService:
         with self._lock:
             images = [{"instance": k[0], "rank": k[1], "device": v["buf"].device, "mib": v["buf"].nbytes // MiB,
                        "has_image": v["descriptor"] is not None} for k, v in sorted(self._images.items())]
-        return {"parked_mib_per_device": {str(d): b // MiB for d, b in per.items()}, "images": images}
+            host = [{"instance": k[0], "rank": k[1], "mib": os.fstat(fd).st_size // MiB} for k, fd in sorted(self._host_images.items())]
+        return {"parked_mib_per_device": {str(d): b // MiB for d, b in per.items()}, "images": images, "host_images": host}
 
     def _pick_device(self, avoid) -> int:
         per = self.parked_bytes_per_device()
@@ -98,13 +102,30 @@ class ParkingService:
                 return None
             return img["buf"], img["descriptor"]
 
+    def deposit_host(self, instance: str, rank: int, fd: int) -> None:
+        """Keep (a dup of) the memfd behind a sleeping instance's host store: image + descriptor, as fma_image_export hands it out."""
+        key = (instance, int(rank))
+        with self._lock:
+            old = self._host_images.pop(key, None)
+            self._host_images[key] = os.dup(fd)
+        if old is not None:
+            os.close(old)
+
+    def lookup_host(self, instance: str, rank: int) -> Optional[int]:
+        with self._lock:
+            return self._host_images.get((instance, int(rank)))
+
     def release(self, instance: str, rank: Optional[int] = None) -> int:
         with self._lock:
             keys = [k for k in self._images if k[0] == instance and (rank is None or k[1] == int(rank))]
             bufs = [self._images.pop(k)["buf"] for k in keys]
+            hkeys = [k for k in self._host_images if k[0] == instance and (rank is None or k[1] == int(rank))]
+            hfds = [self._host_images.pop(k) for k in hkeys]
         for b in bufs:
             b.close()
-        return len(bufs)
+        for fd in hfds:
+            os.close(fd)
+        return len(bufs) + len(hfds)
 
     # ---- socket server ----------------------------------------------------------------------------------------
     def start(self) -> None:
@@ -129,8 +150,15 @@ class ParkingService:
 
     def _handle(self, conn: socket.socket) -> None:
         fd_to_close = None
+        got_fds: list = []
         try:
-            req = json.loads(conn.makefile("r").readline())
+            data, got_fds, _, _ = socket.recv_fds(conn, 1 << 20, 4)
+            while not data.endswith(b"\n"):
+                more = conn.recv(1 << 20)
+                if not more:
+                    break
+                data += more
+            req = json.loads(data.decode())
             op, fds = req.get("op"), []
             if op == "park":
                 buf = self.park(req["instance"], req.get("rank", 0), int(req["bytes"]), req.get("device"), req.get("avoid"))
@@ -148,6 +176,19 @@ class ParkingService:
                     fd_to_close = hit[0].export_fd()
                     fds = [fd_to_close]
                     rep = {"ok": True, "bytes": hit[0].nbytes, "device": hit[0].device, "descriptor": hit[1].hex()}
+            elif op == "deposit_host":
+                if not got_fds:
+                    rep = {"ok": False, "error": "deposit_host needs the store's fd in the ancillary data"}
+                else:
+                    self.deposit_host(req["instance"], req.get("rank", 0), got_fds[0])
+                    rep = {"ok": True}
+            elif op == "lookup_host":
+                hfd = self.lookup_host(req["instance"], req.get("rank", 0))
+                if hfd is None:
+                    rep = {"ok": False, "error": "no host image for that instance / rank"}
+                else:
+                    fds = [hfd]
+                    rep = {"ok": True, "bytes": os.fstat(hfd).st_size}
             elif op == "release":
                 rep = {"ok": True, "released": self.release(req["instance"], req.get("rank"))}
             elif op == "stats":
@@ -163,6 +204,8 @@ class ParkingService:
         finally:
             if fd_to_close is not None:
                 os.close(fd_to_close)
+            for fd in got_fds:
+                os.close(fd)
             conn.close()
 
     def close(self) -> None:
@@ -176,8 +219,12 @@ class ParkingService:
         with self._lock:
             bufs = [v["buf"] for v in self._images.values()]
             self._images.clear()
+            hfds = list(self._host_images.values())
+            self._host_images.clear()
         for b in bufs:
             b.close()
+        for fd in hfds:
+            os.close(fd)
 
 
 class ParkingClient:
@@ -188,10 +235,13 @@ class ParkingClient:
         if not self.sock_path:
             raise RuntimeError("no node agent socket (FMA_NODE_AGENT_SOCK)")
 
-    def _rpc(self, req: dict):
+    def _rpc(self, req: dict, send_fds=()):
         with socket.socket(socket.AF_UNIX, socket.SOCK_STREAM) as s:
             s.connect(self.sock_path)
-            s.sendall((json.dumps(req) + "\n").encode())
+            if send_fds:
+                socket.send_fds(s, [(json.dumps(req) + "\n").encode()], list(send_fds))
+            else:
+                s.sendall((json.dumps(req) + "\n").encode())
             data, fds, _, _ = socket.recv_fds(s, 1 << 22, 1)
             while not data.endswith(b"\n"):
                 more = s.recv(1 << 22)
@@ -225,6 +275,27 @@ class ParkingClient:
         try:
             engine.peer_attach(fd, rep["bytes"])
             engine.image_adopt_parked(bytes.fromhex(rep["descriptor"]), list(tags))
+        finally:
+            os.close(fd)
+        return True
+
+    def deposit_host(self, engine, instance: str, rank: int) -> None:
+        """HOST tier: hand the sleeping image's memfd (store + descriptor; needs FMA_HOST_STORE_SHM=1) to the owner."""
+        fd = engine.image_export()
+        try:
+            rep, _ = self._rpc({"op": "deposit_host", "instance": instance, "rank": rank}, send_fds=[fd])
+        finally:
+            os.close(fd)
+        if not rep.get("ok"):
+            raise RuntimeError(rep.get("error", "deposit_host refused"))
+
+    def adopt_host(self, engine, instance: str, rank: int, tags=("weights",)) -> bool:
+        """If the owner keeps a host image for (instance, rank): adopt it (the engine is then asleep with that image)."""
+        rep, fd = self._rpc({"op": "lookup_host", "instance": instance, "rank": rank})
+        if not rep.get("ok") or fd is None:
+            return False
+        try:
+            engine.image_adopt(fd, list(tags))
         finally:
             os.close(fd)
         return True

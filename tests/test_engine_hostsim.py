@@ -252,6 +252,19 @@ if phase == "park":
     eng.sleep(["weights"], tier=L.FMA_TIER_PEER, flags=L.FMA_FLAG_VERIFY)
     cli.deposit(eng, iid, 0)
     os._exit(0)                                        # dies asleep
+elif phase == "park_host":                             # HOST tier: the memfd behind the store goes to the owner
+    first = 0
+    for i, s in enumerate(table):
+        if s.tag == "weights":
+            eng.fill(i, 78, first); first += s.bytes // 8
+    print(json.dumps(eng.digest_all(["weights"])), flush=True)
+    eng.sleep(["weights"], flags=L.FMA_FLAG_VERIFY)
+    cli.deposit_host(eng, iid, 0)
+    os._exit(0)
+elif phase == "adopt_host":
+    assert cli.adopt(eng, iid, 0) is False and cli.adopt_host(eng, iid, 0) is True and eng.is_sleeping()
+    eng.wake(None, flags=L.FMA_FLAG_VERIFY)
+    print(json.dumps(eng.digest_all(["weights"])), flush=True)
 else:
     assert cli.adopt(eng, iid, 0) is True and eng.is_sleeping()
     eng.wake(None, flags=L.FMA_FLAG_VERIFY)
@@ -285,6 +298,15 @@ assert b.returncode == 0, b.stdout + b.stderr
 assert json.loads(a.stdout.strip().splitlines()[0]) == json.loads(b.stdout.strip().splitlines()[-1])
 assert ParkingClient().stats()["ok"] and ParkingClient().release("Iabci") == 1
 assert svc.stats()["images"] == [] and svc.stats()["parked_mib_per_device"]["1"] == 0
+# the same for the HOST tier: the memfd behind a sleeping instance's store is kept by the owner
+env_h = dict(os.environ, FMA_HOST_STORE_SHM="1")
+c = subprocess.run([sys.executable, script, "park_host", "Ihosti"], capture_output=True, text=True, timeout=300, env=env_h)
+assert c.returncode == 0, c.stdout + c.stderr
+assert [h["instance"] for h in svc.stats()["host_images"]] == ["Ihosti"] and svc.stats()["host_images"][0]["mib"] > 0
+d = subprocess.run([sys.executable, script, "adopt_host", "Ihosti"], capture_output=True, text=True, timeout=300, env=env_h)
+assert d.returncode == 0, d.stdout + d.stderr
+assert json.loads(c.stdout.strip().splitlines()[0]) == json.loads(d.stdout.strip().splitlines()[-1])
+assert ParkingClient().release("Ihosti") == 1 and svc.stats()["host_images"] == []
 svc.close()
 print("parking service ok")
 """ % ROOT
