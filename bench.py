@@ -267,7 +267,7 @@ def run_ours(args) -> None:
                 tj = json.load(open(tp))
                 if abs(tj.get("algorithmic_bytes_per_launch", 0) - bytes_per_launch) <= 0.02 * max(bytes_per_launch, 1):
                     traffic = tj.get("dram_bytes_per_launch")
-                    traffic_src = "profiles/k2_traffic.json: dram__bytes_read+write of one launch of this size under ncu --set full (round-1 capture; a constant, not measured in this run)"
+                    traffic_src = "profiles/k2_traffic.json: dram__bytes_read+write of one launch of this size under ncu --set full (kept capture, profiles/k2_full_r2.md; a constant, not measured in this run)"
                 else:
                     traffic_src = "no ncu capture for this launch size (profiles/k2_traffic.json is for 512 MiB slots)"
             except Exception:
