@@ -1232,6 +1232,25 @@ int fma_peer_attach(fma_engine_t* e, int fd, size_t bytes) {
     return FMA_OK;
 }
 
+// A private, empty host store whose NUMA placement no longer fits the MULTI-PATH configuration (paths set, changed or cleared
+// after it was pinned) is placed again: now, not inside the next sleep.  A store that holds an image, is shared or was adopted
+// stays as it is.
+static int replace_store_for_paths(fma_engine_t* e) {
+    bool image_in_store = false;
+    {
+        std::lock_guard<std::mutex> lk(e->mu);
+        for (const Segment& s : e->segs) image_in_store = image_in_store || (s.has_backup && s.backup_tier == FMA_TIER_HOST);
+    }
+    if (e->host.base && !image_in_store && !e->host.shared && e->host.fd < 0 && e->host.registered && e->host.placed_for != paths_signature(e)) {
+        const size_t cap = e->host.cap;
+        if (e->shadow_tier == FMA_TIER_HOST) invalidate_shadows(e);
+        host_store_free(e->host);
+        int rc = host_store_reserve(e, cap);
+        if (rc != FMA_OK) return rc;
+    }
+    return FMA_OK;
+}
+
 // MULTI-PATH wake: declare the idle peer GPUs whose PCIe links a host-tier wake of this engine may borrow (n = 0: none).
 // slot_bytes / slots: size and depth of the staging buffer each path (own link included) gets; 0 = defaults (128 MiB x 3).
 int fma_paths_set(fma_engine_t* e, const int* helper_devices, int n, size_t slot_bytes, int slots) {
@@ -1241,7 +1260,7 @@ int fma_paths_set(fma_engine_t* e, const int* helper_devices, int n, size_t slot
     DeviceGuard guard(e->device);
     cudaDeviceSynchronize();
     paths_release(e);
-    if (n == 0) return FMA_OK;
+    if (n == 0) return replace_store_for_paths(e);   // a striped store goes back to the engine's own NUMA node
     slot_bytes = round_up(slot_bytes ? slot_bytes : ((size_t)128 << 20), FMA_PAGE_BYTES);
     slots = slots > 0 ? std::min(slots, kMaxRing) : 3;
     int ndev = 0;
@@ -1301,21 +1320,7 @@ int fma_paths_set(fma_engine_t* e, const int* helper_devices, int n, size_t slot
             return fail(rc, "%s", keep);
         }
     }
-    // A private, empty host store that was placed before the paths were known is placed again (striped over the paths' NUMA
-    // nodes): now, not inside the next sleep.  A store that holds an image, is shared or was adopted stays as it is.
-    bool image_in_store = false;
-    {
-        std::lock_guard<std::mutex> lk(e->mu);
-        for (const Segment& s : e->segs) image_in_store = image_in_store || (s.has_backup && s.backup_tier == FMA_TIER_HOST);
-    }
-    if (e->host.base && !image_in_store && !e->host.shared && e->host.fd < 0 && e->host.registered && e->host.placed_for != paths_signature(e)) {
-        const size_t cap = e->host.cap;
-        if (e->shadow_tier == FMA_TIER_HOST) invalidate_shadows(e);
-        host_store_free(e->host);
-        int rc = host_store_reserve(e, cap);
-        if (rc != FMA_OK) return rc;
-    }
-    return FMA_OK;
+    return replace_store_for_paths(e);
 }
 
 int fma_digest_segment(fma_engine_t* e, int index, uint64_t* out) {
