@@ -363,7 +363,8 @@ FMA_API int  fma_stats(fma_engine_t* e, fma_stats_t* out);
 /* Per-phase timeline of the last fma_sleep / fma_wake as text, one event per line:
  *   "<op>,<kind>,<idx>,<t0_ms>,<t1_ms>,<bytes>\n"   (times since the call's entry)
  * kinds: plan, map_ring / map_backed / map_remap (one cuMemCreate+Map+SetAccess each, mapper thread), gate_wait,
- * enqueue, copies_landed, wait_all_mapped, drain, unmap (sleep), kernel (K1/K2/K4/K5 launches, device-timed), total.
+ * enqueue, copies_landed, wait_all_mapped, drain, unmap (sleep), kernel (K1/K2/K4/K5 launches, device-timed), total;
+ * multi-path operations add path_chunks / path_local (idx = the path's GPU, bytes = what that path moved / moved NUMA-locally).
  * The reference has no tracing on this path; this is what shows WHICH phase bounds a wake.
  * Returns the length of the full text (call with buf=NULL to size it), or a negative error. */
 FMA_API int  fma_timeline(fma_engine_t* e, char* buf, size_t cap);
