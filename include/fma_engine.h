@@ -252,6 +252,25 @@ FMA_API int  fma_image_adopt(fma_engine_t* e, int fd, uint64_t tag_mask, uint32_
  * per segment on one link (cumem.py:237-249). */
 FMA_API int  fma_paths_set(fma_engine_t* e, const int* helper_devices, int n, size_t slot_bytes, int slots);
 
+/* ---- MULTI-PATH wake across processes --------------------------------------------------------------------------------------
+ * Under the launcher an instance cannot see (or drive) the idle GPUs whose links it would like to borrow.  The node-level owner
+ * can.  OWNER: fma_helper_open(device) creates one staging buffer per helper GPU (exportable; *out_fd goes to the instance),
+ * fma_store_attach(fd) maps + pins the instance's memfd host store (fma_host_store_share; FMA_HOST_STORE_SHM=1), and
+ * fma_helper_pull(helper, store, mailbox_fd, path_index >= 1, generation, timeout_s) serves one wake on one path: that GPU's copy
+ * engine pulls chunks over that GPU's link and publishes "chunk landed" per slot in the mailbox.  INSTANCE: fma_paths_attach(engine,
+ * staging fds...) maps the staging buffers for ITS GPU (NVLink), creates the mailbox (*out_mailbox_fd: send it, dup'ed, to the
+ * owner) and from then on fma_wake runs K2 on every remote slot the owner reports as landed, while its own link pulls from the
+ * same work counter.  fma_pull_next_generation(engine) is what the owner's helpers must be told to wait for BEFORE fma_wake is
+ * called.  A pull request that never arrives costs nothing but speed: the paths that do work finish the wake. */
+FMA_API int       fma_helper_open(int device, size_t slot_bytes, int slots, uint64_t* out_handle, int* out_fd);
+FMA_API int       fma_helper_close(uint64_t handle);
+FMA_API int       fma_store_attach(int fd, uint64_t* out_handle);
+FMA_API int       fma_store_detach(uint64_t handle);
+FMA_API int       fma_helper_pull(uint64_t helper, uint64_t store, int mailbox_fd, int path_index, uint64_t generation, double timeout_s);
+FMA_API int       fma_paths_attach(fma_engine_t* e, const int* staging_fds, int n, size_t slot_bytes, int slots, int* out_mailbox_fd);
+FMA_API uint64_t  fma_pull_next_generation(fma_engine_t* e);
+FMA_API int       fma_host_store_share(fma_engine_t* e, int* out_fd);
+
 /* ---- node-level parking buffers (exportable) ------------------- */
 /* The reference launcher restricts every instance to its own GPUs (inference_server/launcher/launcher.py:171-187), and
  * whatever an instance allocates dies with it — which is when the controller cold-starts

@@ -139,6 +139,14 @@ _PROTOTYPES = {
     "fma_stats": (C.c_int, [C.c_void_p, C.POINTER(fma_stats_t)]),
     "fma_timeline": (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t]),
     "fma_paths_set": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.c_int, C.c_size_t, C.c_int]),
+    "fma_helper_open": (C.c_int, [C.c_int, C.c_size_t, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_int)]),
+    "fma_helper_close": (C.c_int, [C.c_uint64]),
+    "fma_store_attach": (C.c_int, [C.c_int, C.POINTER(C.c_uint64)]),
+    "fma_store_detach": (C.c_int, [C.c_uint64]),
+    "fma_helper_pull": (C.c_int, [C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_uint64, C.c_double]),
+    "fma_paths_attach": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.c_int, C.c_size_t, C.c_int, C.POINTER(C.c_int)]),
+    "fma_pull_next_generation": (C.c_uint64, [C.c_void_p]),
+    "fma_host_store_share": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
     "fma_parking_create": (C.c_int, [C.c_int, C.c_size_t, C.POINTER(C.c_uint64), C.POINTER(C.c_int)]),
     "fma_parking_export": (C.c_int, [C.c_uint64, C.POINTER(C.c_int), C.POINTER(C.c_uint64)]),
     "fma_parking_destroy": (C.c_int, [C.c_uint64]),

@@ -506,8 +506,15 @@ int host_store_reserve(fma_engine_t* e, size_t bytes) {
 }
 
 void paths_release(fma_engine_t* e) {
+    if (e->mbox) {   // tell a helper that may still be pulling to stop, then let go of the mailbox
+        e->mbox->abort.store(1);
+        munmap(e->mbox, sizeof(PullMailbox));
+        e->mbox = nullptr;
+    }
+    if (e->mbox_fd >= 0) close(e->mbox_fd);
+    e->mbox_fd = -1;
     for (WakePath& p : e->paths) {
-        {
+        if (!p.remote) {
             DeviceGuard g(p.device);
             if (p.copy) cudaStreamSynchronize(p.copy);
             if (p.copy) cudaStreamDestroy(p.copy);
@@ -524,6 +531,7 @@ void paths_release(fma_engine_t* e) {
             g_drv.MemUnmap(p.va, p.bytes);
             g_drv.MemAddressFree(p.va, p.bytes);
         }
+        if (p.remote && p.handle) g_drv.MemRelease(p.handle);
     }
     e->paths.clear();
     e->path_slot_bytes = 0;

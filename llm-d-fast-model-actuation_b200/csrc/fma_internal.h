@@ -38,6 +38,7 @@
 #include "../../include/fma_engine.h"
 #include "fma_kernels.h"
 #include "fma_layout.h"
+#include "fma_pull.h"
 
 namespace fma_impl {
 
@@ -194,7 +195,9 @@ constexpr int kMaxPaths = 8;
 // ITS HBM, from where K2 on the waking GPU gathers them over NVLink / NVSwitch (900 GB/s >> k x 55 GB/s) straight into the
 // destination pages.  A lone wake is then bounded by k links instead of one.
 struct WakePath {
-    int device = -1;
+    int device = -1;                         // -1 for a REMOTE path: a helper GPU this process cannot see (fma_paths_attach)
+    bool remote = false;                     // the node-level owner drives the H2D into this path's slots (fma_pull.h)
+    CUmemGenericAllocationHandle handle = 0; // remote: the imported staging allocation
     int numa_node = -1;                      // of `device` (sysfs); -1 unknown
     CUdeviceptr va = 0;                      // n_slots x slot_bytes in `device`'s HBM; access for `device` and the engine's GPU
     size_t bytes = 0;
@@ -293,6 +296,9 @@ struct fma_engine {
     std::vector<WakePath> paths;
     size_t path_slot_bytes = 0;
     int path_slots = 0;
+    PullMailbox* mbox = nullptr;             // remote paths (fma_paths_attach): shared with the node-level owner
+    int mbox_fd = -1;
+    uint64_t pull_generation = 0;
 
     fma_k_tma_cfg tma = fma_k_default_tma_cfg();
     fma_stats_t st{};

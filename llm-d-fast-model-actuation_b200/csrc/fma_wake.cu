@@ -344,7 +344,29 @@ int wake_multipath(WakePipe& pipe) {
     }
     std::vector<std::atomic<size_t>> q_next(q_node.size());
     for (auto& a : q_next) a.store(0);
+    // REMOTE paths (fma_paths_attach): helpers in the node-level owner's process pull from the SAME work counter, which therefore
+    // lives in the shared mailbox together with the chunk table of this wake (fma_pull.h); published with the generation bump.
+    PullMailbox* mb = e->mbox;
+    if (mb) {
+        if (chunks.size() > kPullMaxChunks) PIPE_CHECK(fail(FMA_EINVAL, "%zu chunks exceed the mailbox's table (use larger path slots)", chunks.size()));
+        for (size_t c = 0; c < chunks.size(); ++c) mb->chunks[c] = PullChunk{src_off[chunks[c].p0], (uint32_t)(chunks[c].np * FMA_PAGE_BYTES), 0};
+        for (uint32_t pi = 0; pi < kPullMaxPaths; ++pi) {
+            mb->helper_error[pi].store(0);
+            mb->helper_seen[pi].store(0);
+            for (uint32_t sl = 0; sl < kPullMaxSlots; ++sl) mb->slot_state[pi][sl].store(0);
+        }
+        mb->abort.store(0);
+        mb->next_chunk.store(0);
+        mb->n_chunks.store((uint32_t)chunks.size());
+        mb->generation.store(++e->pull_generation, std::memory_order_release);   // the helpers start pulling here
+    }
     auto take_chunk = [&](int my_node, size_t* out) -> bool {
+        if (mb) {
+            const uint32_t k = mb->next_chunk.fetch_add(1);
+            if (k >= chunks.size()) return false;
+            *out = k;
+            return true;
+        }
         for (int pass = 0; pass < 2; ++pass)
             for (size_t qi = 0; qi < q_node.size(); ++qi) {
                 if ((pass == 0) != (q_node[qi] == my_node)) continue;   // own node's queue first
@@ -366,11 +388,78 @@ int wake_multipath(WakePipe& pipe) {
         cudaSetDevice(e->device);
         auto failw = [&](int code, const char* what, cudaError_t ce) {
             int expect = FMA_OK;
-            if (error.compare_exchange_strong(expect, code)) snprintf(err_msg, sizeof(err_msg), "%s failed on path %zu (device %d): %s", what, pi, path.device, ce == cudaSuccess ? pipe.map_msg : cudaGetErrorString(ce));
+            if (error.compare_exchange_strong(expect, code)) snprintf(err_msg, sizeof(err_msg), "%s failed on path %zu (device %d): %s", what, pi, path.device, ce == cudaSuccess ? (code == FMA_ESTATE || code == FMA_EINTEGRITY ? what : pipe.map_msg) : cudaGetErrorString(ce));
         };
         cudaError_t ce = cudaStreamWaitEvent(path.kern, ev_tab, 0);
         if (ce != cudaSuccess) return failw(FMA_ECUDA, "cudaStreamWaitEvent(table)", ce);
         uint32_t mine = 0;
+        if (path.remote) {
+            // The owner's helper fills this path's slots in sequence and publishes "chunk c has landed" per slot; K2 gathers the slot
+            // over NVLink and the slot is handed back as soon as that K2 has completed (checked without blocking).
+            std::atomic<uint32_t>* state = mb->slot_state[pi];
+            bool busy[kMaxRing] = {};
+            const double patience = std::max(2.0, (double)env_int("FMA_PULL_TIMEOUT_S", 5));
+            double t_last = now_s();
+            for (;;) {
+                if (error.load() != FMA_OK || mb->abort.load()) {
+                    if (error.load() == FMA_OK) failw(FMA_ESTATE, "the owner's helper aborted the pull", cudaSuccess);
+                    return;
+                }
+                bool progressed = false;
+                for (int sl = 0; sl < e->path_slots; ++sl)      // hand drained slots back
+                    if (busy[sl]) {
+                        cudaError_t q = cudaEventQuery(path.ev_free[sl]);
+                        if (q == cudaSuccess) {
+                            busy[sl] = false;
+                            state[sl].store(0, std::memory_order_release);
+                            progressed = true;
+                        } else if (q != cudaErrorNotReady) {
+                            return failw(FMA_ECUDA, "K2 on a remote slot", q);
+                        } else {
+                            cudaGetLastError();
+                        }
+                    }
+                const int slot = (int)(mine % (uint32_t)e->path_slots);
+                const uint32_t st = busy[slot] ? 0 : state[slot].load(std::memory_order_acquire);
+                if (st == kPullDone) break;
+                // nobody serves this path (no pull request reached the owner, or it came too late) and the other paths have taken
+                // every chunk: nothing will ever arrive here — the wake completes over the paths that did work
+                if (st == 0 && mb->next_chunk.load() >= chunks.size() && mb->helper_seen[pi].load(std::memory_order_acquire) != e->pull_generation) {
+                    bool any_busy = false;
+                    for (int sl = 0; sl < e->path_slots; ++sl) any_busy = any_busy || busy[sl];
+                    if (!any_busy) break;
+                }
+                if (st != 0) {
+                    const size_t c = st - 1;
+                    if (c >= chunks.size()) return failw(FMA_EINTEGRITY, "the mailbox names a chunk that does not exist", cudaSuccess);
+                    const Chunk& ch = chunks[c];
+                    const int mrc = pipe.wait_mapped(ch.need);
+                    if (mrc != FMA_OK) return failw(mrc, "mapping", cudaSuccess);
+                    char* slot_ptr = reinterpret_cast<char*>(path.va) + (size_t)slot * e->path_slot_bytes;
+                    {
+                        std::lock_guard<std::mutex> lk(kt_mu);
+                        const int krc = kt.launch_on(path.kern, nullptr, (uint64_t)(uintptr_t)slot_ptr, e->d_tab + ch.p0, 0, (uint32_t)ch.np);
+                        if (krc != FMA_OK) return failw(krc, "K2 launch", cudaGetLastError());
+                    }
+                    ce = cudaEventRecord(path.ev_free[slot], path.kern);
+                    if (ce != cudaSuccess) return failw(FMA_ECUDA, "cudaEventRecord(slot drained)", ce);
+                    busy[slot] = true;
+                    if (!first_copy_seen.exchange(true)) pipe.first_copy_delay = now_s() - pipe.t_entry;
+                    ++mine;
+                    progressed = true;
+                }
+                if (progressed) {
+                    t_last = now_s();
+                } else {
+                    if (now_s() - t_last > patience) return failw(FMA_ESTATE, "no chunk from the owner's helper within the timeout (is the pull request running?)", cudaSuccess);
+                    std::this_thread::sleep_for(std::chrono::microseconds(20));
+                }
+            }
+            per_path[pi] = mine;
+            ce = cudaEventRecord(path.ev_done, path.kern);
+            if (ce != cudaSuccess) return failw(FMA_ECUDA, "cudaEventRecord(done)", ce);
+            return;
+        }
         for (;;) {
             if (error.load() != FMA_OK) return;
             size_t c = 0;
@@ -413,14 +502,17 @@ int wake_multipath(WakePipe& pipe) {
     for (size_t pi = 0; pi < e->paths.size(); ++pi) th.emplace_back(worker, pi);
     for (auto& t : th) t.join();
     if (error.load() != FMA_OK) {
-        for (WakePath& path : e->paths) cudaStreamSynchronize(path.copy);   // nothing may still be writing the staging slots
+        if (mb) mb->abort.store(1);                                          // the owner's helpers stop pulling
+        for (WakePath& path : e->paths)
+            if (path.copy) cudaStreamSynchronize(path.copy);                 // nothing may still be writing the staging slots
         return fail(error.load(), "%s", err_msg);
     }
     for (size_t pi = 0; pi < e->paths.size(); ++pi) {
         RT(cudaStreamWaitEvent(e->ks, e->paths[pi].ev_done, 0));   // the wake's device-time bracket and the final sync cover every path
         pipe.copy_ops += per_path[pi];
-        e->tl_add("path_chunks", e->paths[pi].device, pipe.t_entry, now_s(), (uint64_t)per_path[pi] * e->path_slot_bytes);
-        e->tl_add("path_local", e->paths[pi].device, pipe.t_entry, now_s(), (uint64_t)per_path_local[pi] * e->path_slot_bytes);
+        const int idx = e->paths[pi].remote ? -(int)pi : e->paths[pi].device;   // remote paths: -(path index), their GPU is not visible here
+        e->tl_add("path_chunks", idx, pipe.t_entry, now_s(), (uint64_t)per_path[pi] * e->path_slot_bytes);
+        e->tl_add("path_local", idx, pipe.t_entry, now_s(), (uint64_t)per_path_local[pi] * e->path_slot_bytes);
     }
     return FMA_OK;
 }

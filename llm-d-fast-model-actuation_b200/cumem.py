@@ -86,6 +86,11 @@ class CuMemAllocator:
         self.current_tag: str = CuMemAllocator.default_tag
         self.allocator_and_pools: dict[str, Any] = {}
         self._reserve_thread: threading.Thread | None = None
+        # MULTI-PATH wake across processes (FMA_REMOTE_PATHS=k): the node agent's helper GPUs pull for this instance; that needs the
+        # host store as a memfd the agent can map, so the switch is thrown before the store is first reserved
+        self._remote = None
+        if int(os.environ.get("FMA_REMOTE_PATHS", "0") or 0) > 0 and os.environ.get("FMA_NODE_AGENT_SOCK"):
+            os.environ["FMA_HOST_STORE_SHM"] = "1"
 
     # ---- registry view -----------------------------------------------------------------
     @property
@@ -154,6 +159,11 @@ class CuMemAllocator:
         torch.cuda.empty_cache()
 
     def wake_up(self, tags: list[str] | None = None) -> None:
+        if self._remote is not None and self.engine.is_sleeping() and _tier_from_env() == L.FMA_TIER_HOST:
+            try:    # the owner's helpers serve the wake that follows; if the request fails, the instance's own link does it all
+                self._remote.request_pull(self.engine, _instance_id(), _rank())
+            except Exception as e:      # noqa: BLE001
+                logger.warning("fma_b200: pull request to the node agent failed (%s): waking over the own link only", e)
         self.engine.wake(tags)
         st = self.engine.stats()
         if st["wake_copy_seconds"] > 0:
@@ -206,6 +216,17 @@ class CuMemAllocator:
                                                                           "mib_histogram": {str(k): v for k, v in sorted(hist.items())}}))
         if tag == "weights" and os.environ.get("FMA_ADOPT_PARKED") == "1" and os.environ.get("FMA_NODE_AGENT_SOCK"):
             self._adopt_parked_image()
+        if tag == "weights" and self._remote is None and int(os.environ.get("FMA_REMOTE_PATHS", "0") or 0) > 0 \
+                and os.environ.get("FMA_NODE_AGENT_SOCK") and _tier_from_env() == L.FMA_TIER_HOST:
+            try:
+                from .parking import ParkingClient
+
+                cli = ParkingClient()
+                n = cli.attach_remote_paths(self.engine, _instance_id(), _rank(), int(os.environ["FMA_REMOTE_PATHS"]), avoid=_own_gpu_indices())
+                self._remote = cli
+                logger.info("fma_b200: %d remote wake path(s) through the node agent's helper GPUs", n)
+            except Exception as e:      # noqa: BLE001
+                logger.warning("fma_b200: no remote wake paths (%s): host-tier wakes use the own link only", e)
         if tag == "weights" and os.environ.get("FMA_PREPIN", "1") != "0" and _tier_from_env() == L.FMA_TIER_HOST:
             self._start_reserve()
 

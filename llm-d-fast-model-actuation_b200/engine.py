@@ -176,6 +176,23 @@ class Engine:
         arr = (C.c_int * max(len(helper_devices), 1))(*helper_devices)
         check(self._lib.fma_paths_set(self._h, arr, len(helper_devices), slot_bytes, slots))
 
+    def paths_attach(self, staging_fds: Sequence[int], slot_bytes: int, slots: int) -> int:
+        """MULTI-PATH wake across processes: the node-level owner's staging buffers (``HelperStaging.fd``) become remote paths.  Returns
+        the mailbox fd (owned by the engine: ``os.dup`` it before sending it away)."""
+        arr = (C.c_int * len(staging_fds))(*staging_fds)
+        mb = C.c_int(-1)
+        check(self._lib.fma_paths_attach(self._h, arr, len(staging_fds), slot_bytes, slots, C.byref(mb)))
+        return int(mb.value)
+
+    def pull_next_generation(self) -> int:
+        return int(self._lib.fma_pull_next_generation(self._h))
+
+    def host_store_share(self) -> int:
+        """fd of the memfd behind the host store (FMA_HOST_STORE_SHM=1), for the owner's ``fma_store_attach``; the caller closes it."""
+        fd = C.c_int(-1)
+        check(self._lib.fma_host_store_share(self._h, C.byref(fd)))
+        return int(fd.value)
+
     def peer_attach(self, fd: int, nbytes: int) -> None:
         """Use a node-level owner's parking buffer (``ParkingBuffer``; fd received over SCM_RIGHTS / inherited) as this engine's
         peer-tier store.  The buffer's GPU need not be visible to this process (launcher.py:171-187 hides it)."""
@@ -347,6 +364,43 @@ class Engine:
         return rows
 
 
+class HelperStaging:
+    """Owner side of a remote wake path: a staging buffer in ``device``'s HBM plus that GPU's copy stream (fma_helper_open).  ``pull``
+    serves one wake of an instance that attached ``fd`` (blocking: run it in a thread per helper)."""
+
+    def __init__(self, device: int, slot_bytes: int = 128 << 20, slots: int = 3):
+        self._lib = L.load_library()
+        h, fd = C.c_uint64(), C.c_int(-1)
+        check(self._lib.fma_helper_open(device, slot_bytes, slots, C.byref(h), C.byref(fd)))
+        self.handle, self.fd, self.device, self.slot_bytes, self.slots = int(h.value), int(fd.value), device, slot_bytes, slots
+
+    def pull(self, store_handle: int, mailbox_fd: int, path_index: int, generation: int, timeout_s: float = 5.0) -> None:
+        check(self._lib.fma_helper_pull(self.handle, store_handle, mailbox_fd, path_index, generation, timeout_s))
+
+    def close(self) -> None:
+        if self.handle:
+            import os
+
+            self._lib.fma_helper_close(self.handle)
+            self.handle = 0
+            try:
+                os.close(self.fd)
+            except OSError:
+                pass
+
+
+def store_attach(fd: int) -> int:
+    """Owner side: map + pin an instance's memfd host store (``Engine.host_store_share``); returns the handle for ``HelperStaging.pull``."""
+    lib = L.load_library()
+    h = C.c_uint64()
+    check(lib.fma_store_attach(fd, C.byref(h)))
+    return int(h.value)
+
+
+def store_detach(handle: int) -> None:
+    check(L.load_library().fma_store_detach(handle))
+
+
 class ParkingBuffer:
     """Node-level owner's side of the peer tier: an exportable VMM allocation in ``device``'s HBM (fma_parking_create).  The
     owner process must see ``device``; instances need not.  ``fd`` / ``export_fd()`` go to instances (``Engine.peer_attach``)."""
@@ -380,4 +434,4 @@ class ParkingBuffer:
                 pass
 
 
-__all__ = ["Engine", "EngineConfig", "SegmentInfo", "FmaError", "ParkingBuffer"]
+__all__ = ["Engine", "EngineConfig", "SegmentInfo", "FmaError", "ParkingBuffer", "HelperStaging", "store_attach", "store_detach"]

@@ -16,6 +16,9 @@ Wire format (one request per connection, JSON line + optional fd in the ancillar
                                                                                 | {"ok": false, "error": "..."}
     {"op": "deposit_host", "instance": id, "rank": r} + fd (memfd host store) -> {"ok": true}     the HOST-tier image (store + descriptor in its tail,
     {"op": "lookup_host",  "instance": id, "rank": r}                        -> {"ok": true} + fd | {"ok": false}   fma_image_export) outlives the instance too
+    {"op": "helpers_open", "instance": id, "rank": r, "n": k, "avoid": [...], "slot_bytes": b, "slots": s}
+                                                                             -> {"ok": true, "devices": [...]} + k fds   MULTI-PATH wake across processes:
+    {"op": "pull", "instance": id, "rank": r, "generation": g} + [mailbox fd, store fd] -> {"ok": true}       the owner's helper GPUs pull for the instance
     {"op": "release", "instance": id[, "rank": r]}                           -> {"ok": true, "released": k}
     {"op": "stats"}                                                          -> {"ok": true, "parked_mib_per_device": {d: MiB}, "images": [...]}
 
@@ -48,6 +51,8 @@ class ParkingService:
         self._lock = threading.Lock()
         self._images: Dict[Tuple[str, int], dict] = {}   # (instance, rank) -> {"buf", "descriptor"}
         self._host_images: Dict[Tuple[str, int], int] = {}   # (instance, rank) -> fd of the memfd host store (image + descriptor)
+        self._helpers: Dict[Tuple[str, int], list] = {}      # (instance, rank) -> [HelperStaging] (remote wake paths, one per helper GPU)
+        self._stores: Dict[Tuple[int, int], int] = {}        # (st_dev, st_ino) of an instance's memfd store -> attached-store handle
         self._srv: Optional[socket.socket] = None
         self._thread: Optional[threading.Thread] = None
         self._stop = False
@@ -115,7 +120,60 @@ class ParkingService:
         with self._lock:
             return self._host_images.get((instance, int(rank)))
 
+    # ---- MULTI-PATH wake across processes (fma_pull.h): helpers owned here pull chunks for an instance that cannot see their GPUs ----
+    def helpers_open(self, instance: str, rank: int, n: int, avoid=None, slot_bytes: int = 128 << 20, slots: int = 3) -> list:
+        from .engine import HelperStaging
+
+        key = (instance, int(rank))
+        with self._lock:
+            have = self._helpers.get(key)
+        if have and len(have) == n and have[0].slot_bytes == slot_bytes and have[0].slots == slots:
+            return have
+        for h in have or []:
+            h.close()
+        cands = [d for d in range(self.n_devices) if d not in set(avoid or [])][: int(n)]
+        made = [HelperStaging(d, slot_bytes, slots) for d in cands]
+        with self._lock:
+            self._helpers[key] = made
+        return made
+
+    def pull(self, instance: str, rank: int, generation: int, mailbox_fd: int, store_fd: int, timeout_s: float = 5.0) -> int:
+        """Start one pull thread per helper of (instance, rank) for the wake `generation`; returns the number of helpers."""
+        from .engine import store_attach
+
+        st = os.fstat(store_fd)
+        skey = (st.st_dev, st.st_ino)
+        with self._lock:
+            helpers = list(self._helpers.get((instance, int(rank)), []))
+            if skey not in self._stores:
+                self._stores[skey] = store_attach(store_fd)
+            store = self._stores[skey]
+        mb = os.dup(mailbox_fd)
+        left = [len(helpers)]
+
+        def run(h, path_index):
+            try:
+                h.pull(store, mb, path_index, generation, timeout_s)
+            except Exception:      # a failed / superseded pull only costs speed: the instance's other paths finish the wake
+                pass
+            finally:
+                with self._lock:
+                    left[0] -= 1
+                    last = left[0] == 0
+                if last:
+                    os.close(mb)
+
+        for k, h in enumerate(helpers):
+            threading.Thread(target=run, args=(h, k + 1), name=f"fma-pull-{h.device}", daemon=True).start()
+        if not helpers:
+            os.close(mb)
+        return len(helpers)
+
     def release(self, instance: str, rank: Optional[int] = None) -> int:
+        with self._lock:
+            for k in [k for k in self._helpers if k[0] == instance and (rank is None or k[1] == int(rank))]:
+                for h in self._helpers.pop(k):
+                    h.close()
         with self._lock:
             keys = [k for k in self._images if k[0] == instance and (rank is None or k[1] == int(rank))]
             bufs = [self._images.pop(k)["buf"] for k in keys]
@@ -189,6 +247,15 @@ class ParkingService:
                 else:
                     fds = [hfd]
                     rep = {"ok": True, "bytes": os.fstat(hfd).st_size}
+            elif op == "helpers_open":
+                hs = self.helpers_open(req["instance"], req.get("rank", 0), int(req["n"]), req.get("avoid"), int(req.get("slot_bytes") or (128 << 20)), int(req.get("slots") or 3))
+                fds = [h.fd for h in hs]
+                rep = {"ok": True, "devices": [h.device for h in hs], "slot_bytes": hs[0].slot_bytes if hs else 0, "slots": hs[0].slots if hs else 0}
+            elif op == "pull":
+                if len(got_fds) < 2:
+                    rep = {"ok": False, "error": "pull needs the mailbox fd and the store fd"}
+                else:
+                    rep = {"ok": True, "helpers": self.pull(req["instance"], req.get("rank", 0), int(req["generation"]), got_fds[0], got_fds[1], float(req.get("timeout_s", 5.0)))}
             elif op == "release":
                 rep = {"ok": True, "released": self.release(req["instance"], req.get("rank"))}
             elif op == "stats":
@@ -234,6 +301,8 @@ class ParkingClient:
         self.sock_path = sock_path or os.environ.get("FMA_NODE_AGENT_SOCK", "")
         if not self.sock_path:
             raise RuntimeError("no node agent socket (FMA_NODE_AGENT_SOCK)")
+        self._mailbox = -1
+        self._last_fds: list = []
 
     def _rpc(self, req: dict, send_fds=()):
         with socket.socket(socket.AF_UNIX, socket.SOCK_STREAM) as s:
@@ -242,13 +311,14 @@ class ParkingClient:
                 socket.send_fds(s, [(json.dumps(req) + "\n").encode()], list(send_fds))
             else:
                 s.sendall((json.dumps(req) + "\n").encode())
-            data, fds, _, _ = socket.recv_fds(s, 1 << 22, 1)
+            data, fds, _, _ = socket.recv_fds(s, 1 << 22, 8)
             while not data.endswith(b"\n"):
                 more = s.recv(1 << 22)
                 if not more:
                     break
                 data += more
         rep = json.loads(data.decode())
+        self._last_fds = list(fds)
         return rep, (fds[0] if fds else None)
 
     def park(self, engine, instance: str, rank: int, nbytes: int, device: Optional[int] = None, avoid=None) -> dict:
@@ -299,6 +369,30 @@ class ParkingClient:
         finally:
             os.close(fd)
         return True
+
+    def attach_remote_paths(self, engine, instance: str, rank: int, n_helpers: int, avoid=None, slot_bytes: int = 128 << 20, slots: int = 3) -> int:
+        """MULTI-PATH wake for an instance that cannot see the helper GPUs: the owner opens one staging buffer per helper, the engine maps
+        them for its GPU (``Engine.paths_attach``) and keeps the mailbox; ``request_pull`` then goes before every host-tier wake."""
+        rep, _ = self._rpc({"op": "helpers_open", "instance": instance, "rank": rank, "n": n_helpers, "avoid": avoid, "slot_bytes": slot_bytes, "slots": slots})
+        fds = list(self._last_fds)
+        try:
+            if not rep.get("ok") or not fds:
+                raise RuntimeError(rep.get("error", "no helper GPU available"))
+            self._mailbox = engine.paths_attach(fds, rep["slot_bytes"], rep["slots"])
+        finally:
+            for fd in fds:
+                os.close(fd)
+        return len(fds)
+
+    def request_pull(self, engine, instance: str, rank: int, timeout_s: float = 5.0) -> int:
+        """Tell the owner's helpers to serve the NEXT wake of this engine (call right before ``Engine.wake``)."""
+        store = engine.host_store_share()
+        try:
+            rep, _ = self._rpc({"op": "pull", "instance": instance, "rank": rank, "generation": engine.pull_next_generation(), "timeout_s": timeout_s},
+                               send_fds=[self._mailbox, store])
+        finally:
+            os.close(store)
+        return int(rep.get("helpers", 0)) if rep.get("ok") else 0
 
     def release(self, instance: str, rank: Optional[int] = None) -> int:
         rep, _ = self._rpc({"op": "release", "instance": instance, "rank": rank})

@@ -6,7 +6,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
+#include <chrono>
 #include <vector>
+#include <unistd.h>
 
 #include "fma_engine.h"
 
@@ -313,6 +316,50 @@ int main() {
         OK(fma_paths_set(a, nullptr, 0, 0, 0));
         OK(fma_sleep(a, 1ull << w, FMA_TIER_HOST, FMA_FLAG_VERIFY));
         OK(fma_wake(a, 0, FMA_FLAG_VERIFY));
+    }
+
+    // MULTI-PATH wake with a REMOTE path (fma_paths_attach / fma_helper_pull): the owner's helper thread pulls chunks of the memfd
+    // host store into its staging slots and publishes them through the mailbox; the engine's remote-path worker runs K2 on them while
+    // its own link pulls from the same counter.  Three wakes: served, not served (no pull request: the own link finishes alone),
+    // and a helper that starts late.
+    {
+        setenv("FMA_HOST_STORE_SHM", "1", 1);
+        fma_engine_t* r = nullptr;
+        OK(fma_engine_create(0, nullptr, &r));
+        const int rw = fma_tag_intern(r, "weights");
+        void* pr[4];
+        const size_t rs[4] = {9 * P, 4 * P, 7 * P, 2 * P};
+        for (int i = 0; i < 4; ++i) { OK(fma_alloc(r, rs[i], rw, &pr[i])); OK(fma_fill_segment(r, i, 900 + i, 0)); }
+        auto before = digests(r);
+        uint64_t helper = 0, store = 0;
+        int staging_fd = -1, mailbox_fd = -1, store_fd = -1;
+        OK(fma_helper_open(1, 2 * P, 2, &helper, &staging_fd));
+        OK(fma_paths_attach(r, &staging_fd, 1, 2 * P, 2, &mailbox_fd));
+        OK(fma_host_reserve(r, 22 * P));
+        OK(fma_host_store_share(r, &store_fd));
+        OK(fma_store_attach(store_fd, &store));
+        for (int round = 0; round < 3; ++round) {
+            OK(fma_sleep(r, 1ull << rw, FMA_TIER_HOST, FMA_FLAG_VERIFY));
+            const uint64_t gen = fma_pull_next_generation(r);
+            std::thread owner;
+            if (round != 1)
+                owner = std::thread([&, gen, round] {
+                    if (round == 2) std::this_thread::sleep_for(std::chrono::milliseconds(3));
+                    int prc = fma_helper_pull(helper, store, mailbox_fd, 1, gen, 5.0);
+                    assert(prc == 0 || round == 2);   // a helper that comes too late may find the wake already finished
+                    (void)prc;
+                });
+            OK(fma_wake(r, 0, FMA_FLAG_VERIFY));
+            if (owner.joinable()) owner.join();
+            auto after = digests(r);
+            for (size_t i = 0; i < before.size(); ++i) assert(after[i] == before[i]);
+        }
+        OK(fma_store_detach(store));
+        OK(fma_helper_close(helper));
+        close(staging_fd);
+        close(store_fd);
+        OK(fma_engine_destroy(r));
+        unsetenv("FMA_HOST_STORE_SHM");
     }
 
     OK(fma_engine_destroy(a));

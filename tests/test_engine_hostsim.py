@@ -21,7 +21,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SIM = os.path.join(ROOT, "tests", "cpp", "hostsim")
 CSRC = os.path.join(ROOT, "llm-d-fast-model-actuation_b200", "csrc")
 INC = ["-I/usr/local/cuda/include", "-I" + CSRC, "-I" + os.path.join(ROOT, "include")]
-HOST_TUS = ["fma_engine.cu", "fma_sleep.cu", "fma_wake.cu", "fma_load.cu", "fma_image.cu", "fma_gate.cu"]   # the host engine (no kernels): csrc/Makefile HOST_SRCS
+HOST_TUS = ["fma_engine.cu", "fma_sleep.cu", "fma_wake.cu", "fma_load.cu", "fma_image.cu", "fma_gate.cu", "fma_pull.cu"]   # the host engine (no kernels): csrc/Makefile HOST_SRCS
 SRCS = ["-x", "c++", *[os.path.join(CSRC, f) for f in HOST_TUS], os.path.join(SIM, "hostsim_cuda.cpp"), os.path.join(SIM, "hostsim_kernels.cpp")]
 
 
@@ -252,6 +252,26 @@ if phase == "park":
     eng.sleep(["weights"], tier=L.FMA_TIER_PEER, flags=L.FMA_FLAG_VERIFY)
     cli.deposit(eng, iid, 0)
     os._exit(0)                                        # dies asleep
+elif phase == "remote_paths":                          # MULTI-PATH wake across processes through the owner's helpers
+    first = 0
+    for i, s in enumerate(table):
+        if s.tag == "weights":
+            eng.fill(i, 79, first); first += s.bytes // 8
+    before = eng.digest_all(["weights"])
+    assert cli.attach_remote_paths(eng, iid, 0, n_helpers=2, avoid=[0], slot_bytes=4 << 20, slots=3) == 2
+    eng.host_reserve(Wb)
+    remote = []
+    for rnd in range(3):
+        eng.sleep(["weights"], flags=L.FMA_FLAG_VERIFY)
+        if rnd != 1:
+            assert cli.request_pull(eng, iid, 0, timeout_s=20.0) == 2
+        eng.wake(None, flags=L.FMA_FLAG_VERIFY)
+        assert eng.digest_all(["weights"]) == before
+        remote.append(sum(r["bytes"] for r in eng.timeline() if r["kind"] == "path_chunks" and r["idx"] < 0))
+    assert remote[0] > 0 and remote[1] == 0 and remote[2] > 0, remote
+    print(json.dumps(remote), flush=True)
+    cli.release(iid)
+    os._exit(0)
 elif phase == "park_host":                             # HOST tier: the memfd behind the store goes to the owner
     first = 0
     for i, s in enumerate(table):
@@ -307,6 +327,9 @@ d = subprocess.run([sys.executable, script, "adopt_host", "Ihosti"], capture_out
 assert d.returncode == 0, d.stdout + d.stderr
 assert json.loads(c.stdout.strip().splitlines()[0]) == json.loads(d.stdout.strip().splitlines()[-1])
 assert ParkingClient().release("Ihosti") == 1 and svc.stats()["host_images"] == []
+# MULTI-PATH wake across processes: the owner's helper GPUs pull for an instance that cannot see them
+e = subprocess.run([sys.executable, script, "remote_paths", "Iremotei"], capture_output=True, text=True, timeout=300, env=dict(env_h, FMA_PULL_TIMEOUT_S="20"))
+assert e.returncode == 0, e.stdout + e.stderr
 svc.close()
 print("parking service ok")
 """ % ROOT

@@ -610,6 +610,135 @@ def _multipath_body(engine, oracle, n, slot_mib, slots, numa_map):
         engine.set_paths([99])
 
 
+# ---- MULTI-PATH wake ACROSS PROCESSES: the owner's helpers pull, the restricted instance gathers (needs >= 2 GPUs) -----------------
+_REMOTE_PATH_INSTANCE = r"""
+import os, sys, json, hashlib, socket
+sys.path.insert(0, {root!r})
+import fma_b200
+from fma_b200 import workloads as W, _lib as L
+sock = socket.socket(fileno=int(sys.argv[1]))            # a socketpair to the owner (the node agent's unix socket in production)
+slot_bytes, slots, mode = int(sys.argv[2]), int(sys.argv[3]), sys.argv[4]
+def rpc(msg, fds=()):
+    socket.send_fds(sock, [(json.dumps(msg) + "\n").encode()], list(fds))
+    data, rfds, _, _ = socket.recv_fds(sock, 1 << 16, 8)
+    return json.loads(data.decode()), list(rfds)
+eng = fma_b200.Engine(0)                                  # the only GPU this process sees
+table = W.allocation_table("tiny-llama-test", kv_cache_bytes=32 << 20, kv_tensors=2)
+ptrs = [eng.alloc(s.bytes, s.tag) for s in table]
+first = 0
+for i, s in enumerate(table):
+    if s.tag == "weights":
+        eng.fill(i, 1234, first); first += s.bytes // 8
+sha = lambda: [hashlib.sha256(eng.read(i, s.bytes)).hexdigest() for i, s in enumerate(table) if s.tag == "weights"]
+before = sha()
+rep, staging = rpc({{"op": "helpers"}})                   # the owner's staging buffers, one fd per helper GPU
+mailbox = eng.paths_attach(staging, slot_bytes, slots)
+for fd in staging: os.close(fd)
+eng.host_reserve(sum(s.bytes for s in table if s.tag == "weights"))
+out = dict(visible=os.environ.get("CUDA_VISIBLE_DEVICES"), rounds=[])
+for rnd in range(3):
+    eng.sleep(["weights"], flags=L.FMA_FLAG_VERIFY)
+    if mode == "served" or (mode == "mixed" and rnd != 1):   # round 1 of "mixed": no pull request reaches the owner
+        store = eng.host_store_share()
+        rpc({{"op": "pull", "generation": eng.pull_next_generation()}}, [os.dup(mailbox), store])
+        os.close(store)
+    eng.wake(None, flags=L.FMA_FLAG_VERIFY)
+    assert [s.va for s in eng.segments()] == ptrs
+    chunks = {{r["idx"]: r["bytes"] for r in eng.timeline() if r["kind"] == "path_chunks"}}
+    out["rounds"].append(dict(same=sha() == before, chunks=chunks))
+out["before"] = before
+rpc({{"op": "bye"}})
+print(json.dumps(out), flush=True)
+eng.close()
+"""
+
+
+@pytest.mark.parametrize("mode", ["served", "mixed"])
+def test_multipath_wake_across_processes_with_a_restricted_instance(built, oracle, tmp_path, mode):
+    """fma_paths_attach / fma_helper_pull: the OWNER (this process, sees every GPU) holds the helpers' staging buffers and, per wake,
+    lets each helper GPU pull chunks of the instance's memfd host store over its own link; the INSTANCE (CUDA_VISIBLE_DEVICES=0)
+    maps the staging buffers for its GPU and runs K2 on every slot the owner reports as landed, while its own link pulls from the
+    same work counter.  Weights == oracle after every wake; chunks really arrived over remote paths; a wake whose pull request
+    never reaches the owner ("mixed", round 1) still completes — over the instance's own link alone."""
+    import hashlib
+    import socket
+    import subprocess
+    import sys
+    import threading
+
+    import fma_b200
+    from fma_b200 import engine as E
+
+    n = _n_gpus()
+    if n < 2:
+        pytest.skip("multi-path wake needs a second GPU")
+    table = _tiny_table()
+    ref, first = [], 0
+    for s in table:
+        if s.tag == "weights":
+            ref.append(hashlib.sha256(oracle.fill(s.bytes, 1234, first).tobytes()).hexdigest())
+            first += s.bytes // 8
+    slot_bytes, slots = 4 << 20, 3
+    helpers = [E.HelperStaging(d, slot_bytes, slots) for d in range(1, min(n, 3))]
+    a, b = socket.socketpair(socket.AF_UNIX, socket.SOCK_STREAM)
+    script = tmp_path / "remote_instance.py"
+    script.write_text(_REMOTE_PATH_INSTANCE.format(root=os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="0", FMA_HOST_STORE_SHM="1", FMA_PULL_TIMEOUT_S="20")
+    proc = subprocess.Popen([sys.executable, str(script), str(b.fileno()), str(slot_bytes), str(slots), mode], pass_fds=[b.fileno()],
+                            stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env)
+    b.close()
+    pulls, stores, errors = [], {}, []
+
+    def serve():          # the owner's side of the protocol (parking.py speaks it over the node agent's socket)
+        try:
+            while True:
+                data, fds, _, _ = socket.recv_fds(a, 1 << 16, 8)
+                if not data:
+                    return
+                msg = json.loads(data.decode())
+                if msg["op"] == "helpers":
+                    socket.send_fds(a, [b'{"ok": true}\n'], [h.fd for h in helpers])
+                elif msg["op"] == "pull":
+                    mailbox_fd, store_fd = fds
+                    st = os.fstat(store_fd)
+                    key = (st.st_dev, st.st_ino)
+                    if key not in stores:
+                        stores[key] = E.store_attach(store_fd)
+                    for k, h in enumerate(helpers):
+                        t = threading.Thread(target=lambda h=h, k=k: h.pull(stores[key], mailbox_fd, k + 1, msg["generation"], 20.0))
+                        t.start(); pulls.append(t)
+                    a.sendall(b'{"ok": true}\n')
+                    os.close(store_fd)                       # the mailbox fd stays open until the pull threads are done
+                else:
+                    a.sendall(b'{"ok": true}\n')
+                    return
+        except Exception as e:      # noqa: BLE001
+            errors.append(e)
+
+    t = threading.Thread(target=serve)
+    t.start()
+    out, err = proc.communicate(timeout=600)
+    t.join(timeout=60)
+    for p in pulls:
+        p.join(timeout=60)
+    for h in helpers:
+        h.close()
+    for sh in stores.values():
+        E.store_detach(sh)
+    assert proc.returncode == 0 and not errors, (out + err)[-3000:] + repr(errors)
+    res = json.loads(out.strip().splitlines()[-1])
+    assert res["visible"] == "0" and res["before"] == ref
+    assert all(r["same"] for r in res["rounds"]) and len(res["rounds"]) == 3
+    total = sum(s.bytes for s in table if s.tag == "weights")
+    for k, r in enumerate(res["rounds"]):
+        assert sum(r["chunks"].values()) >= total
+        remote = sum(v for idx, v in r["chunks"].items() if int(idx) < 0)
+        if mode == "mixed" and k == 1:
+            assert remote == 0                                   # nobody served the remote paths: the own link did everything
+        else:
+            assert remote > 0, r                                 # chunks really came over the owner's helpers
+
+
 # ---- the peer tier under the real launcher: the parking buffer belongs to a node-level owner, the instance sees only its own GPU
 _PARKED_INSTANCE = r"""
 import os, sys, json, hashlib
