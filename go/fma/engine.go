@@ -246,3 +246,55 @@ func (e *Engine) Timeline() (string, error) {
 	}
 	return string(buf[:n]), nil
 }
+
+// ---- multi-path wake across processes (the instance cannot see the helper GPUs; the node-level owner drives them) ----
+
+// HelperOpen (owner side): a staging buffer in one helper GPU's HBM; fd goes to the instance (PathsAttach).
+func HelperOpen(device int, slotBytes uint64, slots int) (handle uint64, fd int, err error) {
+	var h C.uint64_t
+	var f C.int
+	if rc := C.fma_helper_open(C.int(device), C.size_t(slotBytes), C.int(slots), &h, &f); rc != 0 {
+		return 0, -1, lastErr(rc)
+	}
+	return uint64(h), int(f), nil
+}
+
+// StoreAttach (owner side): map + pin the instance's memfd host store (Engine.HostStoreShare).
+func StoreAttach(fd int) (uint64, error) {
+	var h C.uint64_t
+	if rc := C.fma_store_attach(C.int(fd), &h); rc != 0 {
+		return 0, lastErr(rc)
+	}
+	return uint64(h), nil
+}
+
+// HelperPull (owner side, one goroutine per helper and wake): pull chunks over that helper's link until the path is done.
+func HelperPull(helper, store uint64, mailboxFd, pathIndex int, generation uint64, timeoutS float64) error {
+	if rc := C.fma_helper_pull(C.uint64_t(helper), C.uint64_t(store), C.int(mailboxFd), C.int(pathIndex), C.uint64_t(generation), C.double(timeoutS)); rc != 0 {
+		return lastErr(rc)
+	}
+	return nil
+}
+
+// PathsAttach (instance side): the owner's staging buffers become remote wake paths; returns the mailbox fd to send to the owner.
+func (e *Engine) PathsAttach(stagingFds []int, slotBytes uint64, slots int) (int, error) {
+	c := make([]C.int, len(stagingFds))
+	for i, f := range stagingFds {
+		c[i] = C.int(f)
+	}
+	var mb C.int
+	if rc := C.fma_paths_attach(e.h, &c[0], C.int(len(c)), C.size_t(slotBytes), C.int(slots), &mb); rc != 0 {
+		return -1, lastErr(rc)
+	}
+	return int(mb), nil
+}
+
+func (e *Engine) PullNextGeneration() uint64 { return uint64(C.fma_pull_next_generation(e.h)) }
+
+func (e *Engine) HostStoreShare() (int, error) {
+	var fd C.int
+	if rc := C.fma_host_store_share(e.h, &fd); rc != 0 {
+		return -1, lastErr(rc)
+	}
+	return int(fd), nil
+}
