@@ -1630,7 +1630,10 @@ int fma_stats(fma_engine_t* e, fma_stats_t* out) {
         for (const auto& kv : e->units) mapped += kv.second.bytes;
         out->hbm_mapped_bytes = mapped;
     }
-    out->hbm_aux_bytes = (e->ring_attached ? 0 : (uint64_t)e->n_ring * e->ring_slot_bytes) + 2 * e->d_tab_cap * sizeof(uint64_t) +
+    uint64_t own_staging = 0;   // multi-path staging slots that live in THIS GPU's HBM (helpers' slots are their GPUs' business)
+    for (const WakePath& wp : e->paths)
+        if (!wp.remote && wp.device == e->device) own_staging += wp.bytes;
+    out->hbm_aux_bytes = own_staging + (e->ring_attached ? 0 : (uint64_t)e->n_ring * e->ring_slot_bytes) + 2 * e->d_tab_cap * sizeof(uint64_t) +
                          e->desc_cap * (sizeof(fma_k_page_desc) + sizeof(uint64_t)) +
                          e->pdesc_cap * (sizeof(fma_k_pack_desc) + sizeof(uint32_t));
     out->parked_bytes = e->park.cap;
