@@ -38,14 +38,23 @@ def hostsim_lib(tmp_path_factory):
     return out
 
 
+def _xdist():
+    """The ~100 simulated GPU tests are independent (an engine each): spread them over a few workers when pytest-xdist is there."""
+    try:
+        import xdist  # noqa: F401
+    except ImportError:
+        return []
+    return ["-n", str(max(1, min(4, (os.cpu_count() or 2) // 2)))]
+
+
 def test_parity_suite_against_the_host_simulated_engine(hostsim_lib, oracle):
     env = dict(os.environ, FMA_B200_LIB=hostsim_lib, FMA_HOSTSIM="1", HOSTSIM_DEVICES="2")
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), os.path.join(ROOT, "tests", "test_gpu_http.py"), "-x", "-q", "-m", "gpu",
-                        "-k", "not shim and not torch_pool and not full_size", "-p", "no:cacheprovider"],
+                        "-k", "not shim and not torch_pool and not full_size", "-p", "no:cacheprovider", *_xdist()],
                        env=env, cwd=ROOT, capture_output=True, text=True, timeout=900)
     tail = (r.stdout + r.stderr)[-3000:]
     assert r.returncode == 0, tail
-    assert " passed" in r.stdout and "failed" not in r.stdout, tail
+    assert " passed" in r.stdout and "failed" not in r.stdout and " error" not in r.stdout.lower(), tail
 
 
 def test_engine_scenario_under_sanitizers(tmp_path):
