@@ -1302,10 +1302,28 @@ def test_random_alloc_free_sleep_wake_sequences(built, oracle, seed):
     asleep, re-allocations into freed holes, sleeps in every mode on the host / local tier with random ring shapes,
     partial and retried wakes.  Invariants after every step: offloaded segments keep their bytes and their addresses,
     is_sleeping matches the model, accounting adds up."""
+    _random_history(oracle, 1000 + seed, toggle_paths=False)
+
+
+@pytest.mark.parametrize("seed", list(range(1, int(os.environ.get("FMA_TEST_SEEDS", "13")))))
+def test_random_histories_with_the_paths_switched_on_and_off(built, oracle, seed):
+    """The same histories with MULTI-PATH copies (fma_paths_set) switched on, re-shaped and off again between cycles: the
+    staged sleeps and wakes then spread their chunks over the helper GPUs' links (small slots, so every path moves some),
+    the other modes and tiers keep their single-link pipelines, and an image written by one kind of sleep is woken by the
+    other kind of wake.  Needs >= 2 GPUs."""
+    if _n_gpus() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    _random_history(oracle, 5000 + seed, toggle_paths=True)
+
+
+def _random_history(oracle, seed, toggle_paths):
     import fma_b200
 
     L = _L()
-    rng = np.random.default_rng(1000 + seed)
+    rng = np.random.default_rng(seed)
+    helpers_all = list(range(1, min(_n_gpus(), 4))) if toggle_paths else []
+    paths_on = False
+    multi = {"sleeps": 0, "wakes": 0}                                   # cycles that really went over several paths
     tags = ["weights", "kv_cache", "adapters"]
     with fma_b200.Engine(0) as eng:
         live = {}                                                      # ptr -> (tag, bytes or None if contents undefined)
@@ -1342,6 +1360,16 @@ def test_random_alloc_free_sleep_wake_sequences(built, oracle, seed):
                 eng.write(eng.find(ptr), data.tobytes()); live[ptr] = (tag, data)
             mode = [L.FMA_MODE_DIRECT, L.FMA_MODE_STAGED, L.FMA_MODE_KERNEL][int(rng.integers(0, 3))]
             tier = L.FMA_TIER_HOST if rng.random() < 0.7 else L.FMA_TIER_LOCAL
+            if toggle_paths:
+                if rng.random() < 0.6:                                  # staged on the host tier: the combination the paths serve
+                    mode, tier = L.FMA_MODE_STAGED, L.FMA_TIER_HOST
+                r = rng.random()
+                if r < 0.45:                                            # (re-)shape the paths: which helpers, slot size, slots
+                    k = int(rng.integers(1, len(helpers_all) + 1))
+                    eng.set_paths(helpers_all[:k], slot_bytes=int(rng.choice([2, 4, 8])) << 20, slots=int(rng.integers(1, 4)))
+                    paths_on = True
+                elif r < 0.65:
+                    eng.set_paths([]); paths_on = False
             eng.set_option("mode", mode)
             eng.set_option("chunk_bytes", int(rng.choice([2, 4, 6, 32])) << 20)
             eng.set_option("ring_slots", int(rng.integers(2, 5)))
@@ -1349,6 +1377,13 @@ def test_random_alloc_free_sleep_wake_sequences(built, oracle, seed):
             offload = [t for t in ("weights", "adapters") if rng.random() < 0.8]
             eng.sleep(offload, tier=tier, flags=L.FMA_FLAG_VERIFY if rng.random() < 0.5 else 0)
             st = eng.stats()
+            if toggle_paths and paths_on and rng.random() < 0.3:        # the paths change while the image sleeps in the store
+                if rng.random() < 0.5:
+                    eng.set_paths([]); paths_on = False
+                else:
+                    eng.set_paths(helpers_all[:1], slot_bytes=2 << 20, slots=2)
+            if toggle_paths:
+                multi["sleeps"] += any(r["kind"] == "path_chunks" for r in eng.timeline())
             assert st["sleep_bytes_offloaded"] == sum(d.size if d is not None else 0 for t, d in live.values() if t in offload) or \
                 st["sleep_bytes_offloaded"] == sum(eng.segment(eng.find(p)).bytes for p, (t, _) in live.items() if t in offload)
             assert eng.is_sleeping() and st["hbm_mapped_bytes"] == 0
@@ -1363,8 +1398,11 @@ def test_random_alloc_free_sleep_wake_sequences(built, oracle, seed):
                 assert eng.is_sleeping() or len(live) == 1
             order = list(tags); rng.shuffle(order)
             for t in order[:int(rng.integers(0, 3))]:
-                eng.wake([t]); eng.wake([t])
+                eng.wake([t])
+                multi["wakes"] += toggle_paths and any(r["kind"] == "path_chunks" for r in eng.timeline())
+                eng.wake([t])
             eng.wake(None, flags=L.FMA_FLAG_VERIFY)
+            multi["wakes"] += toggle_paths and any(r["kind"] == "path_chunks" for r in eng.timeline())
             assert not eng.is_sleeping()
             check_contents()
             for ptr, (tag, data) in list(live.items()):                 # give discarded segments defined contents again
@@ -1373,6 +1411,7 @@ def test_random_alloc_free_sleep_wake_sequences(built, oracle, seed):
                     d = rng.integers(0, 256, eng.segment(i).bytes, dtype=np.uint8)
                     eng.write(i, d.tobytes()); live[ptr] = (tag, d)
             assert eng.current_usage() == sum(eng.segment(eng.find(p)).bytes for p in live)
+        print(f"history {seed}: multi-path sleeps {multi['sleeps']}, wakes {multi['wakes']}")
 
 
 @pytest.mark.parametrize("pack", [0, 1])
