@@ -150,9 +150,11 @@ int fma_helper_pull(uint64_t helper, uint64_t store, int mailbox_fd, int path_in
     PullMailbox* mb = map_mailbox(mailbox_fd);
     if (!mb) return fail(FMA_ENOMEM, "cannot map the mailbox");
     int rc = FMA_OK;
-    bool superseded = false;   // the instance has moved on to another wake: leave quietly, never touch ITS mailbox state
+    // The mailbox belongs to the instance's wake of `generation`.  Until this helper has CLAIMED its path in that wake, and again
+    // as soon as the instance has moved on, it leaves quietly: it never writes a word of a wake it does not serve.
+    bool serving = false;
     auto done = [&](int code) {
-        if (code != FMA_OK && !superseded) {
+        if (code != FMA_OK && serving && mb->generation.load(std::memory_order_acquire) == generation) {
             mb->helper_error[path_index].store((uint32_t)(-code));
             mb->abort.store(1);
         }
@@ -163,13 +165,36 @@ int fma_helper_pull(uint64_t helper, uint64_t store, int mailbox_fd, int path_in
     if ((int)mb->n_slots != h.slots || mb->slot_bytes != h.slot_bytes) return done(fail(FMA_EINVAL, "mailbox and staging disagree on the slot shape"));
     DeviceGuard guard(h.device);
     double t_last = now_s();
-    while (mb->generation.load(std::memory_order_acquire) != generation) {   // the instance is still planning its wake
-        if (mb->abort.load() || now_s() - t_last > timeout_s) return done(fail(FMA_ESTATE, "the wake of generation %llu never started", (unsigned long long)generation));
+    for (;;) {   // the instance is still planning its wake
+        const uint64_t g = mb->generation.load(std::memory_order_acquire);
+        if (g == generation) break;
+        if (g > generation) return done(fail(FMA_ESTATE, "generation %llu is over (the mailbox is at %llu)", (unsigned long long)generation, (unsigned long long)g));
+        if (now_s() - t_last > timeout_s) return done(fail(FMA_ESTATE, "the wake of generation %llu never started", (unsigned long long)generation));
         nap();
     }
     const uint32_t n = mb->n_chunks.load();
     std::atomic<uint32_t>* state = mb->slot_state[path_index];
-    mb->helper_seen[path_index].store(generation, std::memory_order_release);   // "this path is being served": the instance waits for its kPullDone
+    {   // "this path is being served": the instance waits for its done word.  One helper per path and wake: a repeated request loses here.
+        uint64_t nobody = 0;
+        if (!mb->helper_seen[path_index].compare_exchange_strong(nobody, generation, std::memory_order_acq_rel))
+            return done(fail(FMA_ESTATE, "path %d of generation %llu is already served", path_index, (unsigned long long)generation));
+    }
+    serving = true;
+    bool superseded = false;   // the instance has moved on to another wake
+    // A word goes 0 -> value only.  The slot was free when its copy was issued; if a word of ANOTHER generation sits there now (a helper
+    // left over from an aborted wake got in between), the instance clears it when it looks at the slot: wait for that.  1 = published,
+    // 0 = the instance has moved on, < 0 = error.
+    auto publish = [&](int slot, uint32_t value) -> int {
+        const double t0 = now_s();
+        for (;;) {
+            uint32_t seen = 0;
+            if (state[slot].compare_exchange_strong(seen, pull_word(generation, value), std::memory_order_acq_rel)) return 1;
+            if (mb->generation.load(std::memory_order_acquire) != generation) return 0;
+            if (pull_word_is_of(seen, generation)) return fail(FMA_ESTATE, "slot %d of path %d holds a word this helper did not write", slot, path_index);
+            if (mb->abort.load() || now_s() - t0 > timeout_s) return fail(FMA_ESTATE, "slot %d of path %d never became free", slot, path_index);
+            nap();
+        }
+    };
     struct Fly { int slot; uint32_t chunk; };
     std::deque<Fly> fly;
     uint32_t seq = 0;
@@ -185,7 +210,10 @@ int fma_helper_pull(uint64_t helper, uint64_t store, int mailbox_fd, int path_in
             cudaError_t q = must ? cudaEventSynchronize(h.ev[fly.front().slot]) : cudaEventQuery(h.ev[fly.front().slot]);
             if (q == cudaErrorNotReady) { cudaGetLastError(); break; }
             if (q != cudaSuccess) { rc = fail(FMA_ECUDA, "H2D on helper device %d failed: %s", h.device, cudaGetErrorString(q)); break; }
-            state[fly.front().slot].store(fly.front().chunk + 1, std::memory_order_release);
+            const int pub = mb->generation.load(std::memory_order_acquire) != generation ? 0 : publish(fly.front().slot, fly.front().chunk + 1);
+            if (pub == 0) { superseded = true; rc = fail(FMA_ESTATE, "generation %llu is over", (unsigned long long)generation); }
+            if (pub < 0) rc = pub;
+            if (rc != FMA_OK) break;
             fly.pop_front();
             progressed = true;
         }
@@ -225,9 +253,13 @@ int fma_helper_pull(uint64_t helper, uint64_t store, int mailbox_fd, int path_in
             if (mb->abort.load() || now_s() - t_last > timeout_s) { rc = fail(FMA_ESTATE, "the instance never drained the last slot of path %d", path_index); break; }
             nap();
         }
-        if (rc == FMA_OK && mb->generation.load(std::memory_order_acquire) == generation) state[slot].store(kPullDone, std::memory_order_release);
+        if (rc == FMA_OK && mb->generation.load(std::memory_order_acquire) == generation) {
+            const int pub = publish(slot, kPullDoneValue);
+            if (pub < 0) rc = pub;
+        }
     }
     cudaStreamSynchronize(h.copy);
+    if (superseded) serving = false;
     return done(rc);
 }
 

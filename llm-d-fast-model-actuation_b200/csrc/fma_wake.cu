@@ -420,8 +420,13 @@ int wake_multipath(WakePipe& pipe) {
                         }
                     }
                 const int slot = (int)(mine % (uint32_t)e->path_slots);
-                const uint32_t st = busy[slot] ? 0 : state[slot].load(std::memory_order_acquire);
-                if (st == kPullDone) break;
+                uint32_t st = busy[slot] ? 0 : state[slot].load(std::memory_order_acquire);
+                if (st != 0 && !pull_word_is_of(st, e->pull_generation)) {   // left behind by a helper of an earlier, aborted wake: not ours
+                    state[slot].compare_exchange_strong(st, 0, std::memory_order_acq_rel);
+                    st = 0;
+                }
+                st = pull_word_value(st);
+                if (st == kPullDoneValue) break;
                 // nobody serves this path (no pull request reached the owner, or it came too late) and the other paths have taken
                 // every chunk: nothing will ever arrive here — the wake completes over the paths that did work
                 if (st == 0 && mb->next_chunk.load() >= chunks.size() && mb->helper_seen[pi].load(std::memory_order_acquire) != e->pull_generation) {

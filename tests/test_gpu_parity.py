@@ -636,16 +636,32 @@ mailbox = eng.paths_attach(staging, slot_bytes, slots)
 for fd in staging: os.close(fd)
 eng.host_reserve(sum(s.bytes for s in table if s.tag == "weights"))
 out = dict(visible=os.environ.get("CUDA_VISIBLE_DEVICES"), rounds=[])
+def pull(generation):
+    store = eng.host_store_share()
+    rpc({{"op": "pull", "generation": generation}}, [os.dup(mailbox), store])
+    os.close(store)
+import mmap, struct
+box = mmap.mmap(mailbox, 4096, mmap.MAP_SHARED, mmap.PROT_READ)
 for rnd in range(3):
     eng.sleep(["weights"], flags=L.FMA_FLAG_VERIFY)
     if mode == "served" or (mode == "mixed" and rnd != 1):   # round 1 of "mixed": no pull request reaches the owner
-        store = eng.host_store_share()
-        rpc({{"op": "pull", "generation": eng.pull_next_generation()}}, [os.dup(mailbox), store])
-        os.close(store)
+        pull(eng.pull_next_generation())
+    if mode == "repeated" and rnd == 0:                      # the request arrives twice: two helpers want the same path of the same wake
+        pull(eng.pull_next_generation()); pull(eng.pull_next_generation())
+    if mode == "repeated" and rnd == 1:                      # a request whose wake then moves nothing over the paths (vLLM's wake_up(tags=["kv_cache"]),
+        pull(eng.pull_next_generation())                     # here: a DIRECT wake) leaves helpers waiting; the next cycle asks again for the same generation
+        eng.set_option("mode", L.FMA_MODE_DIRECT)
+        eng.wake(None, flags=L.FMA_FLAG_VERIFY)
+        assert sha() == before
+        eng.set_option("mode", L.FMA_MODE_STAGED)
+        eng.sleep(["weights"], flags=L.FMA_FLAG_VERIFY)
+        pull(eng.pull_next_generation())
+    if mode == "repeated" and rnd == 2:                      # requests for wakes that are over (one long ago, one the latest), then the right one
+        pull(eng.pull_next_generation() - 2); pull(eng.pull_next_generation() - 1); pull(eng.pull_next_generation())
     eng.wake(None, flags=L.FMA_FLAG_VERIFY)
     assert [s.va for s in eng.segments()] == ptrs
     chunks = {{r["idx"]: r["bytes"] for r in eng.timeline() if r["kind"] == "path_chunks"}}
-    out["rounds"].append(dict(same=sha() == before, chunks=chunks))
+    out["rounds"].append(dict(same=sha() == before, chunks=chunks, abort=struct.unpack_from("<I", box, 24)[0]))
 out["before"] = before
 rpc({{"op": "bye"}})
 print(json.dumps(out), flush=True)
@@ -653,7 +669,7 @@ eng.close()
 """
 
 
-@pytest.mark.parametrize("mode", ["served", "mixed"])
+@pytest.mark.parametrize("mode", ["served", "mixed", "repeated"])
 def test_multipath_wake_across_processes_with_a_restricted_instance(built, oracle, tmp_path, mode):
     """fma_paths_attach / fma_helper_pull: the OWNER (this process, sees every GPU) holds the helpers' staging buffers and, per wake,
     lets each helper GPU pull chunks of the instance's memfd host store over its own link; the INSTANCE (CUDA_VISIBLE_DEVICES=0)
@@ -687,7 +703,7 @@ def test_multipath_wake_across_processes_with_a_restricted_instance(built, oracl
     proc = subprocess.Popen([sys.executable, str(script), str(b.fileno()), str(slot_bytes), str(slots), mode], pass_fds=[b.fileno()],
                             stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env)
     b.close()
-    pulls, stores, errors = [], {}, []
+    pulls, stores, errors, outcomes = [], {}, [], []
 
     def serve():          # the owner's side of the protocol (parking.py speaks it over the node agent's socket)
         try:
@@ -704,8 +720,14 @@ def test_multipath_wake_across_processes_with_a_restricted_instance(built, oracl
                     key = (st.st_dev, st.st_ino)
                     if key not in stores:
                         stores[key] = E.store_attach(store_fd)
+                    def one(h, k, generation, store=stores[key], mailbox_fd=mailbox_fd):
+                        try:
+                            h.pull(store, mailbox_fd, k + 1, generation, 20.0)
+                            outcomes.append("ok")
+                        except Exception as e:      # noqa: BLE001 -- a helper that is not needed says why and leaves
+                            outcomes.append(str(e))
                     for k, h in enumerate(helpers):
-                        t = threading.Thread(target=lambda h=h, k=k: h.pull(stores[key], mailbox_fd, k + 1, msg["generation"], 20.0))
+                        t = threading.Thread(target=one, args=(h, k, msg["generation"]))
                         t.start(); pulls.append(t)
                     a.sendall(b'{"ok": true}\n')
                     os.close(store_fd)                       # the mailbox fd stays open until the pull threads are done
@@ -733,10 +755,15 @@ def test_multipath_wake_across_processes_with_a_restricted_instance(built, oracl
     for k, r in enumerate(res["rounds"]):
         assert sum(r["chunks"].values()) >= total
         remote = sum(v for idx, v in r["chunks"].items() if int(idx) < 0)
+        assert r["abort"] == 0                                   # no helper, needed or not, ever flagged the instance's wake
         if mode == "mixed" and k == 1:
             assert remote == 0                                   # nobody served the remote paths: the own link did everything
         else:
             assert remote > 0, r                                 # chunks really came over the owner's helpers
+    if mode == "repeated":      # every path of every wake had exactly one helper; the surplus ones left without touching the mailbox
+        nh = len(helpers)
+        assert len(outcomes) == 7 * nh and outcomes.count("ok") == 3 * nh, outcomes
+        assert sum("already served" in o for o in outcomes) == 3 * nh and sum("is over" in o for o in outcomes) == nh, outcomes
 
 
 # ---- the peer tier under the real launcher: the parking buffer belongs to a node-level owner, the instance sees only its own GPU
