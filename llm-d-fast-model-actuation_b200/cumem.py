@@ -159,7 +159,8 @@ class CuMemAllocator:
         torch.cuda.empty_cache()
 
     def wake_up(self, tags: list[str] | None = None) -> None:
-        if self._remote is not None and self.engine.is_sleeping() and _tier_from_env() == L.FMA_TIER_HOST:
+        moves_an_image = tags is None or any(t != "kv_cache" for t in tags)   # the kv cache is discarded on sleep: waking it copies nothing
+        if self._remote is not None and moves_an_image and self.engine.is_sleeping() and _tier_from_env() == L.FMA_TIER_HOST:
             try:    # the owner's helpers serve the wake that follows; if the request fails, the instance's own link does it all
                 self._remote.request_pull(self.engine, _instance_id(), _rank())
             except Exception as e:      # noqa: BLE001
