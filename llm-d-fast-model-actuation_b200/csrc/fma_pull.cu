@@ -3,6 +3,7 @@
 #include "fma_internal.h"
 
 #include <deque>
+#include <memory>
 
 namespace {
 
@@ -15,16 +16,22 @@ struct HelperStaging {   // owner side: n_slots x slot_bytes in one helper GPU's
     size_t bytes = 0;
     cudaStream_t copy = nullptr;
     cudaEvent_t ev[kMaxRing] = {};
+    std::atomic<int> users{0};          // pulls running on this staging buffer right now
+    std::atomic<bool> closing{false};   // fma_helper_close is waiting for them: leave
 };
 
 struct AttachedStore {   // owner side: another process's memfd host store, mapped and pinned here too
     void* base = nullptr;
     size_t bytes = 0;
+    std::atomic<int> users{0};
+    std::atomic<bool> closing{false};
 };
 
+// A close / detach takes the object out of the table (no new pull finds it), raises `closing` and waits until the pulls that
+// still use it have left; only then are the stream, the mapping and the pinned range torn down.
 std::mutex g_mu;
-std::map<uint64_t, HelperStaging> g_helpers;
-std::map<uint64_t, AttachedStore> g_stores;
+std::map<uint64_t, std::shared_ptr<HelperStaging>> g_helpers;
+std::map<uint64_t, std::shared_ptr<AttachedStore>> g_stores;
 uint64_t g_next = 1;
 
 PullMailbox* map_mailbox(int fd) {
@@ -49,7 +56,8 @@ int fma_helper_open(int device, size_t slot_bytes, int slots, uint64_t* out_hand
     slots = slots > 0 ? std::min(slots, (int)kPullMaxSlots) : 3;
     DeviceGuard guard(device);
     RT(cudaFree(nullptr));
-    HelperStaging h;
+    auto hp = std::make_shared<HelperStaging>();
+    HelperStaging& h = *hp;
     h.device = device;
     h.slot_bytes = slot_bytes;
     h.slots = slots;
@@ -77,20 +85,23 @@ int fma_helper_open(int device, size_t slot_bytes, int slots, uint64_t* out_hand
     for (int i = 0; i < slots; ++i) RT(cudaEventCreateWithFlags(&h.ev[i], cudaEventDisableTiming));
     std::lock_guard<std::mutex> lk(g_mu);
     *out_handle = g_next++;
-    g_helpers[*out_handle] = h;
+    g_helpers[*out_handle] = hp;
     *out_fd = fd;
     return FMA_OK;
 }
 
 int fma_helper_close(uint64_t handle) {
-    HelperStaging h;
+    std::shared_ptr<HelperStaging> hp;
     {
         std::lock_guard<std::mutex> lk(g_mu);
         auto it = g_helpers.find(handle);
         if (it == g_helpers.end()) return fail(FMA_ENOTFOUND, "unknown helper handle");
-        h = it->second;
+        hp = it->second;
         g_helpers.erase(it);
     }
+    HelperStaging& h = *hp;
+    h.closing.store(true);
+    while (h.users.load() > 0) nap();   // a pull notices `closing` within one poll interval (or one chunk copy)
     DeviceGuard guard(h.device);
     cudaStreamSynchronize(h.copy);
     cudaStreamDestroy(h.copy);
@@ -115,20 +126,29 @@ int fma_store_attach(int fd, uint64_t* out_handle) {
         munmap(p, (size_t)sb.st_size);
         return fail(FMA_ENOMEM, "cannot pin the attached store: %s", cudaGetErrorString(r));
     }
+    auto sp = std::make_shared<AttachedStore>();
+    sp->base = p;
+    sp->bytes = (size_t)sb.st_size;
     std::lock_guard<std::mutex> lk(g_mu);
     *out_handle = g_next++;
-    g_stores[*out_handle] = AttachedStore{p, (size_t)sb.st_size};
+    g_stores[*out_handle] = sp;
     return FMA_OK;
 }
 
 int fma_store_detach(uint64_t handle) {
-    std::lock_guard<std::mutex> lk(g_mu);
-    auto it = g_stores.find(handle);
-    if (it == g_stores.end()) return fail(FMA_ENOTFOUND, "unknown store handle");
-    cudaHostUnregister(it->second.base);
-    munmap(it->second.base, it->second.bytes);
+    std::shared_ptr<AttachedStore> sp;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = g_stores.find(handle);
+        if (it == g_stores.end()) return fail(FMA_ENOTFOUND, "unknown store handle");
+        sp = it->second;
+        g_stores.erase(it);
+    }
+    sp->closing.store(true);
+    while (sp->users.load() > 0) nap();
+    cudaHostUnregister(sp->base);
+    munmap(sp->base, sp->bytes);
     cudaGetLastError();
-    g_stores.erase(it);
     return FMA_OK;
 }
 
@@ -136,17 +156,26 @@ int fma_store_detach(uint64_t handle) {
 // shared counter into this helper's staging slots — H2D by THIS GPU's copy engine over THIS GPU's link — and tell the instance, slot
 // by slot, when a chunk has landed.  Blocking; returns when the path is done, the wake is aborted, or nothing moves for timeout_s.
 int fma_helper_pull(uint64_t helper, uint64_t store, int mailbox_fd, int path_index, uint64_t generation, double timeout_s) {
-    HelperStaging h;
-    AttachedStore st;
+    if (path_index < 1 || path_index >= (int)kPullMaxPaths) return fail(FMA_EINVAL, "path index %d", path_index);
+    std::shared_ptr<HelperStaging> hp;
+    std::shared_ptr<AttachedStore> sp;
     {
         std::lock_guard<std::mutex> lk(g_mu);
         auto hi = g_helpers.find(helper);
         auto si = g_stores.find(store);
         if (hi == g_helpers.end() || si == g_stores.end()) return fail(FMA_ENOTFOUND, "unknown helper / store handle");
-        h = hi->second;
-        st = si->second;
+        hp = hi->second;
+        sp = si->second;
+        hp->users.fetch_add(1);   // under g_mu: a close that has already taken the object out of the table is never seen here
+        sp->users.fetch_add(1);
     }
-    if (path_index < 1 || path_index >= (int)kPullMaxPaths) return fail(FMA_EINVAL, "path index %d", path_index);
+    struct Leave {
+        HelperStaging& h; AttachedStore& s;
+        ~Leave() { h.users.fetch_sub(1); s.users.fetch_sub(1); }
+    } leave{*hp, *sp};
+    HelperStaging& h = *hp;
+    AttachedStore& st = *sp;
+    auto closing = [&] { return h.closing.load() || st.closing.load(); };
     PullMailbox* mb = map_mailbox(mailbox_fd);
     if (!mb) return fail(FMA_ENOMEM, "cannot map the mailbox");
     int rc = FMA_OK;
@@ -169,6 +198,7 @@ int fma_helper_pull(uint64_t helper, uint64_t store, int mailbox_fd, int path_in
         const uint64_t g = mb->generation.load(std::memory_order_acquire);
         if (g == generation) break;
         if (g > generation) return done(fail(FMA_ESTATE, "generation %llu is over (the mailbox is at %llu)", (unsigned long long)generation, (unsigned long long)g));
+        if (closing()) return done(fail(FMA_ESTATE, "the helper / the store is being closed"));
         if (now_s() - t_last > timeout_s) return done(fail(FMA_ESTATE, "the wake of generation %llu never started", (unsigned long long)generation));
         nap();
     }
@@ -191,7 +221,7 @@ int fma_helper_pull(uint64_t helper, uint64_t store, int mailbox_fd, int path_in
             if (state[slot].compare_exchange_strong(seen, pull_word(generation, value), std::memory_order_acq_rel)) return 1;
             if (mb->generation.load(std::memory_order_acquire) != generation) return 0;
             if (pull_word_is_of(seen, generation)) return fail(FMA_ESTATE, "slot %d of path %d holds a word this helper did not write", slot, path_index);
-            if (mb->abort.load() || now_s() - t0 > timeout_s) return fail(FMA_ESTATE, "slot %d of path %d never became free", slot, path_index);
+            if (mb->abort.load() || closing() || now_s() - t0 > timeout_s) return fail(FMA_ESTATE, "slot %d of path %d never became free", slot, path_index);
             nap();
         }
     };
@@ -203,6 +233,7 @@ int fma_helper_pull(uint64_t helper, uint64_t store, int mailbox_fd, int path_in
     while (rc == FMA_OK) {
         if (mb->generation.load(std::memory_order_acquire) != generation) { superseded = true; rc = fail(FMA_ESTATE, "generation %llu is over", (unsigned long long)generation); break; }
         if (mb->abort.load()) { rc = fail(FMA_ESTATE, "the wake was aborted"); break; }
+        if (closing()) { rc = fail(FMA_ESTATE, "the helper / the store is being closed"); break; }   // chunks this path took are lost: the wake fails and rolls back
         // publish copies that have landed (block on the oldest when nothing else can be done)
         bool progressed = false;
         while (!fly.empty()) {
@@ -250,7 +281,7 @@ int fma_helper_pull(uint64_t helper, uint64_t store, int mailbox_fd, int path_in
         t_last = now_s();
         while (state[slot].load(std::memory_order_acquire) != 0) {
             if (mb->generation.load(std::memory_order_acquire) != generation) { superseded = true; rc = fail(FMA_ESTATE, "generation %llu is over", (unsigned long long)generation); break; }
-            if (mb->abort.load() || now_s() - t_last > timeout_s) { rc = fail(FMA_ESTATE, "the instance never drained the last slot of path %d", path_index); break; }
+            if (mb->abort.load() || closing() || now_s() - t_last > timeout_s) { rc = fail(FMA_ESTATE, "the instance never drained the last slot of path %d", path_index); break; }
             nap();
         }
         if (rc == FMA_OK && mb->generation.load(std::memory_order_acquire) == generation) {

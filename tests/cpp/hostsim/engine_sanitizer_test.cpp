@@ -354,8 +354,22 @@ int main() {
             auto after = digests(r);
             for (size_t i = 0; i < before.size(); ++i) assert(after[i] == before[i]);
         }
-        OK(fma_store_detach(store));
-        OK(fma_helper_close(helper));
+        // The owner closes a helper and detaches a store while pulls still wait on them (an instance deleted mid-request): close /
+        // detach return only after those pulls have left, and the pulls leave at once instead of waiting out their 30 s.
+        {
+            const uint64_t never = fma_pull_next_generation(r) + 7;
+            int prc[2] = {0, 0};
+            std::thread w0([&] { prc[0] = fma_helper_pull(helper, store, mailbox_fd, 1, never, 30.0); });
+            std::thread w1([&] { prc[1] = fma_helper_pull(helper, store, mailbox_fd, 1, never, 30.0); });
+            std::this_thread::sleep_for(std::chrono::milliseconds(20));
+            const auto t0 = std::chrono::steady_clock::now();
+            OK(fma_store_detach(store));
+            OK(fma_helper_close(helper));
+            w0.join(); w1.join();
+            assert(prc[0] != 0 && prc[1] != 0);
+            assert(std::chrono::steady_clock::now() - t0 < std::chrono::seconds(10));
+            assert(fma_helper_pull(helper, store, mailbox_fd, 1, never, 1.0) != 0);   // both handles are gone
+        }
         close(staging_fd);
         close(store_fd);
         OK(fma_engine_destroy(r));
