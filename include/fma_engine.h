@@ -261,7 +261,10 @@ FMA_API int  fma_paths_set(fma_engine_t* e, const int* helper_devices, int n, si
  * staging fds...) maps the staging buffers for ITS GPU (NVLink), creates the mailbox (*out_mailbox_fd: send it, dup'ed, to the
  * owner) and from then on fma_wake runs K2 on every remote slot the owner reports as landed, while its own link pulls from the
  * same work counter.  fma_pull_next_generation(engine) is what the owner's helpers must be told to wait for BEFORE fma_wake is
- * called.  A pull request that never arrives costs nothing but speed: the paths that do work finish the wake. */
+ * called.  A pull request that never arrives costs nothing but speed: the paths that do work finish the wake.  Exactly one
+ * fma_helper_pull serves a path in a wake: a repeated request, one for a wake that is over, or one whose wake never uses the
+ * paths returns FMA_ESTATE without having written to the mailbox.  fma_helper_close / fma_store_detach make the pulls that still
+ * use the object leave (FMA_ESTATE) and return after they have. */
 FMA_API int       fma_helper_open(int device, size_t slot_bytes, int slots, uint64_t* out_handle, int* out_fd);
 FMA_API int       fma_helper_close(uint64_t handle);
 FMA_API int       fma_store_attach(int fd, uint64_t* out_handle);
