@@ -124,7 +124,12 @@ class CuMemAllocator:
                 from .parking import ParkingClient
 
                 owner = ParkingClient()
-                owner.park(self.engine, _instance_id(), _rank(), nbytes, avoid=_own_gpu_indices())
+                try:
+                    owner.park(self.engine, _instance_id(), _rank(), nbytes, avoid=_own_gpu_indices())
+                except (RuntimeError, OSError, L.FmaError) as e:
+                    # no peer has room (or the agent is gone): the sleep itself must not fail for that — the host tier always works
+                    logger.warning("fma_b200: cannot park %.2f GiB on a peer GPU (%s): sleeping to the host tier instead", nbytes / 1024**3, e)
+                    owner, tier = None, L.FMA_TIER_HOST
             else:
                 # parking GPU for the NVLink tier: FMA_PEER_DEVICE (index among the devices this process sees)
                 peer = int(os.environ.get("FMA_PEER_DEVICE", "-1"))

@@ -73,12 +73,13 @@ class ParkingService:
             host = [{"instance": k[0], "rank": k[1], "mib": os.fstat(fd).st_size // MiB} for k, fd in sorted(self._host_images.items())]
         return {"parked_mib_per_device": {str(d): b // MiB for d, b in per.items()}, "images": images, "host_images": host}
 
-    def _pick_device(self, avoid) -> int:
+    def _candidates(self, avoid) -> list:
+        """GPUs outside `avoid`, least parked bytes first (lowest index on a tie)."""
         per = self.parked_bytes_per_device()
         cands = [d for d in range(self.n_devices) if d not in set(avoid or [])]
         if not cands:
             raise ValueError("no GPU left to park on")
-        return min(cands, key=lambda d: (per[d], d))
+        return sorted(cands, key=lambda d: (per[d], d))
 
     # ---- operations -------------------------------------------------------------------------------------------
     def park(self, instance: str, rank: int, nbytes: int, device: Optional[int] = None, avoid=None):
@@ -90,11 +91,20 @@ class ParkingService:
             return old["buf"]
         if old is not None:
             self.release(instance, rank)
-        dev = self._pick_device(avoid) if device is None else int(device)
-        buf = self._make(dev, int(nbytes))
-        with self._lock:
-            self._images[key] = {"buf": buf, "descriptor": None}
-        return buf
+        # What this service has parked is all it knows about a GPU's HBM: an awake instance may fill the rest.  So the least-loaded
+        # candidate is only tried first; a GPU that cannot take the buffer (cuMemCreate fails) passes it on to the next one, and
+        # only when none can is the park refused — the caller then sleeps to the host tier (cumem.py).
+        last = None
+        for dev in (self._candidates(avoid) if device is None else [int(device)]):
+            try:
+                buf = self._make(dev, int(nbytes))
+            except Exception as e:      # noqa: BLE001
+                last = e
+                continue
+            with self._lock:
+                self._images[key] = {"buf": buf, "descriptor": None}
+            return buf
+        raise RuntimeError(f"no GPU can take {int(nbytes) // MiB} MiB right now: {last}")
 
     def deposit(self, instance: str, rank: int, descriptor: bytes) -> None:
         with self._lock:

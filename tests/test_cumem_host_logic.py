@@ -80,3 +80,30 @@ def test_peer_tier_comes_from_the_environment(alloc, monkeypatch):
     alloc.sleep(offload_tags=("weights",))
     assert ("peer_reserve", 5, 15 * GiB) in alloc.engine.calls
     assert alloc.engine.calls[-1] == ("sleep", ("weights",), L.FMA_TIER_PEER)
+
+
+def test_peer_tier_falls_back_to_the_host_tier_when_no_gpu_can_take_the_image(alloc, monkeypatch, tmp_path, caplog):
+    """Under the node agent the parking buffer is the agent's (parking.py).  If every candidate GPU is full — or the agent is gone —
+    the sleep still has to succeed: it goes to the host tier, as the reference's always does (cumem.py:237-249), and says so."""
+    from fma_b200.parking import ParkingService
+
+    def full(device, nbytes):
+        raise MemoryError(f"cuMemCreate on device {device}: out of memory")
+
+    sock = str(tmp_path / "agent.sock")
+    svc = ParkingService(sock, n_devices=4, make_buffer=full)
+    svc.start()
+    monkeypatch.setenv("FMA_TIER", "peer")
+    monkeypatch.setenv("FMA_NODE_AGENT_SOCK", sock)
+    monkeypatch.setenv("FMA_NODE_GPU_INDICES", "0")
+    try:
+        with caplog.at_level(logging.WARNING, logger="vllm.fma_b200.cumem"):
+            alloc.sleep(offload_tags=("weights",))
+        assert alloc.engine.calls[-1] == ("sleep", ("weights",), L.FMA_TIER_HOST)
+        assert any("sleeping to the host tier instead" in r.getMessage() and "no GPU can take 15360 MiB" in r.getMessage() for r in caplog.records)
+        assert svc.stats()["images"] == []
+    finally:
+        svc.close()
+    alloc.engine.calls.clear()
+    alloc.sleep(offload_tags=("weights",))          # the agent's socket is gone altogether
+    assert alloc.engine.calls[-1] == ("sleep", ("weights",), L.FMA_TIER_HOST)

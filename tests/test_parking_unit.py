@@ -10,8 +10,11 @@ from fma_b200.parking import MiB, ParkingClient, ParkingService
 
 class FakeBuffer:
     made = []
+    full = set()            # GPUs whose HBM an awake instance has filled: creating a buffer there fails
 
     def __init__(self, device, nbytes):
+        if device in FakeBuffer.full:
+            raise MemoryError(f"cuMemCreate on device {device}: out of memory")
         self.device, self.nbytes = device, (nbytes + 2 * MiB - 1) // (2 * MiB) * (2 * MiB)
         self._f = tempfile.TemporaryFile()
         self._f.truncate(self.nbytes)
@@ -70,6 +73,16 @@ def test_placement_accounting_and_protocol(tmp_path):
         assert rep["ok"] is False and fd is None
         rep, _ = cli._rpc({"op": "park", "instance": "Ie", "bytes": 1, "avoid": [0, 1, 2, 3]})
         assert rep["ok"] is False and "no GPU" in rep["error"]
+        # the least-loaded GPU is full (an awake instance owns its HBM): the next candidate takes the buffer; when every candidate is
+        # full the park is refused with a reason (the allocator shim then sleeps to the host tier) and nothing is left behind
+        FakeBuffer.full = {1}
+        assert cli.park(FakeEngine(), "If", 0, 20 * MiB, avoid=[0])["device"] == 3     # loads: 1 -> 0 (full), 3 -> 10, 2 -> 50
+        FakeBuffer.full = {1, 2, 3}
+        before = cli.stats()
+        rep, fd = cli._rpc({"op": "park", "instance": "Ig", "bytes": 20 * MiB, "avoid": [0]})
+        assert rep["ok"] is False and fd is None and "no GPU can take 20 MiB" in rep["error"] and "out of memory" in rep["error"]
+        assert cli.stats() == before
+        FakeBuffer.full = set()
     finally:
         svc.close()
     assert all(b.closed for b in FakeBuffer.made)
