@@ -135,7 +135,13 @@ class CuMemAllocator:
                 peer = int(os.environ.get("FMA_PEER_DEVICE", "-1"))
                 if peer < 0:
                     raise L.FmaError(L.FMA_EINVAL, "FMA_TIER=peer needs FMA_NODE_AGENT_SOCK (node-level owner) or FMA_PEER_DEVICE=<visible device index of the parking GPU>")
-                self.engine.peer_reserve(peer, nbytes)
+                try:
+                    self.engine.peer_reserve(peer, nbytes)
+                except L.FmaError as e:
+                    if e.code != L.FMA_ENOMEM:
+                        raise
+                    logger.warning("fma_b200: GPU %d cannot take %.2f GiB right now (%s): sleeping to the host tier instead", peer, nbytes / 1024**3, e.message)
+                    tier = L.FMA_TIER_HOST
         self.engine.sleep(offload_tags, tier=tier)
         if owner is not None and self.engine.stats()["sleep_bytes_offloaded"]:
             owner.deposit(self.engine, _instance_id(), _rank(), tier)

@@ -81,6 +81,18 @@ def test_peer_tier_comes_from_the_environment(alloc, monkeypatch):
     assert ("peer_reserve", 5, 15 * GiB) in alloc.engine.calls
     assert alloc.engine.calls[-1] == ("sleep", ("weights",), L.FMA_TIER_PEER)
 
+    def no_room(dev, n):
+        raise L.FmaError(L.FMA_ENOMEM, "cuMemCreate(peer store) failed: out of memory")
+    monkeypatch.setattr(alloc.engine, "peer_reserve", no_room)          # the parking GPU is full right now: the sleep goes to the host tier
+    alloc.sleep(offload_tags=("weights",))
+    assert alloc.engine.calls[-1] == ("sleep", ("weights",), L.FMA_TIER_HOST)
+
+    def broken(dev, n):
+        raise L.FmaError(L.FMA_ECUDA, "no NVLink path")
+    monkeypatch.setattr(alloc.engine, "peer_reserve", broken)           # anything else stays loud
+    with pytest.raises(L.FmaError):
+        alloc.sleep(offload_tags=("weights",))
+
 
 def test_peer_tier_falls_back_to_the_host_tier_when_no_gpu_can_take_the_image(alloc, monkeypatch, tmp_path, caplog):
     """Under the node agent the parking buffer is the agent's (parking.py).  If every candidate GPU is full — or the agent is gone —
